@@ -1,0 +1,184 @@
+/*
+ * msd.h -- C ABI of libmsd_b200.so, the sm_100a kernel library behind the restoration hot path
+ * (corrupt -> SatMAE ViT-B + CNN-decoder restore -> MSE+SSIM loss / PSNR.SSIM.SAM metrics).
+ *
+ * The reference (ajammoussi/Multi-Spectral-Satellite-Image-Denoising) is pure Python/PyTorch and has no FFI;
+ * the "interface each entry point replaces" is therefore a reference Python function or nn.Module.forward,
+ * cited per entry as <file>:<lines> relative to the reference tree.  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *  - every pointer named d_* is a DEVICE pointer owned by the caller (PyTorch allocates everything);
+ *    the library owns only the opaque msd_model (tensor maps, tap tables), never frees caller memory;
+ *  - every call is asynchronous and ordered on `stream` (a cudaStream_t passed as void*); no call
+ *    synchronises the device;
+ *  - return value: 0 on success, a negative msd_status otherwise; text via msd_last_error() (thread-local);
+ *  - no C++ types or exceptions cross this boundary.
+ */
+#ifndef MSD_B200_H_
+#define MSD_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum msd_status {
+  MSD_OK = 0,
+  MSD_ERR_INVALID = -1,  /* bad shape / null pointer / misaligned pointer / unsupported option */
+  MSD_ERR_CUDA = -2,     /* a CUDA runtime or driver call failed; see msd_last_error() */
+  MSD_ERR_ARCH = -3,     /* device is not compute capability 10.x (library is sm_100a only) */
+  MSD_ERR_WORKSPACE = -4 /* caller-provided workspace too small */
+} msd_status;
+
+/* Library ABI version (bumped on any signature change). */
+int msd_version(void);
+/* Last error text of the calling thread; valid until the next failing call on that thread. */
+const char* msd_last_error(void);
+/* 0 if the current device is sm_100 (B200); MSD_ERR_ARCH otherwise. */
+int msd_check_device(void);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Counter-based RNG, bit-compatible with the Philox4x32-10 stream PyTorch's CUDA generator produces
+ * (what `torch.randn_like` / `torch.rand` draw when the reference's AddSensorNoise runs on a CUDA
+ * tensor: src/data/transforms.py:90-121).  `torch_grid` is the grid PyTorch would launch for `numel`
+ * (min(SMs * maxThreadsPerSM/256, ceil(numel/256))); the offset increment PyTorch applies afterwards is
+ * returned by msd_philox_offset_increment().
+ * ------------------------------------------------------------------------------------------------- */
+uint64_t msd_philox_offset_increment(int64_t numel, uint32_t torch_grid);
+int msd_philox_normal_f32(float* d_out, int64_t numel, uint64_t seed, uint64_t offset, uint32_t torch_grid,
+                          void* stream);
+int msd_philox_uniform_f32(float* d_out, int64_t numel, uint64_t seed, uint64_t offset, uint32_t torch_grid,
+                           void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Corruption simulator.  Replaces AddSensorNoise.forward (src/data/transforms.py:70-134) and
+ * _add_striping (:136-154) for a batch [B,C,H,W] fp32 NCHW.
+ *   order of draws (identical to the reference): gaussian randn_like (if sg>0), speckle randn_like (if ss>0),
+ *   B x rand(C) (if p>0, one call per sample), thermal randn_like (if st>0), stripe randn(B,C,1,W) (if stripe).
+ *   d_thermal_w : [C] fp32 device, torch.linspace(1,2,C) as the reference builds it (:112-114)
+ *   d_dead_mask : [B*C] uint8 device, OUT (1 = band zeroed); required when p>0
+ *   d_stripe_ws : [B*C*W] fp32 device scratch, required when stripe != 0
+ *   d_patch_bf16: optional OUT [B*(H/16)*(W/16), C*256] bf16, the patch-embed A operand of the noisy image
+ *                 (src/models/encoder.py:48-50 im2col order (c,ky,kx)); NULL to skip
+ *   offset_consumed: OUT, total Philox offset the reference would have consumed (host pointer)
+ * ------------------------------------------------------------------------------------------------- */
+int msd_corrupt_f32(const float* d_clean, float* d_noisy, const float* d_thermal_w, uint8_t* d_dead_mask,
+                    float* d_stripe_ws, void* d_patch_bf16, int B, int C, int H, int W, float sg, float ss, float p,
+                    float st, int stripe, uint64_t seed, uint64_t offset, uint32_t torch_grid_full,
+                    uint32_t torch_grid_mask, uint32_t torch_grid_stripe, uint64_t* offset_consumed, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Fused evaluation metrics.  Replaces MetricsTracker.update's per-sample loop
+ * (src/training/metrics.py:247-256) and calculate_psnr/ssim/sam/rmse (:19-46, 49-121, 124-172, 175-191).
+ *   d_per_image: OUT [B,4] fp64 = {psnr_dB (inf if mse==0), ssim, sam_degrees, rmse} per image
+ *   d_sums     : OUT [5]  fp64 = {sum psnr, sum ssim, sum sam, sum rmse, B}  (the tracker's running sums)
+ *   d_scratch  : [B,4] fp64 device scratch (raw per-image sums), zeroed by the call
+ * ------------------------------------------------------------------------------------------------- */
+int msd_metrics_f32(const float* d_pred, const float* d_target, int B, int C, int H, int W, float data_range,
+                    double* d_per_image, double* d_sums, double* d_scratch, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Training loss.  Replaces CombinedLoss.forward (src/training/losses.py:55-77) = w_mse*MSE + w_ssim*(1-SSIM)
+ * with SSIMLoss._ssim (:123-163): 11x11 Gaussian sigma 1.5, zero padding 5, global mean.
+ *   d_out      : OUT [3] fp32 = {total, mse, 1-ssim}
+ *   d_grad_pred: optional OUT [B,C,H,W] fp32 = grad_scale * d(total)/d(pred); NULL for forward only
+ *   d_ws       : scratch, msd_loss_workspace_bytes() bytes (3 derivative maps + 2 fp64 accumulators)
+ * ------------------------------------------------------------------------------------------------- */
+size_t msd_loss_workspace_bytes(int B, int C, int H, int W);
+int msd_loss_fwd_bwd_f32(const float* d_pred, const float* d_target, int B, int C, int H, int W, float w_mse,
+                         float w_ssim, float data_range, float grad_scale, float* d_out, float* d_grad_pred,
+                         void* d_ws, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Restoration model forward.  Replaces SatMAERestoration.forward (src/models/satmae_restoration.py:81-110):
+ * PatchEmbed (encoder.py:41-52) -> +pos_embed -> 12 pre-norm blocks (encoder.py:120-134 | 154-176) -> LayerNorm
+ * -> 4 x {ConvTranspose2d k2s2 + BN + GELU, 2 x ResidualBlock} (blocks.py:74-85, 113-123) -> head
+ * (decoder.py:76-81).  Eval-mode BatchNorm is folded into the packed weights by the host shim.
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct msd_model msd_model;
+
+typedef struct msd_model_desc {
+  int in_channels;  /* 13 */
+  int image_size;   /* 192 */
+  int patch_size;   /* 16 */
+  int embed_dim;    /* 768 */
+  int depth;        /* 12 */
+  int num_heads;    /* 12 */
+  int mlp_hidden;   /* 3072 */
+  int dec_channels[4]; /* 384,192,96,48 */
+  int out_channels; /* 13 */
+  float ln_eps_block; /* 1e-6 (timm Block) or 1e-5 (reference fallback CustomBlock) */
+  float ln_eps_outer; /* 1e-5: patch_embed.norm and encoder.norm */
+  int gemm_backend;   /* 0 = tcgen05/TMEM/TMA (product path), 1 = legacy mma.sync (A/B baseline) */
+} msd_model_desc;
+
+/* Packed weights, all DEVICE pointers that must outlive the model (the shim keeps the tensors alive).
+ * bf16 matrices are row-major [N, K] (K contiguous).  Conv weights are [Cout, 9*Kpad] tap-major with
+ * Kpad = Cin rounded up to 64; BN already folded (w*gamma/sqrt(var+eps), bias = beta + (b-mean)*scale). */
+typedef struct msd_block_weights {
+  const float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+  const void *w_qkv;  const float *b_qkv;   /* [2304,768]  */
+  const void *w_proj; const float *b_proj;  /* [768,768]   */
+  const void *w_fc1;  const float *b_fc1;   /* [3072,768]  */
+  const void *w_fc2;  const float *b_fc2;   /* [768,3072]  */
+} msd_block_weights;
+
+typedef struct msd_stage_weights {
+  const void *w_up;  const float *b_up;     /* [4*Cout, Cin] rows ordered (di,dj,o); bias [4*Cout] */
+  const void *w_conv[4]; const float *b_conv[4]; /* rb1.conv1, rb1.conv2, rb2.conv1, rb2.conv2 */
+} msd_stage_weights;
+
+typedef struct msd_model_weights {
+  const void *w_pe; const float *b_pe;      /* [768, 3328] */
+  const float *pe_ln_g, *pe_ln_b;
+  const float *pos_embed;                   /* [144,768] fp32 */
+  const msd_block_weights* blocks;          /* [depth] host array */
+  const float *norm_g, *norm_b;
+  msd_stage_weights stages[4];
+  const void *w_head3; const float *b_head3; /* [48, 9*64] */
+  const float *w_head1; const float *b_head1;/* [13,48] fp32, [13] */
+} msd_model_weights;
+
+int msd_model_create(const msd_model_desc* desc, msd_model** out);
+int msd_model_set_weights(msd_model* m, const msd_model_weights* w);
+size_t msd_model_workspace_bytes(const msd_model* m, int B);
+/* d_x: [B,C,S,S] fp32 NCHW (or NULL if d_patch_bf16 given); d_patch_bf16: optional pre-patchified A operand
+ * written by msd_corrupt_f32; d_y: [B,out_channels,S,S] fp32 NCHW; d_ws: workspace (256-byte aligned). */
+int msd_model_forward(msd_model* m, const float* d_x, const void* d_patch_bf16, int B, float* d_y, void* d_ws,
+                      size_t ws_bytes, void* stream);
+/* number of kernels one forward launches (for bench.py's gpu_launches claim) */
+int msd_model_launch_count(const msd_model* m);
+void msd_model_destroy(msd_model* m);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Building blocks, exported so tests can pin each kernel against the oracle separately.
+ * ------------------------------------------------------------------------------------------------- */
+/* y[M,N] = act(A[M,K] . W[N,K]^T + bias); A,W bf16 row-major; out bf16 (out_f32=0) or fp32 (out_f32=1);
+ * act: 0 none, 1 GELU(erf).  resid_f32 != NULL -> out fp32 = resid + A.W^T + bias (may alias out). */
+int msd_linear_bf16(const void* d_a, const void* d_w, const float* d_bias, void* d_out, const float* d_resid,
+                    int M, int N, int K, int act, int out_f32, int backend, void* stream);
+/* 3x3 conv, pad 1, NHWC bf16 with a 1-pixel zero halo: x,y,skip are [B,(H+2),(W+2),C*] bf16; w [Cout, 9*Kpad]. */
+int msd_conv3x3_nhwc_bf16(const void* d_x, const void* d_w, const float* d_bias, const void* d_skip, void* d_y,
+                          int B, int H, int W, int Cin, int Cout, int backend, void* stream);
+/* ConvTranspose2d k2 s2 + bias + GELU: x [B,Hin(+2p),Win(+2p),Cin] bf16 -> y [B,2Hin+2,2Win+2,Cout] haloed. */
+int msd_convt2x2_nhwc_bf16(const void* d_x, const void* d_w, const float* d_bias, void* d_y, int B, int Hin, int Win,
+                           int in_padded, int Cin, int Cout, int backend, void* stream);
+/* out bf16 [M,D] = LayerNorm(x fp32 [M,D]); if pos != NULL first x = LN(x)+pos[m % period] is written back (fp32). */
+int msd_layernorm_f32_bf16(const float* d_x, const float* d_g, const float* d_b, float eps, void* d_out_bf16, int M,
+                           int D, void* stream);
+int msd_layernorm_pos_f32(float* d_x, const float* d_g, const float* d_b, float eps, const float* d_pos, int period,
+                          int M, int D, void* stream);
+/* qkv bf16 [B*T, 3*heads*64] -> out bf16 [B*T, heads*64]; softmax(q k^T / 8) v per (image, head); T <= 256. */
+int msd_attention_bf16(const void* d_qkv, void* d_out, int B, int T, int heads, void* stream);
+/* x [B,C,S,S] fp32 -> A [B*(S/P)^2, C*P*P] bf16, column order (c,ky,kx), token n = (S/P)*py + px. */
+int msd_patchify_bf16(const float* d_x, void* d_a, int B, int C, int S, int P, void* stream);
+/* head 1x1: x haloed NHWC bf16 [B,H+2,W+2,Cin] -> y NCHW fp32 [B,Cout,H,W]; w fp32 [Cout,Cin]. */
+int msd_head1x1_nchw_f32(const void* d_x, const float* d_w, const float* d_b, float* d_y, int B, int H, int W, int Cin,
+                         int Cout, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSD_B200_H_ */

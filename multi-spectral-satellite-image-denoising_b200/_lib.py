@@ -1,0 +1,135 @@
+"""ctypes binding of libmsd_b200.so (include/msd.h).  There is no fallback: if the library is missing or the
+device is not sm_100, every product call raises."""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libmsd_b200.so"
+
+c_void_p, c_int, c_float, c_size_t = C.c_void_p, C.c_int, C.c_float, C.c_size_t
+c_u64, c_u32, c_i64 = C.c_uint64, C.c_uint32, C.c_int64
+
+
+class MsdError(RuntimeError):
+    pass
+
+
+class ModelDesc(C.Structure):
+    _fields_ = [
+        ("in_channels", c_int), ("image_size", c_int), ("patch_size", c_int), ("embed_dim", c_int),
+        ("depth", c_int), ("num_heads", c_int), ("mlp_hidden", c_int), ("dec_channels", c_int * 4),
+        ("out_channels", c_int), ("ln_eps_block", c_float), ("ln_eps_outer", c_float), ("gemm_backend", c_int),
+    ]
+
+
+class BlockWeights(C.Structure):
+    _fields_ = [(n, c_void_p) for n in (
+        "ln1_g", "ln1_b", "ln2_g", "ln2_b", "w_qkv", "b_qkv", "w_proj", "b_proj", "w_fc1", "b_fc1", "w_fc2", "b_fc2")]
+
+
+class StageWeights(C.Structure):
+    _fields_ = [("w_up", c_void_p), ("b_up", c_void_p), ("w_conv", c_void_p * 4), ("b_conv", c_void_p * 4)]
+
+
+class ModelWeights(C.Structure):
+    _fields_ = [
+        ("w_pe", c_void_p), ("b_pe", c_void_p), ("pe_ln_g", c_void_p), ("pe_ln_b", c_void_p), ("pos_embed", c_void_p),
+        ("blocks", C.POINTER(BlockWeights)), ("norm_g", c_void_p), ("norm_b", c_void_p),
+        ("stages", StageWeights * 4), ("w_head3", c_void_p), ("b_head3", c_void_p), ("w_head1", c_void_p),
+        ("b_head1", c_void_p),
+    ]
+
+
+# name -> (restype, argtypes); must list every symbol include/msd.h declares (tests/test_abi.py checks this)
+SIGNATURES = {
+    "msd_version": (c_int, []),
+    "msd_last_error": (C.c_char_p, []),
+    "msd_check_device": (c_int, []),
+    "msd_philox_offset_increment": (c_u64, [c_i64, c_u32]),
+    "msd_philox_normal_f32": (c_int, [c_void_p, c_i64, c_u64, c_u64, c_u32, c_void_p]),
+    "msd_philox_uniform_f32": (c_int, [c_void_p, c_i64, c_u64, c_u64, c_u32, c_void_p]),
+    "msd_corrupt_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                c_float, c_float, c_float, c_float, c_int, c_u64, c_u64, c_u32, c_u32, c_u32,
+                                C.POINTER(c_u64), c_void_p]),
+    "msd_metrics_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p,
+                                c_void_p]),
+    "msd_loss_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "msd_loss_fwd_bwd_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float, c_float, c_float,
+                                     c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "msd_model_create": (c_int, [C.POINTER(ModelDesc), C.POINTER(c_void_p)]),
+    "msd_model_set_weights": (c_int, [c_void_p, C.POINTER(ModelWeights)]),
+    "msd_model_workspace_bytes": (c_size_t, [c_void_p, c_int]),
+    "msd_model_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "msd_model_launch_count": (c_int, [c_void_p]),
+    "msd_model_destroy": (None, [c_void_p]),
+    "msd_linear_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                c_int, c_void_p]),
+    "msd_conv3x3_nhwc_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                      c_int, c_int, c_void_p]),
+    "msd_convt2x2_nhwc_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                       c_int, c_void_p]),
+    "msd_layernorm_f32_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_void_p]),
+    "msd_layernorm_pos_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "msd_attention_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "msd_patchify_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "msd_head1x1_nchw_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                     c_void_p]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the shared library (built by build.py).  Raises MsdError when it is absent -- no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise MsdError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            f"(nvcc, sm_100a).  libmsd_b200 has no CPU or PyTorch fallback.")
+    lib = C.CDLL(str(LIB_PATH))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the ABI lost a symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = load().msd_last_error().decode("utf-8", "replace")
+        raise MsdError(f"libmsd_b200 error {rc}: {msg}")
+
+
+def stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t) -> C.c_void_p:
+    """Device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return C.c_void_p(0)
+    if not t.is_cuda:
+        raise MsdError("libmsd_b200 operates on CUDA tensors only (no CPU path)")
+    if not t.is_contiguous():
+        raise MsdError("tensor must be contiguous")
+    return C.c_void_p(t.data_ptr())
+
+
+_device_ok: set[int] = set()
+
+
+def require_device(device) -> None:
+    """Check once per device that it is sm_100."""
+    import torch
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx in _device_ok:
+        return
+    with torch.cuda.device(idx):
+        check(load().msd_check_device())
+    _device_ok.add(idx)

@@ -1,0 +1,83 @@
+// Shared host/device helpers for libmsd_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include "../../include/msd.h"
+
+// ---------------------------------------------------------------------------------------------------
+// error plumbing: nothing throws across the C ABI; text is kept per thread
+// ---------------------------------------------------------------------------------------------------
+void msd_set_error(const char* fmt, ...);
+
+#define MSD_CHECK_CUDA(expr)                                                                          \
+  do {                                                                                                \
+    cudaError_t _e = (expr);                                                                          \
+    if (_e != cudaSuccess) {                                                                          \
+      msd_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e));            \
+      return MSD_ERR_CUDA;                                                                            \
+    }                                                                                                 \
+  } while (0)
+
+#define MSD_REQUIRE(cond, ...)                                                                        \
+  do {                                                                                                \
+    if (!(cond)) {                                                                                    \
+      msd_set_error(__VA_ARGS__);                                                                     \
+      return MSD_ERR_INVALID;                                                                         \
+    }                                                                                                 \
+  } while (0)
+
+#define MSD_LAUNCH_CHECK() MSD_CHECK_CUDA(cudaGetLastError())
+
+static inline bool msd_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// ---------------------------------------------------------------------------------------------------
+// exact unsigned division by a runtime constant (n < 2^31): q = (umulhi(n, m) + n) >> s
+// ---------------------------------------------------------------------------------------------------
+struct FastDiv {
+  uint32_t d, m, s;
+};
+static inline FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f;
+  f.d = d;
+  uint32_t s = 0;
+  while ((1ull << s) < d) ++s;
+  f.s = s;
+  f.m = (uint32_t)((((1ull << 32) * ((1ull << s) - d)) / d) + 1);
+  return f;
+}
+__device__ __forceinline__ uint32_t fd_div(uint32_t n, const FastDiv& f) {
+  return (__umulhi(n, f.m) + n) >> f.s;
+}
+__device__ __forceinline__ void fd_divmod(uint32_t n, const FastDiv& f, uint32_t& q, uint32_t& r) {
+  q = fd_div(n, f);
+  r = n - q * f.d;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// small device helpers
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// GELU(erf), the nn.GELU() default the reference uses (blocks.py:70, encoder.py:164)
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
+  __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
+  return __bfloat1622float2(v);
+}

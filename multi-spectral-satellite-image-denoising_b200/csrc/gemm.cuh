@@ -1,0 +1,144 @@
+// Problem description + fused epilogues shared by the tcgen05 kernel (gemm_tc5.cu) and the legacy mma.sync
+// kernel (gemm_hmma.cu).  Every dense contraction of the restoration forward pass is ONE shape of this:
+//
+//     D[m, n] = sum_{tap} sum_{k} A[m + tap_off[tap], k] * Wt[n, tap*Kpad + k]        (bf16 x bf16 -> fp32)
+//
+//   linear layers (patch-embed, qkv, proj, fc1, fc2)        : 1 tap, tap_off = {0}
+//   ConvTranspose2d k2 s2 (blocks.py:113-118)               : 1 tap, N = 4*Cout, pixel-shuffle store
+//   Conv2d 3x3 pad 1 (blocks.py:66-72, decoder.py:77)       : 9 taps over the halo-padded NHWC pixel list:
+//        activations are stored [B, H+2, W+2, C] with a zero 1-pixel halo, flattened to rows p; the tap
+//        (dy,dx) is then a constant row shift dy*(W+2)+dx, so the A tile of every tap is a plain 2-D box and
+//        TMA's out-of-bounds zero fill covers the ends of the buffer.  Halo rows compute garbage and are
+//        stored as zeros, which keeps the halo invariant for the next layer.
+#pragma once
+#include "common.cuh"
+
+namespace gemm {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;  // bf16 elements = one 128-byte swizzle atom
+
+enum EpiMode : int { EPI_ROWMAJOR = 0, EPI_CONV = 1, EPI_CONVT = 2 };
+
+struct Problem {
+  // operands
+  const __nv_bfloat16* A;   // [a_rows, ldA]
+  const __nv_bfloat16* Wt;  // [N, num_kb*64]
+  int M, N;                 // output rows / cols (N % 16 == 0)
+  int a_rows, ldA, kvalid;  // A extent; kvalid = valid K per tap (<= kb_per_tap*64), the rest reads as zero
+  int num_kb, kb_per_tap;
+  int tap_off[9];
+  // epilogue
+  int mode, act, out_f32;
+  const float* bias;        // [N] or null
+  void* out;
+  int ldo;                  // row pitch of out (elements)
+  const float* resid;       // EPI_ROWMAJOR: fp32 residual [M, ldo] (may alias out) or null
+  const __nv_bfloat16* skip;// EPI_CONV: skip tensor (same layout as out) or null
+  // EPI_CONV: rows are padded pixels p of [B, H+2, W+2]
+  FastDiv plane, pitch;
+  int H, W;
+  // EPI_CONVT: rows are input pixels ([B,Hin,Win] or padded), cols n = (di*2+dj)*Cout + o
+  FastDiv in_plane, in_pitch, cout_div;
+  int in_pad, Hin, Win;
+  int out_plane, out_pitch; // (2Hin+2)*(2Win+2), 2Win+2
+};
+
+__device__ __forceinline__ float apply_act(float v, int act) { return act ? gelu_erf(v) : v; }
+
+// store NV (2, 8 or 16) consecutive output columns n..n+NV-1 of output row m; v = raw accumulators
+template <int NV>
+__device__ __forceinline__ void epilogue_store(const Problem& p, int m, int n, float (&v)[NV]) {
+  if (m >= p.M || n >= p.N) return;
+  if (p.bias != nullptr) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] += __ldg(p.bias + n + i);
+  }
+  if (p.mode == EPI_ROWMAJOR) {
+    const size_t off = (size_t)m * p.ldo + n;
+    if (p.resid != nullptr) {
+#pragma unroll
+      for (int i = 0; i < NV; i += 2) {
+        const float2 r = *reinterpret_cast<const float2*>(p.resid + off + i);
+        v[i] += r.x; v[i + 1] += r.y;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = apply_act(v[i], p.act);
+    if (p.out_f32) {
+      float* o = reinterpret_cast<float*>(p.out) + off;
+      if constexpr (NV % 4 == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < NV; i += 2) *reinterpret_cast<float2*>(o + i) = make_float2(v[i], v[i + 1]);
+      }
+    } else {
+      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + off;
+      if constexpr (NV % 8 == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; i += 8)
+          *reinterpret_cast<uint4*>(o + i) = make_uint4(pack_bf16x2(v[i], v[i + 1]), pack_bf16x2(v[i + 2], v[i + 3]),
+                                                        pack_bf16x2(v[i + 4], v[i + 5]), pack_bf16x2(v[i + 6], v[i + 7]));
+      } else {
+#pragma unroll
+        for (int i = 0; i < NV; i += 2) *reinterpret_cast<uint32_t*>(o + i) = pack_bf16x2(v[i], v[i + 1]);
+      }
+    }
+    return;
+  }
+  size_t off;
+  bool interior;
+  if (p.mode == EPI_CONV) {
+    uint32_t img, rem, yy, xx;
+    fd_divmod((uint32_t)m, p.plane, img, rem);
+    fd_divmod(rem, p.pitch, yy, xx);
+    interior = yy >= 1 && yy <= (uint32_t)p.H && xx >= 1 && xx <= (uint32_t)p.W;
+    off = (size_t)m * p.ldo + n;
+    if (interior && p.skip != nullptr) {
+#pragma unroll
+      for (int i = 0; i < NV; i += 2) {
+        const float2 s = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(p.skip + off + i));
+        v[i] += s.x; v[i + 1] += s.y;
+      }
+    }
+  } else {  // EPI_CONVT
+    uint32_t img, rem, yy, xx;
+    if (p.in_pad) {
+      fd_divmod((uint32_t)m, p.in_plane, img, rem);
+      fd_divmod(rem, p.in_pitch, yy, xx);
+      interior = yy >= 1 && yy <= (uint32_t)p.Hin && xx >= 1 && xx <= (uint32_t)p.Win;
+      yy -= 1; xx -= 1;
+    } else {
+      fd_divmod((uint32_t)m, p.in_plane, img, rem);
+      fd_divmod(rem, p.in_pitch, yy, xx);
+      interior = true;
+    }
+    if (!interior) return;  // nothing to scatter from a halo row
+    uint32_t q, o;
+    fd_divmod((uint32_t)n, p.cout_div, q, o);
+    const uint32_t opix = img * (uint32_t)p.out_plane + (2 * yy + (q >> 1) + 1) * (uint32_t)p.out_pitch + (2 * xx + (q & 1) + 1);
+    off = (size_t)opix * p.ldo + o;
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = interior ? apply_act(v[i], p.act) : 0.0f;
+  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + off;
+  if constexpr (NV % 8 == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; i += 8)
+      *reinterpret_cast<uint4*>(o + i) = make_uint4(pack_bf16x2(v[i], v[i + 1]), pack_bf16x2(v[i + 2], v[i + 3]),
+                                                    pack_bf16x2(v[i + 4], v[i + 5]), pack_bf16x2(v[i + 6], v[i + 7]));
+  } else {
+#pragma unroll
+    for (int i = 0; i < NV; i += 2) *reinterpret_cast<uint32_t*>(o + i) = pack_bf16x2(v[i], v[i + 1]);
+  }
+}
+
+// host launchers (one per backend)
+int launch_tc5(const Problem& p, cudaStream_t s);
+int launch_hmma(const Problem& p, cudaStream_t s);
+
+inline int launch(const Problem& p, int backend, cudaStream_t s) { return backend == 1 ? launch_hmma(p, s) : launch_tc5(p, s); }
+
+}  // namespace gemm

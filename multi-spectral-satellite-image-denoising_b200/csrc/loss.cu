@@ -1,0 +1,179 @@
+// Training loss forward + analytic backward (reference: src/training/losses.py).
+//   CombinedLoss.forward (:55-77): total = w_mse * mean((p-t)^2) + w_ssim * (1 - mean(ssim_map))
+//   SSIMLoss._ssim (:123-163): five zero-padded Gaussian blurs (p, t, p*p, t*t, p*t), C1/C2 from data_range.
+// The reference gets d(total)/d(pred) from autograd through 5 depthwise convs; here it is closed-form:
+//   S = A1*A2/(B1*B2),  A1 = 2 mu1 mu2 + C1, A2 = 2 (e12 - mu1 mu2) + C2, B1 = mu1^2 + mu2^2 + C1,
+//   B2 = (e11 - mu1^2) + (e22 - mu2^2) + C2
+//   dS/de12 = 2 A1/(B1 B2);  dS/de11 = -S/B2;  dS/dmu1 = 2 mu2 (A2 - A1)/(B1 B2) - 2 mu1 S (1/B1 - 1/B2)
+//   d mean(S)/dp = (1/N) [ blur(dS/dmu1) + 2 p blur(dS/de11) + t blur(dS/de12) ]   (the window is symmetric and
+//   the padding is zero, so the blur is self-adjoint).
+// Pass 1 (fwd): blur 5 maps, reduce sum((p-t)^2) and sum(S), write the 3 derivative maps.
+// Pass 2 (bwd): blur the 3 derivative maps and combine with p, t into grad_pred.
+#include "common.cuh"
+#include "ssim_tile.cuh"
+
+namespace {
+
+using namespace ssim;
+
+struct FwdSmem {
+  RawTile<2> raw;
+  HBlur<5> hb;
+  double red[2][kThreads / 32];
+};
+struct BwdSmem {
+  RawTile<3> raw;
+  HBlur<3> hb;
+};
+
+template <bool kWriteDeriv>
+__global__ void __launch_bounds__(kThreads, 2)
+loss_fwd_kernel(const float* __restrict__ pred, const float* __restrict__ target, int H, int W, int tiles_x, int tiles_y,
+                SsimConsts consts, size_t numel, float* __restrict__ deriv /*[3][numel]*/, double* __restrict__ acc /*[2]*/) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  FwdSmem& sm = *reinterpret_cast<FwdSmem*>(smem_raw);
+  const int tile = blockIdx.x % (tiles_x * tiles_y);
+  const int plane = blockIdx.x / (tiles_x * tiles_y);
+  const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+  const int y0 = ty * TH, x0 = tx * TW;
+  const size_t poff = (size_t)plane * H * W;
+  load_raw_plane(sm.raw.v[0], pred + poff, y0, x0, H, W);
+  load_raw_plane(sm.raw.v[1], target + poff, y0, x0, H, W);
+  __syncthreads();
+  hpass<2, 5>(sm.raw, sm.hb, [](int m, const float (&px)[2]) -> float {
+    return m == 0 ? px[0] : m == 1 ? px[1] : m == 2 ? px[0] * px[0] : m == 3 ? px[1] * px[1] : px[0] * px[1];
+  });
+  __syncthreads();
+  float res[5][8];
+  vpass<5>(sm.hb, res);
+  const int x = threadIdx.x & 63, h = threadIdx.x >> 6;
+  float s_ssim = 0.0f, s_sq = 0.0f;
+  if (x0 + x < W) {
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {
+      const int yy = y0 + 8 * h + o;
+      if (yy >= H) continue;
+      const float mu1 = res[0][o], mu2 = res[1][o], e11 = res[2][o], e22 = res[3][o], e12 = res[4][o];
+      const float mu1_sq = mu1 * mu1, mu2_sq = mu2 * mu2, mu1_mu2 = mu1 * mu2;
+      const float A1 = 2.0f * mu1_mu2 + consts.C1;
+      const float A2 = 2.0f * (e12 - mu1_mu2) + consts.C2;
+      const float B1 = mu1_sq + mu2_sq + consts.C1;
+      const float B2 = (e11 - mu1_sq) + (e22 - mu2_sq) + consts.C2;
+      const float S = (A1 * A2) / (B1 * B2);
+      s_ssim += S;
+      const float d = sm.raw.v[0][8 * h + o + R][x + R] - sm.raw.v[1][8 * h + o + R][x + R];
+      s_sq = fmaf(d, d, s_sq);
+      if (kWriteDeriv) {
+        const float inv = 1.0f / (B1 * B2);
+        const float dmu1 = 2.0f * mu2 * (A2 - A1) * inv - 2.0f * mu1 * S * (1.0f / B1 - 1.0f / B2);
+        const float de11 = -S / B2;
+        const float de12 = 2.0f * A1 * inv;
+        const size_t e = poff + (size_t)yy * W + (x0 + x);
+        deriv[e] = dmu1;
+        deriv[numel + e] = de11;
+        deriv[2 * numel + e] = de12;
+      }
+    }
+  }
+  double d_ssim = warp_sum_d((double)s_ssim), d_sq = warp_sum_d((double)s_sq);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { sm.red[0][warp] = d_sq; sm.red[1][warp] = d_ssim; }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    double t = 0.0;
+    for (int w = 0; w < kThreads / 32; ++w) t += sm.red[threadIdx.x][w];
+    atomicAdd(acc + threadIdx.x, t);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 2)
+loss_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ target, const float* __restrict__ deriv, int H,
+                int W, int tiles_x, int tiles_y, size_t numel, float k_ssim /* -w_ssim*scale/N */,
+                float k_mse /* 2*w_mse*scale/N */, float* __restrict__ grad) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  BwdSmem& sm = *reinterpret_cast<BwdSmem*>(smem_raw);
+  const int tile = blockIdx.x % (tiles_x * tiles_y);
+  const int plane = blockIdx.x / (tiles_x * tiles_y);
+  const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+  const int y0 = ty * TH, x0 = tx * TW;
+  const size_t poff = (size_t)plane * H * W;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) load_raw_plane(sm.raw.v[i], deriv + (size_t)i * numel + poff, y0, x0, H, W);
+  __syncthreads();
+  hpass<3, 3>(sm.raw, sm.hb, [](int m, const float (&px)[3]) -> float { return m == 0 ? px[0] : m == 1 ? px[1] : px[2]; });
+  __syncthreads();
+  float res[3][8];
+  vpass<3>(sm.hb, res);
+  const int x = threadIdx.x & 63, h = threadIdx.x >> 6;
+  if (x0 + x < W) {
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {
+      const int yy = y0 + 8 * h + o;
+      if (yy >= H) continue;
+      const size_t e = poff + (size_t)yy * W + (x0 + x);
+      const float p = __ldg(pred + e), t = __ldg(target + e);
+      const float gs = res[0][o] + 2.0f * p * res[1][o] + t * res[2][o];
+      grad[e] = k_ssim * gs + k_mse * (p - t);
+    }
+  }
+}
+
+__global__ void loss_finalize_kernel(const double* __restrict__ acc, double n, float w_mse, float w_ssim, float* out) {
+  const float mse = (float)(acc[0] / n);
+  const float ssim_loss = 1.0f - (float)(acc[1] / n);
+  out[0] = w_mse * mse + w_ssim * ssim_loss;
+  out[1] = mse;
+  out[2] = ssim_loss;
+}
+
+}  // namespace
+
+extern "C" size_t msd_loss_workspace_bytes(int B, int C, int H, int W) {
+  size_t numel = (size_t)B * C * H * W;
+  return 256 + 3 * numel * sizeof(float);
+}
+
+extern "C" int msd_loss_fwd_bwd_f32(const float* d_pred, const float* d_target, int B, int C, int H, int W, float w_mse,
+                                    float w_ssim, float data_range, float grad_scale, float* d_out, float* d_grad_pred,
+                                    void* d_ws, size_t ws_bytes, void* stream) {
+  MSD_REQUIRE(d_pred && d_target && d_out && d_ws, "loss: null pointer");
+  MSD_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, "loss: bad shape [%d,%d,%d,%d]", B, C, H, W);
+  const size_t numel = (size_t)B * C * H * W;
+  MSD_REQUIRE(numel < (1ull << 31), "loss: tensor too large");
+  const size_t need = d_grad_pred ? msd_loss_workspace_bytes(B, C, H, W) : 256;
+  if (ws_bytes < need) {
+    msd_set_error("loss: workspace %zu < %zu bytes", ws_bytes, need);
+    return MSD_ERR_WORKSPACE;
+  }
+  MSD_REQUIRE((reinterpret_cast<uintptr_t>(d_ws) & 255u) == 0, "loss: workspace must be 256-byte aligned");
+  cudaStream_t s = (cudaStream_t)stream;
+  double* acc = reinterpret_cast<double*>(d_ws);
+  float* deriv = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(d_ws) + 256);
+  MSD_CHECK_CUDA(cudaMemsetAsync(acc, 0, 2 * sizeof(double), s));
+  SsimConsts consts;
+  consts.C1 = (float)((0.01 * (double)data_range) * (0.01 * (double)data_range));
+  consts.C2 = (float)((0.03 * (double)data_range) * (0.03 * (double)data_range));
+  static bool attr_set = false;
+  if (!attr_set) {
+    MSD_CHECK_CUDA(cudaFuncSetAttribute(loss_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FwdSmem)));
+    MSD_CHECK_CUDA(cudaFuncSetAttribute(loss_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FwdSmem)));
+    MSD_CHECK_CUDA(cudaFuncSetAttribute(loss_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdSmem)));
+    attr_set = true;
+  }
+  const int tiles_x = (W + TW - 1) / TW, tiles_y = (H + TH - 1) / TH;
+  const unsigned blocks = (unsigned)B * C * tiles_x * tiles_y;
+  if (d_grad_pred)
+    loss_fwd_kernel<true><<<blocks, kThreads, sizeof(FwdSmem), s>>>(d_pred, d_target, H, W, tiles_x, tiles_y, consts, numel, deriv, acc);
+  else
+    loss_fwd_kernel<false><<<blocks, kThreads, sizeof(FwdSmem), s>>>(d_pred, d_target, H, W, tiles_x, tiles_y, consts, numel, nullptr, acc);
+  MSD_LAUNCH_CHECK();
+  loss_finalize_kernel<<<1, 1, 0, s>>>(acc, (double)numel, w_mse, w_ssim, d_out);
+  MSD_LAUNCH_CHECK();
+  if (d_grad_pred) {
+    const float k_ssim = (float)(-(double)w_ssim * (double)grad_scale / (double)numel);
+    const float k_mse = (float)(2.0 * (double)w_mse * (double)grad_scale / (double)numel);
+    loss_bwd_kernel<<<blocks, kThreads, sizeof(BwdSmem), s>>>(d_pred, d_target, deriv, H, W, tiles_x, tiles_y, numel, k_ssim, k_mse, d_grad_pred);
+    MSD_LAUNCH_CHECK();
+  }
+  return MSD_OK;
+}

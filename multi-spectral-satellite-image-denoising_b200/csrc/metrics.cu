@@ -1,0 +1,161 @@
+// Fused evaluation metrics (reference: src/training/metrics.py).
+//   MetricsTracker.update (:247-256) loops over the batch and calls calculate_psnr/ssim/sam/rmse per image,
+//   each ending in .item() (4*B device->host syncs).  Here: two streaming kernels accumulate raw per-image
+//   sums in fp64, a third turns them into {psnr, ssim, sam, rmse} per image and the tracker's running sums,
+//   all on the device; the host reads 5 doubles once per batch.
+//
+//   ssim_mse_kernel: one CTA per (plane b*C+c, 32x64 tile): sum (p-t)^2 and sum ssim_map     (:39, :105-121)
+//   sam_kernel     : one thread per pixel, 13-band dot / norms / acos                         (:155-170)
+// Algorithmic HBM bytes: 2 tensors * 4 B per element per kernel.
+#include "common.cuh"
+#include "ssim_tile.cuh"
+
+namespace {
+
+using namespace ssim;
+
+struct SsimSmem {
+  RawTile<2> raw;
+  HBlur<5> hb;
+  double red[3][kThreads / 32];
+};
+
+__global__ void __launch_bounds__(kThreads, 2)
+ssim_mse_kernel(const float* __restrict__ pred, const float* __restrict__ target, int C, int H, int W, int tiles_x,
+                int tiles_y, SsimConsts consts, double* __restrict__ acc /*[B][4]*/) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SsimSmem& sm = *reinterpret_cast<SsimSmem*>(smem_raw);
+  const int tile = blockIdx.x % (tiles_x * tiles_y);
+  const int plane = blockIdx.x / (tiles_x * tiles_y);
+  const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+  const int y0 = ty * TH, x0 = tx * TW;
+  const size_t poff = (size_t)plane * H * W;
+
+  load_raw_plane(sm.raw.v[0], pred + poff, y0, x0, H, W);
+  load_raw_plane(sm.raw.v[1], target + poff, y0, x0, H, W);
+  __syncthreads();
+  // maps: p, t, p*p, t*t, p*t   (metrics.py:105-117)
+  hpass<2, 5>(sm.raw, sm.hb, [](int m, const float (&px)[2]) -> float {
+    return m == 0 ? px[0] : m == 1 ? px[1] : m == 2 ? px[0] * px[0] : m == 3 ? px[1] * px[1] : px[0] * px[1];
+  });
+  __syncthreads();
+  float res[5][8];
+  vpass<5>(sm.hb, res);
+
+  const int x = threadIdx.x & 63, h = threadIdx.x >> 6;
+  float s_ssim = 0.0f, s_sq = 0.0f, s_abs = 0.0f;
+  if (x0 + x < W) {
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {
+      int yy = y0 + 8 * h + o;
+      if (yy < H) {
+        s_ssim += ssim_value(res[0][o], res[1][o], res[2][o], res[3][o], res[4][o], consts);
+        float d = sm.raw.v[0][8 * h + o + R][x + R] - sm.raw.v[1][8 * h + o + R][x + R];
+        s_sq = fmaf(d, d, s_sq);
+        s_abs += fabsf(d);
+      }
+    }
+  }
+  double d_ssim = warp_sum_d((double)s_ssim), d_sq = warp_sum_d((double)s_sq), d_abs = warp_sum_d((double)s_abs);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { sm.red[0][warp] = d_sq; sm.red[1][warp] = d_ssim; sm.red[2][warp] = d_abs; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double t = 0.0;
+    for (int w = 0; w < kThreads / 32; ++w) t += sm.red[threadIdx.x][w];
+    // scratch slots: 0 = sum (p-t)^2, 1 = sum ssim_map, 2 = sum SAM degrees (sam_kernel), 3 = sum |p-t|
+    atomicAdd(acc + (size_t)(plane / C) * 4 + (threadIdx.x == 2 ? 3 : threadIdx.x), t);
+  }
+}
+
+// SAM: angle between the C-band spectra of each pixel (metrics.py:150-170)
+__global__ void __launch_bounds__(256)
+sam_kernel(const float* __restrict__ pred, const float* __restrict__ target, int C, int HW, int chunks_per_image,
+           float eps, double* __restrict__ acc) {
+  const int b = blockIdx.x / chunks_per_image;
+  const int chunk = blockIdx.x - b * chunks_per_image;
+  const float* p = pred + (size_t)b * C * HW;
+  const float* t = target + (size_t)b * C * HW;
+  float sum_deg = 0.0f;
+  for (int pix = chunk * 1024 + threadIdx.x; pix < min(HW, (chunk + 1) * 1024); pix += 256) {
+    float dot = 0.0f, pp = 0.0f, tt = 0.0f;
+    for (int c = 0; c < C; ++c) {
+      float a = __ldg(p + (size_t)c * HW + pix), bb = __ldg(t + (size_t)c * HW + pix);
+      dot = fmaf(a, bb, dot);
+      pp = fmaf(a, a, pp);
+      tt = fmaf(bb, bb, tt);
+    }
+    float pn = sqrtf(pp) + eps, tn = sqrtf(tt) + eps;
+    float cosang = dot / (pn * tn);
+    cosang = fminf(fmaxf(cosang, -1.0f), 1.0f);
+    sum_deg += acosf(cosang) * 57.29577951308232f;  // torch.rad2deg
+  }
+  __shared__ double red[8];
+  double d = warp_sum_d((double)sum_deg);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = d;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tsum = 0.0;
+    for (int w = 0; w < 8; ++w) tsum += red[w];
+    atomicAdd(acc + (size_t)b * 4 + 2, tsum);
+  }
+}
+
+// per-image metrics + the tracker's running sums (metrics.py:39-46, 121, 170, 189-191, 252-258)
+__global__ void metrics_finalize_kernel(const double* __restrict__ acc, int B, int C, int HW, double data_range,
+                                        double* __restrict__ per_image, double* __restrict__ sums) {
+  __shared__ double sh[4][32];
+  double loc[4] = {0, 0, 0, 0};
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    const double n = (double)C * HW;
+    // F.mse_loss(...).item() is an fp32 value; the dB / sqrt are done in fp64 on it
+    const double mse = (double)(float)(acc[b * 4 + 0] / n);
+    const double psnr = (mse == 0.0) ? (double)INFINITY : 10.0 * log10(data_range * data_range / mse);
+    const double ssimv = (double)(float)(acc[b * 4 + 1] / n);
+    const double sam = (double)(float)(acc[b * 4 + 2] / (double)HW);
+    const double rmse = sqrt(mse);
+    per_image[b * 4 + 0] = psnr; per_image[b * 4 + 1] = ssimv; per_image[b * 4 + 2] = sam; per_image[b * 4 + 3] = rmse;
+    loc[0] += psnr; loc[1] += ssimv; loc[2] += sam; loc[3] += rmse;
+  }
+  for (int k = 0; k < 4; ++k) {
+    double v = warp_sum_d(loc[k]);
+    if ((threadIdx.x & 31) == 0) sh[k][threadIdx.x >> 5] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sh[threadIdx.x][w];
+    sums[threadIdx.x] = t;
+  }
+  if (threadIdx.x == 0) sums[4] = (double)B;
+}
+
+}  // namespace
+
+extern "C" int msd_metrics_f32(const float* d_pred, const float* d_target, int B, int C, int H, int W, float data_range,
+                               double* d_per_image, double* d_sums, double* d_scratch, void* stream) {
+  MSD_REQUIRE(d_pred && d_target && d_per_image && d_sums && d_scratch, "metrics: null pointer");
+  MSD_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, "metrics: bad shape [%d,%d,%d,%d]", B, C, H, W);
+  MSD_REQUIRE((int64_t)B * C * H * W < (1ll << 31), "metrics: tensor too large");
+  cudaStream_t s = (cudaStream_t)stream;
+  MSD_CHECK_CUDA(cudaMemsetAsync(d_scratch, 0, sizeof(double) * 4 * (size_t)B, s));
+  const int tiles_x = (W + TW - 1) / TW, tiles_y = (H + TH - 1) / TH;
+  SsimConsts consts;
+  consts.C1 = (float)((0.01 * (double)data_range) * (0.01 * (double)data_range));
+  consts.C2 = (float)((0.03 * (double)data_range) * (0.03 * (double)data_range));
+  static bool attr_set = false;
+  if (!attr_set) {
+    MSD_CHECK_CUDA(cudaFuncSetAttribute(ssim_mse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SsimSmem)));
+    attr_set = true;
+  }
+  const unsigned blocks = (unsigned)B * C * tiles_x * tiles_y;
+  ssim_mse_kernel<<<blocks, kThreads, sizeof(SsimSmem), s>>>(d_pred, d_target, C, H, W, tiles_x, tiles_y, consts, d_scratch);
+  MSD_LAUNCH_CHECK();
+  const int HW = H * W;
+  const int chunks = (HW + 1023) / 1024;
+  sam_kernel<<<(unsigned)B * chunks, 256, 0, s>>>(d_pred, d_target, C, HW, chunks, 1e-8f, d_scratch);
+  MSD_LAUNCH_CHECK();
+  metrics_finalize_kernel<<<1, 256, 0, s>>>(d_scratch, B, C, HW, (double)data_range, d_per_image, d_sums);
+  MSD_LAUNCH_CHECK();
+  return MSD_OK;
+}

@@ -1,0 +1,310 @@
+// Restoration model forward (reference: SatMAERestoration.forward, src/models/satmae_restoration.py:81-110) as a
+// fixed sequence of libmsd kernels, plus the exported building blocks (linear / conv3x3 / convT) the tests pin.
+//
+// Data layout in HBM (workspace, per batch of B images; S=192, G=12, T=144 tokens, E=768):
+//   a_pe  bf16 [B*T, 13*256]   patch-embed A operand (or supplied by msd_corrupt_f32)
+//   x     fp32 [B*T, E]        residual stream (kept fp32: 12 blocks of accumulation)
+//   xn    bf16 [B*T, E]        LayerNorm output = A operand of qkv / fc1 / first ConvTranspose (tokens ARE the
+//                              NHWC 12x12x768 feature map, so satmae_restoration.py:128-133's transpose is a no-op)
+//   qkv   bf16 [B*T, 3E], att bf16 [B*T, E], h bf16 [B*T, 4E]
+//   decoder stage s: three ping-pong buffers bf16 [B, H_s+2, W_s+2, C_s] (zero halo), H_s = 24,48,96,192
+#include "gemm.cuh"
+#include <new>
+#include <vector>
+
+namespace {
+
+using gemm::Problem;
+
+int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+void init_problem(Problem& p) {
+  memset(&p, 0, sizeof(p));
+  p.plane = p.pitch = p.in_plane = p.in_pitch = p.cout_div = make_fastdiv(1);
+}
+
+int make_linear(Problem& p, const void* a, const void* w, const float* bias, void* out, const float* resid, int M, int N,
+                int K, int act, int out_f32) {
+  MSD_REQUIRE(a && w && out, "linear: null pointer");
+  MSD_REQUIRE(M > 0 && N > 0 && K > 0 && K % 8 == 0 && N % 16 == 0, "linear: bad shape M=%d N=%d K=%d", M, N, K);
+  MSD_REQUIRE(resid == nullptr || out_f32, "linear: residual add requires fp32 output");
+  init_problem(p);
+  p.A = reinterpret_cast<const __nv_bfloat16*>(a);
+  p.Wt = reinterpret_cast<const __nv_bfloat16*>(w);
+  p.M = M; p.N = N;
+  p.a_rows = M; p.ldA = K; p.kvalid = K;
+  p.kb_per_tap = round_up(K, 64) / 64; p.num_kb = p.kb_per_tap;
+  p.mode = gemm::EPI_ROWMAJOR; p.act = act; p.out_f32 = out_f32;
+  p.bias = bias; p.out = out; p.ldo = N; p.resid = resid;
+  return MSD_OK;
+}
+
+int make_conv3x3(Problem& p, const void* x, const void* w, const float* bias, const void* skip, void* y, int B, int H,
+                 int W, int Cin, int Cout) {
+  MSD_REQUIRE(x && w && y, "conv3x3: null pointer");
+  MSD_REQUIRE(B > 0 && H > 0 && W > 0 && Cin % 8 == 0 && Cout % 16 == 0, "conv3x3: bad shape B=%d H=%d W=%d Cin=%d Cout=%d", B, H, W, Cin, Cout);
+  const long long rows = (long long)B * (H + 2) * (W + 2);
+  MSD_REQUIRE(rows < (1ll << 31), "conv3x3: too many pixels");
+  init_problem(p);
+  p.A = reinterpret_cast<const __nv_bfloat16*>(x);
+  p.Wt = reinterpret_cast<const __nv_bfloat16*>(w);
+  p.M = (int)rows; p.N = Cout;
+  p.a_rows = (int)rows; p.ldA = Cin; p.kvalid = Cin;
+  p.kb_per_tap = round_up(Cin, 64) / 64; p.num_kb = 9 * p.kb_per_tap;
+  for (int ky = 0; ky < 3; ++ky)
+    for (int kx = 0; kx < 3; ++kx) p.tap_off[ky * 3 + kx] = (ky - 1) * (W + 2) + (kx - 1);
+  p.mode = gemm::EPI_CONV; p.act = 1; p.out_f32 = 0;
+  p.bias = bias; p.out = y; p.ldo = Cout;
+  p.skip = reinterpret_cast<const __nv_bfloat16*>(skip);
+  p.plane = make_fastdiv((uint32_t)((H + 2) * (W + 2)));
+  p.pitch = make_fastdiv((uint32_t)(W + 2));
+  p.H = H; p.W = W;
+  return MSD_OK;
+}
+
+int make_convt(Problem& p, const void* x, const void* w, const float* bias, void* y, int B, int Hin, int Win, int in_padded,
+               int Cin, int Cout) {
+  MSD_REQUIRE(x && w && y, "convt: null pointer");
+  MSD_REQUIRE(B > 0 && Hin > 0 && Win > 0 && Cin % 8 == 0 && Cout % 16 == 0, "convt: bad shape");
+  const int ph = in_padded ? Hin + 2 : Hin, pw = in_padded ? Win + 2 : Win;
+  const long long rows = (long long)B * ph * pw;
+  MSD_REQUIRE(rows < (1ll << 31) && (long long)B * (2 * Hin + 2) * (2 * Win + 2) < (1ll << 31), "convt: too many pixels");
+  init_problem(p);
+  p.A = reinterpret_cast<const __nv_bfloat16*>(x);
+  p.Wt = reinterpret_cast<const __nv_bfloat16*>(w);
+  p.M = (int)rows; p.N = 4 * Cout;
+  p.a_rows = (int)rows; p.ldA = Cin; p.kvalid = Cin;
+  p.kb_per_tap = round_up(Cin, 64) / 64; p.num_kb = p.kb_per_tap;
+  p.mode = gemm::EPI_CONVT; p.act = 1; p.out_f32 = 0;
+  p.bias = bias; p.out = y; p.ldo = Cout;
+  p.in_plane = make_fastdiv((uint32_t)(ph * pw));
+  p.in_pitch = make_fastdiv((uint32_t)pw);
+  p.cout_div = make_fastdiv((uint32_t)Cout);
+  p.in_pad = in_padded; p.Hin = Hin; p.Win = Win;
+  p.out_plane = (2 * Hin + 2) * (2 * Win + 2);
+  p.out_pitch = 2 * Win + 2;
+  return MSD_OK;
+}
+
+// zero the 1-pixel halo of a [B, H+2, W+2, C] bf16 buffer (the ConvTranspose scatter only writes the interior)
+__global__ void __launch_bounds__(256) zero_halo_kernel(__nv_bfloat16* __restrict__ buf, int B, int H, int W, int C) {
+  const int per_img = 2 * (W + 2) + 2 * H;  // halo pixels per image
+  const int vec = C / 8;
+  const size_t total = (size_t)B * per_img * vec;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
+    const int v = (int)(i % vec);
+    const size_t t = i / vec;
+    const int k = (int)(t % per_img);
+    const int b = (int)(t / per_img);
+    int yy, xx;
+    if (k < W + 2) { yy = 0; xx = k; }
+    else if (k < 2 * (W + 2)) { yy = H + 1; xx = k - (W + 2); }
+    else { const int r = k - 2 * (W + 2); yy = 1 + (r >> 1); xx = (r & 1) ? W + 1 : 0; }
+    *reinterpret_cast<uint4*>(buf + (((size_t)b * (H + 2) + yy) * (W + 2) + xx) * C + v * 8) = make_uint4(0, 0, 0, 0);
+  }
+}
+
+int zero_halo(void* buf, int B, int H, int W, int C, cudaStream_t s) {
+  const size_t total = (size_t)B * (2 * (W + 2) + 2 * H) * (C / 8);
+  const unsigned blocks = (unsigned)((total + 255) / 256 < 148u * 8u ? (total + 255) / 256 : 148u * 8u);
+  zero_halo_kernel<<<blocks, 256, 0, s>>>(reinterpret_cast<__nv_bfloat16*>(buf), B, H, W, C);
+  MSD_LAUNCH_CHECK();
+  return MSD_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------- blocks
+extern "C" int msd_linear_bf16(const void* d_a, const void* d_w, const float* d_bias, void* d_out, const float* d_resid,
+                               int M, int N, int K, int act, int out_f32, int backend, void* stream) {
+  Problem p;
+  int rc = make_linear(p, d_a, d_w, d_bias, d_out, d_resid, M, N, K, act, out_f32);
+  if (rc) return rc;
+  return gemm::launch(p, backend, (cudaStream_t)stream);
+}
+
+extern "C" int msd_conv3x3_nhwc_bf16(const void* d_x, const void* d_w, const float* d_bias, const void* d_skip, void* d_y,
+                                     int B, int H, int W, int Cin, int Cout, int backend, void* stream) {
+  Problem p;
+  int rc = make_conv3x3(p, d_x, d_w, d_bias, d_skip, d_y, B, H, W, Cin, Cout);
+  if (rc) return rc;
+  return gemm::launch(p, backend, (cudaStream_t)stream);
+}
+
+extern "C" int msd_convt2x2_nhwc_bf16(const void* d_x, const void* d_w, const float* d_bias, void* d_y, int B, int Hin,
+                                      int Win, int in_padded, int Cin, int Cout, int backend, void* stream) {
+  Problem p;
+  int rc = make_convt(p, d_x, d_w, d_bias, d_y, B, Hin, Win, in_padded, Cin, Cout);
+  if (rc) return rc;
+  rc = zero_halo(d_y, B, 2 * Hin, 2 * Win, Cout, (cudaStream_t)stream);
+  if (rc) return rc;
+  return gemm::launch(p, backend, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------------------------- model
+struct msd_model {
+  msd_model_desc d;
+  msd_model_weights w;
+  std::vector<msd_block_weights> blocks;
+  bool has_weights = false;
+  int grid, tokens;
+};
+
+namespace {
+
+struct WsLayout {
+  size_t a_pe, x, xn, qkv, att, h, stage[4][3], total;
+};
+
+size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+WsLayout ws_layout(const msd_model* m, int B) {
+  WsLayout L;
+  const msd_model_desc& d = m->d;
+  const size_t M = (size_t)B * m->tokens, E = d.embed_dim;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += align256(bytes); return o; };
+  L.a_pe = take(M * (size_t)d.in_channels * d.patch_size * d.patch_size * 2);
+  L.x = take(M * E * 4);
+  L.xn = take(M * E * 2);
+  L.qkv = take(M * 3 * E * 2);
+  L.att = take(M * E * 2);
+  L.h = take(M * (size_t)d.mlp_hidden * 2);
+  int hw = m->grid;
+  for (int s = 0; s < 4; ++s) {
+    hw *= 2;
+    for (int k = 0; k < 3; ++k) L.stage[s][k] = take((size_t)B * (hw + 2) * (hw + 2) * d.dec_channels[s] * 2);
+  }
+  L.total = off;
+  return L;
+}
+
+}  // namespace
+
+extern "C" int msd_model_create(const msd_model_desc* desc, msd_model** out) {
+  MSD_REQUIRE(desc && out, "model_create: null pointer");
+  MSD_REQUIRE(desc->embed_dim == desc->num_heads * 64, "model_create: head dim must be 64 (embed_dim %d, heads %d)", desc->embed_dim, desc->num_heads);
+  MSD_REQUIRE(desc->image_size % desc->patch_size == 0 && desc->patch_size == 16, "model_create: patch_size must be 16 and divide image_size");
+  MSD_REQUIRE(desc->embed_dim % 128 == 0 && desc->embed_dim <= 1024 && desc->mlp_hidden % 64 == 0, "model_create: unsupported widths");
+  for (int s = 0; s < 4; ++s) MSD_REQUIRE(desc->dec_channels[s] % 16 == 0 && desc->dec_channels[s] > 0, "model_create: decoder channels must be multiples of 16");
+  MSD_REQUIRE(desc->dec_channels[3] <= 64 && desc->out_channels <= 16, "model_create: head supports <=64 input and <=16 output channels");
+  MSD_REQUIRE(desc->depth > 0 && desc->depth <= 64, "model_create: bad depth");
+  msd_model* m = new (std::nothrow) msd_model();
+  MSD_REQUIRE(m != nullptr, "model_create: out of memory");
+  m->d = *desc;
+  m->grid = desc->image_size / desc->patch_size;
+  m->tokens = m->grid * m->grid;
+  *out = m;
+  return MSD_OK;
+}
+
+extern "C" int msd_model_set_weights(msd_model* m, const msd_model_weights* w) {
+  MSD_REQUIRE(m && w && w->blocks, "model_set_weights: null pointer");
+  m->w = *w;
+  m->blocks.assign(w->blocks, w->blocks + m->d.depth);
+  m->w.blocks = m->blocks.data();
+  m->has_weights = true;
+  return MSD_OK;
+}
+
+extern "C" size_t msd_model_workspace_bytes(const msd_model* m, int B) {
+  if (!m || B <= 0) return 0;
+  return ws_layout(m, B).total;
+}
+
+extern "C" int msd_model_launch_count(const msd_model* m) {
+  if (!m) return 0;
+  // patchify + pe gemm + ln_pos + depth*(ln, qkv, attn, proj, ln, fc1, fc2) + final ln
+  // + 4*(zero_halo + convT + 4 conv) + head conv + head 1x1
+  return 3 + 7 * m->d.depth + 1 + 4 * 6 + 2;
+}
+
+extern "C" void msd_model_destroy(msd_model* m) { delete m; }
+
+#define MSD_TRY(expr)        \
+  do {                       \
+    int _rc = (expr);        \
+    if (_rc) return _rc;     \
+  } while (0)
+
+extern "C" int msd_model_forward(msd_model* m, const float* d_x, const void* d_patch_bf16, int B, float* d_y, void* d_ws,
+                                 size_t ws_bytes, void* stream) {
+  MSD_REQUIRE(m && m->has_weights, "model_forward: weights not set");
+  MSD_REQUIRE((d_x || d_patch_bf16) && d_y && d_ws && B > 0, "model_forward: null pointer");
+  MSD_REQUIRE((reinterpret_cast<uintptr_t>(d_ws) & 255u) == 0, "model_forward: workspace must be 256-byte aligned");
+  const WsLayout L = ws_layout(m, B);
+  if (ws_bytes < L.total) {
+    msd_set_error("model_forward: workspace %zu < %zu bytes", ws_bytes, L.total);
+    return MSD_ERR_WORKSPACE;
+  }
+  const msd_model_desc& d = m->d;
+  const msd_model_weights& w = m->w;
+  cudaStream_t s = (cudaStream_t)stream;
+  unsigned char* ws = reinterpret_cast<unsigned char*>(d_ws);
+  const int M = B * m->tokens, E = d.embed_dim, Kpe = d.in_channels * d.patch_size * d.patch_size;
+  const int be = d.gemm_backend;
+  float* x = reinterpret_cast<float*>(ws + L.x);
+  void *xn = ws + L.xn, *qkv = ws + L.qkv, *att = ws + L.att, *h = ws + L.h;
+  Problem p;
+
+  // PatchEmbed: conv k16 s16 == GEMM over patchified pixels, + bias; LayerNorm(eps 1e-5); + pos_embed (encoder.py:48-52, 309)
+  const void* a_pe = d_patch_bf16;
+  if (!a_pe) {
+    MSD_TRY(msd_patchify_bf16(d_x, ws + L.a_pe, B, d.in_channels, d.image_size, d.patch_size, stream));
+    a_pe = ws + L.a_pe;
+  }
+  MSD_TRY(make_linear(p, a_pe, w.w_pe, w.b_pe, x, nullptr, M, E, Kpe, 0, 1));
+  MSD_TRY(gemm::launch(p, be, s));
+  MSD_TRY(msd_layernorm_pos_f32(x, w.pe_ln_g, w.pe_ln_b, d.ln_eps_outer, w.pos_embed, m->tokens, M, E, stream));
+
+  // 12 pre-norm blocks (encoder.py:312-319): x += proj(attn(LN1 x)); x += fc2(GELU(fc1(LN2 x)))
+  for (int l = 0; l < d.depth; ++l) {
+    const msd_block_weights& bw = m->blocks[l];
+    MSD_TRY(msd_layernorm_f32_bf16(x, bw.ln1_g, bw.ln1_b, d.ln_eps_block, xn, M, E, stream));
+    MSD_TRY(make_linear(p, xn, bw.w_qkv, bw.b_qkv, qkv, nullptr, M, 3 * E, E, 0, 0));
+    MSD_TRY(gemm::launch(p, be, s));
+    MSD_TRY(msd_attention_bf16(qkv, att, B, m->tokens, d.num_heads, stream));
+    MSD_TRY(make_linear(p, att, bw.w_proj, bw.b_proj, x, x, M, E, E, 0, 1));
+    MSD_TRY(gemm::launch(p, be, s));
+    MSD_TRY(msd_layernorm_f32_bf16(x, bw.ln2_g, bw.ln2_b, d.ln_eps_block, xn, M, E, stream));
+    MSD_TRY(make_linear(p, xn, bw.w_fc1, bw.b_fc1, h, nullptr, M, d.mlp_hidden, E, 1, 0));
+    MSD_TRY(gemm::launch(p, be, s));
+    MSD_TRY(make_linear(p, h, bw.w_fc2, bw.b_fc2, x, x, M, E, d.mlp_hidden, 0, 1));
+    MSD_TRY(gemm::launch(p, be, s));
+  }
+  // final LayerNorm (encoder.py:322); tokens [B,144,768] are the NHWC [B,12,12,768] map (satmae_restoration.py:128-133)
+  MSD_TRY(msd_layernorm_f32_bf16(x, w.norm_g, w.norm_b, d.ln_eps_outer, xn, M, E, stream));
+
+  // decoder (decoder.py:101-118): 4 x { ConvT k2s2 + BN + GELU ; 2 x ResidualBlock }, BN folded into the weights
+  const void* cur = xn;
+  int hw = m->grid, cin = E, in_pad = 0;
+  for (int st = 0; st < 4; ++st) {
+    const msd_stage_weights& sw = w.stages[st];
+    const int cout = d.dec_channels[st];
+    void *X = ws + L.stage[st][0], *Y = ws + L.stage[st][1], *Z = ws + L.stage[st][2];
+    MSD_TRY(zero_halo(X, B, 2 * hw, 2 * hw, cout, s));
+    MSD_TRY(make_convt(p, cur, sw.w_up, sw.b_up, X, B, hw, hw, in_pad, cin, cout));
+    MSD_TRY(gemm::launch(p, be, s));
+    hw *= 2;
+    // ResidualBlock 1: Z = GELU(X + BN(conv(GELU(BN(conv X)))))   (blocks.py:74-85)
+    MSD_TRY(make_conv3x3(p, X, sw.w_conv[0], sw.b_conv[0], nullptr, Y, B, hw, hw, cout, cout));
+    MSD_TRY(gemm::launch(p, be, s));
+    MSD_TRY(make_conv3x3(p, Y, sw.w_conv[1], sw.b_conv[1], X, Z, B, hw, hw, cout, cout));
+    MSD_TRY(gemm::launch(p, be, s));
+    // ResidualBlock 2: X = GELU(Z + ...)
+    MSD_TRY(make_conv3x3(p, Z, sw.w_conv[2], sw.b_conv[2], nullptr, Y, B, hw, hw, cout, cout));
+    MSD_TRY(gemm::launch(p, be, s));
+    MSD_TRY(make_conv3x3(p, Y, sw.w_conv[3], sw.b_conv[3], Z, X, B, hw, hw, cout, cout));
+    MSD_TRY(gemm::launch(p, be, s));
+    cur = X; cin = cout; in_pad = 1;
+  }
+  // head (decoder.py:76-81): conv3x3 + bias + BN + GELU, then conv1x1 -> NCHW fp32
+  {
+    const int c = d.dec_channels[3];
+    void* Y = ws + L.stage[3][1];
+    MSD_TRY(make_conv3x3(p, cur, w.w_head3, w.b_head3, nullptr, Y, B, hw, hw, c, c));
+    MSD_TRY(gemm::launch(p, be, s));
+    MSD_TRY(msd_head1x1_nchw_f32(Y, w.w_head1, w.b_head1, d_y, B, hw, hw, c, d.out_channels, stream));
+  }
+  return MSD_OK;
+}
