@@ -1,0 +1,120 @@
+"""Host-side logic (runs on the CPU): parameter tree / state-dict compatibility with the reference, key-layout
+adapter, and the weight packing + implicit-GEMM indexing the CUDA kernels rely on (emulated in fp32)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+import emulate
+import recipes
+from msd_b200.models import SatMAERestoration, convert_block_keys
+from msd_b200.models.satmae_restoration import pack_conv3x3, pack_convt2x2
+
+
+@pytest.fixture(scope="module")
+def model():
+    torch.manual_seed(42)
+    return SatMAERestoration(recipes.base_config(), block_layout="fallback")
+
+
+def test_state_dict_matches_reference_init(model, golden_model):
+    """seed-42 construction reproduces the reference's 284 tensors (checksums recorded from the reference)."""
+    sd = model.state_dict()
+    assert list(sd.keys()) == list(golden_model["state/keys"])
+    np.testing.assert_allclose([v.double().sum().item() for v in sd.values()], golden_model["state/sum"], rtol=0, atol=1e-9)
+    np.testing.assert_allclose([v.double().abs().sum().item() for v in sd.values()], golden_model["state/abssum"], rtol=1e-12)
+
+
+def test_parameter_counts(model):
+    c = model.count_parameters()
+    assert c["encoder_total"] == 87_724_800 and c["decoder_total"] == 8_646_397 and c["total"] == 96_371_197
+    assert c["frozen"] == 42_527_232 and c["trainable"] == 53_843_965
+    assert model.encoder.patch_embed.proj.weight.requires_grad and model.encoder.pos_embed.requires_grad
+    assert not any(p.requires_grad for p in model.encoder.blocks[0].parameters())
+    assert all(p.requires_grad for p in model.encoder.blocks[6].parameters())
+
+
+def test_optimizer_groups(model):
+    groups = model.get_optimizer_param_groups("1e-4", weight_decay=0.05)
+    assert len(groups) == 2 and groups[0]["lr"] == pytest.approx(1e-5) and groups[1]["lr"] == pytest.approx(1e-4)
+    assert sum(p.numel() for p in groups[0]["params"]) == 45_197_568
+    assert sum(p.numel() for p in groups[1]["params"]) == 8_646_397
+
+
+def test_timm_and_fallback_layouts_interchange(model):
+    sd = model.state_dict()
+    timm_sd = convert_block_keys(sd, "timm")
+    assert "encoder.blocks.3.attn.qkv.weight" in timm_sd and "encoder.blocks.3.mlp.fc2.bias" in timm_sd
+    assert not any("in_proj" in k for k in timm_sd)
+    m2 = SatMAERestoration(recipes.base_config(), block_layout="timm")
+    assert m2.encoder.ln_eps_block == 1e-6 and model.encoder.ln_eps_block == 1e-5
+    m2.load_state_dict(sd, strict=True)          # fallback keys into a timm-layout module
+    m3 = SatMAERestoration(recipes.base_config(), block_layout="fallback")
+    m3.load_state_dict(m2.state_dict(), strict=True)   # and back
+    for k, v in sd.items():
+        assert torch.equal(m3.state_dict()[k], v), k
+
+
+def test_forward_rejects_cpu_and_training(model):
+    from msd_b200 import MsdError
+    model.eval()
+    with pytest.raises(MsdError):
+        model(torch.zeros(1, 13, 192, 192))
+    with pytest.raises(AssertionError):
+        model(torch.zeros(1, 12, 192, 192))
+
+
+@pytest.mark.parametrize("cin,cout,H,W", [(48, 48, 6, 5), (96, 32, 4, 7), (64, 16, 3, 3)])
+def test_conv3x3_packing_and_tap_table(cin, cout, H, W):
+    torch.manual_seed(0)
+    conv = nn.Conv2d(cin, cout, 3, padding=1, bias=False)
+    bn = nn.BatchNorm2d(cout).eval()
+    bn.running_mean.normal_(0, 0.2); bn.running_var.uniform_(0.5, 1.5); bn.weight.data.normal_(1, 0.1); bn.bias.data.normal_(0, 0.1)
+    x = torch.randn(2, cin, H, W)
+    skip = torch.randn(2, cout, H, W)
+    with torch.no_grad():
+        ref = F.gelu(skip + bn(conv(x)))
+        w, b = pack_conv3x3(conv, bn)
+        got = emulate.conv3x3_rows(emulate.halo_nhwc(x), w.float(), b, H, W, skip=emulate.halo_nhwc(skip))
+    assert w.shape == (cout, 9 * ((cin + 63) // 64 * 64)) and w.dtype == torch.bfloat16
+    assert torch.all(got[:, 0] == 0) and torch.all(got[:, :, 0] == 0) and torch.all(got[:, -1] == 0) and torch.all(got[:, :, -1] == 0)
+    # bf16 weights -> ~3 significant digits
+    torch.testing.assert_close(emulate.unhalo_nchw(got), ref, rtol=0, atol=0.05)
+    with torch.no_grad():
+        scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+        w32 = (conv.weight * scale.view(-1, 1, 1, 1)).permute(0, 2, 3, 1)
+        kpad = w.shape[1] // 9
+        w_exact = torch.zeros(cout, 3, 3, kpad); w_exact[..., :cin] = w32
+        got32 = emulate.conv3x3_rows(emulate.halo_nhwc(x), w_exact.reshape(cout, -1), b, H, W, skip=emulate.halo_nhwc(skip))
+    torch.testing.assert_close(emulate.unhalo_nchw(got32), ref, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("cin,cout,Hin,Win,padded", [(96, 48, 3, 4, True), (64, 32, 2, 2, False), (128, 16, 3, 3, True)])
+def test_convt_packing_and_pixel_shuffle(cin, cout, Hin, Win, padded):
+    torch.manual_seed(1)
+    ct = nn.ConvTranspose2d(cin, cout, 2, stride=2)
+    bn = nn.BatchNorm2d(cout).eval()
+    bn.running_mean.normal_(0, 0.2); bn.running_var.uniform_(0.5, 1.5); bn.weight.data.normal_(1, 0.1); bn.bias.data.normal_(0, 0.1)
+    x = torch.randn(2, cin, Hin, Win)
+    with torch.no_grad():
+        ref = F.gelu(bn(ct(x)))
+        w, b = pack_convt2x2(ct, bn)
+        xin = emulate.halo_nhwc(x) if padded else x.permute(0, 2, 3, 1).contiguous()
+        scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+        w32 = (ct.weight * scale.view(1, -1, 1, 1)).permute(2, 3, 1, 0).reshape(4 * cout, cin)
+        got = emulate.convt2x2_rows(xin, w32, b, Hin, Win, padded)
+    assert w.shape == (4 * cout, (cin + 63) // 64 * 64)
+    torch.testing.assert_close(w.float()[:, :cin], w32, rtol=0.01, atol=1e-3)
+    torch.testing.assert_close(emulate.unhalo_nchw(got), ref, rtol=1e-4, atol=1e-4)
+
+
+def test_patch_embed_weight_is_im2col_order(model):
+    """conv k16 s16 == (c,ky,kx)-ordered patch rows x proj.weight.reshape(768,-1)^T (encoder.py:48-50)."""
+    x = recipes.model_input(1)
+    pe = model.encoder.patch_embed.proj
+    with torch.no_grad():
+        ref = pe(x).flatten(2).transpose(1, 2)[0]
+        patches = x[0].reshape(13, 12, 16, 12, 16).permute(1, 3, 0, 2, 4).reshape(144, 13 * 256)   # n = 12*py+px
+        got = patches @ pe.weight.reshape(768, -1).t() + pe.bias
+    torch.testing.assert_close(got, ref, rtol=1e-4, atol=1e-4)
