@@ -74,7 +74,8 @@ int msd_corrupt_f32(const float* d_clean, float* d_noisy, const float* d_thermal
  * (src/training/metrics.py:247-256) and calculate_psnr/ssim/sam/rmse (:19-46, 49-121, 124-172, 175-191).
  *   d_per_image: OUT [B,4] fp64 = {psnr_dB (inf if mse==0), ssim, sam_degrees, rmse} per image
  *   d_sums     : OUT [5]  fp64 = {sum psnr, sum ssim, sum sam, sum rmse, B}  (the tracker's running sums)
- *   d_scratch  : [B,4] fp64 device scratch (raw per-image sums), zeroed by the call
+ *   d_scratch  : OUT [B,4] fp64 raw per-image sums {sum (p-t)^2, sum ssim_map, sum SAM degrees, sum |p-t|}
+ *                (whole-batch calculate_* and calculate_mae (:194-209) are derived from these)
  * ------------------------------------------------------------------------------------------------- */
 int msd_metrics_f32(const float* d_pred, const float* d_target, int B, int C, int H, int W, float data_range,
                     double* d_per_image, double* d_sums, double* d_scratch, void* stream);
@@ -150,6 +151,12 @@ int msd_model_forward(msd_model* m, const float* d_x, const void* d_patch_bf16, 
                       size_t ws_bytes, void* stream);
 /* number of kernels one forward launches (for bench.py's gpu_launches claim) */
 int msd_model_launch_count(const msd_model* m);
+/* Optional live profile: when enabled, msd_model_forward brackets every launch with CUDA events on `stream`.
+ * After the stream is synchronised, msd_model_profile_read returns the number of launches of the LAST forward and
+ * fills per-launch milliseconds, kind (0 = tensor-core GEMM/conv kernel, 1 = attention, 2 = LayerNorm, 3 = other)
+ * and algorithmic FLOPs (2*M*N*K on the unpadded shapes of SURVEY Appendix A). */
+int msd_model_profile_enable(msd_model* m, int enable);
+int msd_model_profile_read(msd_model* m, float* ms_out, int* kind_out, double* flops_out, int capacity);
 void msd_model_destroy(msd_model* m);
 
 /* ---------------------------------------------------------------------------------------------------

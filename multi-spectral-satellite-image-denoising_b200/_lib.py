@@ -63,6 +63,8 @@ SIGNATURES = {
     "msd_model_workspace_bytes": (c_size_t, [c_void_p, c_int]),
     "msd_model_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "msd_model_launch_count": (c_int, [c_void_p]),
+    "msd_model_profile_enable": (c_int, [c_void_p, c_int]),
+    "msd_model_profile_read": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int]),
     "msd_model_destroy": (None, [c_void_p]),
     "msd_linear_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                 c_int, c_void_p]),

@@ -148,6 +148,12 @@ struct msd_model {
   std::vector<msd_block_weights> blocks;
   bool has_weights = false;
   int grid, tokens;
+  // optional per-launch CUDA-event profile (bench.py's live roofline measurement)
+  bool profile = false;
+  std::vector<cudaEvent_t> ev;      // 2 per launch
+  std::vector<int> prof_kind;       // 0 gemm/conv (tensor path), 1 attention, 2 layernorm, 3 other
+  std::vector<double> prof_flops;   // algorithmic FLOPs of the launch (2*M*N*K on unpadded shapes)
+  int prof_count = 0;
 };
 
 namespace {
@@ -219,13 +225,60 @@ extern "C" int msd_model_launch_count(const msd_model* m) {
   return 3 + 7 * m->d.depth + 1 + 4 * 6 + 2;
 }
 
-extern "C" void msd_model_destroy(msd_model* m) { delete m; }
+extern "C" void msd_model_destroy(msd_model* m) {
+  if (!m) return;
+  for (cudaEvent_t e : m->ev) cudaEventDestroy(e);
+  delete m;
+}
+
+extern "C" int msd_model_profile_enable(msd_model* m, int enable) {
+  MSD_REQUIRE(m != nullptr, "profile_enable: null model");
+  if (enable && m->ev.empty()) {
+    const int n = msd_model_launch_count(m) + 8;
+    m->ev.resize(2 * (size_t)n);
+    for (auto& e : m->ev) MSD_CHECK_CUDA(cudaEventCreate(&e));
+    m->prof_kind.assign(n, 0);
+    m->prof_flops.assign(n, 0.0);
+  }
+  m->profile = enable != 0;
+  m->prof_count = 0;
+  return MSD_OK;
+}
+
+extern "C" int msd_model_profile_read(msd_model* m, float* ms_out, int* kind_out, double* flops_out, int capacity) {
+  MSD_REQUIRE(m && ms_out && kind_out && flops_out, "profile_read: null pointer");
+  const int n = m->prof_count < capacity ? m->prof_count : capacity;
+  for (int i = 0; i < n; ++i) {
+    MSD_CHECK_CUDA(cudaEventElapsedTime(&ms_out[i], m->ev[2 * i], m->ev[2 * i + 1]));
+    kind_out[i] = m->prof_kind[i];
+    flops_out[i] = m->prof_flops[i];
+  }
+  return n;
+}
 
 #define MSD_TRY(expr)        \
   do {                       \
     int _rc = (expr);        \
     if (_rc) return _rc;     \
   } while (0)
+
+// run one launch, bracketed by CUDA events on the launching stream when profiling is on
+#define MSD_RUN(kind, flops, expr)                                                      \
+  do {                                                                                  \
+    const int _i = m->prof_count;                                                       \
+    if (m->profile) {                                                                   \
+      if ((size_t)(2 * _i + 1) >= m->ev.size()) { msd_set_error("profile: event pool too small"); return MSD_ERR_INVALID; } \
+      MSD_CHECK_CUDA(cudaEventRecord(m->ev[2 * _i], s));                                \
+    }                                                                                   \
+    MSD_TRY(expr);                                                                      \
+    if (m->profile) {                                                                   \
+      MSD_CHECK_CUDA(cudaEventRecord(m->ev[2 * _i + 1], s));                            \
+      m->prof_kind[_i] = (kind); m->prof_flops[_i] = (flops);                           \
+      m->prof_count = _i + 1;                                                           \
+    }                                                                                   \
+  } while (0)
+
+static double linear_flops(int M, int N, int K) { return 2.0 * M * N * K; }
 
 extern "C" int msd_model_forward(msd_model* m, const float* d_x, const void* d_patch_bf16, int B, float* d_y, void* d_ws,
                                  size_t ws_bytes, void* stream) {
@@ -247,33 +300,34 @@ extern "C" int msd_model_forward(msd_model* m, const float* d_x, const void* d_p
   void *xn = ws + L.xn, *qkv = ws + L.qkv, *att = ws + L.att, *h = ws + L.h;
   Problem p;
 
+  m->prof_count = 0;
   // PatchEmbed: conv k16 s16 == GEMM over patchified pixels, + bias; LayerNorm(eps 1e-5); + pos_embed (encoder.py:48-52, 309)
   const void* a_pe = d_patch_bf16;
   if (!a_pe) {
-    MSD_TRY(msd_patchify_bf16(d_x, ws + L.a_pe, B, d.in_channels, d.image_size, d.patch_size, stream));
+    MSD_RUN(3, 0.0, msd_patchify_bf16(d_x, ws + L.a_pe, B, d.in_channels, d.image_size, d.patch_size, stream));
     a_pe = ws + L.a_pe;
   }
   MSD_TRY(make_linear(p, a_pe, w.w_pe, w.b_pe, x, nullptr, M, E, Kpe, 0, 1));
-  MSD_TRY(gemm::launch(p, be, s));
-  MSD_TRY(msd_layernorm_pos_f32(x, w.pe_ln_g, w.pe_ln_b, d.ln_eps_outer, w.pos_embed, m->tokens, M, E, stream));
+  MSD_RUN(0, linear_flops(M, E, Kpe), gemm::launch(p, be, s));
+  MSD_RUN(2, 0.0, msd_layernorm_pos_f32(x, w.pe_ln_g, w.pe_ln_b, d.ln_eps_outer, w.pos_embed, m->tokens, M, E, stream));
 
   // 12 pre-norm blocks (encoder.py:312-319): x += proj(attn(LN1 x)); x += fc2(GELU(fc1(LN2 x)))
   for (int l = 0; l < d.depth; ++l) {
     const msd_block_weights& bw = m->blocks[l];
-    MSD_TRY(msd_layernorm_f32_bf16(x, bw.ln1_g, bw.ln1_b, d.ln_eps_block, xn, M, E, stream));
+    MSD_RUN(2, 0.0, msd_layernorm_f32_bf16(x, bw.ln1_g, bw.ln1_b, d.ln_eps_block, xn, M, E, stream));
     MSD_TRY(make_linear(p, xn, bw.w_qkv, bw.b_qkv, qkv, nullptr, M, 3 * E, E, 0, 0));
-    MSD_TRY(gemm::launch(p, be, s));
-    MSD_TRY(msd_attention_bf16(qkv, att, B, m->tokens, d.num_heads, stream));
+    MSD_RUN(0, linear_flops(M, 3 * E, E), gemm::launch(p, be, s));
+    MSD_RUN(1, 4.0 * B * d.num_heads * (double)m->tokens * m->tokens * 64, msd_attention_bf16(qkv, att, B, m->tokens, d.num_heads, stream));
     MSD_TRY(make_linear(p, att, bw.w_proj, bw.b_proj, x, x, M, E, E, 0, 1));
-    MSD_TRY(gemm::launch(p, be, s));
-    MSD_TRY(msd_layernorm_f32_bf16(x, bw.ln2_g, bw.ln2_b, d.ln_eps_block, xn, M, E, stream));
+    MSD_RUN(0, linear_flops(M, E, E), gemm::launch(p, be, s));
+    MSD_RUN(2, 0.0, msd_layernorm_f32_bf16(x, bw.ln2_g, bw.ln2_b, d.ln_eps_block, xn, M, E, stream));
     MSD_TRY(make_linear(p, xn, bw.w_fc1, bw.b_fc1, h, nullptr, M, d.mlp_hidden, E, 1, 0));
-    MSD_TRY(gemm::launch(p, be, s));
+    MSD_RUN(0, linear_flops(M, d.mlp_hidden, E), gemm::launch(p, be, s));
     MSD_TRY(make_linear(p, h, bw.w_fc2, bw.b_fc2, x, x, M, E, d.mlp_hidden, 0, 1));
-    MSD_TRY(gemm::launch(p, be, s));
+    MSD_RUN(0, linear_flops(M, E, d.mlp_hidden), gemm::launch(p, be, s));
   }
   // final LayerNorm (encoder.py:322); tokens [B,144,768] are the NHWC [B,12,12,768] map (satmae_restoration.py:128-133)
-  MSD_TRY(msd_layernorm_f32_bf16(x, w.norm_g, w.norm_b, d.ln_eps_outer, xn, M, E, stream));
+  MSD_RUN(2, 0.0, msd_layernorm_f32_bf16(x, w.norm_g, w.norm_b, d.ln_eps_outer, xn, M, E, stream));
 
   // decoder (decoder.py:101-118): 4 x { ConvT k2s2 + BN + GELU ; 2 x ResidualBlock }, BN folded into the weights
   const void* cur = xn;
@@ -282,20 +336,21 @@ extern "C" int msd_model_forward(msd_model* m, const float* d_x, const void* d_p
     const msd_stage_weights& sw = w.stages[st];
     const int cout = d.dec_channels[st];
     void *X = ws + L.stage[st][0], *Y = ws + L.stage[st][1], *Z = ws + L.stage[st][2];
-    MSD_TRY(zero_halo(X, B, 2 * hw, 2 * hw, cout, s));
+    MSD_RUN(3, 0.0, zero_halo(X, B, 2 * hw, 2 * hw, cout, s));
     MSD_TRY(make_convt(p, cur, sw.w_up, sw.b_up, X, B, hw, hw, in_pad, cin, cout));
-    MSD_TRY(gemm::launch(p, be, s));
+    MSD_RUN(0, 2.0 * B * hw * hw * 4.0 * cout * cin, gemm::launch(p, be, s));
     hw *= 2;
+    const double cf = 2.0 * B * hw * hw * (double)cout * 9.0 * cout;
     // ResidualBlock 1: Z = GELU(X + BN(conv(GELU(BN(conv X)))))   (blocks.py:74-85)
     MSD_TRY(make_conv3x3(p, X, sw.w_conv[0], sw.b_conv[0], nullptr, Y, B, hw, hw, cout, cout));
-    MSD_TRY(gemm::launch(p, be, s));
+    MSD_RUN(0, cf, gemm::launch(p, be, s));
     MSD_TRY(make_conv3x3(p, Y, sw.w_conv[1], sw.b_conv[1], X, Z, B, hw, hw, cout, cout));
-    MSD_TRY(gemm::launch(p, be, s));
+    MSD_RUN(0, cf, gemm::launch(p, be, s));
     // ResidualBlock 2: X = GELU(Z + ...)
     MSD_TRY(make_conv3x3(p, Z, sw.w_conv[2], sw.b_conv[2], nullptr, Y, B, hw, hw, cout, cout));
-    MSD_TRY(gemm::launch(p, be, s));
+    MSD_RUN(0, cf, gemm::launch(p, be, s));
     MSD_TRY(make_conv3x3(p, Y, sw.w_conv[3], sw.b_conv[3], Z, X, B, hw, hw, cout, cout));
-    MSD_TRY(gemm::launch(p, be, s));
+    MSD_RUN(0, cf, gemm::launch(p, be, s));
     cur = X; cin = cout; in_pad = 1;
   }
   // head (decoder.py:76-81): conv3x3 + bias + BN + GELU, then conv1x1 -> NCHW fp32
@@ -303,8 +358,8 @@ extern "C" int msd_model_forward(msd_model* m, const float* d_x, const void* d_p
     const int c = d.dec_channels[3];
     void* Y = ws + L.stage[3][1];
     MSD_TRY(make_conv3x3(p, cur, w.w_head3, w.b_head3, nullptr, Y, B, hw, hw, c, c));
-    MSD_TRY(gemm::launch(p, be, s));
-    MSD_TRY(msd_head1x1_nchw_f32(Y, w.w_head1, w.b_head1, d_y, B, hw, hw, c, d.out_channels, stream));
+    MSD_RUN(0, 2.0 * B * hw * hw * (double)c * 9.0 * c, gemm::launch(p, be, s));
+    MSD_RUN(3, 2.0 * B * hw * hw * (double)c * d.out_channels, msd_head1x1_nchw_f32(Y, w.w_head1, w.b_head1, d_y, B, hw, hw, c, d.out_channels, stream));
   }
   return MSD_OK;
 }

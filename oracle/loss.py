@@ -39,4 +39,4 @@ def combined_loss_and_grad(pred: torch.Tensor, target: torch.Tensor, mse_weight=
     p = pred.detach().to(dtype).clone().requires_grad_(True)
     total, mse, sl = combined_loss(p, target.detach().to(dtype), mse_weight, ssim_weight, data_range)
     total.backward()
-    return float(total), float(mse), float(sl), p.grad.detach()
+    return total.item(), mse.item(), sl.item(), p.grad.detach()
