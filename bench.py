@@ -1,0 +1,300 @@
+#!/usr/bin/env python
+"""bench.py -- images/sec of the restoration hot path (corrupt -> restore -> metrics) on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one rank per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU path (oracle port), host cores
+
+Workload (BASELINE.json configs[1], "C2"): a step = one pass over a batch of 256 synthetic 13x192x192 tiles per GPU:
+AddSensorNoise (base.yaml noise) -> SatMAERestoration forward (ViT-B encoder + CNN decoder, bf16 tensor cores, fp32
+accumulate / residual) -> MetricsTracker.update (PSNR / SSIM / SAM / RMSE per image).  Random-init weights
+(seed 42, the reference's own constructor order), EuroSAT-shaped synthetic tiles.
+
+  value : whole-job img/s with the clean batch already resident in HBM (device-timed, max over ranks)
+  e2e   : the same step through the public API with the clean batch in pinned HOST memory: H2D copy of the
+          batch + one D2H read of the 5 fp64 metric sums inside the timed region, every step
+  roofline     : the tcgen05 GEMM / implicit-conv kernel family (97% of the FLOPs), timed live per launch with CUDA
+                 events on the launching stream during a second pass over the same steps
+  cpu_baseline : the oracle's torch-eager restatement of the reference's CPU path on a bounded sample (rank 0, N=1)
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+for _p in (str(ROOT), str(ROOT / "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+import recipes  # noqa: E402
+
+BATCH = 256                       # tiles per GPU per step (config C2)
+TILE_ELEMS = 13 * 192 * 192
+FWD_GFLOP_PER_IMG = 53.357        # 2*M*N*K over all GEMM/conv layers
+METRIC = "13x192x192 images/sec restore+metrics"
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return {"hbm_gbs": d["hbm_gbs"], "tf_burst": d["bf16_tflops"], "tf_sustained": d["bf16_tflops_sustained"], "src": "measured"}
+    return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.proc = gpu_index, None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+        return self
+
+    def __exit__(self, *exc):
+        self.rows = []
+        if self.proc is None:
+            return
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) >= 8:
+                self.rows.append(f)
+
+    def summary(self):
+        if not getattr(self, "rows", None):
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[4 + i].lower().startswith("active") for r in self.rows)]
+        power = [float(r[3]) for r in self.rows if r[3].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][2]) if self.rows else None,
+                "reasons": reasons, "power_w_max": max(power) if power else None, "samples": len(self.rows)}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def cpu_port_run(steps: int, warmup: int, sample_b: int = 8):
+    """The reference's CPU hot path (oracle port, torch eager fp32, all host threads) on `sample_b` tiles per step."""
+    from oracle import reference_port as rp
+    from msd_b200.models import SatMAERestoration
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(42)
+    sd = {k: v.clone() for k, v in SatMAERestoration(recipes.base_config(), block_layout="fallback").state_dict().items()}
+    clean, _ = recipes.eurosat_tiles(sample_b, seed=3)
+    tracker = rp.MetricsTracker()
+    torch.manual_seed(42)
+    for _ in range(warmup):
+        rp.hot_path_step(sd, clean, recipes.NOISE_CONFIGS["base"], tracker)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        rp.hot_path_step(sd, clean, recipes.NOISE_CONFIGS["base"], tracker)
+    dt = time.perf_counter() - t0
+    return {"value": sample_b * steps / dt, "ms_per_step": 1e3 * dt / steps, "cores": cores, "threads": torch.get_num_threads(),
+            "sample": f"{steps} steps x {sample_b} tiles (corrupt -> restore -> per-image PSNR/SSIM/SAM/RMSE), torch eager fp32, "
+                      f"{warmup} warm-up"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    steps = max(1, min(args.steps, 5))
+    r = cpu_port_run(steps, max(1, min(args.warmup, 2)))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "img/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": max(1, min(args.warmup, 2)), "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C2 hot path (corrupt -> SatMAE ViT-B restore -> metrics), bounded CPU sample of 8 tiles/step",
+                   "tile": "13x192x192", "weights": "random-init seed 42", "noise": "configs/base.yaml"},
+        "cpu_baseline": {"value": r["value"], "unit": "img/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------ CUDA arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="msd", choices=["msd", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--backend", type=int, default=0, help="0 tcgen05 (product), 1 legacy mma.sync (A/B)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-out", default=None, help="write the per-launch event profile (json) here")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch.distributed as dist
+    from msd_b200 import _lib
+    from msd_b200.data import AddSensorNoise
+    from msd_b200.models import SatMAERestoration
+    from msd_b200.training import MetricsTracker
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- libmsd_b200 has no CPU path (use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    W = max(3, args.warmup)
+    K, B = args.steps, args.batch
+
+    torch.manual_seed(42)
+    model = SatMAERestoration(recipes.base_config(), block_layout="fallback", gemm_backend=args.backend).eval().to(dev)
+    noise = AddSensorNoise(*recipes.NOISE_CONFIGS["base"])
+    # each rank owns its own shard of tiles (weak scaling: B tiles per GPU), seeded by global shard index
+    clean_host, _ = recipes.eurosat_tiles(32, seed=100 + rank)
+    clean_host = clean_host.repeat(B // 32 + 1, 1, 1, 1)[:B].contiguous().pin_memory()
+    clean_dev = clean_host.to(dev)
+    patches = torch.empty(B * 144, 13 * 256, dtype=torch.bfloat16, device=dev)
+    torch.manual_seed(1234 + rank)
+    tracker = MetricsTracker()
+
+    def step(clean):
+        noisy = noise(clean, patch_out=patches)          # fused corruption, also emits the patch-embed operand
+        restored = model(noisy, patches=patches)
+        tracker.update(restored, clean)
+        return restored
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    with torch.no_grad():
+        for _ in range(W):
+            step(clean_dev)
+        # ---------------- value: inputs resident in HBM, metric sums stay on the device, one allreduce at the end
+        def resident():
+            step(clean_dev)
+        tracker.reset()
+        with ClockSampler(local) as clk:
+            ms_total = timed(lambda: resident(), K)
+            if world > 1:
+                tracker.all_reduce()
+        metrics_dev = tracker.compute()
+        # ---------------- e2e: host buffers in, metric sums out, every step
+        def e2e_step():
+            c = clean_host.to(dev, non_blocking=True)
+            t = MetricsTracker()
+            noisy = noise(c, patch_out=patches)
+            restored = model(noisy, patches=patches)
+            t.update(restored, c)
+            return t.compute()                              # D2H of 5 fp64 (sync)
+        for _ in range(2):
+            e2e_step()
+        ms_e2e = timed(lambda: e2e_step(), K)
+        # ---------------- roofline: per-launch CUDA events inside the library, same steps again
+        lib = _lib.load()
+        _lib.check(lib.msd_model_profile_enable(model._handle, 1))
+        cap = 256
+        ms_buf, kind_buf, fl_buf = (ctypes.c_float * cap)(), (ctypes.c_int * cap)(), (ctypes.c_double * cap)()
+        agg = {}
+        per_launch = None
+        for it in range(K):
+            step(clean_dev)
+            torch.cuda.synchronize()
+            n = lib.msd_model_profile_read(model._handle, ms_buf, kind_buf, fl_buf, cap)
+            rows = [(ms_buf[i], kind_buf[i], fl_buf[i]) for i in range(n)]
+            per_launch = rows if per_launch is None else [(a[0] + b[0], a[1], a[2]) for a, b in zip(per_launch, rows)]
+        _lib.check(lib.msd_model_profile_enable(model._handle, 0))
+        per_launch = [(ms / K, kind, fl) for ms, kind, fl in per_launch]
+        for ms, kind, fl in per_launch:
+            a = agg.setdefault(kind, [0.0, 0.0, 0])
+            a[0] += ms; a[1] += fl; a[2] += 1
+
+    ms_step = ms_total / K
+    value = world * B * K / (ms_total / 1e3)
+    e2e_value = world * B * K / (ms_e2e / 1e3)
+    pk = peaks()
+    gemm_ms, gemm_flops, gemm_n = agg.get(0, [0.0, 0.0, 0])
+    achieved_tf = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+    launches_per_step = 2 + (model.launches_per_forward() - 1) + 3      # corrupt(2) + forward (patchify fused away) + metrics(3)
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "img/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "C2: corrupt + SatMAE ViT-B restoration forward + PSNR/SSIM/SAM/RMSE, batch 256 tiles/GPU (13x192x192)",
+                   "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world} (batch-sharded, metric-sum allreduce only)",
+                   "weights": "random-init seed 42 (reference constructor order), eval-mode BN folded",
+                   "noise": "gaussian 0.015, speckle 0.008, dead-band 0.08, thermal 0.005 (configs/base.yaml)",
+                   "gemm_backend": "tcgen05" if args.backend == 0 else "mma.sync",
+                   "l2": "per-step working set (491 MB clean + 6.2 GB activations) exceeds the 126 MB L2; no flush needed"},
+        "e2e": {"value": e2e_value, "unit": "img/s", "ms_per_step": ms_e2e / K, "h2d_bytes_per_step": B * TILE_ELEMS * 4,
+                "d2h_bytes_per_step": 40},
+        "gpu_launches": launches_per_step * K,
+        "roofline": {"bound": "tensor", "kernel": "gemm_tc5_kernel<BN> (tcgen05 GEMM + implicit 3x3 conv family)" if args.backend == 0 else "gemm_hmma_kernel<BN>",
+                     "achieved": achieved_tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": achieved_tf / pk["tf_sustained"],
+                     "peak_source": f"{pk['src']} bf16_tflops_sustained (kernel timed inside a long step)",
+                     "traffic": None, "launches_per_step": gemm_n, "ms_per_step": gemm_ms,
+                     "algorithmic_gflop_per_step": gemm_flops / 1e9,
+                     "share_of_step": gemm_ms / ms_step if ms_step > 0 else None,
+                     "other_ms_per_step": {"attention": agg.get(1, [0])[0], "layernorm": agg.get(2, [0])[0], "other_model": agg.get(3, [0])[0]},
+                     "forward_tflops_whole_step": B * FWD_GFLOP_PER_IMG / ms_step / 1e3},
+        "clocks": clk.summary(),
+        "quality": {k: float(v) for k, v in metrics_dev.items()},
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = cpu_port_run(steps=8, warmup=1)
+        line["cpu_baseline"] = {"value": r["value"], "unit": "img/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+    if rank == 0:
+        if args.profile_out:
+            Path(args.profile_out).parent.mkdir(parents=True, exist_ok=True)
+            names = {0: "gemm/conv", 1: "attention", 2: "layernorm", 3: "other"}
+            Path(args.profile_out).write_text(json.dumps(
+                {"ms_per_step": ms_step, "launches": [{"i": i, "kind": names[k], "ms": ms, "gflop": fl / 1e9,
+                                                       "tflops": (fl / ms / 1e9) if ms > 0 and fl > 0 else None}
+                                                      for i, (ms, k, fl) in enumerate(per_launch)]}, indent=1))
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -55,8 +55,8 @@ def torch_cuda_draws(seed: int, offset: int, numel: int, torch_grid: int) -> np.
 
 
 def curand_uniform(x: np.ndarray) -> np.ndarray:
-    """_curand_uniform: x * 2^-32 + 2^-33 as one fp32 fused multiply-add -> (0, 1]."""
-    return (x.astype(np.float64) * 2.0 ** -32 + 2.0 ** -33).astype(np.float32)
+    """_curand_uniform: (float)x * 2^-32 + 2^-33 -- x is rounded to fp32 first, then one fused multiply-add -> (0, 1]."""
+    return (x.astype(np.float32).astype(np.float64) * 2.0 ** -32 + 2.0 ** -33).astype(np.float32)
 
 
 def torch_cuda_rand(seed: int, offset: int, numel: int, torch_grid: int) -> np.ndarray:
