@@ -1,0 +1,446 @@
+// tcgen05 / TMEM / TMA GEMM + implicit 3x3 convolution for sm_100a (the product path of every dense contraction
+// in SatMAERestoration.forward; shapes in SURVEY Appendix A).
+//
+// Persistent, warp-specialised, one CTA per SM:
+//   warp 0   : TMA producer  -- cp.async.bulk.tensor.2d of the A box [128 rows x 64 k] (row = m0 + tap shift) and
+//              the W box [BN rows x 64 k] into a kStages-deep 128B-swizzled shared-memory ring (mbarrier full/empty)
+//   warp 1   : MMA issuer    -- one thread issues 4 x tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16) per
+//              stage into one of two TMEM accumulator buffers, tcgen05.commit releases the stage / publishes the tile
+//   warp 2   : TMEM allocator
+//   warps 4-7: epilogue      -- per column slab: tcgen05.ld 32x32b.x16 (thread = one accumulator row) -> TMEM is
+//              released as soon as the last slab is in registers -> fp32 slab staged in a per-warp padded smem tile
+//              -> re-read with lanes running along the columns, so that bias / residual / skip loads and the
+//              fused GELU / pixel-shuffle / halo-zero stores are coalesced row segments instead of 32 scattered rows;
+//              all of it overlaps the next tile's MMAs (two TMEM accumulator buffers)
+// Accumulators are fp32 in TMEM (2 x BN columns), operands bf16.
+#pragma once
+#include "gemm.cuh"
+#include <cuda.h>
+
+namespace gemm {
+namespace tc5 {
+
+constexpr int kThreads = 256;
+constexpr uint32_t A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
+constexpr uint64_t kSpinLimit = 4000000000ull;             // ~2 s of SM clocks: trap instead of hanging the GPU
+
+template <int BN>
+struct Cfg {
+  static constexpr uint32_t B_STAGE_BYTES = BN * BLOCK_K * 2;
+  static constexpr uint32_t STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  // epilogue staging: slab of SC fp32 columns x 32 rows per epilogue warp, row pitch padded by 16 B (conflict-free)
+  static constexpr int SC = (BN == 256) ? 32 : (BN % 64 == 0) ? 64 : (BN % 48 == 0) ? 48 : (BN % 32 == 0) ? 32 : 16;
+  static constexpr int UPR = SC / 4;                       // 16-byte units per staged row
+  static constexpr uint32_t STG_PITCH = SC * 4 + 16;
+  static constexpr int UB = (UPR % 8 == 0) ? 8 : 4;         // units per lane whose loads are batched in phase B
+  static constexpr uint32_t STG_WARP_BYTES = 32 * STG_PITCH + BN * 4;   // staged slab + this tile's bias slice
+  static constexpr uint32_t STG_BYTES = 4 * STG_WARP_BYTES;
+  static constexpr int kStagesRaw = (int)((227u * 1024u - 1024u - 256u - STG_BYTES) / STAGE_BYTES);
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  static constexpr uint32_t SMEM_BYTES = kStages * STAGE_BYTES + STG_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static_assert(BN % SC == 0 && SC % 16 == 0, "slab must tile BN in 16-column TMEM loads");
+  static_assert(kStages >= 3, "pipeline too shallow");
+  static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N for M=128 must be a multiple of 16 in [16,256]");
+  static_assert(B_STAGE_BYTES % 1024 == 0, "stage bases must stay 1024-byte aligned for SWIZZLE_128B");
+};
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t}\n"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if ((uint64_t)(clock64() - t0) > kSpinLimit) {
+      printf("libmsd_b200 gemm_tc5: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* tm, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tcgen05_mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 16 consecutive fp32 accumulator columns of this thread's TMEM lane; completion via tmem_ld_wait()
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
+
+constexpr uint32_t kRowSkip = 0xFFFFFFFFu;   // row produces no output (beyond M, or a halo row of a ConvTranspose input)
+constexpr uint32_t kRowHalo = 0x80000000u;   // EPI_CONV halo row: stored as zeros
+
+// Per-row output coordinate, computed once per tile by the lane that owns the accumulator row:
+//   EPI_ROWMAJOR: m              EPI_CONV: m | kRowHalo?        EPI_CONVT: output pixel of sub-position (0,0)
+__device__ __forceinline__ uint32_t row_info(const Problem& p, int m) {
+  if (m >= p.M) return kRowSkip;
+  if (p.mode == EPI_ROWMAJOR) return (uint32_t)m;
+  uint32_t img, rem, yy, xx;
+  if (p.mode == EPI_CONV) {
+    fd_divmod((uint32_t)m, p.plane, img, rem);
+    fd_divmod(rem, p.pitch, yy, xx);
+    const bool interior = yy >= 1 && yy <= (uint32_t)p.H && xx >= 1 && xx <= (uint32_t)p.W;
+    return (uint32_t)m | (interior ? 0u : kRowHalo);
+  }
+  fd_divmod((uint32_t)m, p.in_plane, img, rem);
+  fd_divmod(rem, p.in_pitch, yy, xx);
+  if (p.in_pad) {
+    if (!(yy >= 1 && yy <= (uint32_t)p.Hin && xx >= 1 && xx <= (uint32_t)p.Win)) return kRowSkip;
+    yy -= 1; xx -= 1;
+  }
+  return img * (uint32_t)p.out_plane + (2 * yy + 1) * (uint32_t)p.out_pitch + (2 * xx + 1);
+}
+
+// Phase B of the epilogue works on 16-byte units = 4 consecutive output columns n..n+3 of the row described by `pix`.
+// Global loads (residual / skip) are issued for a whole batch of units BEFORE any arithmetic or store, so that several
+// independent requests per lane are in flight (the stores may alias the loads as far as the compiler knows).
+__device__ __forceinline__ size_t unit_offset(const Problem& p, uint32_t pix, int n) {
+  if (p.mode == EPI_CONVT) {  // column n = (di*2+dj)*Cout + o -> output pixel (2y+di, 2x+dj), channel o
+    uint32_t q, o;
+    fd_divmod((uint32_t)n, p.cout_div, q, o);
+    return (size_t)(pix + (q >> 1) * (uint32_t)p.out_pitch + (q & 1)) * p.ldo + o;
+  }
+  return (size_t)(pix & ~kRowHalo) * p.ldo + n;
+}
+
+__device__ __forceinline__ void finish_unit(const Problem& p, uint32_t pix, size_t off, float4 v) {
+  if (pix == kRowSkip) return;
+  const bool zero = (p.mode == EPI_CONV) && (pix & kRowHalo) != 0;
+  if (zero) v = make_float4(0.f, 0.f, 0.f, 0.f);
+  else if (p.act) { v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w); }
+  if (p.out_f32) *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off) = v;
+  else *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+//   [0,14) start address >> 4, [16,30) leading byte offset >> 4 (unused for one swizzle atom along K),
+//   [32,46) stride byte offset >> 4 = 8 rows * 128 B, [46,48) version = 1 (sm_100), [61,64) layout = 2 (128B swizzle)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(1024u >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): c=f32 [4,6)=1, a=bf16 [7,10)=1, b=bf16 [10,13)=1,
+// a/b K-major (bits 15,16 = 0), n>>3 at [17,23), m>>4 at [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------------ epilogue
+// Fused epilogues, one instruction stream each (selected per launch from the Problem, see classify()):
+enum Epi : int {
+  E_RM_F32 = 0,     // out fp32 [M,N] = acc + bias                                  (patch embedding)
+  E_RM_BF16,        // out bf16 = acc + bias                                         (qkv)
+  E_RM_BF16_GELU,   // out bf16 = GELU(acc + bias)                                   (fc1)
+  E_RM_F32_RESID,   // out fp32 = resid + acc + bias, in place                       (attention proj, fc2)
+  E_CONV,           // haloed NHWC bf16 = GELU(acc + bias), halo rows zeroed         (ResidualBlock conv 1, head conv)
+  E_CONV_SKIP,      // haloed NHWC bf16 = GELU(acc + bias + skip)                    (ResidualBlock conv 2)
+  E_CONVT,          // pixel-shuffle scatter of GELU(acc + bias)                     (ConvTranspose2d k2 s2)
+  E_GENERIC         // any other combination of the Problem's flags (slower, runtime-branched)
+};
+
+__host__ inline int classify(const Problem& p) {
+  const bool idx32 = (unsigned long long)p.M * (unsigned long long)p.ldo < (1ull << 31);
+  if (!idx32) return E_GENERIC;
+  if (p.mode == EPI_ROWMAJOR) {
+    if (p.out_f32 && !p.act && p.resid == nullptr) return E_RM_F32;
+    if (p.out_f32 && !p.act && p.resid != nullptr) return E_RM_F32_RESID;
+    if (!p.out_f32 && p.resid == nullptr) return p.act ? E_RM_BF16_GELU : E_RM_BF16;
+    return E_GENERIC;
+  }
+  if (p.mode == EPI_CONV && p.act && !p.out_f32) return p.skip ? E_CONV_SKIP : E_CONV;
+  if (p.mode == EPI_CONVT && p.act && !p.out_f32 &&
+      (unsigned long long)(p.M / (int)p.in_plane.d + 1) * p.out_plane * p.ldo < (1ull << 31)) return E_CONVT;
+  return E_GENERIC;
+}
+
+template <int BN, int EPI>
+__device__ __forceinline__ void epilogue_tile(const Problem& p, unsigned char* stg, const float* sbias, uint32_t taddr,
+                                              uint64_t* tmem_empty_bar, int mrow0, int n0, int lane) {
+  using C = Cfg<BN>;
+  constexpr bool kRowMajor = EPI == E_RM_F32 || EPI == E_RM_BF16 || EPI == E_RM_BF16_GELU || EPI == E_RM_F32_RESID;
+  constexpr bool kConv = EPI == E_CONV || EPI == E_CONV_SKIP;
+  constexpr bool kF32 = EPI == E_RM_F32 || EPI == E_RM_F32_RESID;
+  constexpr bool kGelu = EPI == E_RM_BF16_GELU || kConv || EPI == E_CONVT;
+  // per-row facts, owned by the lane whose TMEM row it is; phase B looks rows up by ballot mask / shuffle
+  const uint32_t rowpix = (EPI == E_GENERIC || EPI == E_CONVT || kConv) ? row_info(p, mrow0 + lane) : 0u;
+  const uint32_t halo_mask = kConv ? __ballot_sync(0xffffffffu, (rowpix & kRowHalo) != 0 && rowpix != kRowSkip) : 0u;
+  const int rows_valid = p.M - mrow0;   // rows rr < rows_valid exist (row-major / conv)
+  const uint32_t ldo = (uint32_t)p.ldo;
+#pragma unroll 1
+  for (int slab = 0; slab < BN / C::SC; ++slab) {
+    // ---- phase A: this lane's accumulator row -> registers -> padded smem row
+    uint32_t r[C::SC];
+#pragma unroll
+    for (int c = 0; c < C::SC / 16; ++c) tmem_ld16(taddr + slab * C::SC + c * 16, &r[c * 16]);
+    tmem_ld_wait();
+    if (slab == BN / C::SC - 1) {
+      // the whole accumulator has left TMEM: hand the buffer back to the MMA warp before the stores
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty_bar);
+    }
+    uint4* srow = reinterpret_cast<uint4*>(stg + lane * C::STG_PITCH);
+#pragma unroll
+    for (int c = 0; c < C::UPR; ++c) srow[c] = make_uint4(r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
+    __syncwarp();
+    // ---- phase B: lanes run along the columns; UB 16-byte units (4 columns each) per lane per batch
+    const int nslab = slab * C::SC;
+#pragma unroll 1
+    for (int ub = 0; ub < C::UPR / C::UB; ++ub) {
+      float4 v[C::UB];
+      uint32_t off[C::UB];     // element offset into out (32-bit: classify() guarantees it fits)
+      bool live[C::UB];
+#pragma unroll
+      for (int j = 0; j < C::UB; ++j) {
+        const int u = (ub * C::UB + j) * 32 + lane;
+        const int rr = u / C::UPR, cu = u - rr * C::UPR;
+        const int n = n0 + nslab + cu * 4;
+        v[j] = *reinterpret_cast<const float4*>(stg + rr * C::STG_PITCH + cu * 16);
+        const float4 b = *reinterpret_cast<const float4*>(sbias + nslab + cu * 4);
+        v[j].x += b.x; v[j].y += b.y; v[j].z += b.z; v[j].w += b.w;
+        if (kRowMajor || kConv) {
+          live[j] = rr < rows_valid;
+          off[j] = (uint32_t)(mrow0 + rr) * ldo + (uint32_t)n;
+        } else if (EPI == E_CONVT) {
+          const uint32_t pix = __shfl_sync(0xffffffffu, rowpix, rr);
+          live[j] = pix != kRowSkip;
+          uint32_t qq, o;
+          fd_divmod((uint32_t)n, p.cout_div, qq, o);
+          off[j] = (pix + (qq >> 1) * (uint32_t)p.out_pitch + (qq & 1)) * ldo + o;
+        } else {  // E_GENERIC keeps 64-bit offsets and every runtime flag
+          const uint32_t pix = __shfl_sync(0xffffffffu, rowpix, rr);
+          const size_t o64 = unit_offset(p, pix, n);
+          float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (pix != kRowSkip) {
+            if (p.resid != nullptr) e = *reinterpret_cast<const float4*>(p.resid + o64);
+            else if (p.skip != nullptr && !(pix & kRowHalo)) {
+              const uint2 s2 = *reinterpret_cast<const uint2*>(p.skip + o64);
+              const float2 a = unpack_bf16x2(s2.x), c2 = unpack_bf16x2(s2.y);
+              e = make_float4(a.x, a.y, c2.x, c2.y);
+            }
+          }
+          v[j].x += e.x; v[j].y += e.y; v[j].z += e.z; v[j].w += e.w;
+          finish_unit(p, pix, o64, v[j]);
+          live[j] = false;
+          off[j] = 0;
+        }
+      }
+      if (EPI == E_GENERIC) continue;
+      // extra operands: all loads of the batch are in flight before the first use
+      if (EPI == E_RM_F32_RESID) {
+        float4 e[C::UB];
+#pragma unroll
+        for (int j = 0; j < C::UB; ++j) e[j] = live[j] ? *reinterpret_cast<const float4*>(p.resid + off[j]) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < C::UB; ++j) { v[j].x += e[j].x; v[j].y += e[j].y; v[j].z += e[j].z; v[j].w += e[j].w; }
+      }
+      if (EPI == E_CONV_SKIP) {
+        uint2 e[C::UB];
+#pragma unroll
+        for (int j = 0; j < C::UB; ++j) e[j] = live[j] ? __ldg(reinterpret_cast<const uint2*>(p.skip + off[j])) : make_uint2(0u, 0u);
+#pragma unroll
+        for (int j = 0; j < C::UB; ++j) {
+          const float2 a = unpack_bf16x2(e[j].x), b = unpack_bf16x2(e[j].y);
+          v[j].x += a.x; v[j].y += a.y; v[j].z += b.x; v[j].w += b.y;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < C::UB; ++j) {
+        if (kGelu) { v[j].x = gelu_erf(v[j].x); v[j].y = gelu_erf(v[j].y); v[j].z = gelu_erf(v[j].z); v[j].w = gelu_erf(v[j].w); }
+        if (kConv) {
+          const int rr = ((ub * C::UB + j) * 32 + lane) / C::UPR;
+          if ((halo_mask >> rr) & 1u) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (live[j]) {
+          if (kF32) *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off[j]) = v[j];
+          else *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off[j]) = make_uint2(pack_bf16x2(v[j].x, v[j].y), pack_bf16x2(v[j].z, v[j].w));
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ kernel
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Problem p,
+                int tiles_m, int tiles_n, int epi) {
+  using C = Cfg<BN>;
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  unsigned char* smem_a = smem;
+  unsigned char* smem_b = smem + C::kStages * A_STAGE_BYTES;
+  unsigned char* smem_stg = smem + C::kStages * C::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_stg + C::STG_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + C::kStages;
+  uint64_t* tmem_full = bars + 2 * C::kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < C::kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_ptr)), "r"(C::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const int num_tiles = tiles_m * tiles_n;
+
+  if (warp == 0 && lane == 0) {
+    // ===== TMA producer =====
+    int stage = 0; uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / tiles_n) * BLOCK_M, n0 = (tile % tiles_n) * BN;
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        const int tap = kb / p.kb_per_tap, kc = kb - tap * p.kb_per_tap;
+        mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);
+        tma_load_2d(&tmA, &full[stage], smem_a + stage * A_STAGE_BYTES, kc * BLOCK_K, m0 + p.tap_off[tap]);
+        tma_load_2d(&tmB, &full[stage], smem_b + stage * C::B_STAGE_BYTES, kb * BLOCK_K, n0);
+        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===== MMA issuer =====
+    constexpr uint32_t idesc = make_idesc(BLOCK_M, BN);
+    int stage = 0; uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const uint32_t as = it & 1, aphase = (it >> 1) & 1;
+      mbar_wait(&tmem_empty[as], aphase ^ 1);
+      tcgen05_fence_after();
+      const uint32_t tmem_d = tmem_base + as * BN;
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        mbar_wait(&full[stage], phase);
+        tcgen05_fence_after();
+        const uint64_t da = make_smem_desc(smem_u32(smem_a + stage * A_STAGE_BYTES));
+        const uint64_t db = make_smem_desc(smem_u32(smem_b + stage * C::B_STAGE_BYTES));
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / 16; ++k) {
+          // advance 16 bf16 = 32 bytes inside the 128-byte swizzle atom: +2 in the (addr >> 4) field
+          tcgen05_mma_bf16(tmem_d, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        tcgen05_commit(&empty[stage]);               // frees the smem stage once these MMAs retire
+        if (kb == p.num_kb - 1) tcgen05_commit(&tmem_full[as]);  // accumulator complete -> epilogue
+        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: warp (4+q) owns TMEM lanes 32q..32q+31 = output rows 32q..32q+31 of the tile =====
+    const int q = warp - 4;
+    unsigned char* stg = smem_stg + q * C::STG_WARP_BYTES;
+    float* sbias = reinterpret_cast<float*>(stg + 32 * C::STG_PITCH);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const uint32_t as = it & 1, aphase = (it >> 1) & 1;
+      const int m0 = (tile / tiles_n) * BLOCK_M, n0 = (tile % tiles_n) * BN;
+      // this tile's bias slice -> smem (private to the warp), issued before waiting for the accumulator
+      for (int i = lane; i < BN; i += 32) sbias[i] = (p.bias != nullptr) ? __ldg(p.bias + n0 + i) : 0.0f;
+      mbar_wait(&tmem_full[as], aphase);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
+      // one specialised instruction stream per fused epilogue (the switch is per tile, the loops inside are branch-free)
+      switch (epi) {
+        case E_RM_F32:        epilogue_tile<BN, E_RM_F32>(p, stg, sbias, taddr, &tmem_empty[as], m0 + q * 32, n0, lane); break;
+        case E_RM_BF16:       epilogue_tile<BN, E_RM_BF16>(p, stg, sbias, taddr, &tmem_empty[as], m0 + q * 32, n0, lane); break;
+        case E_RM_BF16_GELU:  epilogue_tile<BN, E_RM_BF16_GELU>(p, stg, sbias, taddr, &tmem_empty[as], m0 + q * 32, n0, lane); break;
+        case E_RM_F32_RESID:  epilogue_tile<BN, E_RM_F32_RESID>(p, stg, sbias, taddr, &tmem_empty[as], m0 + q * 32, n0, lane); break;
+        case E_CONV:          epilogue_tile<BN, E_CONV>(p, stg, sbias, taddr, &tmem_empty[as], m0 + q * 32, n0, lane); break;
+        case E_CONV_SKIP:     epilogue_tile<BN, E_CONV_SKIP>(p, stg, sbias, taddr, &tmem_empty[as], m0 + q * 32, n0, lane); break;
+        case E_CONVT:         epilogue_tile<BN, E_CONVT>(p, stg, sbias, taddr, &tmem_empty[as], m0 + q * 32, n0, lane); break;
+        default:              epilogue_tile<BN, E_GENERIC>(p, stg, sbias, taddr, &tmem_empty[as], m0 + q * 32, n0, lane); break;
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(C::TMEM_COLS) : "memory");
+  }
+}
+
+
+// host: launch one BN instantiation (defined in gemm_tc5.cu, instantiated per BN in gemm_tc5_bn*.cu)
+template <int BN>
+int launch_bn(const Problem& p, cudaStream_t s);
+int make_map(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t rows, uint64_t ld, uint32_t box_rows);
+int num_sms();
+
+template <int BN>
+int launch_bn(const Problem& p, cudaStream_t s) {
+  using C = Cfg<BN>;
+  CUtensorMap tmA, tmB;
+  int rc = make_map(&tmA, p.A, (uint64_t)p.kvalid, (uint64_t)p.a_rows, (uint64_t)p.ldA, BLOCK_M);
+  if (rc) return rc;
+  rc = make_map(&tmB, p.Wt, (uint64_t)p.num_kb * BLOCK_K, (uint64_t)p.N, (uint64_t)p.num_kb * BLOCK_K, BN);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MSD_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc5_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int tiles_m = (p.M + BLOCK_M - 1) / BLOCK_M, tiles_n = p.N / BN;
+  const int tiles = tiles_m * tiles_n;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  gemm_tc5_kernel<BN><<<grid, kThreads, C::SMEM_BYTES, s>>>(tmA, tmB, p, tiles_m, tiles_n, classify(p));
+  MSD_LAUNCH_CHECK();
+  return MSD_OK;
+}
+
+}  // namespace tc5
+}  // namespace gemm
