@@ -117,7 +117,7 @@ typedef struct msd_model_desc {
 
 /* Packed weights, all DEVICE pointers that must outlive the model (the shim keeps the tensors alive).
  * bf16 matrices are row-major [N, K] (K contiguous).  Conv weights are [Cout, 9*Kpad] tap-major with
- * Kpad = Cin rounded up to 64; BN already folded (w*gamma/sqrt(var+eps), bias = beta + (b-mean)*scale). */
+ * Kpad = Cin rounded up to 64 (10*Kpad, last tap = identity, for the second conv of a ResidualBlock); BN already folded (w*gamma/sqrt(var+eps), bias = beta + (b-mean)*scale). */
 typedef struct msd_block_weights {
   const float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
   const void *w_qkv;  const float *b_qkv;   /* [2304,768]  */
@@ -166,7 +166,9 @@ void msd_model_destroy(msd_model* m);
  * act: 0 none, 1 GELU(erf).  resid_f32 != NULL -> out fp32 = resid + A.W^T + bias (may alias out). */
 int msd_linear_bf16(const void* d_a, const void* d_w, const float* d_bias, void* d_out, const float* d_resid,
                     int M, int N, int K, int act, int out_f32, int backend, void* stream);
-/* 3x3 conv, pad 1, NHWC bf16 with a 1-pixel zero halo: x,y,skip are [B,(H+2),(W+2),C*] bf16; w [Cout, 9*Kpad]. */
+/* 3x3 conv, pad 1, + bias + GELU, NHWC bf16 with a 1-pixel zero halo: x,y,skip are [B,(H+2),(W+2),C*] bf16;
+ * w [Cout, 9*Kpad]; with a skip tensor (Cin == Cout) w is [Cout, 10*Kpad], the tenth tap being the identity, and the
+ * result is GELU(conv + bias + skip) -- the skip connection is accumulated by the tensor cores like any other tap. */
 int msd_conv3x3_nhwc_bf16(const void* d_x, const void* d_w, const float* d_bias, const void* d_skip, void* d_y,
                           int B, int H, int W, int Cin, int Cout, int backend, void* stream);
 /* ConvTranspose2d k2 s2 + bias + GELU: x [B,Hin(+2p),Win(+2p),Cin] bf16 -> y [B,2Hin+2,2Win+2,Cout] haloed. */

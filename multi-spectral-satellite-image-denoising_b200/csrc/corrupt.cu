@@ -18,16 +18,35 @@ namespace {
 
 constexpr int kThreads = 256;
 
-// One curand_normal4 / curand_uniform4 draw of torch-thread `tid` in its `round`-th call.
-__device__ __forceinline__ float4 torch_normal4(uint64_t seed, uint64_t offset, uint32_t tid, uint32_t round) {
-  curandStatePhilox4_32_10_t st;
-  curand_init(seed, (unsigned long long)tid, offset + 4ull * round, &st);
-  return curand_normal4(&st);
+// Philox4x32-10 (Salmon et al., Random123; the generator behind curandStatePhilox4_32_10_t): counter = 128 bits,
+// key = 64 bits, 10 rounds of two 32x32->64 multiplies + xors, key bumped by the Weyl constants between rounds.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
 }
+// The 4 words torch-thread `tid` obtains from its `round`-th curand4 call: curand_init(seed, subsequence = tid,
+// offset) puts tid in counter words 2..3 and offset/4 in words 0..1; every call advances the low counter by one.
+__device__ __forceinline__ uint4 torch_draw4(uint64_t seed, uint64_t offset, uint32_t tid, uint32_t round) {
+  const uint64_t lo = (offset >> 2) + round;
+  return philox4x32_10(make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), tid, 0u), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+}
+// curand_normal4 = two Box-Muller pairs (curand_normal.h:70-87, cuRAND's own device routine, so the bits match)
+__device__ __forceinline__ float4 torch_normal4(uint64_t seed, uint64_t offset, uint32_t tid, uint32_t round) {
+  const uint4 x = torch_draw4(seed, offset, tid, round);
+  const float2 a = _curand_box_muller(x.x, x.y), b = _curand_box_muller(x.z, x.w);
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+// curand_uniform4 = _curand_uniform on each word: x * 2^-32 + 2^-33 -> (0, 1]
 __device__ __forceinline__ float4 torch_uniform4(uint64_t seed, uint64_t offset, uint32_t tid, uint32_t round) {
-  curandStatePhilox4_32_10_t st;
-  curand_init(seed, (unsigned long long)tid, offset + 4ull * round, &st);
-  return curand_uniform4(&st);
+  const uint4 x = torch_draw4(seed, offset, tid, round);
+  return make_float4(_curand_uniform(x.x), _curand_uniform(x.y), _curand_uniform(x.z), _curand_uniform(x.w));
 }
 // torch's normal_ transform is rand * std + mean with std = 1, mean = 0 (one fused multiply-add)
 __device__ __forceinline__ float torch_normal_xf(float r) { return __fmaf_rn(r, 1.0f, 0.0f); }
@@ -40,12 +59,9 @@ __device__ __forceinline__ float torch_uniform_xf(float r) {
 template <bool kNormal>
 __global__ void __launch_bounds__(kThreads) philox_fill_kernel(float* __restrict__ out, int64_t numel, uint64_t seed,
                                                                uint64_t offset, uint32_t T) {
-  // work item = (round, tid); component ii goes to element round*4T + ii*T + tid
-  const int64_t item = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-  const int64_t rounds = (numel - 1) / (4ll * T) + 1;
-  if (item >= rounds * (int64_t)T) return;
-  const uint32_t round = (uint32_t)(item / T);
-  const uint32_t tid = (uint32_t)(item - (int64_t)round * T);
+  // work item = (round = blockIdx.y, tid); component ii goes to element round*4T + ii*T + tid  (T % 256 == 0)
+  const uint32_t round = blockIdx.y;
+  const uint32_t tid = blockIdx.x * kThreads + threadIdx.x;
   float4 r = kNormal ? torch_normal4(seed, offset, tid, round) : torch_uniform4(seed, offset, tid, round);
   const float v[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
@@ -91,10 +107,8 @@ struct CorruptParams {
 };
 
 __global__ void __launch_bounds__(kThreads) corrupt_kernel(const CorruptParams p) {
-  const int64_t item = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-  if (item >= (int64_t)p.rounds * p.T) return;
-  const uint32_t round = (uint32_t)(item / p.T);
-  const uint32_t tid = (uint32_t)(item - (int64_t)round * p.T);
+  const uint32_t round = blockIdx.y;                               // torch-thread call number
+  const uint32_t tid = blockIdx.x * kThreads + threadIdx.x;       // torch-thread index (T % 256 == 0)
   const int64_t e0 = (int64_t)round * 4 * p.T + tid;
 
   float x[4];
@@ -166,9 +180,8 @@ static int philox_fill(float* d_out, int64_t numel, uint64_t seed, uint64_t offs
   MSD_REQUIRE(numel < (1ll << 31), "philox_fill: numel must be < 2^31");
   const uint32_t T = 256u * torch_grid;
   const int64_t rounds = (numel - 1) / (4ll * T) + 1;
-  const int64_t items = rounds * T;
-  const unsigned blocks = (unsigned)((items + kThreads - 1) / kThreads);
-  philox_fill_kernel<kNormal><<<blocks, kThreads, 0, (cudaStream_t)stream>>>(d_out, numel, seed, offset, T);
+  MSD_REQUIRE(rounds <= 65535, "philox_fill: too many rounds (%lld)", (long long)rounds);
+  philox_fill_kernel<kNormal><<<dim3(T / kThreads, (unsigned)rounds), kThreads, 0, (cudaStream_t)stream>>>(d_out, numel, seed, offset, T);
   MSD_LAUNCH_CHECK();
   return MSD_OK;
 }
@@ -232,9 +245,8 @@ extern "C" int msd_corrupt_f32(const float* d_clean, float* d_noisy, const float
   cp.sg = sg; cp.ss = ss; cp.st = st;
   cp.seed = seed; cp.off_g = off_g; cp.off_s = off_s; cp.off_t = off_t;
   cp.P = 16; cp.gridw = W / 16;
-  const int64_t items = (int64_t)cp.rounds * cp.T;
-  const unsigned blocks = (unsigned)((items + kThreads - 1) / kThreads);
-  corrupt_kernel<<<blocks, kThreads, 0, s>>>(cp);
+  MSD_REQUIRE(cp.rounds <= 65535, "corrupt: too many rounds");
+  corrupt_kernel<<<dim3(cp.T / kThreads, cp.rounds), kThreads, 0, s>>>(cp);
   MSD_LAUNCH_CHECK();
   return MSD_OK;
 }

@@ -27,7 +27,8 @@ struct Problem {
   int M, N;                 // output rows / cols (N % 16 == 0)
   int a_rows, ldA, kvalid;  // A extent; kvalid = valid K per tap (<= kb_per_tap*64), the rest reads as zero
   int num_kb, kb_per_tap;
-  int tap_off[9];
+  int tap_off[10];
+  int skip_tap;             // >= 0: tap whose A operand is `skip` (same shape as A) and whose weights are the identity
   // epilogue
   int mode, act, out_f32;
   const float* bias;        // [N] or null
@@ -96,7 +97,7 @@ __device__ __forceinline__ void epilogue_store(const Problem& p, int m, int n, f
     fd_divmod(rem, p.pitch, yy, xx);
     interior = yy >= 1 && yy <= (uint32_t)p.H && xx >= 1 && xx <= (uint32_t)p.W;
     off = (size_t)m * p.ldo + n;
-    if (interior && p.skip != nullptr) {
+    if (interior && p.skip != nullptr && p.skip_tap < 0) {
 #pragma unroll
       for (int i = 0; i < NV; i += 2) {
         const float2 s = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(p.skip + off + i));

@@ -40,12 +40,13 @@ __global__ void __launch_bounds__(kThreads) gemm_hmma_kernel(const Problem p, in
   auto load_stage = [&](int kb, int buf) {
     const int tap = kb / p.kb_per_tap, kc = kb - tap * p.kb_per_tap;
     const int row_shift = p.tap_off[tap];
+    const __nv_bfloat16* Abase = (tap == p.skip_tap) ? p.skip : p.A;   // skip connection rides along as an identity tap
     for (int i = threadIdx.x; i < BLOCK_M * 8; i += kThreads) {
       const int r = i >> 3, ch = i & 7;
       const long long grow = (long long)m0 + r + row_shift;
       const int kcol = kc * BLOCK_K + ch * 8;
       const bool valid = grow >= 0 && grow < p.a_rows && kcol < p.kvalid;
-      const __nv_bfloat16* src = valid ? p.A + (size_t)grow * p.ldA + kcol : p.A;
+      const __nv_bfloat16* src = valid ? Abase + (size_t)grow * p.ldA + kcol : Abase;
       cp_async16_zfill(&As[buf][r][ch * 8], src, valid);
     }
     for (int i = threadIdx.x; i < BN * 8; i += kThreads) {

@@ -7,7 +7,9 @@
 //   warp 1   : MMA issuer    -- one thread issues 4 x tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16) per
 //              stage into one of two TMEM accumulator buffers, tcgen05.commit releases the stage / publishes the tile
 //   warp 2   : TMEM allocator
-//   warps 4-7: epilogue      -- per column slab: tcgen05.ld 32x32b.x16 (thread = one accumulator row) -> TMEM is
+//   warps 4-11: epilogue     -- two groups of four warps; group g drains TMEM accumulator buffer g (even / odd tiles), so
+//              two tiles' epilogues are in flight and every SM sub-partition has two epilogue warps to interleave.
+//              Per column slab: tcgen05.ld 32x32b.x16 (thread = one accumulator row) -> TMEM is
 //              released as soon as the last slab is in registers -> fp32 slab staged in a per-warp padded smem tile
 //              -> re-read with lanes running along the columns, so that bias / residual / skip loads and the
 //              fused GELU / pixel-shuffle / halo-zero stores are coalesced row segments instead of 32 scattered rows;
@@ -20,7 +22,7 @@
 namespace gemm {
 namespace tc5 {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;   // 4 control warps + 2 epilogue groups of 4 warps
 constexpr uint32_t A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
 constexpr uint64_t kSpinLimit = 4000000000ull;             // ~2 s of SM clocks: trap instead of hanging the GPU
 
@@ -34,13 +36,14 @@ struct Cfg {
   static constexpr uint32_t STG_PITCH = SC * 4 + 16;
   static constexpr int UB = (UPR % 8 == 0) ? 8 : 4;         // units per lane whose loads are batched in phase B
   static constexpr uint32_t STG_WARP_BYTES = 32 * STG_PITCH + BN * 4;   // staged slab + this tile's bias slice
-  static constexpr uint32_t STG_BYTES = 4 * STG_WARP_BYTES;
+  static constexpr uint32_t STG_BYTES = 8 * STG_WARP_BYTES;            // two epilogue groups of four warps
   static constexpr int kStagesRaw = (int)((227u * 1024u - 1024u - 256u - STG_BYTES) / STAGE_BYTES);
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   static constexpr uint32_t SMEM_BYTES = kStages * STAGE_BYTES + STG_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static_assert(BN % SC == 0 && SC % 16 == 0, "slab must tile BN in 16-column TMEM loads");
   static_assert(kStages >= 3, "pipeline too shallow");
+  static_assert(SMEM_BYTES <= 227u * 1024u, "shared memory budget");
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N for M=128 must be a multiple of 16 in [16,256]");
   static_assert(B_STAGE_BYTES % 1024 == 0, "stage bases must stay 1024-byte aligned for SWIZZLE_128B");
 };
@@ -189,7 +192,7 @@ __host__ inline int classify(const Problem& p) {
     if (!p.out_f32 && p.resid == nullptr) return p.act ? E_RM_BF16_GELU : E_RM_BF16;
     return E_GENERIC;
   }
-  if (p.mode == EPI_CONV && p.act && !p.out_f32) return p.skip ? E_CONV_SKIP : E_CONV;
+  if (p.mode == EPI_CONV && p.act && !p.out_f32) return (p.skip && p.skip_tap < 0) ? E_CONV_SKIP : E_CONV;
   if (p.mode == EPI_CONVT && p.act && !p.out_f32 &&
       (unsigned long long)(p.M / (int)p.in_plane.d + 1) * p.out_plane * p.ldo < (1ull << 31)) return E_CONVT;
   return E_GENERIC;
@@ -255,7 +258,7 @@ __device__ __forceinline__ void epilogue_tile(const Problem& p, unsigned char* s
           float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
           if (pix != kRowSkip) {
             if (p.resid != nullptr) e = *reinterpret_cast<const float4*>(p.resid + o64);
-            else if (p.skip != nullptr && !(pix & kRowHalo)) {
+            else if (p.skip != nullptr && p.skip_tap < 0 && !(pix & kRowHalo)) {
               const uint2 s2 = *reinterpret_cast<const uint2*>(p.skip + o64);
               const float2 a = unpack_bf16x2(s2.x), c2 = unpack_bf16x2(s2.y);
               e = make_float4(a.x, a.y, c2.x, c2.y);
@@ -306,8 +309,8 @@ __device__ __forceinline__ void epilogue_tile(const Problem& p, unsigned char* s
 // ------------------------------------------------------------------------------------------------ kernel
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Problem p,
-                int tiles_m, int tiles_n, int epi) {
+gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmS, const Problem p, int tiles_m, int tiles_n, int epi) {
   using C = Cfg<BN>;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
@@ -350,7 +353,8 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         mbar_wait(&empty[stage], phase ^ 1);
         const int tap = kb / p.kb_per_tap, kc = kb - tap * p.kb_per_tap;
         mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);
-        tma_load_2d(&tmA, &full[stage], smem_a + stage * A_STAGE_BYTES, kc * BLOCK_K, m0 + p.tap_off[tap]);
+        // the skip connection of a ResidualBlock rides along as one more tap: A = skip tensor, W = identity
+        tma_load_2d(tap == p.skip_tap ? &tmS : &tmA, &full[stage], smem_a + stage * A_STAGE_BYTES, kc * BLOCK_K, m0 + p.tap_off[tap]);
         tma_load_2d(&tmB, &full[stage], smem_b + stage * C::B_STAGE_BYTES, kb * BLOCK_K, n0);
         if (++stage == C::kStages) { stage = 0; phase ^= 1; }
       }
@@ -381,12 +385,13 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
     }
   } else if (warp >= 4) {
-    // ===== epilogue: warp (4+q) owns TMEM lanes 32q..32q+31 = output rows 32q..32q+31 of the tile =====
-    const int q = warp - 4;
-    unsigned char* stg = smem_stg + q * C::STG_WARP_BYTES;
+    // ===== epilogue: warp w reads TMEM lanes 32*(w%4).. (hardware rule), group g = (w-4)/4 owns accumulator buffer g =====
+    const int q = warp & 3, grp = (warp - 4) >> 2;
+    unsigned char* stg = smem_stg + (warp - 4) * C::STG_WARP_BYTES;
     float* sbias = reinterpret_cast<float*>(stg + 32 * C::STG_PITCH);
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      if ((it & 1) != grp) continue;
       const uint32_t as = it & 1, aphase = (it >> 1) & 1;
       const int m0 = (tile / tiles_n) * BLOCK_M, n0 = (tile % tiles_n) * BN;
       // this tile's bias slice -> smem (private to the warp), issued before waiting for the accumulator
@@ -429,6 +434,11 @@ int launch_bn(const Problem& p, cudaStream_t s) {
   if (rc) return rc;
   rc = make_map(&tmB, p.Wt, (uint64_t)p.num_kb * BLOCK_K, (uint64_t)p.N, (uint64_t)p.num_kb * BLOCK_K, BN);
   if (rc) return rc;
+  CUtensorMap tmS = tmA;
+  if (p.skip_tap >= 0) {
+    rc = make_map(&tmS, p.skip, (uint64_t)p.kvalid, (uint64_t)p.a_rows, (uint64_t)p.ldA, BLOCK_M);
+    if (rc) return rc;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     MSD_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc5_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
@@ -437,7 +447,7 @@ int launch_bn(const Problem& p, cudaStream_t s) {
   const int tiles_m = (p.M + BLOCK_M - 1) / BLOCK_M, tiles_n = p.N / BN;
   const int tiles = tiles_m * tiles_n;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_tc5_kernel<BN><<<grid, kThreads, C::SMEM_BYTES, s>>>(tmA, tmB, p, tiles_m, tiles_n, classify(p));
+  gemm_tc5_kernel<BN><<<grid, kThreads, C::SMEM_BYTES, s>>>(tmA, tmB, tmS, p, tiles_m, tiles_n, classify(p));
   MSD_LAUNCH_CHECK();
   return MSD_OK;
 }

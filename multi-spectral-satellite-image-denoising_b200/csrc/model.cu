@@ -20,6 +20,7 @@ int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 void init_problem(Problem& p) {
   memset(&p, 0, sizeof(p));
+  p.skip_tap = -1;
   p.plane = p.pitch = p.in_plane = p.in_pitch = p.cout_div = make_fastdiv(1);
 }
 
@@ -56,6 +57,11 @@ int make_conv3x3(Problem& p, const void* x, const void* w, const float* bias, co
   p.mode = gemm::EPI_CONV; p.act = 1; p.out_f32 = 0;
   p.bias = bias; p.out = y; p.ldo = Cout;
   p.skip = reinterpret_cast<const __nv_bfloat16*>(skip);
+  if (skip != nullptr) {
+    // skip connection = a tenth tap: A = skip tensor at row shift 0, W block = identity (packed by the host shim)
+    MSD_REQUIRE(Cin == Cout, "conv3x3: a skip connection needs Cin == Cout (got %d, %d)", Cin, Cout);
+    p.skip_tap = 9; p.tap_off[9] = 0; p.num_kb = 10 * p.kb_per_tap;
+  }
   p.plane = make_fastdiv((uint32_t)((H + 2) * (W + 2)));
   p.pitch = make_fastdiv((uint32_t)(W + 2));
   p.H = H; p.W = W;
@@ -340,7 +346,7 @@ extern "C" int msd_model_forward(msd_model* m, const float* d_x, const void* d_p
     MSD_TRY(make_convt(p, cur, sw.w_up, sw.b_up, X, B, hw, hw, in_pad, cin, cout));
     MSD_RUN(0, 2.0 * B * hw * hw * 4.0 * cout * cin, gemm::launch(p, be, s));
     hw *= 2;
-    const double cf = 2.0 * B * hw * hw * (double)cout * 9.0 * cout;
+    const double cf = 2.0 * B * hw * hw * (double)cout * 9.0 * cout;   // algorithmic: the identity skip tap is not counted
     // ResidualBlock 1: Z = GELU(X + BN(conv(GELU(BN(conv X)))))   (blocks.py:74-85)
     MSD_TRY(make_conv3x3(p, X, sw.w_conv[0], sw.b_conv[0], nullptr, Y, B, hw, hw, cout, cout));
     MSD_RUN(0, cf, gemm::launch(p, be, s));

@@ -38,14 +38,22 @@ struct HBlur {
 };
 
 // load the (TH+10) x (TW+10) halo tile of `plane` (row pitch W) into raw[i]; out-of-image -> 0 (zero padding)
+// All loads of the thread are issued before the first shared-memory store (14 independent requests in flight).
 __device__ __forceinline__ void load_raw_plane(float (*dst)[PW], const float* __restrict__ plane, int y0, int x0, int H,
                                                int W) {
-  for (int idx = threadIdx.x; idx < IH * PW; idx += kThreads) {
-    int r = idx / PW, j = idx - r * PW;
-    int gy = y0 - R + r, gx = x0 - R + j;
-    float v = 0.0f;
-    if (j < IW && gy >= 0 && gy < H && gx >= 0 && gx < W) v = __ldg(plane + (size_t)gy * W + gx);
-    dst[r][j] = v;
+  constexpr int PER = (IH * PW + kThreads - 1) / kThreads;
+  float tmp[PER];
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const int idx = threadIdx.x + i * kThreads;
+    const int r = idx / PW, j = idx - r * PW;
+    const int gy = y0 - R + r, gx = x0 - R + j;
+    tmp[i] = (idx < IH * PW && j < IW && gy >= 0 && gy < H && gx >= 0 && gx < W) ? __ldg(plane + (size_t)gy * W + gx) : 0.0f;
+  }
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const int idx = threadIdx.x + i * kThreads;
+    if (idx < IH * PW) dst[idx / PW][idx % PW] = tmp[i];
   }
 }
 

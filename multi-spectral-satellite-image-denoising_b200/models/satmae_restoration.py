@@ -41,13 +41,19 @@ def _bn_fold(bn: nn.BatchNorm2d):
     return scale, shift
 
 
-def pack_conv3x3(conv: nn.Conv2d, bn: nn.BatchNorm2d):
-    """[Cout,Cin,3,3] (+BN) -> bf16 [Cout, 9*Kpad] tap-major (ky,kx,ci), fp32 bias [Cout]."""
+def pack_conv3x3(conv: nn.Conv2d, bn: nn.BatchNorm2d, with_skip: bool = False):
+    """[Cout,Cin,3,3] (+BN) -> bf16 [Cout, 9*Kpad] tap-major (ky,kx,ci), fp32 bias [Cout].
+
+    with_skip: append a tenth tap holding the identity, so that the ResidualBlock's `x + block(x)` (blocks.py:85) is
+    accumulated by the same tensor-core loop (A operand of that tap = the skip tensor)."""
     scale, shift = _bn_fold(bn)
     w = conv.weight.float() * scale.view(-1, 1, 1, 1)
     cout, cin = w.shape[:2]
     kpad = (cin + 63) // 64 * 64
     w = _pad_k(w.permute(0, 2, 3, 1).contiguous(), kpad).reshape(cout, 9 * kpad)
+    if with_skip:
+        assert cin == cout, "skip connection needs Cin == Cout"
+        w = torch.cat([w, _pad_k(torch.eye(cout, device=w.device, dtype=w.dtype), kpad)], dim=1)
     bias = shift if conv.bias is None else shift + conv.bias.float() * scale
     return _bf16(w), bias.contiguous()
 
@@ -154,8 +160,8 @@ class SatMAERestoration(nn.Module):
             sw.w_up, sw.b_up = _lib.ptr(wt), _lib.ptr(bias)
             k = 0
             for rb in mods[s * per_stage + 1:(s + 1) * per_stage]:
-                for conv, bn in ((rb.block[0], rb.block[1]), (rb.block[3], rb.block[4])):
-                    wt, bias = pack_conv3x3(conv, bn)
+                for conv, bn, skip in ((rb.block[0], rb.block[1], False), (rb.block[3], rb.block[4], True)):
+                    wt, bias = pack_conv3x3(conv, bn, with_skip=skip)
                     keep.extend([wt, bias])
                     sw.w_conv[k], sw.b_conv[k] = _lib.ptr(wt).value, _lib.ptr(bias).value
                     k += 1

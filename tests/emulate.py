@@ -22,7 +22,8 @@ def conv3x3_rows(x_halo: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tenso
     """x_halo [B,H+2,W+2,Cin]; w_packed [Cout, 9*Kpad]; returns [B,H+2,W+2,Cout] with a zero halo (EPI_CONV)."""
     B, _, _, cin = x_halo.shape
     cout = w_packed.shape[0]
-    kpad = w_packed.shape[1] // 9
+    kpad = (cin + 63) // 64 * 64
+    ntaps = w_packed.shape[1] // kpad          # 10 when the identity skip tap is packed
     rows = x_halo.reshape(-1, cin)
     M = rows.shape[0]
     acc = torch.zeros(M, cout)
@@ -41,7 +42,10 @@ def conv3x3_rows(x_halo: torch.Tensor, w_packed: torch.Tensor, bias: torch.Tenso
     yy, xx = rem // (W + 2), rem % (W + 2)
     interior = (yy >= 1) & (yy <= H) & (xx >= 1) & (xx <= W)
     if skip is not None:
-        acc = acc + skip.reshape(-1, cout)
+        if ntaps == 10:   # the skip connection is the tenth tap: A = skip rows (shift 0), W = identity block
+            acc = acc + skip.reshape(-1, cout)[:, :cin] @ w_packed[:, 9 * kpad:9 * kpad + cin].t()
+        else:
+            acc = acc + skip.reshape(-1, cout)
     if act:
         acc = torch.nn.functional.gelu(acc)
     acc = torch.where(interior[:, None], acc, torch.zeros_like(acc))

@@ -77,11 +77,14 @@ def test_conv3x3_vs_torch(backend, cin, cout, H, W, B):
     with torch.no_grad():
         w, b = pack_conv3x3(conv, bn)
         xh, sh = _bf(emulate.halo_nhwc(x)).cuda(), _bf(emulate.halo_nhwc(skip)).cuda()
-        ref_skip = emulate.conv3x3_rows(emulate.halo_nhwc(x), w.float(), b, H, W, skip=emulate.halo_nhwc(skip))
         ref_plain = emulate.conv3x3_rows(emulate.halo_nhwc(x), w.float(), b, H, W)
-    y = gh.conv3x3(xh, w.cuda(), b.cuda(), sh, B, H, W, cin, cout, backend)
-    _close(y.cpu(), ref_skip)
-    assert torch.all(y[:, 0] == 0) and torch.all(y[:, -1] == 0) and torch.all(y[:, :, 0] == 0) and torch.all(y[:, :, -1] == 0)
+    if cin == cout:   # ResidualBlock second conv: skip connection packed as the identity tenth tap
+        with torch.no_grad():
+            ws, _ = pack_conv3x3(conv, bn, with_skip=True)
+            ref_skip = emulate.conv3x3_rows(emulate.halo_nhwc(x), ws.float(), b, H, W, skip=emulate.halo_nhwc(skip))
+        y = gh.conv3x3(xh, ws.cuda(), b.cuda(), sh, B, H, W, cin, cout, backend)
+        _close(y.cpu(), ref_skip)
+        assert torch.all(y[:, 0] == 0) and torch.all(y[:, -1] == 0) and torch.all(y[:, :, 0] == 0) and torch.all(y[:, :, -1] == 0)
     y = gh.conv3x3(xh, w.cuda(), b.cuda(), None, B, H, W, cin, cout, backend)
     _close(y.cpu(), ref_plain)
     with torch.no_grad():

@@ -65,7 +65,7 @@ def test_forward_rejects_cpu_and_training(model):
         model(torch.zeros(1, 12, 192, 192))
 
 
-@pytest.mark.parametrize("cin,cout,H,W", [(48, 48, 6, 5), (96, 32, 4, 7), (64, 16, 3, 3)])
+@pytest.mark.parametrize("cin,cout,H,W", [(48, 48, 6, 5), (96, 32, 4, 7), (64, 16, 3, 3), (96, 96, 5, 4)])
 def test_conv3x3_packing_and_tap_table(cin, cout, H, W):
     torch.manual_seed(0)
     conv = nn.Conv2d(cin, cout, 3, padding=1, bias=False)
@@ -75,16 +75,16 @@ def test_conv3x3_packing_and_tap_table(cin, cout, H, W):
     skip = torch.randn(2, cout, H, W)
     with torch.no_grad():
         ref = F.gelu(skip + bn(conv(x)))
-        w, b = pack_conv3x3(conv, bn)
+        w, b = pack_conv3x3(conv, bn, with_skip=(cin == cout))     # identity tenth tap when the shapes allow it
         got = emulate.conv3x3_rows(emulate.halo_nhwc(x), w.float(), b, H, W, skip=emulate.halo_nhwc(skip))
-    assert w.shape == (cout, 9 * ((cin + 63) // 64 * 64)) and w.dtype == torch.bfloat16
+    assert w.shape == (cout, (10 if cin == cout else 9) * ((cin + 63) // 64 * 64)) and w.dtype == torch.bfloat16
     assert torch.all(got[:, 0] == 0) and torch.all(got[:, :, 0] == 0) and torch.all(got[:, -1] == 0) and torch.all(got[:, :, -1] == 0)
     # bf16 weights -> ~3 significant digits
     torch.testing.assert_close(emulate.unhalo_nchw(got), ref, rtol=0, atol=0.05)
     with torch.no_grad():
         scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
         w32 = (conv.weight * scale.view(-1, 1, 1, 1)).permute(0, 2, 3, 1)
-        kpad = w.shape[1] // 9
+        kpad = (cin + 63) // 64 * 64
         w_exact = torch.zeros(cout, 3, 3, kpad); w_exact[..., :cin] = w32
         got32 = emulate.conv3x3_rows(emulate.halo_nhwc(x), w_exact.reshape(cout, -1), b, H, W, skip=emulate.halo_nhwc(skip))
     torch.testing.assert_close(emulate.unhalo_nchw(got32), ref, rtol=1e-4, atol=1e-4)

@@ -57,7 +57,7 @@ def conv(name, C, H, skip):
         return
     x = torch.randn(B, H + 2, H + 2, C, device=dev).to(bf)
     kpad = (C + 63) // 64 * 64
-    w = (torch.randn(C, 9 * kpad, device=dev) * (9 * C) ** -0.5).to(bf)
+    w = (torch.randn(C, (10 if skip else 9) * kpad, device=dev) * (9 * C) ** -0.5).to(bf)
     bias = torch.randn(C, device=dev)
     y = torch.empty_like(x)
     sk = torch.randn_like(x) if skip else None
