@@ -28,6 +28,7 @@ struct Problem {
   int a_rows, ldA, kvalid;  // A extent; kvalid = valid K per tap (<= kb_per_tap*64), the rest reads as zero
   int num_kb, kb_per_tap;
   int tap_off[10];
+  int dbg_shift, dbg_bo;    // experiment knobs (tools/desc_probe.py): unaligned A window start / descriptor base offset
   int skip_tap;             // >= 0: tap whose A operand is `skip` (same shape as A) and whose weights are the identity
   // epilogue
   int mode, act, out_f32;

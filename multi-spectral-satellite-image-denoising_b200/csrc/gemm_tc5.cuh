@@ -18,18 +18,32 @@
 #pragma once
 #include "gemm.cuh"
 #include <cuda.h>
+#include <stdlib.h>
 
 namespace gemm {
 namespace tc5 {
 
 constexpr int kThreads = 384;   // 4 control warps + 2 epilogue groups of 4 warps
-constexpr uint32_t A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
 constexpr uint64_t kSpinLimit = 4000000000ull;             // ~2 s of SM clocks: trap instead of hanging the GPU
 
-template <int BN>
+// MODE 0: one A box [128 rows x 64 k] + one W box per pipeline stage (linear layers, ConvTranspose, wide convs).
+// MODE 1: 3x3 conv, "dx-merged": one A box of 136 rows per (dy, k-block) serves the three taps dx = -1, 0, +1 as row-
+//         shifted windows of the same swizzled buffer (the UMMA descriptor start may sit anywhere inside a 1024-byte
+//         swizzle atom as long as the base-offset field stays 0 -- verified by tools/desc_probe.py), so the activation
+//         tile crosses L2->SM 3x instead of 9x; the stage also carries the three taps' W boxes.
+// MODE 2: MODE 1 + the whole packed weight matrix resident in shared memory (N == BN, one k-block per tap: the
+//         48-channel stage, 60 KB), so a stage is the A box only.
+constexpr int MODE_PLAIN = 0, MODE_MERGE3 = 1, MODE_MERGE3_RESIDENT = 2;
+constexpr int MERGE_ROWS = 136;   // 128 + 2 shifted rows, rounded up to a whole 8-row swizzle atom
+
+template <int BN, int MODE = MODE_PLAIN>
 struct Cfg {
-  static constexpr uint32_t B_STAGE_BYTES = BN * BLOCK_K * 2;
+  static constexpr uint32_t W_BOX_BYTES = BN * BLOCK_K * 2;
+  static constexpr uint32_t A_BOX_BYTES = (MODE == MODE_PLAIN ? BLOCK_M : MERGE_ROWS) * BLOCK_K * 2;
+  static constexpr uint32_t A_STAGE_BYTES = (A_BOX_BYTES + 1023u) & ~1023u;
+  static constexpr uint32_t B_STAGE_BYTES = MODE == MODE_PLAIN ? W_BOX_BYTES : MODE == MODE_MERGE3 ? 3 * W_BOX_BYTES : 0;
   static constexpr uint32_t STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr uint32_t RESIDENT_BYTES = MODE == MODE_MERGE3_RESIDENT ? 10 * W_BOX_BYTES : 0;
   // epilogue staging: slab of SC fp32 columns x 32 rows per epilogue warp, row pitch padded by 16 B (conflict-free)
   static constexpr int SC = (BN == 256) ? 32 : (BN % 64 == 0) ? 64 : (BN % 48 == 0) ? 48 : (BN % 32 == 0) ? 32 : 16;
   static constexpr int UPR = SC / 4;                       // 16-byte units per staged row
@@ -37,15 +51,15 @@ struct Cfg {
   static constexpr int UB = (UPR % 8 == 0) ? 8 : 4;         // units per lane whose loads are batched in phase B
   static constexpr uint32_t STG_WARP_BYTES = 32 * STG_PITCH + BN * 4;   // staged slab + this tile's bias slice
   static constexpr uint32_t STG_BYTES = 8 * STG_WARP_BYTES;            // two epilogue groups of four warps
-  static constexpr int kStagesRaw = (int)((227u * 1024u - 1024u - 256u - STG_BYTES) / STAGE_BYTES);
+  static constexpr int kStagesRaw = (int)((227u * 1024u - 1024u - 256u - STG_BYTES - RESIDENT_BYTES) / STAGE_BYTES);
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-  static constexpr uint32_t SMEM_BYTES = kStages * STAGE_BYTES + STG_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr uint32_t SMEM_BYTES = kStages * STAGE_BYTES + RESIDENT_BYTES + STG_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static_assert(BN % SC == 0 && SC % 16 == 0, "slab must tile BN in 16-column TMEM loads");
   static_assert(kStages >= 3, "pipeline too shallow");
   static_assert(SMEM_BYTES <= 227u * 1024u, "shared memory budget");
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N for M=128 must be a multiple of 16 in [16,256]");
-  static_assert(B_STAGE_BYTES % 1024 == 0, "stage bases must stay 1024-byte aligned for SWIZZLE_128B");
+  static_assert(W_BOX_BYTES % 1024 == 0, "stage bases must stay 1024-byte aligned for SWIZZLE_128B");
 };
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -84,6 +98,12 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* tm, uint64_t* bar
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n"
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
+}
+// one lane of a converged warp; keeps the surrounding loop warp-uniform so that descriptors live in uniform registers
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
@@ -307,22 +327,25 @@ __device__ __forceinline__ void epilogue_tile(const Problem& p, unsigned char* s
 }
 
 // ------------------------------------------------------------------------------------------------ kernel
-template <int BN>
+template <int BN, int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmS, const Problem p, int tiles_m, int tiles_n, int epi) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, MODE>;
+  constexpr uint32_t A_STAGE_BYTES = C::A_STAGE_BYTES;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
   unsigned char* smem_a = smem;
-  unsigned char* smem_b = smem + C::kStages * A_STAGE_BYTES;
-  unsigned char* smem_stg = smem + C::kStages * C::STAGE_BYTES;
+  unsigned char* smem_b = smem + C::kStages * A_STAGE_BYTES;                 // per-stage W boxes (MODE 0 / 1)
+  unsigned char* smem_res = smem + C::kStages * C::STAGE_BYTES;              // resident weights (MODE 2)
+  unsigned char* smem_stg = smem_res + C::RESIDENT_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_stg + C::STG_BYTES);
   uint64_t* full = bars;
   uint64_t* empty = bars + C::kStages;
   uint64_t* tmem_full = bars + 2 * C::kStages;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* res_full = tmem_empty + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -332,6 +355,7 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < C::kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+    mbar_init(res_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (warp == 2) {
@@ -341,47 +365,126 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);   // same word for every lane; shuffle makes it provably uniform
   const int num_tiles = tiles_m * tiles_n;
 
-  if (warp == 0 && lane == 0) {
+  // merged modes walk (dy, k-block) steps, then the k-blocks of the identity skip tap
+  const int kbpt = p.kb_per_tap;
+  const int conv_steps = 3 * kbpt, merged_steps = conv_steps + (p.skip_tap >= 0 ? kbpt : 0);
+
+  // Producer and MMA warps run their loops with all 32 lanes converged and let one elected lane issue the
+  // asynchronous instructions: operands are then provably warp-uniform (uniform registers, no per-MMA waterfall).
+  if (warp == 0) {
     // ===== TMA producer =====
     int stage = 0; uint32_t phase = 0;
+    if constexpr (MODE == MODE_MERGE3_RESIDENT) {
+      // the whole packed weight matrix (<= 10 taps x one k-block) stays in shared memory for the life of the CTA
+      if (elect_one()) {
+        mbar_arrive_expect_tx(res_full, (uint32_t)p.num_kb * C::W_BOX_BYTES);
+        for (int kb = 0; kb < p.num_kb; ++kb) tma_load_2d(&tmB, res_full, smem_res + kb * C::W_BOX_BYTES, kb * BLOCK_K, 0);
+      }
+      __syncwarp();
+    }
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile / tiles_n) * BLOCK_M, n0 = (tile % tiles_n) * BN;
-      for (int kb = 0; kb < p.num_kb; ++kb) {
-        mbar_wait(&empty[stage], phase ^ 1);
-        const int tap = kb / p.kb_per_tap, kc = kb - tap * p.kb_per_tap;
-        mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);
-        // the skip connection of a ResidualBlock rides along as one more tap: A = skip tensor, W = identity
-        tma_load_2d(tap == p.skip_tap ? &tmS : &tmA, &full[stage], smem_a + stage * A_STAGE_BYTES, kc * BLOCK_K, m0 + p.tap_off[tap]);
-        tma_load_2d(&tmB, &full[stage], smem_b + stage * C::B_STAGE_BYTES, kb * BLOCK_K, n0);
-        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+      if constexpr (MODE == MODE_PLAIN) {
+        int tap = 0, kc = 0;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&full[stage], C::A_BOX_BYTES + C::W_BOX_BYTES);
+            // the skip connection of a ResidualBlock rides along as one more tap: A = skip tensor, W = identity
+            tma_load_2d(tap == p.skip_tap ? &tmS : &tmA, &full[stage], smem_a + stage * A_STAGE_BYTES, kc * BLOCK_K, m0 + p.tap_off[tap] - p.dbg_shift);
+            tma_load_2d(&tmB, &full[stage], smem_b + stage * C::B_STAGE_BYTES, kb * BLOCK_K, n0);
+          }
+          __syncwarp();
+          if (++kc == kbpt) { kc = 0; ++tap; }
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+      } else {
+        for (int st = 0; st < merged_steps; ++st) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          const bool is_skip = st >= conv_steps;
+          const int dy = is_skip ? 0 : st / kbpt, kc = is_skip ? st - conv_steps : st - dy * kbpt;
+          const int nw = (MODE == MODE_MERGE3) ? (is_skip ? 1 : 3) : 0;
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&full[stage], C::A_BOX_BYTES + nw * C::W_BOX_BYTES);
+            // rows m0 + off(dy, dx=-1) .. +135: windows at +0 / +1 / +2 rows are the dx = -1 / 0 / +1 taps;
+            // the skip tensor is loaded one row early too and read through the middle window
+            tma_load_2d(is_skip ? &tmS : &tmA, &full[stage], smem_a + stage * A_STAGE_BYTES, kc * BLOCK_K,
+                        is_skip ? m0 - 1 : m0 + p.tap_off[3 * dy]);
+            if constexpr (MODE == MODE_MERGE3) {
+              for (int j = 0; j < nw; ++j) {
+                const int tap = is_skip ? p.skip_tap : 3 * dy + j;
+                tma_load_2d(&tmB, &full[stage], smem_b + stage * C::B_STAGE_BYTES + j * C::W_BOX_BYTES, (tap * kbpt + kc) * BLOCK_K, n0);
+              }
+            }
+          }
+          __syncwarp();
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {
     // ===== MMA issuer =====
     constexpr uint32_t idesc = make_idesc(BLOCK_M, BN);
     int stage = 0; uint32_t phase = 0;
     int it = 0;
+    if constexpr (MODE == MODE_MERGE3_RESIDENT) { mbar_wait(res_full, 0); tcgen05_fence_after(); }
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const uint32_t as = it & 1, aphase = (it >> 1) & 1;
       mbar_wait(&tmem_empty[as], aphase ^ 1);
       tcgen05_fence_after();
       const uint32_t tmem_d = tmem_base + as * BN;
-      for (int kb = 0; kb < p.num_kb; ++kb) {
-        mbar_wait(&full[stage], phase);
-        tcgen05_fence_after();
-        const uint64_t da = make_smem_desc(smem_u32(smem_a + stage * A_STAGE_BYTES));
-        const uint64_t db = make_smem_desc(smem_u32(smem_b + stage * C::B_STAGE_BYTES));
+      if constexpr (MODE == MODE_PLAIN) {
+        int kc = 0;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tcgen05_fence_after();
+          // only the 16-wide K slices that hold valid channels are issued (K = 48 or 96 does not fill the last block)
+          const int nk = min(BLOCK_K / 16, (p.kvalid - kc * BLOCK_K + 15) / 16);
+          if (elect_one()) {
+            const uint64_t da = make_smem_desc(smem_u32(smem_a + stage * A_STAGE_BYTES) + 128u * p.dbg_shift) | ((uint64_t)(p.dbg_bo & 7) << 49);
+            const uint64_t db = make_smem_desc(smem_u32(smem_b + stage * C::B_STAGE_BYTES));
 #pragma unroll
-        for (int k = 0; k < BLOCK_K / 16; ++k) {
-          // advance 16 bf16 = 32 bytes inside the 128-byte swizzle atom: +2 in the (addr >> 4) field
-          tcgen05_mma_bf16(tmem_d, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BLOCK_K / 16; ++k) {
+              // advance 16 bf16 = 32 bytes inside the 128-byte swizzle atom: +2 in the (addr >> 4) field
+              if (k < nk) tcgen05_mma_bf16(tmem_d, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            tcgen05_commit(&empty[stage]);               // frees the smem stage once these MMAs retire
+            if (kb == p.num_kb - 1) tcgen05_commit(&tmem_full[as]);  // accumulator complete -> epilogue
+          }
+          __syncwarp();
+          if (++kc == kbpt) kc = 0;
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
-        tcgen05_commit(&empty[stage]);               // frees the smem stage once these MMAs retire
-        if (kb == p.num_kb - 1) tcgen05_commit(&tmem_full[as]);  // accumulator complete -> epilogue
-        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+      } else {
+        for (int st = 0; st < merged_steps; ++st) {
+          mbar_wait(&full[stage], phase);
+          tcgen05_fence_after();
+          const bool is_skip = st >= conv_steps;
+          const int dy = is_skip ? 0 : st / kbpt, kc = is_skip ? st - conv_steps : st - dy * kbpt;
+          const int nk = min(BLOCK_K / 16, (p.kvalid - kc * BLOCK_K + 15) / 16);
+          if (elect_one()) {
+            const uint32_t a_base = smem_u32(smem_a + stage * A_STAGE_BYTES);
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {                                    // window j = rows +j = tap dx = j - 1
+              if (is_skip ? (j != 1) : false) continue;
+              const int tap = is_skip ? p.skip_tap : 3 * dy + j;
+              const uint32_t b_addr = (MODE == MODE_MERGE3_RESIDENT)
+                                          ? smem_u32(smem_res + (tap * kbpt + kc) * C::W_BOX_BYTES)
+                                          : smem_u32(smem_b + stage * C::B_STAGE_BYTES + (is_skip ? 0 : j) * C::W_BOX_BYTES);
+              const uint64_t da = make_smem_desc(a_base + 128u * j), db = make_smem_desc(b_addr);
+#pragma unroll
+              for (int k = 0; k < BLOCK_K / 16; ++k)
+                if (k < nk) tcgen05_mma_bf16(tmem_d, da + 2u * k, db + 2u * k, idesc, (st | j | k) != 0 ? 1u : 0u);
+            }
+            tcgen05_commit(&empty[stage]);
+            if (st == merged_steps - 1) tcgen05_commit(&tmem_full[as]);
+          }
+          __syncwarp();
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
       }
     }
   } else if (warp >= 4) {
@@ -420,36 +523,57 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 }
 
 
-// host: launch one BN instantiation (defined in gemm_tc5.cu, instantiated per BN in gemm_tc5_bn*.cu)
-template <int BN>
-int launch_bn(const Problem& p, cudaStream_t s);
+// host: launch one BN instantiation (instantiated per BN in gemm_tc5_bn*.cu)
 int make_map(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t rows, uint64_t ld, uint32_t box_rows);
 int num_sms();
 
-template <int BN>
-int launch_bn(const Problem& p, cudaStream_t s) {
-  using C = Cfg<BN>;
+template <int BN, int MODE>
+int launch_mode(const Problem& p, cudaStream_t s) {
+  using C = Cfg<BN, MODE>;
+  const uint32_t a_box_rows = MODE == MODE_PLAIN ? BLOCK_M : MERGE_ROWS;
   CUtensorMap tmA, tmB;
-  int rc = make_map(&tmA, p.A, (uint64_t)p.kvalid, (uint64_t)p.a_rows, (uint64_t)p.ldA, BLOCK_M);
+  int rc = make_map(&tmA, p.A, (uint64_t)p.kvalid, (uint64_t)p.a_rows, (uint64_t)p.ldA, a_box_rows);
   if (rc) return rc;
   rc = make_map(&tmB, p.Wt, (uint64_t)p.num_kb * BLOCK_K, (uint64_t)p.N, (uint64_t)p.num_kb * BLOCK_K, BN);
   if (rc) return rc;
   CUtensorMap tmS = tmA;
   if (p.skip_tap >= 0) {
-    rc = make_map(&tmS, p.skip, (uint64_t)p.kvalid, (uint64_t)p.a_rows, (uint64_t)p.ldA, BLOCK_M);
+    rc = make_map(&tmS, p.skip, (uint64_t)p.kvalid, (uint64_t)p.a_rows, (uint64_t)p.ldA, a_box_rows);
     if (rc) return rc;
   }
   static bool attr_set = false;
   if (!attr_set) {
-    MSD_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc5_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
+    MSD_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc5_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
     attr_set = true;
   }
   const int tiles_m = (p.M + BLOCK_M - 1) / BLOCK_M, tiles_n = p.N / BN;
   const int tiles = tiles_m * tiles_n;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_tc5_kernel<BN><<<grid, kThreads, C::SMEM_BYTES, s>>>(tmA, tmB, tmS, p, tiles_m, tiles_n, classify(p));
+  gemm_tc5_kernel<BN, MODE><<<grid, kThreads, C::SMEM_BYTES, s>>>(tmA, tmB, tmS, p, tiles_m, tiles_n, classify(p));
   MSD_LAUNCH_CHECK();
   return MSD_OK;
+}
+
+// is this Problem a 3x3 conv whose taps are laid out as (dy, dx) row shifts of one pitch?  (what MODE 1/2 assume)
+__host__ inline bool is_conv3x3(const Problem& p) {
+  if (p.mode != EPI_CONV || p.num_kb < 9 * p.kb_per_tap) return false;
+  for (int dy = 0; dy < 3; ++dy)
+    if (p.tap_off[3 * dy + 1] != p.tap_off[3 * dy] + 1 || p.tap_off[3 * dy + 2] != p.tap_off[3 * dy] + 2) return false;
+  return p.tap_off[4] == 0 && p.dbg_shift == 0;
+}
+
+template <int BN>
+int launch_bn(const Problem& p, cudaStream_t s) {
+  if constexpr (BN == 48 || BN == 96) {
+    static const bool no_merge = getenv("MSD_NO_MERGE3") != nullptr;     // A/B switch for the profiles
+    if (!no_merge && is_conv3x3(p)) {
+      if constexpr (BN == 48) {
+        if (p.N == BN && p.kb_per_tap == 1 && p.num_kb <= 10) return launch_mode<BN, MODE_MERGE3_RESIDENT>(p, s);
+      }
+      return launch_mode<BN, MODE_MERGE3>(p, s);
+    }
+  }
+  return launch_mode<BN, MODE_PLAIN>(p, s);
 }
 
 }  // namespace tc5

@@ -10,6 +10,7 @@
 //   decoder stage s: three ping-pong buffers bf16 [B, H_s+2, W_s+2, C_s] (zero halo), H_s = 24,48,96,192
 #include "gemm.cuh"
 #include <new>
+#include <stdlib.h>
 #include <vector>
 
 namespace {
@@ -126,6 +127,8 @@ extern "C" int msd_linear_bf16(const void* d_a, const void* d_w, const float* d_
   Problem p;
   int rc = make_linear(p, d_a, d_w, d_bias, d_out, d_resid, M, N, K, act, out_f32);
   if (rc) return rc;
+  if (const char* e = getenv("MSD_DBG_SHIFT")) p.dbg_shift = atoi(e);   // descriptor experiments only
+  if (const char* e = getenv("MSD_DBG_BO")) p.dbg_bo = atoi(e);
   return gemm::launch(p, backend, (cudaStream_t)stream);
 }
 

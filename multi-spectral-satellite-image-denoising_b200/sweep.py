@@ -1,0 +1,104 @@
+"""Batch-sharded evaluation sweep (BASELINE.json config C3: PSNR/SSIM/SAM over 27,000 EuroSAT-shaped tiles at 1/2/4/8
+GPUs).  The reference has no distributed code; semantics = "its evaluate_model applied to every tile".
+
+One process per GPU.  The sweep is cut into fixed global batches; rank r takes a contiguous range of them.  Batch k is
+generated and corrupted from seed `seed + k` whatever rank runs it, so the result is independent of the GPU count.
+The only collective is one NCCL all_reduce(SUM) of the tracker's fp64[5] running sums at the end.
+
+    torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 -m msd_b200.sweep --tiles 27000 --batch 250
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+from typing import Callable, Dict, Tuple
+
+import torch
+
+
+def shard_batches(n_batches: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous [start, end) range of global batch indices owned by `rank` (sizes differ by at most one)."""
+    if not (0 <= rank < world):
+        raise ValueError(f"rank {rank} outside world {world}")
+    base, extra = divmod(n_batches, world)
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+def batch_sizes(n_tiles: int, batch: int):
+    """Sizes of the global batches covering n_tiles (the last one may be ragged)."""
+    full, rest = divmod(n_tiles, batch)
+    return [batch] * full + ([rest] if rest else [])
+
+
+def synthetic_tiles(n: int, seed: int, device) -> torch.Tensor:
+    """EuroSAT-shaped clean tiles: U[0,0.52] 64x64 reflectance -> bilinear 192 -> clamp -> (x-0.5)/0.25,
+    i.e. src/data/dataset.py:168-186 applied to synthetic digital numbers; generated on the device from `seed`."""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    raw = torch.rand(n, 13, 64, 64, generator=g, device=device) * 0.52
+    x = torch.nn.functional.interpolate(raw, size=192, mode="bilinear", align_corners=False).clamp_(0, 1)
+    return ((x - 0.5) / 0.25).contiguous()
+
+
+@torch.no_grad()
+def evaluation_sweep(model, noise, n_tiles: int, batch: int, rank: int = 0, world: int = 1, seed: int = 42,
+                     tile_fn: Callable = synthetic_tiles, tracker=None, all_reduce: bool = True) -> Dict[str, float]:
+    from .training.metrics import MetricsTracker
+    device = next(model.parameters()).device
+    sizes = batch_sizes(n_tiles, batch)
+    lo, hi = shard_batches(len(sizes), rank, world)
+    tracker = tracker or MetricsTracker()
+    model.eval()
+    for k in range(lo, hi):
+        clean = tile_fn(sizes[k], seed + k, device)
+        torch.manual_seed(seed + k)                 # corruption of batch k does not depend on who runs it
+        noisy = noise(clean)
+        tracker.update(model(noisy), clean)
+    if world > 1 and all_reduce:
+        if tracker._acc is None:                    # a rank with no batches still joins the collective
+            tracker._acc = torch.zeros(5, dtype=torch.float64, device=device)
+        tracker.all_reduce()
+    return tracker.compute()
+
+
+def main():
+    import torch.distributed as dist
+    from .data import AddSensorNoise
+    from .models import SatMAERestoration
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--tiles", type=int, default=27000)
+    ap.add_argument("--batch", type=int, default=250)
+    ap.add_argument("--seed", type=int, default=42)
+    ap.add_argument("--checkpoint", default=None)
+    args = ap.parse_args()
+    world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", "1"), ("RANK", "0"), ("LOCAL_RANK", "0")))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    cfg = {"data": {"num_bands": 13, "image_size": 192, "patch_size": 16},
+           "model": {"encoder": {"pretrained_path": None, "freeze_layers": None, "gradient_checkpointing": False,
+                                 "input_channels": 13, "patch_size": 16, "embed_dim": 768, "depth": 12, "num_heads": 12},
+                     "decoder": {"channels": [384, 192, 96, 48], "output_channels": 13}}}
+    torch.manual_seed(42)
+    model = SatMAERestoration(cfg)
+    if args.checkpoint:
+        model.load_state_dict(torch.load(args.checkpoint, map_location="cpu")["model_state_dict"])
+    model = model.eval().cuda()
+    noise = AddSensorNoise(0.015, 0.008, 0.08, 0.005)      # configs/base.yaml:20-24
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    metrics = evaluation_sweep(model, noise, args.tiles, args.batch, rank, world, args.seed)
+    e1.record()
+    torch.cuda.synchronize()
+    if rank == 0:
+        print(json.dumps({"tiles": args.tiles, "world": world, "seconds": e0.elapsed_time(e1) / 1e3,
+                          "tiles_per_s": args.tiles / (e0.elapsed_time(e1) / 1e3), **metrics}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

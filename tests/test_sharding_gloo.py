@@ -1,0 +1,68 @@
+"""Multi-rank host logic on the CPU: shard partition of the evaluation sweep and the metric-sum all-reduce
+(world_size 2, gloo, 127.0.0.1).  The CUDA arithmetic is covered by the -m gpu tests; here the tracker's device
+accumulator is filled by hand so that the collective path itself runs without a GPU."""
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from msd_b200.sweep import batch_sizes, shard_batches
+from msd_b200.training.metrics import MetricsTracker
+
+
+@pytest.mark.parametrize("n_tiles,batch,world", [(27000, 250, 1), (27000, 250, 8), (27000, 256, 8), (1000, 256, 3), (5, 8, 4), (0, 8, 2)])
+def test_shards_cover_every_batch_exactly_once(n_tiles, batch, world):
+    sizes = batch_sizes(n_tiles, batch)
+    assert sum(sizes) == n_tiles and all(0 < s <= batch for s in sizes)
+    seen = []
+    counts = []
+    for r in range(world):
+        lo, hi = shard_batches(len(sizes), r, world)
+        assert 0 <= lo <= hi <= len(sizes)
+        seen.extend(range(lo, hi))
+        counts.append(hi - lo)
+    assert seen == list(range(len(sizes)))              # contiguous, ordered, no gaps, no overlap
+    assert max(counts) - min(counts) <= 1
+    with pytest.raises(ValueError):
+        shard_batches(len(sizes), world, world)
+
+
+def _worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    t = MetricsTracker()
+    # what fused_metrics would have accumulated on this rank: sum psnr, sum ssim, sum sam, sum rmse, count
+    t._acc = torch.tensor([30.0 * (rank + 1), 0.9 * (rank + 1), 2.0 * (rank + 1), 0.05 * (rank + 1), float(rank + 1)], dtype=torch.float64)
+    t._dirty = True
+    t.all_reduce()
+    out[rank] = (t.compute(), t.count)
+    dist.destroy_process_group()
+
+
+def test_metric_sums_allreduce_world2():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, 29517, out), nprocs=world, join=True)
+    for rank in range(world):
+        m, count = out[rank]
+        assert count == 3                                   # 1 + 2 images
+        assert m["psnr"] == pytest.approx(90.0 / 3) and m["ssim"] == pytest.approx(2.7 / 3)
+        assert m["sam"] == pytest.approx(6.0 / 3) and m["rmse"] == pytest.approx(0.15 / 3)
+
+
+def test_launcher_rebinds_reference_names():
+    from pathlib import Path
+    ref = Path("/root/reference")
+    if not (ref / "src").exists():
+        pytest.skip("reference tree not present on this machine")
+    import subprocess, sys
+    code = ("import sys; sys.path.insert(0, %r); from pathlib import Path; from msd_b200.run import rebind; "
+            "done = rebind(Path('/root/reference')); import src.training.eval as e, src.data.dataloader as d, src.utils; "
+            "import msd_b200.training.metrics as M, msd_b200.data as D; "
+            "assert e.MetricsTracker is M.MetricsTracker and d.AddSensorNoise is D.AddSensorNoise and len(done) >= 20") % str(Path(__file__).resolve().parent.parent)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
