@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
@@ -87,9 +88,28 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return fmaf(hx, copysignf(erf_abs, z), hx);
 }
 
+// GELU of four values that are about to be rounded to bf16, evaluated two-at-a-time in half2:
+//   0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3)))  with MUFU.TANH.F16x2  (7 instructions per pair instead of ~30).
+// |tanh-form - erf-form| <= 3e-4 and the fp16 evaluation error (~1e-3 relative) are both below the bf16 rounding
+// (4e-3 relative) applied right after; used only by the bf16-output GEMM epilogues.
+__device__ __forceinline__ __half2 gelu_h2(__half2 x) {
+  const __half2 c0 = __float2half2_rn(0.7978845608f), c1 = __float2half2_rn(0.0356774081f), half = __float2half2_rn(0.5f);
+  const __half2 u = __hmul2(x, __hfma2(__hmul2(x, x), c1, c0));
+  uint32_t ui = *reinterpret_cast<const uint32_t*>(&u), ti;
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(ti) : "r"(ui));
+  const __half2 t = *reinterpret_cast<const __half2*>(&ti);
+  const __half2 hx = __hmul2(x, half);
+  return __hfma2(hx, t, hx);
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ uint2 gelu4_to_bf16(float4 v) {
+  const float2 a = __half22float2(gelu_h2(__floats2half2_rn(v.x, v.y)));
+  const float2 b = __half22float2(gelu_h2(__floats2half2_rn(v.z, v.w)));
+  return make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(b.x, b.y));
 }
 __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);

@@ -311,14 +311,16 @@ __device__ __forceinline__ void epilogue_tile(const Problem& p, unsigned char* s
       }
 #pragma unroll
       for (int j = 0; j < C::UB; ++j) {
-        if (kGelu) { v[j].x = gelu_erf(v[j].x); v[j].y = gelu_erf(v[j].y); v[j].z = gelu_erf(v[j].z); v[j].w = gelu_erf(v[j].w); }
-        if (kConv) {
-          const int rr = ((ub * C::UB + j) * 32 + lane) / C::UPR;
-          if ((halo_mask >> rr) & 1u) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        if (live[j]) {
-          if (kF32) *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off[j]) = v[j];
-          else *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off[j]) = make_uint2(pack_bf16x2(v[j].x, v[j].y), pack_bf16x2(v[j].z, v[j].w));
+        if (kF32) {
+          if (live[j]) *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off[j]) = v[j];
+        } else {
+          // GELU variants all store bf16: the activation is evaluated pairwise in half2 (common.cuh: gelu4_to_bf16)
+          uint2 o = kGelu ? gelu4_to_bf16(v[j]) : make_uint2(pack_bf16x2(v[j].x, v[j].y), pack_bf16x2(v[j].z, v[j].w));
+          if (kConv) {
+            const int rr = ((ub * C::UB + j) * 32 + lane) / C::UPR;
+            if ((halo_mask >> rr) & 1u) o = make_uint2(0u, 0u);
+          }
+          if (live[j]) *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off[j]) = o;
         }
       }
     }
