@@ -190,6 +190,30 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
+// Up to four K=16 MMAs over one 64-wide k-block.  a_lo / b_lo = (shared address >> 4) of the operand tiles; the K-major
+// SWIZZLE_128B descriptor's high word is a constant, and advancing 16 bf16 (32 bytes) inside the 128-byte swizzle atom
+// is +2 in the address field.  One straight-line sequence per slice count keeps every operand in uniform registers.
+__device__ __forceinline__ void mma_kblock(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t a_hi_extra, uint32_t idesc,
+                                           int nk, uint32_t acc) {
+  constexpr uint32_t HI = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO = 1024 B, version 1, SWIZZLE_128B
+  const uint64_t da = ((uint64_t)(HI | a_hi_extra) << 32) | a_lo, db = ((uint64_t)HI << 32) | b_lo;
+  if (nk == 4) {
+    tcgen05_mma_bf16(tmem_d, da, db, idesc, acc);
+    tcgen05_mma_bf16(tmem_d, da + 2, db + 2, idesc, 1u);
+    tcgen05_mma_bf16(tmem_d, da + 4, db + 4, idesc, 1u);
+    tcgen05_mma_bf16(tmem_d, da + 6, db + 6, idesc, 1u);
+  } else if (nk == 3) {
+    tcgen05_mma_bf16(tmem_d, da, db, idesc, acc);
+    tcgen05_mma_bf16(tmem_d, da + 2, db + 2, idesc, 1u);
+    tcgen05_mma_bf16(tmem_d, da + 4, db + 4, idesc, 1u);
+  } else if (nk == 2) {
+    tcgen05_mma_bf16(tmem_d, da, db, idesc, acc);
+    tcgen05_mma_bf16(tmem_d, da + 2, db + 2, idesc, 1u);
+  } else {
+    tcgen05_mma_bf16(tmem_d, da, db, idesc, acc);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ epilogue
 // Fused epilogues, one instruction stream each (selected per launch from the Problem, see classify()):
 enum Epi : int {
@@ -212,7 +236,7 @@ __host__ inline int classify(const Problem& p) {
     if (!p.out_f32 && p.resid == nullptr) return p.act ? E_RM_BF16_GELU : E_RM_BF16;
     return E_GENERIC;
   }
-  if (p.mode == EPI_CONV && p.act && !p.out_f32) return (p.skip && p.skip_tap < 0) ? E_CONV_SKIP : E_CONV;
+  if (p.mode == EPI_CONV && p.act && !p.out_f32) return (p.skip && p.skip_tap < 0) ? E_GENERIC : E_CONV;   // epilogue-loaded skip: generic path
   if (p.mode == EPI_CONVT && p.act && !p.out_f32 &&
       (unsigned long long)(p.M / (int)p.in_plane.d + 1) * p.out_plane * p.ldo < (1ull << 31)) return E_CONVT;
   return E_GENERIC;
@@ -231,6 +255,60 @@ __device__ __forceinline__ void epilogue_tile(const Problem& p, unsigned char* s
   const uint32_t halo_mask = kConv ? __ballot_sync(0xffffffffu, (rowpix & kRowHalo) != 0 && rowpix != kRowSkip) : 0u;
   const int rows_valid = p.M - mrow0;   // rows rr < rows_valid exist (row-major / conv)
   const uint32_t ldo = (uint32_t)p.ldo;
+  if constexpr (EPI == E_RM_BF16 || EPI == E_RM_BF16_GELU || EPI == E_CONV || EPI == E_CONVT) {
+    // ---- bf16 outputs: bias + GELU + rounding happen in phase A, on the lane that owns the accumulator row (halo rows
+    // are zeroed there too), so the staged slab is already the final bf16 data and phase B is a pure 16-byte copy loop.
+    constexpr int UPRB = C::SC / 8;                       // 16-byte units (8 bf16) per staged row
+    constexpr uint32_t PITCHB = C::SC * 2 + 16;           // odd number of 16-byte units: conflict-free row-per-lane writes
+    const bool zero_row = kConv && (rowpix & kRowHalo) != 0;
+#pragma unroll 1
+    for (int slab = 0; slab < BN / C::SC; ++slab) {
+      uint32_t r[C::SC];
+#pragma unroll
+      for (int c = 0; c < C::SC / 16; ++c) tmem_ld16(taddr + slab * C::SC + c * 16, &r[c * 16]);
+      tmem_ld_wait();
+      if (slab == BN / C::SC - 1) {
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tmem_empty_bar);
+      }
+      const int nslab = slab * C::SC;
+      uint4* srow = reinterpret_cast<uint4*>(stg + lane * PITCHB);
+#pragma unroll
+      for (int c = 0; c < UPRB; ++c) {
+        const float4 b0 = *reinterpret_cast<const float4*>(sbias + nslab + 8 * c);       // warp-uniform address: broadcast
+        const float4 b1 = *reinterpret_cast<const float4*>(sbias + nslab + 8 * c + 4);
+        const float4 v0 = make_float4(__uint_as_float(r[8 * c]) + b0.x, __uint_as_float(r[8 * c + 1]) + b0.y,
+                                      __uint_as_float(r[8 * c + 2]) + b0.z, __uint_as_float(r[8 * c + 3]) + b0.w);
+        const float4 v1 = make_float4(__uint_as_float(r[8 * c + 4]) + b1.x, __uint_as_float(r[8 * c + 5]) + b1.y,
+                                      __uint_as_float(r[8 * c + 6]) + b1.z, __uint_as_float(r[8 * c + 7]) + b1.w);
+        uint2 o0 = kGelu ? gelu4_to_bf16(v0) : make_uint2(pack_bf16x2(v0.x, v0.y), pack_bf16x2(v0.z, v0.w));
+        uint2 o1 = kGelu ? gelu4_to_bf16(v1) : make_uint2(pack_bf16x2(v1.x, v1.y), pack_bf16x2(v1.z, v1.w));
+        if (zero_row) { o0 = make_uint2(0u, 0u); o1 = o0; }
+        srow[c] = make_uint4(o0.x, o0.y, o1.x, o1.y);
+      }
+      __syncwarp();
+      __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(p.out);
+#pragma unroll
+      for (int j = 0; j < UPRB; ++j) {
+        const int u = j * 32 + lane;
+        const int rr = u / UPRB, cu = u - rr * UPRB;
+        const uint4 v = *reinterpret_cast<const uint4*>(stg + rr * PITCHB + cu * 16);
+        const int n = n0 + nslab + cu * 8;
+        if (EPI == E_CONVT) {
+          const uint32_t pix = __shfl_sync(0xffffffffu, rowpix, rr);
+          uint32_t qq, o;
+          fd_divmod((uint32_t)n, p.cout_div, qq, o);
+          if (pix != kRowSkip)
+            *reinterpret_cast<uint4*>(outp + (pix + (qq >> 1) * (uint32_t)p.out_pitch + (qq & 1)) * ldo + o) = v;
+        } else {
+          if (rr < rows_valid) *reinterpret_cast<uint4*>(outp + (uint32_t)(mrow0 + rr) * ldo + (uint32_t)n) = v;
+        }
+      }
+      __syncwarp();
+    }
+    return;
+  }
 #pragma unroll 1
   for (int slab = 0; slab < BN / C::SC; ++slab) {
     // ---- phase A: this lane's accumulator row -> registers -> padded smem row
@@ -342,9 +420,9 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   unsigned char* smem_res = smem + C::kStages * C::STAGE_BYTES;              // resident weights (MODE 2)
   unsigned char* smem_stg = smem_res + C::RESIDENT_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_stg + C::STG_BYTES);
-  uint64_t* full = bars;
-  uint64_t* empty = bars + C::kStages;
-  uint64_t* tmem_full = bars + 2 * C::kStages;
+  uint64_t* full = bars;                     // [2][kStages]: one set per MMA issuer (tile parity), see the issuer loop
+  uint64_t* empty = bars + 2 * C::kStages;
+  uint64_t* tmem_full = bars + 3 * C::kStages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint64_t* res_full = tmem_empty + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_full + 1);
@@ -355,7 +433,7 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < C::kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < C::kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&full[C::kStages + i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
     mbar_init(res_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -372,10 +450,14 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
   // merged modes walk (dy, k-block) steps, then the k-blocks of the identity skip tap
   const int kbpt = p.kb_per_tap;
-  const int conv_steps = 3 * kbpt, merged_steps = conv_steps + (p.skip_tap >= 0 ? kbpt : 0);
+  const int n_dy = 3, has_skip = p.skip_tap >= 0 ? 1 : 0;
+  // 16-wide K slices of the last k-block of a tap that hold valid channels (K = 48 or 96 does not fill it)
+  const int nk_last = min(BLOCK_K / 16, (p.kvalid - (kbpt - 1) * BLOCK_K + 15) / 16);
 
   // Producer and MMA warps run their loops with all 32 lanes converged and let one elected lane issue the
-  // asynchronous instructions: operands are then provably warp-uniform (uniform registers, no per-MMA waterfall).
+  // asynchronous instructions.  Both loops are the serial critical path of a CTA (one warp each, nothing to hide
+  // instruction latency behind), so they are written as plain nested counters: no division, no per-MMA descriptor
+  // rebuild -- descriptors are a 32-bit base + small adds, the high word is a constant.
   if (warp == 0) {
     // ===== TMA producer =====
     int stage = 0; uint32_t phase = 0;
@@ -387,8 +469,12 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
       __syncwarp();
     }
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile / tiles_n) * BLOCK_M, n0 = (tile % tiles_n) * BN;
+    const int tap0 = p.tap_off[0], tap3 = p.tap_off[3], tap6 = p.tap_off[6];
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int tm = tile / tiles_n;
+      const int m0 = tm * BLOCK_M, n0 = (tile - tm * tiles_n) * BN;
+      uint64_t* full = bars + (it & 1u) * C::kStages;      // the issuer that owns this tile listens on its own barrier set
       if constexpr (MODE == MODE_PLAIN) {
         int tap = 0, kc = 0;
         for (int kb = 0; kb < p.num_kb; ++kb) {
@@ -404,88 +490,107 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
       } else {
-        for (int st = 0; st < merged_steps; ++st) {
-          mbar_wait(&empty[stage], phase ^ 1);
-          const bool is_skip = st >= conv_steps;
-          const int dy = is_skip ? 0 : st / kbpt, kc = is_skip ? st - conv_steps : st - dy * kbpt;
-          const int nw = (MODE == MODE_MERGE3) ? (is_skip ? 1 : 3) : 0;
-          if (elect_one()) {
-            mbar_arrive_expect_tx(&full[stage], C::A_BOX_BYTES + nw * C::W_BOX_BYTES);
-            // rows m0 + off(dy, dx=-1) .. +135: windows at +0 / +1 / +2 rows are the dx = -1 / 0 / +1 taps;
-            // the skip tensor is loaded one row early too and read through the middle window
-            tma_load_2d(is_skip ? &tmS : &tmA, &full[stage], smem_a + stage * A_STAGE_BYTES, kc * BLOCK_K,
-                        is_skip ? m0 - 1 : m0 + p.tap_off[3 * dy]);
-            if constexpr (MODE == MODE_MERGE3) {
-              for (int j = 0; j < nw; ++j) {
-                const int tap = is_skip ? p.skip_tap : 3 * dy + j;
-                tma_load_2d(&tmB, &full[stage], smem_b + stage * C::B_STAGE_BYTES + j * C::W_BOX_BYTES, (tap * kbpt + kc) * BLOCK_K, n0);
+        // rows m0 + off(dy, dx=-1) .. +135: windows at +0 / +1 / +2 rows are the dx = -1 / 0 / +1 taps;
+        // the skip tensor is loaded one row early too and read through the middle window
+        for (int dy = 0; dy < n_dy + has_skip; ++dy) {
+          const bool is_skip = dy == n_dy;
+          const int row = is_skip ? m0 - 1 : m0 + (dy == 0 ? tap0 : dy == 1 ? tap3 : tap6);
+          const int wcol0 = (is_skip ? p.skip_tap : 3 * dy) * kbpt * BLOCK_K;
+          for (int kc = 0; kc < kbpt; ++kc) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            if (elect_one()) {
+              if constexpr (MODE == MODE_MERGE3) {
+                mbar_arrive_expect_tx(&full[stage], C::A_BOX_BYTES + (is_skip ? 1u : 3u) * C::W_BOX_BYTES);
+                unsigned char* sb = smem_b + stage * C::B_STAGE_BYTES;
+                tma_load_2d(&tmB, &full[stage], sb, wcol0 + kc * BLOCK_K, n0);
+                if (!is_skip) {
+                  tma_load_2d(&tmB, &full[stage], sb + C::W_BOX_BYTES, wcol0 + (kbpt + kc) * BLOCK_K, n0);
+                  tma_load_2d(&tmB, &full[stage], sb + 2 * C::W_BOX_BYTES, wcol0 + (2 * kbpt + kc) * BLOCK_K, n0);
+                }
+              } else {
+                mbar_arrive_expect_tx(&full[stage], C::A_BOX_BYTES);
               }
+              tma_load_2d(is_skip ? &tmS : &tmA, &full[stage], smem_a + stage * A_STAGE_BYTES, kc * BLOCK_K, row);
             }
+            __syncwarp();
+            if (++stage == C::kStages) { stage = 0; phase ^= 1; }
           }
-          __syncwarp();
-          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
-  } else if (warp == 1) {
-    // ===== MMA issuer =====
+  } else if (warp == 1 || warp == 3) {
+    // ===== MMA issuers: warp 1 takes this CTA's even tiles (accumulator buffer 0), warp 3 the odd ones (buffer 1).
+    // One warp's issue loop costs several hundred cycles of dependent scalar work per tile, which is more than the
+    // tensor time of a narrow tile (N = 48: 27 MMAs x 24 cycles); two issuers overlap that latency.  Both walk the same
+    // shared-memory ring: a warp skips the other's tile by advancing its ring position by one tile's worth of stages.
     constexpr uint32_t idesc = make_idesc(BLOCK_M, BN);
-    int stage = 0; uint32_t phase = 0;
-    int it = 0;
+    const uint32_t par = warp == 1 ? 0u : 1u;
+    const uint32_t a_lo0 = (smem_u32(smem_a) & 0x3FFFFu) >> 4, b_lo0 = (smem_u32(smem_b) & 0x3FFFFu) >> 4;
+    const uint32_t r_lo0 = (smem_u32(smem_res) & 0x3FFFFu) >> 4;
+    const int steps_per_tile = MODE == MODE_PLAIN ? p.num_kb : (n_dy + has_skip) * kbpt;
+    const uint32_t tmem_d = tmem_base + par * BN;
+    int gstep = 0;
+    uint32_t it = 0;
+    // Each issuer has its own `full` barrier per stage (the producer signals the set of the tile's owner), and keeps one
+    // parity bit per stage: a parity wait is only unambiguous for a waiter that has seen every earlier phase itself.
+    uint64_t* full = bars + par * C::kStages;
+    uint32_t pmask = 0;
     if constexpr (MODE == MODE_MERGE3_RESIDENT) { mbar_wait(res_full, 0); tcgen05_fence_after(); }
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const uint32_t as = it & 1, aphase = (it >> 1) & 1;
-      mbar_wait(&tmem_empty[as], aphase ^ 1);
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it, gstep += steps_per_tile) {
+      if ((it & 1u) != par) continue;
+      int stage = gstep % C::kStages;
+      mbar_wait(&tmem_empty[par], ((it >> 1) & 1u) ^ 1u);
       tcgen05_fence_after();
-      const uint32_t tmem_d = tmem_base + as * BN;
+      uint32_t acc = 0;                                   // first MMA of the tile overwrites the accumulator
       if constexpr (MODE == MODE_PLAIN) {
         int kc = 0;
         for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait(&full[stage], phase);
+          mbar_wait(&full[stage], (pmask >> stage) & 1u);
+          pmask ^= 1u << stage;
           tcgen05_fence_after();
-          // only the 16-wide K slices that hold valid channels are issued (K = 48 or 96 does not fill the last block)
-          const int nk = min(BLOCK_K / 16, (p.kvalid - kc * BLOCK_K + 15) / 16);
+          const int nk = (kc == kbpt - 1) ? nk_last : BLOCK_K / 16;
           if (elect_one()) {
-            const uint64_t da = make_smem_desc(smem_u32(smem_a + stage * A_STAGE_BYTES) + 128u * p.dbg_shift) | ((uint64_t)(p.dbg_bo & 7) << 49);
-            const uint64_t db = make_smem_desc(smem_u32(smem_b + stage * C::B_STAGE_BYTES));
-#pragma unroll
-            for (int k = 0; k < BLOCK_K / 16; ++k) {
-              // advance 16 bf16 = 32 bytes inside the 128-byte swizzle atom: +2 in the (addr >> 4) field
-              if (k < nk) tcgen05_mma_bf16(tmem_d, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
-            }
+            const uint32_t a_lo = a_lo0 + stage * (A_STAGE_BYTES >> 4) + 8u * p.dbg_shift;
+            const uint32_t b_lo = b_lo0 + stage * (C::B_STAGE_BYTES >> 4);
+            mma_kblock(tmem_d, a_lo, b_lo, (uint32_t)(p.dbg_bo & 7) << 17, idesc, nk, acc);
             tcgen05_commit(&empty[stage]);               // frees the smem stage once these MMAs retire
-            if (kb == p.num_kb - 1) tcgen05_commit(&tmem_full[as]);  // accumulator complete -> epilogue
+            if (kb == p.num_kb - 1) tcgen05_commit(&tmem_full[par]);  // accumulator complete -> epilogue
           }
           __syncwarp();
+          acc = 1;
           if (++kc == kbpt) kc = 0;
-          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+          if (++stage == C::kStages) stage = 0;
         }
       } else {
-        for (int st = 0; st < merged_steps; ++st) {
-          mbar_wait(&full[stage], phase);
-          tcgen05_fence_after();
-          const bool is_skip = st >= conv_steps;
-          const int dy = is_skip ? 0 : st / kbpt, kc = is_skip ? st - conv_steps : st - dy * kbpt;
-          const int nk = min(BLOCK_K / 16, (p.kvalid - kc * BLOCK_K + 15) / 16);
-          if (elect_one()) {
-            const uint32_t a_base = smem_u32(smem_a + stage * A_STAGE_BYTES);
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {                                    // window j = rows +j = tap dx = j - 1
-              if (is_skip ? (j != 1) : false) continue;
-              const int tap = is_skip ? p.skip_tap : 3 * dy + j;
-              const uint32_t b_addr = (MODE == MODE_MERGE3_RESIDENT)
-                                          ? smem_u32(smem_res + (tap * kbpt + kc) * C::W_BOX_BYTES)
-                                          : smem_u32(smem_b + stage * C::B_STAGE_BYTES + (is_skip ? 0 : j) * C::W_BOX_BYTES);
-              const uint64_t da = make_smem_desc(a_base + 128u * j), db = make_smem_desc(b_addr);
-#pragma unroll
-              for (int k = 0; k < BLOCK_K / 16; ++k)
-                if (k < nk) tcgen05_mma_bf16(tmem_d, da + 2u * k, db + 2u * k, idesc, (st | j | k) != 0 ? 1u : 0u);
+        for (int dy = 0; dy < n_dy + has_skip; ++dy) {
+          const bool is_skip = dy == n_dy;
+          for (int kc = 0; kc < kbpt; ++kc) {
+            mbar_wait(&full[stage], (pmask >> stage) & 1u);
+            pmask ^= 1u << stage;
+            tcgen05_fence_after();
+            const int nk = (kc == kbpt - 1) ? nk_last : BLOCK_K / 16;
+            const bool last = (dy == n_dy + has_skip - 1) && (kc == kbpt - 1);
+            if (elect_one()) {
+              const uint32_t a_lo = a_lo0 + stage * (A_STAGE_BYTES >> 4);
+              if (is_skip) {                                                 // identity tap through the middle window
+                const uint32_t b_lo = (MODE == MODE_MERGE3_RESIDENT) ? r_lo0 + (p.skip_tap * kbpt + kc) * (C::W_BOX_BYTES >> 4)
+                                                                     : b_lo0 + stage * (C::B_STAGE_BYTES >> 4);
+                mma_kblock(tmem_d, a_lo + 8u, b_lo, 0u, idesc, nk, acc);
+              } else {
+                const uint32_t b_lo = (MODE == MODE_MERGE3_RESIDENT) ? r_lo0 + (3 * dy * kbpt + kc) * (C::W_BOX_BYTES >> 4)
+                                                                     : b_lo0 + stage * (C::B_STAGE_BYTES >> 4);
+                const uint32_t b_step = (MODE == MODE_MERGE3_RESIDENT ? kbpt : 1) * (C::W_BOX_BYTES >> 4);
+                mma_kblock(tmem_d, a_lo, b_lo, 0u, idesc, nk, acc);                       // dx = -1
+                mma_kblock(tmem_d, a_lo + 8u, b_lo + b_step, 0u, idesc, nk, 1u);           // dx =  0 (one row = 128 B down)
+                mma_kblock(tmem_d, a_lo + 16u, b_lo + 2u * b_step, 0u, idesc, nk, 1u);     // dx = +1
+              }
+              tcgen05_commit(&empty[stage]);
+              if (last) tcgen05_commit(&tmem_full[par]);
             }
-            tcgen05_commit(&empty[stage]);
-            if (st == merged_steps - 1) tcgen05_commit(&tmem_full[as]);
+            __syncwarp();
+            acc = 1;
+            if (++stage == C::kStages) stage = 0;
           }
-          __syncwarp();
-          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -511,7 +616,6 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         case E_RM_BF16_GELU:  epilogue_tile<BN, E_RM_BF16_GELU>(p, stg, sbias, taddr, &tmem_empty[as], m0 + q * 32, n0, lane); break;
         case E_RM_F32_RESID:  epilogue_tile<BN, E_RM_F32_RESID>(p, stg, sbias, taddr, &tmem_empty[as], m0 + q * 32, n0, lane); break;
         case E_CONV:          epilogue_tile<BN, E_CONV>(p, stg, sbias, taddr, &tmem_empty[as], m0 + q * 32, n0, lane); break;
-        case E_CONV_SKIP:     epilogue_tile<BN, E_CONV_SKIP>(p, stg, sbias, taddr, &tmem_empty[as], m0 + q * 32, n0, lane); break;
         case E_CONVT:         epilogue_tile<BN, E_CONVT>(p, stg, sbias, taddr, &tmem_empty[as], m0 + q * 32, n0, lane); break;
         default:              epilogue_tile<BN, E_GENERIC>(p, stg, sbias, taddr, &tmem_empty[as], m0 + q * 32, n0, lane); break;
       }

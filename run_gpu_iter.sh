@@ -1,8 +1,3 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests -q -p no:cacheprovider -m gpu -x > gpurun_out/t_gpu.log 2>&1; echo "gpu tests rc=$?"; tail -n 4 gpurun_out/t_gpu.log
-timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --profile-out gpurun_out/profile_tc5.json > gpurun_out/bench_tc5.json 2> gpurun_out/bench_tc5.err; echo "bench rc=$?"; tail -n 3 gpurun_out/bench_tc5.err
-python - <<'PY'
-import json
-b=json.load(open('gpurun_out/bench_tc5.json'))
-print({k:b[k] for k in ('value','ms_per_step')}, 'e2e', b['e2e']['value'], 'gemm TF/s', b['roofline']['achieved'], 'gemm ms', b['roofline']['ms_per_step'], b['roofline']['other_ms_per_step'], b['clocks'])
-PY
+timeout 600 python -m pytest tests/test_gpu_model.py -q -p no:cacheprovider -x > gpurun_out/t_model.log 2>&1; echo "model rc=$?"; tail -n 5 gpurun_out/t_model.log
+python tools/gemm_bench.py > gpurun_out/gemm_bench.log 2>&1; cat gpurun_out/gemm_bench.log
