@@ -23,7 +23,8 @@
 namespace gemm {
 namespace tc5 {
 
-constexpr int kThreads = 384;   // 4 control warps + 2 epilogue groups of 4 warps
+constexpr int kEpiWarps = 16;    // 2 accumulator buffers x 4 TMEM lane quadrants x 2 column halves
+constexpr int kThreads = 128 + 32 * kEpiWarps;   // 4 control warps (TMA producer, 2 MMA issuers, TMEM allocator) + epilogue
 constexpr uint64_t kSpinLimit = 4000000000ull;             // ~2 s of SM clocks: trap instead of hanging the GPU
 
 // MODE 0: one A box [128 rows x 64 k] + one W box per pipeline stage (linear layers, ConvTranspose, wide convs).
@@ -44,13 +45,19 @@ struct Cfg {
   static constexpr uint32_t B_STAGE_BYTES = MODE == MODE_PLAIN ? W_BOX_BYTES : MODE == MODE_MERGE3 ? 3 * W_BOX_BYTES : 0;
   static constexpr uint32_t STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr uint32_t RESIDENT_BYTES = MODE == MODE_MERGE3_RESIDENT ? 10 * W_BOX_BYTES : 0;
-  // epilogue staging: slab of SC fp32 columns x 32 rows per epilogue warp, row pitch padded by 16 B (conflict-free)
-  static constexpr int SC = (BN == 256) ? 32 : (BN % 64 == 0) ? 64 : (BN % 48 == 0) ? 48 : (BN % 32 == 0) ? 32 : 16;
-  static constexpr int UPR = SC / 4;                       // 16-byte units per staged row
-  static constexpr uint32_t STG_PITCH = SC * 4 + 16;
-  static constexpr int UB = (UPR % 8 == 0) ? 8 : 4;         // units per lane whose loads are batched in phase B
-  static constexpr uint32_t STG_WARP_BYTES = 32 * STG_PITCH + BN * 4;   // staged slab + this tile's bias slice
-  static constexpr uint32_t STG_BYTES = 8 * STG_WARP_BYTES;            // two epilogue groups of four warps
+  // epilogue staging: slabs of SC accumulator columns x 32 rows per epilogue warp (fp32 or bf16), row pitch padded by 16 B
+  // (an odd number of 16-byte units: row-per-lane writes are conflict-free)
+  // narrow tiles (one slab) run with a single column half = 8 epilogue warps: more warps would only take issue slots
+  // from the producer / MMA issuer warps, which are the critical path there
+  static constexpr int SC = (BN % 32 == 0) ? 32 : (BN % 48 == 0) ? 48 : 16;
+  static constexpr int NSLAB = BN / SC;
+  static constexpr int SLAB_SPLIT = (NSLAB + 1) / 2;         // column half 0 owns slabs [0, SLAB_SPLIT), half 1 the rest
+  // plain mode may stage fp32 rows (fp32-output epilogues); the merged conv modes only ever stage bf16
+  static constexpr uint32_t STG_PITCH = (MODE == MODE_PLAIN ? SC * 4 : SC * 2) + 16;
+  static constexpr uint32_t STG_WARP_BYTES = 32 * STG_PITCH + SLAB_SPLIT * SC * 4;   // staged slab + this warp's bias slice
+  static constexpr int EPI_WARPS = NSLAB >= 2 ? kEpiWarps : kEpiWarps / 2;
+  static constexpr int THREADS = 128 + 32 * EPI_WARPS;
+  static constexpr uint32_t STG_BYTES = EPI_WARPS * STG_WARP_BYTES;
   static constexpr int kStagesRaw = (int)((227u * 1024u - 1024u - 256u - STG_BYTES - RESIDENT_BYTES) / STAGE_BYTES);
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
@@ -128,6 +135,17 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
 
+// explicit shared-space accesses for the epilogue staging buffers (generic LD/ST on a pointer derived from the dynamic
+// smem base go through the long-latency generic path and serialise against each other)
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};\n" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 constexpr uint32_t kRowSkip = 0xFFFFFFFFu;   // row produces no output (beyond M, or a halo row of a ConvTranspose input)
 constexpr uint32_t kRowHalo = 0x80000000u;   // EPI_CONV halo row: stored as zeros
 
@@ -150,27 +168,6 @@ __device__ __forceinline__ uint32_t row_info(const Problem& p, int m) {
     yy -= 1; xx -= 1;
   }
   return img * (uint32_t)p.out_plane + (2 * yy + 1) * (uint32_t)p.out_pitch + (2 * xx + 1);
-}
-
-// Phase B of the epilogue works on 16-byte units = 4 consecutive output columns n..n+3 of the row described by `pix`.
-// Global loads (residual / skip) are issued for a whole batch of units BEFORE any arithmetic or store, so that several
-// independent requests per lane are in flight (the stores may alias the loads as far as the compiler knows).
-__device__ __forceinline__ size_t unit_offset(const Problem& p, uint32_t pix, int n) {
-  if (p.mode == EPI_CONVT) {  // column n = (di*2+dj)*Cout + o -> output pixel (2y+di, 2x+dj), channel o
-    uint32_t q, o;
-    fd_divmod((uint32_t)n, p.cout_div, q, o);
-    return (size_t)(pix + (q >> 1) * (uint32_t)p.out_pitch + (q & 1)) * p.ldo + o;
-  }
-  return (size_t)(pix & ~kRowHalo) * p.ldo + n;
-}
-
-__device__ __forceinline__ void finish_unit(const Problem& p, uint32_t pix, size_t off, float4 v) {
-  if (pix == kRowSkip) return;
-  const bool zero = (p.mode == EPI_CONV) && (pix & kRowHalo) != 0;
-  if (zero) v = make_float4(0.f, 0.f, 0.f, 0.f);
-  else if (p.act) { v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w); }
-  if (p.out_f32) *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off) = v;
-  else *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
 }
 
 // K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
@@ -221,8 +218,7 @@ enum Epi : int {
   E_RM_BF16,        // out bf16 = acc + bias                                         (qkv)
   E_RM_BF16_GELU,   // out bf16 = GELU(acc + bias)                                   (fc1)
   E_RM_F32_RESID,   // out fp32 = resid + acc + bias, in place                       (attention proj, fc2)
-  E_CONV,           // haloed NHWC bf16 = GELU(acc + bias), halo rows zeroed         (ResidualBlock conv 1, head conv)
-  E_CONV_SKIP,      // haloed NHWC bf16 = GELU(acc + bias + skip)                    (ResidualBlock conv 2)
+  E_CONV,           // haloed NHWC bf16 = GELU(acc + bias), halo rows zeroed         (every 3x3 conv; a ResidualBlock's skip is a 10th tap)
   E_CONVT,          // pixel-shuffle scatter of GELU(acc + bias)                     (ConvTranspose2d k2 s2)
   E_GENERIC         // any other combination of the Problem's flags (slower, runtime-branched)
 };
@@ -242,173 +238,124 @@ __host__ inline int classify(const Problem& p) {
   return E_GENERIC;
 }
 
+// One epilogue warp = one TMEM lane quadrant (32 accumulator rows) x one column half of the tile.  Per slab of SC columns:
+//   phase A (lane = accumulator row): tcgen05.ld -> + bias (broadcast ld.shared) -> [GELU, bf16 rounding, halo-row zeroing]
+//            -> padded shared-memory row; the TMEM buffer is handed back as soon as the warp's last slab is in registers
+//   phase B (lanes run along the columns): 16-byte units are read back and stored as coalesced row segments; the fp32
+//            residual variant loads its operand there (batched, all loads in flight before the first add)
 template <int BN, int EPI>
-__device__ __forceinline__ void epilogue_tile(const Problem& p, unsigned char* stg, const float* sbias, uint32_t taddr,
-                                              uint64_t* tmem_empty_bar, int mrow0, int n0, int lane) {
+__device__ __forceinline__ void epilogue_tile(const Problem& p, uint32_t stg_s, uint32_t bias_s, uint32_t taddr,
+                                              uint64_t* tmem_empty_bar, int mrow0, int n0, int lane, int slab_begin, int slab_end) {
   using C = Cfg<BN>;
-  constexpr bool kRowMajor = EPI == E_RM_F32 || EPI == E_RM_BF16 || EPI == E_RM_BF16_GELU || EPI == E_RM_F32_RESID;
-  constexpr bool kConv = EPI == E_CONV || EPI == E_CONV_SKIP;
+  constexpr bool kConv = EPI == E_CONV;
   constexpr bool kF32 = EPI == E_RM_F32 || EPI == E_RM_F32_RESID;
   constexpr bool kGelu = EPI == E_RM_BF16_GELU || kConv || EPI == E_CONVT;
-  // per-row facts, owned by the lane whose TMEM row it is; phase B looks rows up by ballot mask / shuffle
+  constexpr int UPR = kF32 ? C::SC / 4 : C::SC / 8;        // 16-byte units per staged row (a power of two)
+  constexpr uint32_t PITCH = (kF32 ? C::SC * 4 : C::SC * 2) + 16;
   const uint32_t rowpix = (EPI == E_GENERIC || EPI == E_CONVT || kConv) ? row_info(p, mrow0 + lane) : 0u;
-  const uint32_t halo_mask = kConv ? __ballot_sync(0xffffffffu, (rowpix & kRowHalo) != 0 && rowpix != kRowSkip) : 0u;
+  const bool zero_row = kConv && (rowpix & kRowHalo) != 0;
   const int rows_valid = p.M - mrow0;   // rows rr < rows_valid exist (row-major / conv)
   const uint32_t ldo = (uint32_t)p.ldo;
-  if constexpr (EPI == E_RM_BF16 || EPI == E_RM_BF16_GELU || EPI == E_CONV || EPI == E_CONVT) {
-    // ---- bf16 outputs: bias + GELU + rounding happen in phase A, on the lane that owns the accumulator row (halo rows
-    // are zeroed there too), so the staged slab is already the final bf16 data and phase B is a pure 16-byte copy loop.
-    constexpr int UPRB = C::SC / 8;                       // 16-byte units (8 bf16) per staged row
-    constexpr uint32_t PITCHB = C::SC * 2 + 16;           // odd number of 16-byte units: conflict-free row-per-lane writes
-    const bool zero_row = kConv && (rowpix & kRowHalo) != 0;
-#pragma unroll 1
-    for (int slab = 0; slab < BN / C::SC; ++slab) {
-      uint32_t r[C::SC];
-#pragma unroll
-      for (int c = 0; c < C::SC / 16; ++c) tmem_ld16(taddr + slab * C::SC + c * 16, &r[c * 16]);
-      tmem_ld_wait();
-      if (slab == BN / C::SC - 1) {
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tmem_empty_bar);
-      }
-      const int nslab = slab * C::SC;
-      uint4* srow = reinterpret_cast<uint4*>(stg + lane * PITCHB);
-#pragma unroll
-      for (int c = 0; c < UPRB; ++c) {
-        const float4 b0 = *reinterpret_cast<const float4*>(sbias + nslab + 8 * c);       // warp-uniform address: broadcast
-        const float4 b1 = *reinterpret_cast<const float4*>(sbias + nslab + 8 * c + 4);
-        const float4 v0 = make_float4(__uint_as_float(r[8 * c]) + b0.x, __uint_as_float(r[8 * c + 1]) + b0.y,
-                                      __uint_as_float(r[8 * c + 2]) + b0.z, __uint_as_float(r[8 * c + 3]) + b0.w);
-        const float4 v1 = make_float4(__uint_as_float(r[8 * c + 4]) + b1.x, __uint_as_float(r[8 * c + 5]) + b1.y,
-                                      __uint_as_float(r[8 * c + 6]) + b1.z, __uint_as_float(r[8 * c + 7]) + b1.w);
-        uint2 o0 = kGelu ? gelu4_to_bf16(v0) : make_uint2(pack_bf16x2(v0.x, v0.y), pack_bf16x2(v0.z, v0.w));
-        uint2 o1 = kGelu ? gelu4_to_bf16(v1) : make_uint2(pack_bf16x2(v1.x, v1.y), pack_bf16x2(v1.z, v1.w));
-        if (zero_row) { o0 = make_uint2(0u, 0u); o1 = o0; }
-        srow[c] = make_uint4(o0.x, o0.y, o1.x, o1.y);
-      }
-      __syncwarp();
-      __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(p.out);
-#pragma unroll
-      for (int j = 0; j < UPRB; ++j) {
-        const int u = j * 32 + lane;
-        const int rr = u / UPRB, cu = u - rr * UPRB;
-        const uint4 v = *reinterpret_cast<const uint4*>(stg + rr * PITCHB + cu * 16);
-        const int n = n0 + nslab + cu * 8;
-        if (EPI == E_CONVT) {
-          const uint32_t pix = __shfl_sync(0xffffffffu, rowpix, rr);
-          uint32_t qq, o;
-          fd_divmod((uint32_t)n, p.cout_div, qq, o);
-          if (pix != kRowSkip)
-            *reinterpret_cast<uint4*>(outp + (pix + (qq >> 1) * (uint32_t)p.out_pitch + (qq & 1)) * ldo + o) = v;
-        } else {
-          if (rr < rows_valid) *reinterpret_cast<uint4*>(outp + (uint32_t)(mrow0 + rr) * ldo + (uint32_t)n) = v;
-        }
-      }
-      __syncwarp();
-    }
+  if (slab_begin >= slab_end) {          // a one-slab tile leaves the second column half idle: just release the buffer
+    tcgen05_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(tmem_empty_bar);
     return;
   }
 #pragma unroll 1
-  for (int slab = 0; slab < BN / C::SC; ++slab) {
-    // ---- phase A: this lane's accumulator row -> registers -> padded smem row
+  for (int slab = slab_begin; slab < slab_end; ++slab) {
     uint32_t r[C::SC];
 #pragma unroll
     for (int c = 0; c < C::SC / 16; ++c) tmem_ld16(taddr + slab * C::SC + c * 16, &r[c * 16]);
     tmem_ld_wait();
-    if (slab == BN / C::SC - 1) {
-      // the whole accumulator has left TMEM: hand the buffer back to the MMA warp before the stores
+    if (slab == slab_end - 1) {
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tmem_empty_bar);
     }
-    uint4* srow = reinterpret_cast<uint4*>(stg + lane * C::STG_PITCH);
-#pragma unroll
-    for (int c = 0; c < C::UPR; ++c) srow[c] = make_uint4(r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
-    __syncwarp();
-    // ---- phase B: lanes run along the columns; UB 16-byte units (4 columns each) per lane per batch
     const int nslab = slab * C::SC;
-#pragma unroll 1
-    for (int ub = 0; ub < C::UPR / C::UB; ++ub) {
-      float4 v[C::UB];
-      uint32_t off[C::UB];     // element offset into out (32-bit: classify() guarantees it fits)
-      bool live[C::UB];
+    if constexpr (EPI == E_GENERIC) {
+      // any other flag combination: straight from registers, one accumulator row per lane (slow, rarely used)
 #pragma unroll
-      for (int j = 0; j < C::UB; ++j) {
-        const int u = (ub * C::UB + j) * 32 + lane;
-        const int rr = u / C::UPR, cu = u - rr * C::UPR;
-        const int n = n0 + nslab + cu * 4;
-        v[j] = *reinterpret_cast<const float4*>(stg + rr * C::STG_PITCH + cu * 16);
-        const float4 b = *reinterpret_cast<const float4*>(sbias + nslab + cu * 4);
-        v[j].x += b.x; v[j].y += b.y; v[j].z += b.z; v[j].w += b.w;
-        if (kRowMajor || kConv) {
-          live[j] = rr < rows_valid;
-          off[j] = (uint32_t)(mrow0 + rr) * ldo + (uint32_t)n;
-        } else if (EPI == E_CONVT) {
+      for (int c = 0; c < C::SC / 16; ++c) {
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[c * 16 + i]);
+        epilogue_store<16>(p, mrow0 + lane, n0 + nslab + c * 16, v);
+      }
+    } else {
+      // ---- phase A
+      const uint32_t bsl = bias_s + (uint32_t)(slab - slab_begin) * (C::SC * 4);
+#pragma unroll
+      for (int c = 0; c < C::SC / 4; ++c) {
+        const uint4 b = lds128(bsl + 16 * c);               // warp-uniform address: broadcast
+        r[4 * c] = __float_as_uint(__uint_as_float(r[4 * c]) + __uint_as_float(b.x));
+        r[4 * c + 1] = __float_as_uint(__uint_as_float(r[4 * c + 1]) + __uint_as_float(b.y));
+        r[4 * c + 2] = __float_as_uint(__uint_as_float(r[4 * c + 2]) + __uint_as_float(b.z));
+        r[4 * c + 3] = __float_as_uint(__uint_as_float(r[4 * c + 3]) + __uint_as_float(b.w));
+      }
+      if constexpr (kF32) {
+#pragma unroll
+        for (int c = 0; c < UPR; ++c) sts128(stg_s + lane * PITCH + c * 16, make_uint4(r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]));
+      } else {
+#pragma unroll
+        for (int c = 0; c < UPR; ++c) {
+          const float4 v0 = make_float4(__uint_as_float(r[8 * c]), __uint_as_float(r[8 * c + 1]), __uint_as_float(r[8 * c + 2]), __uint_as_float(r[8 * c + 3]));
+          const float4 v1 = make_float4(__uint_as_float(r[8 * c + 4]), __uint_as_float(r[8 * c + 5]), __uint_as_float(r[8 * c + 6]), __uint_as_float(r[8 * c + 7]));
+          uint2 o0 = kGelu ? gelu4_to_bf16(v0) : make_uint2(pack_bf16x2(v0.x, v0.y), pack_bf16x2(v0.z, v0.w));
+          uint2 o1 = kGelu ? gelu4_to_bf16(v1) : make_uint2(pack_bf16x2(v1.x, v1.y), pack_bf16x2(v1.z, v1.w));
+          if (zero_row) { o0 = make_uint2(0u, 0u); o1 = o0; }
+          sts128(stg_s + lane * PITCH + c * 16, make_uint4(o0.x, o0.y, o1.x, o1.y));
+        }
+      }
+      __syncwarp();
+      // ---- phase B
+      constexpr int EPU = kF32 ? 4 : 8;                     // elements per 16-byte unit
+      uint4 v[UPR];
+      uint32_t off[UPR];
+      bool live[UPR];
+#pragma unroll
+      for (int j = 0; j < UPR; ++j) {
+        const int u = j * 32 + lane;
+        const int rr = u / UPR, cu = u % UPR;
+        v[j] = lds128(stg_s + rr * PITCH + cu * 16);
+        const int n = n0 + nslab + cu * EPU;
+        if constexpr (EPI == E_CONVT) {
           const uint32_t pix = __shfl_sync(0xffffffffu, rowpix, rr);
-          live[j] = pix != kRowSkip;
           uint32_t qq, o;
           fd_divmod((uint32_t)n, p.cout_div, qq, o);
+          live[j] = pix != kRowSkip;
           off[j] = (pix + (qq >> 1) * (uint32_t)p.out_pitch + (qq & 1)) * ldo + o;
-        } else {  // E_GENERIC keeps 64-bit offsets and every runtime flag
-          const uint32_t pix = __shfl_sync(0xffffffffu, rowpix, rr);
-          const size_t o64 = unit_offset(p, pix, n);
-          float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (pix != kRowSkip) {
-            if (p.resid != nullptr) e = *reinterpret_cast<const float4*>(p.resid + o64);
-            else if (p.skip != nullptr && p.skip_tap < 0 && !(pix & kRowHalo)) {
-              const uint2 s2 = *reinterpret_cast<const uint2*>(p.skip + o64);
-              const float2 a = unpack_bf16x2(s2.x), c2 = unpack_bf16x2(s2.y);
-              e = make_float4(a.x, a.y, c2.x, c2.y);
-            }
-          }
-          v[j].x += e.x; v[j].y += e.y; v[j].z += e.z; v[j].w += e.w;
-          finish_unit(p, pix, o64, v[j]);
-          live[j] = false;
-          off[j] = 0;
-        }
-      }
-      if (EPI == E_GENERIC) continue;
-      // extra operands: all loads of the batch are in flight before the first use
-      if (EPI == E_RM_F32_RESID) {
-        float4 e[C::UB];
-#pragma unroll
-        for (int j = 0; j < C::UB; ++j) e[j] = live[j] ? *reinterpret_cast<const float4*>(p.resid + off[j]) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int j = 0; j < C::UB; ++j) { v[j].x += e[j].x; v[j].y += e[j].y; v[j].z += e[j].z; v[j].w += e[j].w; }
-      }
-      if (EPI == E_CONV_SKIP) {
-        uint2 e[C::UB];
-#pragma unroll
-        for (int j = 0; j < C::UB; ++j) e[j] = live[j] ? __ldg(reinterpret_cast<const uint2*>(p.skip + off[j])) : make_uint2(0u, 0u);
-#pragma unroll
-        for (int j = 0; j < C::UB; ++j) {
-          const float2 a = unpack_bf16x2(e[j].x), b = unpack_bf16x2(e[j].y);
-          v[j].x += a.x; v[j].y += a.y; v[j].z += b.x; v[j].w += b.y;
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < C::UB; ++j) {
-        if (kF32) {
-          if (live[j]) *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off[j]) = v[j];
         } else {
-          // GELU variants all store bf16: the activation is evaluated pairwise in half2 (common.cuh: gelu4_to_bf16)
-          uint2 o = kGelu ? gelu4_to_bf16(v[j]) : make_uint2(pack_bf16x2(v[j].x, v[j].y), pack_bf16x2(v[j].z, v[j].w));
-          if (kConv) {
-            const int rr = ((ub * C::UB + j) * 32 + lane) / C::UPR;
-            if ((halo_mask >> rr) & 1u) o = make_uint2(0u, 0u);
-          }
-          if (live[j]) *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off[j]) = o;
+          live[j] = rr < rows_valid;
+          off[j] = (uint32_t)(mrow0 + rr) * ldo + (uint32_t)n;
         }
       }
+      if constexpr (EPI == E_RM_F32_RESID) {
+        float4 e[UPR];
+#pragma unroll
+        for (int j = 0; j < UPR; ++j) e[j] = live[j] ? *reinterpret_cast<const float4*>(p.resid + off[j]) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < UPR; ++j) {
+          v[j].x = __float_as_uint(__uint_as_float(v[j].x) + e[j].x); v[j].y = __float_as_uint(__uint_as_float(v[j].y) + e[j].y);
+          v[j].z = __float_as_uint(__uint_as_float(v[j].z) + e[j].z); v[j].w = __float_as_uint(__uint_as_float(v[j].w) + e[j].w);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < UPR; ++j) {
+        if (live[j]) {
+          if constexpr (kF32) *reinterpret_cast<uint4*>(reinterpret_cast<float*>(p.out) + off[j]) = v[j];
+          else *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off[j]) = v[j];
+        }
+      }
+      __syncwarp();
     }
-    __syncwarp();
   }
 }
 
 // ------------------------------------------------------------------------------------------------ kernel
 template <int BN, int MODE>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__((Cfg<BN, MODE>::THREADS), 1)
 gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmS, const Problem p, int tiles_m, int tiles_n, int epi) {
   using C = Cfg<BN, MODE>;
@@ -434,7 +381,7 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < C::kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&full[C::kStages + i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], C::EPI_WARPS / 2); }
     mbar_init(res_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
@@ -595,30 +542,53 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
     }
   } else if (warp >= 4) {
-    // ===== epilogue: warp w reads TMEM lanes 32*(w%4).. (hardware rule), group g = (w-4)/4 owns accumulator buffer g =====
-    const int q = warp & 3, grp = (warp - 4) >> 2;
-    unsigned char* stg = smem_stg + (warp - 4) * C::STG_WARP_BYTES;
-    float* sbias = reinterpret_cast<float*>(stg + 32 * C::STG_PITCH);
-    int it = 0;
+    // ===== epilogue: warp w may only read TMEM lanes 32*(w%4).. (hardware rule).  e = w-4: bit 2 selects the accumulator
+    // buffer (even / odd tiles of this CTA), bit 3 the column half of the tile =====
+    const int e = warp - 4;
+    const int q = warp & 3, grp = (e >> 2) & 1, half = e >> 3;
+    const uint32_t stg_s = smem_u32(smem_stg + e * C::STG_WARP_BYTES);
+    const uint32_t bias_s = stg_s + 32 * C::STG_PITCH;
+    const int slab_begin = half ? C::SLAB_SPLIT : 0, slab_end = half ? C::NSLAB : C::SLAB_SPLIT;
+    const int ncols = (slab_end - slab_begin) * C::SC;
+    int it = 0, bias_n0 = -1;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       if ((it & 1) != grp) continue;
       const uint32_t as = it & 1, aphase = (it >> 1) & 1;
-      const int m0 = (tile / tiles_n) * BLOCK_M, n0 = (tile % tiles_n) * BN;
-      // this tile's bias slice -> smem (private to the warp), issued before waiting for the accumulator
-      for (int i = lane; i < BN; i += 32) sbias[i] = (p.bias != nullptr) ? __ldg(p.bias + n0 + i) : 0.0f;
+      const int tm = tile / tiles_n;
+      const int m0 = tm * BLOCK_M, n0 = (tile - tm * tiles_n) * BN;
+      // this warp's bias slice -> smem (private to the warp), fetched before waiting for the accumulator and only when
+      // the tile column changed (never again for N == BN, i.e. every conv layer)
+      if (n0 != bias_n0) {
+        bias_n0 = n0;
+        float b[(C::SLAB_SPLIT * C::SC + 31) / 32];
+#pragma unroll
+        for (int k = 0; k < (C::SLAB_SPLIT * C::SC + 31) / 32; ++k) {
+          const int i = k * 32 + lane;
+          b[k] = (p.bias != nullptr && i < ncols) ? __ldg(p.bias + n0 + slab_begin * C::SC + i) : 0.0f;
+        }
+        __syncwarp();                                     // the previous tile's readers are done
+#pragma unroll
+        for (int k = 0; k < (C::SLAB_SPLIT * C::SC + 31) / 32; ++k) {
+          const int i = k * 32 + lane;
+          if (i < ncols) asm volatile("st.shared.f32 [%0], %1;\n" ::"r"(bias_s + 4u * i), "f"(b[k]) : "memory");
+        }
+        __syncwarp();
+      }
       mbar_wait(&tmem_full[as], aphase);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
       // one specialised instruction stream per fused epilogue (the switch is per tile, the loops inside are branch-free)
+#define MSD_EPI_CASE(E) case E: epilogue_tile<BN, E>(p, stg_s, bias_s, taddr, &tmem_empty[as], m0 + q * 32, n0, lane, slab_begin, slab_end); break;
       switch (epi) {
-        case E_RM_F32:        epilogue_tile<BN, E_RM_F32>(p, stg, sbias, taddr, &tmem_empty[as], m0 + q * 32, n0, lane); break;
-        case E_RM_BF16:       epilogue_tile<BN, E_RM_BF16>(p, stg, sbias, taddr, &tmem_empty[as], m0 + q * 32, n0, lane); break;
-        case E_RM_BF16_GELU:  epilogue_tile<BN, E_RM_BF16_GELU>(p, stg, sbias, taddr, &tmem_empty[as], m0 + q * 32, n0, lane); break;
-        case E_RM_F32_RESID:  epilogue_tile<BN, E_RM_F32_RESID>(p, stg, sbias, taddr, &tmem_empty[as], m0 + q * 32, n0, lane); break;
-        case E_CONV:          epilogue_tile<BN, E_CONV>(p, stg, sbias, taddr, &tmem_empty[as], m0 + q * 32, n0, lane); break;
-        case E_CONVT:         epilogue_tile<BN, E_CONVT>(p, stg, sbias, taddr, &tmem_empty[as], m0 + q * 32, n0, lane); break;
-        default:              epilogue_tile<BN, E_GENERIC>(p, stg, sbias, taddr, &tmem_empty[as], m0 + q * 32, n0, lane); break;
+        MSD_EPI_CASE(E_RM_F32)
+        MSD_EPI_CASE(E_RM_BF16)
+        MSD_EPI_CASE(E_RM_BF16_GELU)
+        MSD_EPI_CASE(E_RM_F32_RESID)
+        MSD_EPI_CASE(E_CONV)
+        MSD_EPI_CASE(E_CONVT)
+        default: epilogue_tile<BN, E_GENERIC>(p, stg_s, bias_s, taddr, &tmem_empty[as], m0 + q * 32, n0, lane, slab_begin, slab_end); break;
       }
+#undef MSD_EPI_CASE
     }
   }
   tcgen05_fence_before();
@@ -655,7 +625,7 @@ int launch_mode(const Problem& p, cudaStream_t s) {
   const int tiles_m = (p.M + BLOCK_M - 1) / BLOCK_M, tiles_n = p.N / BN;
   const int tiles = tiles_m * tiles_n;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_tc5_kernel<BN, MODE><<<grid, kThreads, C::SMEM_BYTES, s>>>(tmA, tmB, tmS, p, tiles_m, tiles_n, classify(p));
+  gemm_tc5_kernel<BN, MODE><<<grid, C::THREADS, C::SMEM_BYTES, s>>>(tmA, tmB, tmS, p, tiles_m, tiles_n, classify(p));
   MSD_LAUNCH_CHECK();
   return MSD_OK;
 }
