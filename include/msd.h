@@ -187,6 +187,19 @@ int msd_patchify_bf16(const float* d_x, void* d_a, int B, int C, int S, int P, v
 int msd_head1x1_nchw_f32(const void* d_x, const float* d_w, const float* d_b, float* d_y, int B, int H, int W, int Cin,
                          int Cout, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------
+ * Weight-gradient contractions of the training step (what autograd computes for nn.Linear / nn.Conv2d in the reference's
+ * Trainer.train_epoch, src/training/trainer.py:141-146 -> loss.backward()).  Both ACCUMULATE into fp32 outputs the
+ * caller zeroed (the contraction is split across CTAs and merged with fp32 atomics).
+ *   linear : d_dw[out_f, in_f] (row pitch ldo) += dY[rows, out_f]^T . X[rows, in_f]          (bf16 operands)
+ *   conv3x3: x [B,H+2,W+2,Cin], dc [B,H+2,W+2,Cout] haloed NHWC bf16, halo rows of dc zero;
+ *            d_dw[9][cinpad][ldo] (tap = ky*3+kx major) += sum_p x[p + off_tap, ci] . dc[p, co]
+ * ------------------------------------------------------------------------------------------------- */
+int msd_wgrad_linear_bf16(const void* d_dy, int ld_dy, const void* d_x, int ld_x, float* d_dw, int ldo, long long rows,
+                          int out_f, int in_f, void* stream);
+int msd_wgrad_conv3x3_bf16(const void* d_x, const void* d_dc, float* d_dw, int B, int H, int W, int Cin, int Cout, int cinpad,
+                           int ldo, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

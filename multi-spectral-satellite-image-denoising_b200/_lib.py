@@ -78,6 +78,10 @@ SIGNATURES = {
     "msd_patchify_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "msd_head1x1_nchw_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                      c_void_p]),
+    "msd_wgrad_linear_bf16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, C.c_longlong, c_int, c_int,
+                                      c_void_p]),
+    "msd_wgrad_conv3x3_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                       c_void_p]),
 }
 
 _lib = None

@@ -101,13 +101,14 @@ int launch_layernorm(float* x, const float* g, const float* b, float eps, __nv_b
 // head 1x1 conv: haloed NHWC bf16 [B,H+2,W+2,Cin] -> NCHW fp32 [B,Cout,H,W]; one thread per pixel,
 // weights [Cout,Cin] fp32 broadcast from smem.  Cin <= 64, Cout <= 16.
 // ---------------------------------------------------------------------------------------------------
+template <int CIN, int COUT>   // compile-time upper bounds of Cin (multiple of 8) / Cout: <48,13> is the reference model
 __global__ void __launch_bounds__(256) head1x1_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
                                                       const float* __restrict__ bias, float* __restrict__ y, int B, int H,
                                                       int W, int Cin, int Cout) {
-  __shared__ float sw[16 * 64];
+  __shared__ __align__(16) float sw[COUT * CIN];
   __shared__ float sb[16];
   for (int i = threadIdx.x; i < Cout * Cin; i += 256) sw[i] = w[i];
-  if (threadIdx.x < Cout) sb[threadIdx.x] = bias[threadIdx.x];
+  if (threadIdx.x < 16) sb[threadIdx.x] = threadIdx.x < Cout ? bias[threadIdx.x] : 0.0f;
   __syncthreads();
   const size_t npix = (size_t)B * H * W;
   for (size_t p = (size_t)blockIdx.x * 256 + threadIdx.x; p < npix; p += (size_t)gridDim.x * 256) {
@@ -115,9 +116,9 @@ __global__ void __launch_bounds__(256) head1x1_kernel(const __nv_bfloat16* __res
     const int rem = (int)(p - (size_t)b * H * W);
     const int yy = rem / W, xx = rem - yy * W;
     const __nv_bfloat16* src = x + (((size_t)b * (H + 2) + (yy + 1)) * (W + 2) + (xx + 1)) * Cin;
-    float in[64];
+    float in[CIN];
 #pragma unroll
-    for (int c8 = 0; c8 < 8; ++c8) {
+    for (int c8 = 0; c8 < CIN / 8; ++c8) {
       if (c8 * 8 < Cin) {
         const uint4 u = __ldg(reinterpret_cast<const uint4*>(src + c8 * 8));
         float2 f;
@@ -127,13 +128,25 @@ __global__ void __launch_bounds__(256) head1x1_kernel(const __nv_bfloat16* __res
         f = unpack_bf16x2(u.w); in[c8 * 8 + 6] = f.x; in[c8 * 8 + 7] = f.y;
       }
     }
-    for (int o = 0; o < Cout; ++o) {
-      float acc = sb[o];
+    // weights are read as broadcast 128-bit shared loads (one per 4 FMAs): the FMA pipe, not the LSU, sets the pace
+    float acc[COUT];
 #pragma unroll
-      for (int c = 0; c < 64; ++c)
-        if (c < Cin) acc = fmaf(in[c], sw[o * Cin + c], acc);
-      y[(((size_t)b * Cout + o) * H + yy) * W + xx] = acc;
+    for (int o = 0; o < COUT; ++o) acc[o] = sb[o];
+#pragma unroll
+    for (int c4 = 0; c4 < CIN / 4; ++c4) {
+      if (c4 * 4 < Cin) {
+#pragma unroll
+        for (int o = 0; o < COUT; ++o) {
+          if (o < Cout) {
+            const float4 w4 = *reinterpret_cast<const float4*>(&sw[o * Cin + c4 * 4]);
+            acc[o] = fmaf(in[c4 * 4 + 3], w4.w, fmaf(in[c4 * 4 + 2], w4.z, fmaf(in[c4 * 4 + 1], w4.y, fmaf(in[c4 * 4], w4.x, acc[o]))));
+          }
+        }
+      }
     }
+#pragma unroll
+    for (int o = 0; o < COUT; ++o)
+      if (o < Cout) y[(((size_t)b * Cout + o) * H + yy) * W + xx] = acc[o];
   }
 }
 
@@ -170,7 +183,10 @@ extern "C" int msd_head1x1_nchw_f32(const void* d_x, const float* d_w, const flo
   MSD_REQUIRE(Cin % 8 == 0 && Cin <= 64 && Cout <= 16 && Cout > 0, "head1x1: Cin=%d (<=64, %%8) Cout=%d (<=16)", Cin, Cout);
   const size_t npix = (size_t)B * H * W;
   const unsigned blocks = (unsigned)((npix + 255) / 256 < 148u * 8u ? (npix + 255) / 256 : 148u * 8u);
-  head1x1_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(d_x), d_w, d_b, d_y, B, H, W, Cin, Cout);
+  if (Cin == 48 && Cout == 13)
+    head1x1_kernel<48, 13><<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(d_x), d_w, d_b, d_y, B, H, W, Cin, Cout);
+  else
+    head1x1_kernel<64, 16><<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(d_x), d_w, d_b, d_y, B, H, W, Cin, Cout);
   MSD_LAUNCH_CHECK();
   return MSD_OK;
 }
