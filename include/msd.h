@@ -200,6 +200,38 @@ int msd_wgrad_linear_bf16(const void* d_dy, int ld_dy, const void* d_x, int ld_x
 int msd_wgrad_conv3x3_bf16(const void* d_x, const void* d_dc, float* d_dw, int B, int H, int W, int Cin, int Cout, int cinpad,
                            int ldo, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------
+ * Bandwidth-bound pieces of the training step (csrc/train_kernels.cu, attention_bwd.cu), exported so the tests can pin
+ * each against torch autograd.  Layouts as in the forward: decoder tensors are haloed NHWC bf16 [B,H+2,W+2,C].
+ * ------------------------------------------------------------------------------------------------- */
+/* d_sums fp64 [C] = column sums of a bf16 [rows, C] matrix (bias gradients); msd_f64_to_f32 converts the result. */
+int msd_colsum_bf16(const void* d_a, long long rows, int C, double* d_sums, void* stream);
+int msd_f64_to_f32(const double* d_in, float* d_out, int n, void* stream);
+/* nn.BatchNorm2d in training mode (blocks.py:69, 84, 117; decoder.py:78) over a raw conv output c (halo rows zero):
+ * d_stats fp32 [4][C] = {gamma*rstd, beta - mean*gamma*rstd, mean, rstd}; running stats updated in place; d_sums fp64 [2][C] scratch */
+int msd_bn_stats_bf16(const void* d_c, int B, int H, int W, int C, const float* d_gamma, const float* d_beta, float eps,
+                      float momentum, float* d_running_mean, float* d_running_var, float* d_stats, double* d_sums, void* stream);
+/* y = GELU(BN(c) [+ skip]) on interior pixels, zero halo */
+int msd_bn_act_fwd_bf16(const void* d_c, const void* d_skip, const float* d_stats, void* d_y, int B, int H, int W, int C, void* stream);
+/* backward of the above: d_dz = grad of the pre-activation (= grad of the skip input), d_dc = grad of c (may alias d_dz),
+ * d_dgamma / d_dbeta fp32 [C] (overwritten; NULL to skip), d_coef fp32 [2][C] and d_sums fp64 [2][C] scratch */
+int msd_bn_act_bwd_bf16(const void* d_dy, const void* d_c, const void* d_skip, const float* d_stats, void* d_dz, void* d_dc,
+                        float* d_dgamma, float* d_dbeta, float* d_coef, double* d_sums, int B, int H, int W, int C, void* stream);
+/* d_out = d_dh * gelu'(d_hpre), n bf16 elements (n % 8 == 0), in place allowed */
+int msd_gelu_bwd_bf16(const void* d_dh, const void* d_hpre, void* d_out, long long n, void* stream);
+/* LayerNorm backward over [M, D=768]: d_dy bf16 (or fp32 when dy_is_f32), d_x fp32 LN input; d_g fp32 [M,D] = (accumulate ?
+ * d_g : 0) + dx; optional bf16 copy of d_g; d_dgamma / d_dbeta fp32 [D] ACCUMULATED into (NULL for frozen layers) */
+int msd_layernorm_bwd(const void* d_dy, int dy_is_f32, const float* d_x, const float* d_gamma, float eps, float* d_g, int accumulate,
+                      void* d_g_bf16, float* d_dgamma, float* d_dbeta, int M, int D, void* stream);
+/* ConvTranspose2d k2 s2 backward gather: d_dy haloed [B,2Hin+2,2Win+2,C] -> d_dys [rows_in, 4*C] (q = di*2+dj major) */
+int msd_convt_unshuffle_bf16(const void* d_dy, void* d_dys, int B, int Hin, int Win, int in_padded, int C, void* stream);
+/* head 1x1 backward: d_dy fp32 NCHW -> d_dh bf16 haloed [B,H+2,W+2,Cin] and d_dyt bf16 [rows,16] (dy on the pixel list) */
+int msd_head1x1_bwd(const float* d_dy, const float* d_w, void* d_dh, void* d_dyt, int B, int H, int W, int Cin, int Cout, void* stream);
+/* d_out[i] = sum_b d_in[b*n + i] */
+int msd_batch_sum_f32(const float* d_in, float* d_out, int B, long long n, void* stream);
+/* attention backward: d_dqkv bf16 [B*T, 3*heads*64] from qkv and the gradient of the attention output */
+int msd_attention_bwd_bf16(const void* d_qkv, const void* d_dout, void* d_dqkv, int B, int T, int heads, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -80,6 +80,20 @@ SIGNATURES = {
                                      c_void_p]),
     "msd_wgrad_linear_bf16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, C.c_longlong, c_int, c_int,
                                       c_void_p]),
+    "msd_colsum_bf16": (c_int, [c_void_p, C.c_longlong, c_int, c_void_p, c_void_p]),
+    "msd_f64_to_f32": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
+    "msd_bn_stats_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_float, c_void_p,
+                                  c_void_p, c_void_p, c_void_p, c_void_p]),
+    "msd_bn_act_fwd_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "msd_bn_act_bwd_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                    c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "msd_gelu_bwd_bf16": (c_int, [c_void_p, c_void_p, c_void_p, C.c_longlong, c_void_p]),
+    "msd_layernorm_bwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_float, c_void_p, c_int, c_void_p, c_void_p,
+                                  c_void_p, c_int, c_int, c_void_p]),
+    "msd_convt_unshuffle_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "msd_head1x1_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "msd_batch_sum_f32": (c_int, [c_void_p, c_void_p, c_int, C.c_longlong, c_void_p]),
+    "msd_attention_bwd_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "msd_wgrad_conv3x3_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                        c_void_p]),
 }

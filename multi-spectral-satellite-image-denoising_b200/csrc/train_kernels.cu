@@ -1,0 +1,565 @@
+// Bandwidth-bound kernels of the training step (everything around the tensor-core GEMMs): training-mode BatchNorm
+// (batch statistics, reference blocks.py:66-72 / 113-118 nn.BatchNorm2d in .train()), its backward, LayerNorm backward,
+// GELU backward, bias gradients (column sums), the pixel un-shuffle of the ConvTranspose backward, the head 1x1 backward
+// and the positional-embedding gradient.  Each makes one pass over its operands with 128-bit accesses; per-channel sums
+// are accumulated in registers, reduced per block in shared memory and merged with fp64 / fp32 atomics.
+//
+// Layout conventions (see model.cu): decoder activations are NHWC bf16 [B, H+2, W+2, C] with a zero 1-pixel halo,
+// "rows" = padded pixels; encoder activations are [tokens, features].
+#include "common.cuh"
+
+namespace {
+
+constexpr int kBlock = 256;
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  float2 t;
+  t = unpack_bf16x2(u.x); f[0] = t.x; f[1] = t.y;
+  t = unpack_bf16x2(u.y); f[2] = t.x; f[3] = t.y;
+  t = unpack_bf16x2(u.z); f[4] = t.x; f[5] = t.y;
+  t = unpack_bf16x2(u.w); f[6] = t.x; f[7] = t.y;
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+}
+// exact-erf GELU and its derivative (nn.GELU() default): gelu'(z) = Phi(z) + z phi(z)
+__device__ __forceinline__ float gelu_fwd(float z) { return 0.5f * z * (1.0f + erff(z * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_grad(float z) {
+  return 0.5f * (1.0f + erff(z * 0.70710678118654752f)) + z * 0.3989422804014327f * __expf(-0.5f * z * z);
+}
+__device__ __forceinline__ bool interior_row(uint32_t p, const FastDiv& plane, const FastDiv& pitch, int H, int W) {
+  uint32_t img, rem, yy, xx;
+  fd_divmod(p, plane, img, rem);
+  fd_divmod(rem, pitch, yy, xx);
+  return yy >= 1 && yy <= (uint32_t)H && xx >= 1 && xx <= (uint32_t)W;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Per-column sums over the rows of a bf16 [rows, C] matrix:  NS = 1: sum a;  NS = 2: sum a, sum a*a;
+// with a second matrix b and per-channel (mean, rstd): sum a, sum a * (b - mean) * rstd     (BatchNorm backward)
+// Thread t owns the 8-channel vector t % VPR of rows t / VPR, t / VPR + RPI, ...; block partials -> fp64 atomics.
+// ---------------------------------------------------------------------------------------------------
+template <int MODE>   // 0: sum a | 1: sum a, sum a^2 | 2: sum a, sum a*xhat(b)
+__global__ void __launch_bounds__(kBlock) colsum_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
+                                                        const float* __restrict__ stats /* [4][C]: .., .., mean, rstd */,
+                                                        double* __restrict__ sums /* [2][C] */, long long rows, int C, int ld) {
+  extern __shared__ float sh[];   // [2][kBlock][8]
+  const int vpr = C >> 3;
+  const int rpi = kBlock / vpr;
+  const int v = threadIdx.x % vpr, r0 = threadIdx.x / vpr;
+  float s1[8], s2[8], mean[8], rstd[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { s1[i] = 0.f; s2[i] = 0.f; mean[i] = 0.f; rstd[i] = 1.f; }
+  if (MODE == 2 && r0 < rpi) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { mean[i] = stats[2 * C + v * 8 + i]; rstd[i] = stats[3 * C + v * 8 + i]; }
+  }
+  if (r0 < rpi) {
+    for (long long row = (long long)blockIdx.x * rpi + r0; row < rows; row += (long long)gridDim.x * rpi) {
+      float fa[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(a + row * ld + v * 8)), fa);
+      if (MODE == 2) {
+        float fb[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(b + row * ld + v * 8)), fb);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s1[i] += fa[i]; s2[i] = fmaf(fa[i], (fb[i] - mean[i]) * rstd[i], s2[i]); }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s1[i] += fa[i]; if (MODE == 1) s2[i] = fmaf(fa[i], fa[i], s2[i]); }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { sh[threadIdx.x * 8 + i] = s1[i]; sh[(kBlock + threadIdx.x) * 8 + i] = s2[i]; }
+  __syncthreads();
+  // thread (v, i) of the first C threads folds the rpi row-groups
+  for (int c = threadIdx.x; c < C; c += kBlock) {
+    const int vv = c >> 3, ii = c & 7;
+    double t1 = 0.0, t2 = 0.0;
+    for (int g = 0; g < rpi; ++g) {
+      t1 += sh[(g * vpr + vv) * 8 + ii];
+      t2 += sh[(kBlock + g * vpr + vv) * 8 + ii];
+    }
+    atomicAdd(&sums[c], t1);
+    if (MODE != 0) atomicAdd(&sums[C + c], t2);
+  }
+}
+
+// BatchNorm finalize (training): batch mean / biased variance -> scale, shift, mean, rstd; running statistics are
+// updated in place with momentum (unbiased variance), as nn.BatchNorm2d does.
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, double count, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float eps, float momentum, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var, float* __restrict__ stats, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double mean = sums[c] / count;
+  double var = sums[C + c] / count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float sc = gamma[c] * rstd;
+  stats[c] = sc;
+  stats[C + c] = beta[c] - (float)mean * sc;
+  stats[2 * C + c] = (float)mean;
+  stats[3 * C + c] = rstd;
+  if (running_mean != nullptr) {
+    running_mean[c] = (1.0f - momentum) * running_mean[c] + momentum * (float)mean;
+    running_var[c] = (1.0f - momentum) * running_var[c] + momentum * (float)(var * count / (count > 1.0 ? count - 1.0 : 1.0));
+  }
+}
+
+// y = GELU(scale * c + shift [+ skip]) on interior pixels, 0 on the halo
+__global__ void __launch_bounds__(kBlock) bn_act_fwd_kernel(const __nv_bfloat16* __restrict__ c, const __nv_bfloat16* __restrict__ skip,
+                                                            const float* __restrict__ stats, __nv_bfloat16* __restrict__ y,
+                                                            long long rows, int C, FastDiv plane, FastDiv pitch, int H, int W) {
+  const int vpr = C >> 3;
+  const long long total = rows * vpr;
+  for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < total; i += (long long)gridDim.x * kBlock) {
+    const long long row = i / vpr;
+    const int v = (int)(i - row * vpr);
+    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+    if (interior_row((uint32_t)row, plane, pitch, H, W)) {
+      float f[8], s[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(c + row * C + v * 8)), f);
+      if (skip != nullptr) unpack8(__ldg(reinterpret_cast<const uint4*>(skip + row * C + v * 8)), s);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float z = fmaf(f[k], __ldg(stats + v * 8 + k), __ldg(stats + C + v * 8 + k));
+        if (skip != nullptr) z += s[k];
+        f[k] = gelu_fwd(z);
+      }
+      o = pack8(f);
+    }
+    *reinterpret_cast<uint4*>(y + row * C + v * 8) = o;
+  }
+}
+
+// BatchNorm + GELU backward, pass 1: dz = dy * gelu'(scale c + shift [+ skip]) (0 on the halo), written as bf16, and the
+// per-channel sums  sum dz,  sum dz * xhat  are accumulated
+__global__ void __launch_bounds__(kBlock) bn_act_bwd1_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ c,
+                                                             const __nv_bfloat16* __restrict__ skip, const float* __restrict__ stats,
+                                                             __nv_bfloat16* __restrict__ dz, double* __restrict__ sums, long long rows,
+                                                             int C, FastDiv plane, FastDiv pitch, int H, int W) {
+  extern __shared__ float sh[];
+  const int vpr = C >> 3;
+  const int rpi = kBlock / vpr;
+  const int v = threadIdx.x % vpr, r0 = threadIdx.x / vpr;
+  float s1[8], s2[8], sc[8], sf[8], mean[8], rstd[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { s1[i] = 0.f; s2[i] = 0.f; sc[i] = sf[i] = mean[i] = 0.f; rstd[i] = 1.f; }
+  if (r0 < rpi) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      sc[i] = stats[v * 8 + i]; sf[i] = stats[C + v * 8 + i]; mean[i] = stats[2 * C + v * 8 + i]; rstd[i] = stats[3 * C + v * 8 + i];
+    }
+    for (long long row = (long long)blockIdx.x * rpi + r0; row < rows; row += (long long)gridDim.x * rpi) {
+      uint4 o = make_uint4(0u, 0u, 0u, 0u);
+      if (interior_row((uint32_t)row, plane, pitch, H, W)) {
+        float g[8], f[8], s[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(dy + row * C + v * 8)), g);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(c + row * C + v * 8)), f);
+        if (skip != nullptr) unpack8(__ldg(reinterpret_cast<const uint4*>(skip + row * C + v * 8)), s);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          float z = fmaf(f[k], sc[k], sf[k]);
+          if (skip != nullptr) z += s[k];
+          const float d = g[k] * gelu_grad(z);
+          g[k] = d;
+          s1[k] += d;
+          s2[k] = fmaf(d, (f[k] - mean[k]) * rstd[k], s2[k]);
+        }
+        o = pack8(g);
+      }
+      *reinterpret_cast<uint4*>(dz + row * C + v * 8) = o;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { sh[threadIdx.x * 8 + i] = s1[i]; sh[(kBlock + threadIdx.x) * 8 + i] = s2[i]; }
+  __syncthreads();
+  for (int ch = threadIdx.x; ch < C; ch += kBlock) {
+    const int vv = ch >> 3, ii = ch & 7;
+    double t1 = 0.0, t2 = 0.0;
+    for (int g = 0; g < rpi; ++g) {
+      t1 += sh[(g * vpr + vv) * 8 + ii];
+      t2 += sh[(kBlock + g * vpr + vv) * 8 + ii];
+    }
+    atomicAdd(&sums[ch], t1);
+    atomicAdd(&sums[C + ch], t2);
+  }
+}
+
+// BatchNorm backward finalize: dgamma = sum dz*xhat, dbeta = sum dz, coefficients k1 = sum dz / N, k2 = sum dz*xhat / N
+__global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums, double count, float* __restrict__ dgamma,
+                                       float* __restrict__ dbeta, float* __restrict__ coef, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  if (dgamma != nullptr) dgamma[c] = (float)sums[C + c];
+  if (dbeta != nullptr) dbeta[c] = (float)sums[c];
+  coef[c] = (float)(sums[c] / count);
+  coef[C + c] = (float)(sums[C + c] / count);
+}
+
+// pass 2: dc = gamma*rstd * (dz - k1 - xhat * k2) on interior pixels, 0 on the halo
+__global__ void __launch_bounds__(kBlock) bn_act_bwd2_kernel(const __nv_bfloat16* __restrict__ dz, const __nv_bfloat16* __restrict__ c,
+                                                             const float* __restrict__ stats, const float* __restrict__ coef,
+                                                             __nv_bfloat16* __restrict__ dc, long long rows, int C, FastDiv plane,
+                                                             FastDiv pitch, int H, int W) {
+  const int vpr = C >> 3;
+  const long long total = rows * vpr;
+  for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < total; i += (long long)gridDim.x * kBlock) {
+    const long long row = i / vpr;
+    const int v = (int)(i - row * vpr);
+    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+    if (interior_row((uint32_t)row, plane, pitch, H, W)) {
+      float g[8], f[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(dz + row * C + v * 8)), g);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(c + row * C + v * 8)), f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int ch = v * 8 + k;
+        const float xh = (f[k] - __ldg(stats + 2 * C + ch)) * __ldg(stats + 3 * C + ch);
+        g[k] = __ldg(stats + ch) * (g[k] - __ldg(coef + ch) - xh * __ldg(coef + C + ch));
+      }
+      o = pack8(g);
+    }
+    *reinterpret_cast<uint4*>(dc + row * C + v * 8) = o;
+  }
+}
+
+// fp64 [n] -> fp32 [n] (bias gradients out of the column-sum accumulators)
+__global__ void f64_to_f32_kernel(const double* __restrict__ in, float* __restrict__ out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (float)in[i];
+}
+
+// dh_pre = dh * gelu'(h_pre), bf16 elementwise (in place allowed)
+__global__ void __launch_bounds__(kBlock) gelu_bwd_kernel(const __nv_bfloat16* __restrict__ dh, const __nv_bfloat16* __restrict__ hpre,
+                                                          __nv_bfloat16* __restrict__ out, long long nvec) {
+  for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < nvec; i += (long long)gridDim.x * kBlock) {
+    float g[8], z[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(dh) + i), g);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(hpre) + i), z);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) g[k] *= gelu_grad(z[k]);
+    reinterpret_cast<uint4*>(out)[i] = pack8(g);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// LayerNorm backward, one warp per row (D = 32 * 4 * NV):
+//   dxh = dy * gamma;  dx = rstd * (dxh - mean(dxh) - xhat * mean(dxh * xhat));  dgamma += dy * xhat;  dbeta += dy
+// dy is bf16 (GRAD_F32 = 0) or fp32.  g_out fp32 (+= when `accumulate`), optional bf16 copy of the result.
+// ---------------------------------------------------------------------------------------------------
+template <int NV, int GRAD_F32>
+__global__ void __launch_bounds__(kBlock) ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x,
+                                                        const float* __restrict__ gamma, float eps, float* __restrict__ g_out,
+                                                        int accumulate, __nv_bfloat16* __restrict__ g_bf16,
+                                                        float* __restrict__ dgamma, float* __restrict__ dbeta, int M) {
+  constexpr int D = 128 * NV;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float gam[NV][4], dg[NV][4], db[NV][4];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const float4 t = *reinterpret_cast<const float4*>(gamma + (v * 32 + lane) * 4);
+    gam[v][0] = t.x; gam[v][1] = t.y; gam[v][2] = t.z; gam[v][3] = t.w;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) dg[v][k] = db[v][k] = 0.f;
+  }
+  for (int row = blockIdx.x * (kBlock / 32) + warp; row < M; row += gridDim.x * (kBlock / 32)) {
+    float xv[NV][4], dyv[NV][4];
+    float s = 0.f;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const float4 t = *reinterpret_cast<const float4*>(x + (size_t)row * D + (v * 32 + lane) * 4);
+      xv[v][0] = t.x; xv[v][1] = t.y; xv[v][2] = t.z; xv[v][3] = t.w;
+      s += t.x + t.y + t.z + t.w;
+      if (GRAD_F32) {
+        const float4 u = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dy_) + (size_t)row * D + (v * 32 + lane) * 4);
+        dyv[v][0] = u.x; dyv[v][1] = u.y; dyv[v][2] = u.z; dyv[v][3] = u.w;
+      } else {
+        const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(dy_) + (size_t)row * D + (v * 32 + lane) * 4);
+        const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+        dyv[v][0] = a.x; dyv[v][1] = a.y; dyv[v][2] = b.x; dyv[v][3] = b.y;
+      }
+    }
+    const float mean = warp_sum(s) * (1.0f / D);
+    float var = 0.f;
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { xv[v][k] -= mean; var = fmaf(xv[v][k], xv[v][k], var); }
+    const float rstd = rsqrtf(warp_sum(var) * (1.0f / D) + eps);
+    float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        xv[v][k] *= rstd;                       // xhat
+        const float dxh = dyv[v][k] * gam[v][k];
+        m1 += dxh;
+        m2 = fmaf(dxh, xv[v][k], m2);
+        dg[v][k] = fmaf(dyv[v][k], xv[v][k], dg[v][k]);
+        db[v][k] += dyv[v][k];
+      }
+    m1 = warp_sum(m1) * (1.0f / D);
+    m2 = warp_sum(m2) * (1.0f / D);
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      float o[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) o[k] = rstd * (dyv[v][k] * gam[v][k] - m1 - xv[v][k] * m2);
+      float* gp = g_out + (size_t)row * D + (v * 32 + lane) * 4;
+      if (accumulate) {
+        const float4 t = *reinterpret_cast<const float4*>(gp);
+        o[0] += t.x; o[1] += t.y; o[2] += t.z; o[3] += t.w;
+      }
+      *reinterpret_cast<float4*>(gp) = make_float4(o[0], o[1], o[2], o[3]);
+      if (g_bf16 != nullptr)
+        *reinterpret_cast<uint2*>(g_bf16 + (size_t)row * D + (v * 32 + lane) * 4) = make_uint2(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]));
+    }
+  }
+  if (dgamma == nullptr) return;      // frozen LayerNorm: no parameter gradients
+  // fold the 8 warps of the block (one shared buffer, used for dgamma then dbeta), then one atomic per column per block
+  __shared__ float s_red[kBlock / 32][D];
+#pragma unroll 1
+  for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) s_red[warp][(v * 32 + lane) * 4 + k] = pass == 0 ? dg[v][k] : db[v][k];
+    __syncthreads();
+    for (int c = threadIdx.x; c < D; c += kBlock) {
+      float a = 0.f;
+#pragma unroll
+      for (int w = 0; w < kBlock / 32; ++w) a += s_red[w][c];
+      atomicAdd((pass == 0 ? dgamma : dbeta) + c, a);
+    }
+    __syncthreads();
+  }
+}
+
+// ConvTranspose2d k2 s2 backward gather: dys[m, q*C + o] = dy[outpix(m, q), o] for interior input pixels m, 0 for halo
+// rows (input layout [B, Hin(+2), Win(+2)] pixel list, output haloed [B, 2Hin+2, 2Win+2, C])
+__global__ void __launch_bounds__(kBlock) unshuffle_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dys,
+                                                           long long rows, int C, FastDiv in_plane, FastDiv in_pitch, int in_pad,
+                                                           int Hin, int Win) {
+  const int vpr = C >> 3;
+  const long long total = rows * 4 * vpr;
+  const int out_pitch = 2 * Win + 2;
+  const long long out_plane = (long long)(2 * Hin + 2) * out_pitch;
+  for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < total; i += (long long)gridDim.x * kBlock) {
+    const long long m = i / (4 * vpr);
+    const int rem = (int)(i - m * 4 * vpr);
+    const int q = rem / vpr, v = rem - q * vpr;
+    uint32_t img, r2, yy, xx;
+    fd_divmod((uint32_t)m, in_plane, img, r2);
+    fd_divmod(r2, in_pitch, yy, xx);
+    bool ok = true;
+    if (in_pad) { ok = yy >= 1 && yy <= (uint32_t)Hin && xx >= 1 && xx <= (uint32_t)Win; yy -= 1; xx -= 1; }
+    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+    if (ok) {
+      const long long op = (long long)img * out_plane + (long long)(2 * yy + (q >> 1) + 1) * out_pitch + (2 * xx + (q & 1) + 1);
+      o = __ldg(reinterpret_cast<const uint4*>(dy + op * C + v * 8));
+    }
+    *reinterpret_cast<uint4*>(dys + m * (4 * C) + q * C + v * 8) = o;
+  }
+}
+
+// head 1x1 backward: dy fp32 NCHW [B,Cout,H,W] ->  dh bf16 haloed NHWC [B,H+2,W+2,Cin] = sum_o dy[o] w[o,c] (halo 0)
+// and dyt bf16 [rows, 16] = dy transposed to the pixel list (columns >= Cout and halo rows zero), the operand of the
+// weight / bias gradient contractions.  One thread per padded pixel.
+template <int CIN>
+__global__ void __launch_bounds__(kBlock) head1x1_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ w,
+                                                             __nv_bfloat16* __restrict__ dh, __nv_bfloat16* __restrict__ dyt, int B,
+                                                             int H, int W, int Cin, int Cout) {
+  __shared__ __align__(16) float sw[16 * CIN];
+  for (int i = threadIdx.x; i < 16 * CIN; i += kBlock) sw[i] = (i / CIN < Cout && i % CIN < Cin) ? w[(i / CIN) * Cin + i % CIN] : 0.f;
+  __syncthreads();
+  const long long rows = (long long)B * (H + 2) * (W + 2);
+  for (long long p = (long long)blockIdx.x * kBlock + threadIdx.x; p < rows; p += (long long)gridDim.x * kBlock) {
+    const int b = (int)(p / ((H + 2) * (W + 2)));
+    const int rem = (int)(p - (long long)b * (H + 2) * (W + 2));
+    const int yy = rem / (W + 2), xx = rem - yy * (W + 2);
+    const bool ok = yy >= 1 && yy <= H && xx >= 1 && xx <= W;
+    float g[16];
+#pragma unroll
+    for (int o = 0; o < 16; ++o) g[o] = (ok && o < Cout) ? __ldg(dy + (((size_t)b * Cout + o) * H + (yy - 1)) * W + (xx - 1)) : 0.f;
+    uint4* t = reinterpret_cast<uint4*>(dyt + p * 16);
+    t[0] = make_uint4(pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], g[3]), pack_bf16x2(g[4], g[5]), pack_bf16x2(g[6], g[7]));
+    t[1] = make_uint4(pack_bf16x2(g[8], g[9]), pack_bf16x2(g[10], g[11]), pack_bf16x2(g[12], g[13]), pack_bf16x2(g[14], g[15]));
+#pragma unroll
+    for (int c8 = 0; c8 < CIN / 8; ++c8) {
+      if (c8 * 8 < Cin) {
+        float acc[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+#pragma unroll
+        for (int o = 0; o < 16; ++o) {
+          const float4 w0 = *reinterpret_cast<const float4*>(&sw[o * CIN + c8 * 8]);
+          const float4 w1 = *reinterpret_cast<const float4*>(&sw[o * CIN + c8 * 8 + 4]);
+          acc[0] = fmaf(g[o], w0.x, acc[0]); acc[1] = fmaf(g[o], w0.y, acc[1]); acc[2] = fmaf(g[o], w0.z, acc[2]); acc[3] = fmaf(g[o], w0.w, acc[3]);
+          acc[4] = fmaf(g[o], w1.x, acc[4]); acc[5] = fmaf(g[o], w1.y, acc[5]); acc[6] = fmaf(g[o], w1.z, acc[6]); acc[7] = fmaf(g[o], w1.w, acc[7]);
+        }
+        *reinterpret_cast<uint4*>(dh + p * Cin + c8 * 8) = pack8(acc);
+      }
+    }
+  }
+}
+
+// out[i] = sum_b in[b * n + i]   (positional-embedding gradient: sum over the batch)
+__global__ void __launch_bounds__(kBlock) batch_sum_kernel(const float* __restrict__ in, float* __restrict__ out, int B, long long n) {
+  for (long long i = ((long long)blockIdx.x * kBlock + threadIdx.x) * 4; i < n; i += (long long)gridDim.x * kBlock * 4) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int b = 0; b < B; ++b) {
+      const float4 t = *reinterpret_cast<const float4*>(in + (size_t)b * n + i);
+      acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+    }
+    *reinterpret_cast<float4*>(out + i) = acc;
+  }
+}
+
+unsigned grid_for(long long work_items, int per_sm = 8) {
+  const long long blocks = (work_items + kBlock - 1) / kBlock;
+  const long long cap = 148ll * per_sm;
+  return (unsigned)(blocks < 1 ? 1 : blocks < cap ? blocks : cap);
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------- C ABI
+extern "C" int msd_colsum_bf16(const void* d_a, long long rows, int C, double* d_sums, void* stream) {
+  MSD_REQUIRE(d_a && d_sums && rows > 0 && C % 8 == 0, "colsum: bad arguments (C=%d)", C);
+  MSD_CHECK_CUDA(cudaMemsetAsync(d_sums, 0, sizeof(double) * C, (cudaStream_t)stream));
+  for (int c0 = 0; c0 < C; c0 += 2048) {      // 256 threads x 8 channels per pass over the rows
+    const int cc = C - c0 < 2048 ? C - c0 : 2048;
+    const int rpi = kBlock / (cc / 8);
+    colsum_kernel<0><<<grid_for((rows + rpi - 1) / rpi * kBlock, 4), kBlock, 2 * kBlock * 8 * sizeof(float), (cudaStream_t)stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(d_a) + c0, nullptr, nullptr, d_sums + c0, rows, cc, C);
+    MSD_LAUNCH_CHECK();
+  }
+  return MSD_OK;
+}
+
+extern "C" int msd_f64_to_f32(const double* d_in, float* d_out, int n, void* stream) {
+  MSD_REQUIRE(d_in && d_out && n > 0, "f64_to_f32: bad arguments");
+  f64_to_f32_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_in, d_out, n);
+  MSD_LAUNCH_CHECK();
+  return MSD_OK;
+}
+
+// training-mode BatchNorm statistics of a raw conv output c [B,H+2,W+2,C] (halo rows zero): d_stats fp32 [4][C] =
+// {gamma*rstd, beta - mean*gamma*rstd, mean, rstd}; running statistics updated in place (momentum, unbiased variance)
+extern "C" int msd_bn_stats_bf16(const void* d_c, int B, int H, int W, int C, const float* d_gamma, const float* d_beta, float eps,
+                                 float momentum, float* d_running_mean, float* d_running_var, float* d_stats, double* d_sums,
+                                 void* stream) {
+  MSD_REQUIRE(d_c && d_gamma && d_beta && d_stats && d_sums, "bn_stats: null pointer");
+  MSD_REQUIRE(C % 8 == 0 && C / 8 <= kBlock && C <= 1024, "bn_stats: unsupported channel count %d", C);
+  cudaStream_t s = (cudaStream_t)stream;
+  const long long rows = (long long)B * (H + 2) * (W + 2);
+  MSD_CHECK_CUDA(cudaMemsetAsync(d_sums, 0, sizeof(double) * 2 * C, s));
+  const int rpi = kBlock / (C / 8);
+  colsum_kernel<1><<<grid_for((rows + rpi - 1) / rpi * kBlock, 4), kBlock, 2 * kBlock * 8 * sizeof(float), s>>>(
+      reinterpret_cast<const __nv_bfloat16*>(d_c), nullptr, nullptr, d_sums, rows, C, C);
+  MSD_LAUNCH_CHECK();
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(d_sums, (double)B * H * W, d_gamma, d_beta, eps, momentum, d_running_mean,
+                                                      d_running_var, d_stats, C);
+  MSD_LAUNCH_CHECK();
+  return MSD_OK;
+}
+
+extern "C" int msd_bn_act_fwd_bf16(const void* d_c, const void* d_skip, const float* d_stats, void* d_y, int B, int H, int W, int C,
+                                   void* stream) {
+  MSD_REQUIRE(d_c && d_stats && d_y && C % 8 == 0, "bn_act_fwd: bad arguments");
+  const long long rows = (long long)B * (H + 2) * (W + 2);
+  MSD_REQUIRE(rows < (1ll << 31), "bn_act_fwd: too many pixels");
+  bn_act_fwd_kernel<<<grid_for(rows * (C / 8)), kBlock, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(d_c), reinterpret_cast<const __nv_bfloat16*>(d_skip), d_stats,
+      reinterpret_cast<__nv_bfloat16*>(d_y), rows, C, make_fastdiv((uint32_t)((H + 2) * (W + 2))), make_fastdiv((uint32_t)(W + 2)), H, W);
+  MSD_LAUNCH_CHECK();
+  return MSD_OK;
+}
+
+// BatchNorm(train) + GELU backward: d_dy grad of y = GELU(BN(c) [+ skip]); outputs d_dz (grad of the pre-activation: also
+// the gradient of the skip input), d_dc (grad of the raw conv output; may alias d_dz), d_dgamma / d_dbeta fp32 [C].
+extern "C" int msd_bn_act_bwd_bf16(const void* d_dy, const void* d_c, const void* d_skip, const float* d_stats, void* d_dz, void* d_dc,
+                                   float* d_dgamma, float* d_dbeta, float* d_coef, double* d_sums, int B, int H, int W, int C,
+                                   void* stream) {
+  MSD_REQUIRE(d_dy && d_c && d_stats && d_dz && d_dc && d_coef && d_sums, "bn_act_bwd: null pointer");
+  MSD_REQUIRE(C % 8 == 0 && C / 8 <= kBlock, "bn_act_bwd: unsupported channel count %d", C);
+  cudaStream_t s = (cudaStream_t)stream;
+  const long long rows = (long long)B * (H + 2) * (W + 2);
+  MSD_REQUIRE(rows < (1ll << 31), "bn_act_bwd: too many pixels");
+  const FastDiv plane = make_fastdiv((uint32_t)((H + 2) * (W + 2))), pitch = make_fastdiv((uint32_t)(W + 2));
+  MSD_CHECK_CUDA(cudaMemsetAsync(d_sums, 0, sizeof(double) * 2 * C, s));
+  const int rpi = kBlock / (C / 8);
+  bn_act_bwd1_kernel<<<grid_for((rows + rpi - 1) / rpi * kBlock, 4), kBlock, 2 * kBlock * 8 * sizeof(float), s>>>(
+      reinterpret_cast<const __nv_bfloat16*>(d_dy), reinterpret_cast<const __nv_bfloat16*>(d_c),
+      reinterpret_cast<const __nv_bfloat16*>(d_skip), d_stats, reinterpret_cast<__nv_bfloat16*>(d_dz), d_sums, rows, C, plane, pitch, H, W);
+  MSD_LAUNCH_CHECK();
+  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(d_sums, (double)B * H * W, d_dgamma, d_dbeta, d_coef, C);
+  MSD_LAUNCH_CHECK();
+  bn_act_bwd2_kernel<<<grid_for(rows * (C / 8)), kBlock, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(d_dz),
+                                                                 reinterpret_cast<const __nv_bfloat16*>(d_c), d_stats, d_coef,
+                                                                 reinterpret_cast<__nv_bfloat16*>(d_dc), rows, C, plane, pitch, H, W);
+  MSD_LAUNCH_CHECK();
+  return MSD_OK;
+}
+
+extern "C" int msd_gelu_bwd_bf16(const void* d_dh, const void* d_hpre, void* d_out, long long n, void* stream) {
+  MSD_REQUIRE(d_dh && d_hpre && d_out && n > 0 && n % 8 == 0, "gelu_bwd: bad arguments");
+  gelu_bwd_kernel<<<grid_for(n / 8), kBlock, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(d_dh),
+                                                                        reinterpret_cast<const __nv_bfloat16*>(d_hpre),
+                                                                        reinterpret_cast<__nv_bfloat16*>(d_out), n / 8);
+  MSD_LAUNCH_CHECK();
+  return MSD_OK;
+}
+
+// LayerNorm backward over rows of width D (768 in the reference model): see ln_bwd_kernel.  d_dgamma/d_dbeta are
+// ACCUMULATED into (zero them first); NULL skips the parameter gradients (frozen blocks).
+extern "C" int msd_layernorm_bwd(const void* d_dy, int dy_is_f32, const float* d_x, const float* d_gamma, float eps, float* d_g,
+                                 int accumulate, void* d_g_bf16, float* d_dgamma, float* d_dbeta, int M, int D, void* stream) {
+  MSD_REQUIRE(d_dy && d_x && d_gamma && d_g && M > 0, "layernorm_bwd: null pointer");
+  MSD_REQUIRE(D == 768, "layernorm_bwd: only D=768 is built (got %d)", D);
+  MSD_REQUIRE((d_dgamma == nullptr) == (d_dbeta == nullptr), "layernorm_bwd: dgamma and dbeta go together");
+  cudaStream_t s = (cudaStream_t)stream;
+  const unsigned blocks = (unsigned)(M / 8 + 1 < 148 * 2 ? M / 8 + 1 : 148 * 2);
+  if (dy_is_f32)
+    ln_bwd_kernel<6, 1><<<blocks, kBlock, 0, s>>>(d_dy, d_x, d_gamma, eps, d_g, accumulate, reinterpret_cast<__nv_bfloat16*>(d_g_bf16), d_dgamma, d_dbeta, M);
+  else
+    ln_bwd_kernel<6, 0><<<blocks, kBlock, 0, s>>>(d_dy, d_x, d_gamma, eps, d_g, accumulate, reinterpret_cast<__nv_bfloat16*>(d_g_bf16), d_dgamma, d_dbeta, M);
+  MSD_LAUNCH_CHECK();
+  return MSD_OK;
+}
+
+extern "C" int msd_convt_unshuffle_bf16(const void* d_dy, void* d_dys, int B, int Hin, int Win, int in_padded, int C, void* stream) {
+  MSD_REQUIRE(d_dy && d_dys && C % 8 == 0, "unshuffle: bad arguments");
+  const int ph = in_padded ? Hin + 2 : Hin, pw = in_padded ? Win + 2 : Win;
+  const long long rows = (long long)B * ph * pw;
+  MSD_REQUIRE(rows < (1ll << 31), "unshuffle: too many pixels");
+  unshuffle_kernel<<<grid_for(rows * 4 * (C / 8)), kBlock, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(d_dy), reinterpret_cast<__nv_bfloat16*>(d_dys), rows, C,
+      make_fastdiv((uint32_t)(ph * pw)), make_fastdiv((uint32_t)pw), in_padded, Hin, Win);
+  MSD_LAUNCH_CHECK();
+  return MSD_OK;
+}
+
+extern "C" int msd_head1x1_bwd(const float* d_dy, const float* d_w, void* d_dh, void* d_dyt, int B, int H, int W, int Cin, int Cout,
+                               void* stream) {
+  MSD_REQUIRE(d_dy && d_w && d_dh && d_dyt, "head1x1_bwd: null pointer");
+  MSD_REQUIRE(Cin % 8 == 0 && Cin <= 64 && Cout <= 16 && Cout > 0, "head1x1_bwd: Cin=%d (<=64, %%8) Cout=%d (<=16)", Cin, Cout);
+  const long long rows = (long long)B * (H + 2) * (W + 2);
+  if (Cin <= 48)
+    head1x1_bwd_kernel<48><<<grid_for(rows), kBlock, 0, (cudaStream_t)stream>>>(d_dy, d_w, reinterpret_cast<__nv_bfloat16*>(d_dh),
+                                                                               reinterpret_cast<__nv_bfloat16*>(d_dyt), B, H, W, Cin, Cout);
+  else
+    head1x1_bwd_kernel<64><<<grid_for(rows), kBlock, 0, (cudaStream_t)stream>>>(d_dy, d_w, reinterpret_cast<__nv_bfloat16*>(d_dh),
+                                                                               reinterpret_cast<__nv_bfloat16*>(d_dyt), B, H, W, Cin, Cout);
+  MSD_LAUNCH_CHECK();
+  return MSD_OK;
+}
+
+extern "C" int msd_batch_sum_f32(const float* d_in, float* d_out, int B, long long n, void* stream) {
+  MSD_REQUIRE(d_in && d_out && B > 0 && n > 0 && n % 4 == 0, "batch_sum: bad arguments");
+  batch_sum_kernel<<<grid_for(n / 4), kBlock, 0, (cudaStream_t)stream>>>(d_in, d_out, B, n);
+  MSD_LAUNCH_CHECK();
+  return MSD_OK;
+}

@@ -72,3 +72,169 @@ def test_wgrad_conv3x3(B, H, W, cin, cout):
     got = dw.cpu()[:, :cin, :].permute(2, 1, 0).reshape(cout, cin, 3, 3)
     _close(got, ref, 2e-3)
     assert dw[:, cin:, :].abs().max().item() == 0 if cinpad > cin else True
+
+
+# ----------------------------------------------------------------------------------------------- elementwise / reductions
+def _interior(t_halo):
+    return t_halo[:, 1:-1, 1:-1, :]
+
+
+def test_colsum_and_batch_sum():
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(1)
+    for rows, C in [(1000, 48), (5000, 768), (300, 3072), (77, 2304), (4000, 16)]:
+        a = _bf(torch.randn(rows, C, generator=g)).cuda()
+        sums = torch.empty(C, dtype=torch.float64, device="cuda")
+        _lib.check(lib.msd_colsum_bf16(_lib.ptr(a), rows, C, _lib.ptr(sums), _lib.stream_ptr()))
+        ref = a.double().sum(0)
+        assert (sums - ref).abs().max().item() <= 1e-3 * ref.abs().max().item() + 1e-4
+        out = torch.empty(C, device="cuda")
+        _lib.check(lib.msd_f64_to_f32(_lib.ptr(sums), _lib.ptr(out), C, _lib.stream_ptr()))
+        assert torch.equal(out, sums.float())
+    x = torch.randn(5, 144 * 768, generator=g).cuda()
+    out = torch.empty(144 * 768, device="cuda")
+    _lib.check(lib.msd_batch_sum_f32(_lib.ptr(x), _lib.ptr(out), 5, 144 * 768, _lib.stream_ptr()))
+    assert torch.allclose(out, x.sum(0), atol=1e-5)
+
+
+@pytest.mark.parametrize("B,H,W,C,with_skip", [(2, 8, 8, 48, False), (3, 10, 6, 96, True), (2, 24, 24, 384, True), (4, 20, 20, 192, False)])
+def test_batchnorm_train_fwd_bwd(B, H, W, C, with_skip):
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(B + C)
+    c = _bf(torch.randn(B, C, H, W, generator=g) * 1.5 + 0.3).float()
+    skip = _bf(torch.randn(B, C, H, W, generator=g)).float() if with_skip else None
+    gamma = (1 + 0.2 * torch.randn(C, generator=g))
+    beta = 0.1 * torch.randn(C, generator=g)
+    dy = _bf(torch.randn(B, C, H, W, generator=g)).float()
+    # torch reference (fp32 autograd, training-mode BN)
+    cr = c.clone().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    sr = skip.clone().requires_grad_(True) if with_skip else None
+    rm, rv = torch.zeros(C), torch.ones(C)
+    z = F.batch_norm(cr, rm, rv, gr, br, True, 0.1, 1e-5)
+    if with_skip:
+        z = z + sr
+    y_ref = F.gelu(z)
+    y_ref.backward(dy)
+    # CUDA path
+    ch = _halo(c).cuda()
+    sh = _halo(skip).cuda() if with_skip else None
+    stats = torch.empty(4, C, device="cuda")
+    sums = torch.empty(2, C, dtype=torch.float64, device="cuda")
+    rm_d, rv_d = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+    s = _lib.stream_ptr()
+    gamma_d, beta_d = gamma.cuda(), beta.cuda()          # keep the device copies alive across the asynchronous calls
+    _lib.check(lib.msd_bn_stats_bf16(_lib.ptr(ch), B, H, W, C, _lib.ptr(gamma_d), _lib.ptr(beta_d), 1e-5, 0.1, _lib.ptr(rm_d),
+                                     _lib.ptr(rv_d), _lib.ptr(stats), _lib.ptr(sums), s))
+    assert torch.allclose(rm_d.cpu(), rm, atol=1e-5) and torch.allclose(rv_d.cpu(), rv, atol=1e-4)
+    y = torch.full((B, H + 2, W + 2, C), 7.0, device="cuda", dtype=torch.bfloat16)
+    _lib.check(lib.msd_bn_act_fwd_bf16(_lib.ptr(ch), _lib.ptr(sh), _lib.ptr(stats), _lib.ptr(y), B, H, W, C, s))
+    _close(_interior(y).cpu().permute(0, 3, 1, 2), y_ref.detach(), 1e-2)
+    assert y[:, 0].abs().max().item() == 0 and y[:, :, 0].abs().max().item() == 0 and y[:, -1].abs().max().item() == 0
+    dyh = _halo(dy).cuda()
+    dz = torch.full_like(y, 7.0)
+    dc = torch.full_like(y, 7.0)
+    dgam, dbet = torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
+    coef = torch.empty(2, C, device="cuda")
+    _lib.check(lib.msd_bn_act_bwd_bf16(_lib.ptr(dyh), _lib.ptr(ch), _lib.ptr(sh), _lib.ptr(stats), _lib.ptr(dz), _lib.ptr(dc),
+                                       _lib.ptr(dgam), _lib.ptr(dbet), _lib.ptr(coef), _lib.ptr(sums), B, H, W, C, s))
+    _close(_interior(dc).cpu().permute(0, 3, 1, 2), cr.grad, 1.5e-2)
+    _close(dgam.cpu(), gr.grad, 1e-2)
+    _close(dbet.cpu(), br.grad, 1e-2)
+    if with_skip:
+        _close(_interior(dz).cpu().permute(0, 3, 1, 2), sr.grad, 1e-2)
+    assert dc[:, 0].abs().max().item() == 0 and dz[:, :, -1].abs().max().item() == 0
+
+
+def test_gelu_bwd():
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(5)
+    h = _bf(torch.randn(1000, 3072, generator=g) * 2).float().requires_grad_(True)
+    dh = _bf(torch.randn(1000, 3072, generator=g)).float()
+    F.gelu(h).backward(dh)
+    out = torch.empty(1000, 3072, device="cuda", dtype=torch.bfloat16)
+    dh_d, h_d = _bf(dh).cuda(), _bf(h.detach()).cuda()
+    _lib.check(lib.msd_gelu_bwd_bf16(_lib.ptr(dh_d), _lib.ptr(h_d), _lib.ptr(out), 1000 * 3072, _lib.stream_ptr()))
+    _close(out.cpu(), h.grad, 1e-2)
+
+
+@pytest.mark.parametrize("M,f32_grad,accumulate,frozen", [(300, False, True, False), (1000, True, False, False), (77, False, False, True)])
+def test_layernorm_bwd(M, f32_grad, accumulate, frozen):
+    lib = _lib.load()
+    D = 768
+    g = torch.Generator().manual_seed(M)
+    x = (torch.randn(M, D, generator=g) * 2 + 0.5).requires_grad_(True)
+    gamma = (1 + 0.3 * torch.randn(D, generator=g)).requires_grad_(True)
+    beta = torch.zeros(D, requires_grad=True)
+    dy = torch.randn(M, D, generator=g)
+    if not f32_grad:
+        dy = _bf(dy).float()
+    F.layer_norm(x, (D,), gamma, beta, 1e-6).backward(dy)
+    g0 = torch.randn(M, D, generator=g)
+    g_d = g0.clone().cuda()
+    gbf = torch.empty(M, D, device="cuda", dtype=torch.bfloat16)
+    dgam, dbet = torch.zeros(D, device="cuda"), torch.zeros(D, device="cuda")
+    dy_d = dy.cuda() if f32_grad else _bf(dy).cuda()
+    x_d, gamma_d = x.detach().cuda(), gamma.detach().cuda()
+    _lib.check(lib.msd_layernorm_bwd(_lib.ptr(dy_d), int(f32_grad), _lib.ptr(x_d), _lib.ptr(gamma_d), 1e-6,
+                                     _lib.ptr(g_d), int(accumulate), _lib.ptr(gbf), None if frozen else _lib.ptr(dgam),
+                                     None if frozen else _lib.ptr(dbet), M, D, _lib.stream_ptr()))
+    want = x.grad + (g0 if accumulate else 0)
+    _close(g_d.cpu(), want, 1e-4)
+    _close(gbf.cpu(), want, 1e-2)
+    if not frozen:
+        _close(dgam.cpu(), gamma.grad, 1e-4)
+        _close(dbet.cpu(), beta.grad, 1e-4)
+
+
+@pytest.mark.parametrize("B,Hin,padded,C", [(2, 6, True, 48), (3, 12, False, 384), (2, 5, True, 96)])
+def test_convt_unshuffle(B, Hin, padded, C):
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(C)
+    dy = _bf(torch.randn(B, 2 * Hin + 2, 2 * Hin + 2, C, generator=g)).cuda()
+    ph = Hin + 2 if padded else Hin
+    dys = torch.full((B * ph * ph, 4 * C), 7.0, device="cuda", dtype=torch.bfloat16)
+    _lib.check(lib.msd_convt_unshuffle_bf16(_lib.ptr(dy), _lib.ptr(dys), B, Hin, Hin, int(padded), C, _lib.stream_ptr()))
+    got = dys.view(B, ph, ph, 4, C)
+    inner = got[:, 1:-1, 1:-1] if padded else got
+    for q in range(4):
+        di, dj = q >> 1, q & 1
+        ref = dy[:, 1 + di:1 + di + 2 * Hin:2, 1 + dj:1 + dj + 2 * Hin:2, :]
+        assert torch.equal(inner[:, :, :, q, :], ref)
+    if padded:
+        assert got[:, 0].abs().max().item() == 0 and got[:, :, -1].abs().max().item() == 0
+
+
+def test_head1x1_bwd():
+    lib = _lib.load()
+    B, H, W, Cin, Cout = 2, 16, 12, 48, 13
+    g = torch.Generator().manual_seed(9)
+    dy = torch.randn(B, Cout, H, W, generator=g)
+    w = torch.randn(Cout, Cin, generator=g) * 0.2
+    dh = torch.full((B, H + 2, W + 2, Cin), 7.0, device="cuda", dtype=torch.bfloat16)
+    dyt = torch.full((B * (H + 2) * (W + 2), 16), 7.0, device="cuda", dtype=torch.bfloat16)
+    dy_d, w_d = dy.cuda(), w.cuda()
+    _lib.check(lib.msd_head1x1_bwd(_lib.ptr(dy_d), _lib.ptr(w_d), _lib.ptr(dh), _lib.ptr(dyt), B, H, W, Cin, Cout, _lib.stream_ptr()))
+    ref = torch.einsum("bohw,oc->bhwc", dy, w)
+    _close(_interior(dh).cpu(), ref, 1e-2)
+    assert dh[:, 0].abs().max().item() == 0
+    t = dyt.view(B, H + 2, W + 2, 16)
+    _close(t[:, 1:-1, 1:-1, :Cout].cpu(), dy.permute(0, 2, 3, 1), 1e-2)
+    assert t[..., Cout:].abs().max().item() == 0 and t[:, 0].abs().max().item() == 0
+
+
+def test_attention_bwd():
+    lib = _lib.load()
+    B, T, heads = 3, 144, 12
+    E = heads * 64
+    g = torch.Generator().manual_seed(11)
+    qkv = _bf(torch.randn(B * T, 3 * E, generator=g)).float().requires_grad_(True)
+    dout = _bf(torch.randn(B * T, E, generator=g)).float()
+    t = qkv.reshape(B, T, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    att = torch.softmax((t[0] @ t[1].transpose(-2, -1)) * 0.125, dim=-1) @ t[2]
+    att.transpose(1, 2).reshape(B * T, E).backward(dout)
+    dqkv = torch.full((B * T, 3 * E), 7.0, device="cuda", dtype=torch.bfloat16)
+    qkv_d, dout_d = _bf(qkv.detach()).cuda(), _bf(dout).cuda()
+    _lib.check(lib.msd_attention_bwd_bf16(_lib.ptr(qkv_d), _lib.ptr(dout_d), _lib.ptr(dqkv), B, T, heads, _lib.stream_ptr()))
+    for i, name in enumerate(("dq", "dk", "dv")):
+        _close(dqkv[:, i * E:(i + 1) * E].cpu(), qkv.grad[:, i * E:(i + 1) * E], 2e-2)
