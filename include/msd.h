@@ -217,6 +217,8 @@ int msd_bn_act_fwd_bf16(const void* d_c, const void* d_skip, const float* d_stat
  * d_dgamma / d_dbeta fp32 [C] (overwritten; NULL to skip), d_coef fp32 [2][C] and d_sums fp64 [2][C] scratch */
 int msd_bn_act_bwd_bf16(const void* d_dy, const void* d_c, const void* d_skip, const float* d_stats, void* d_dz, void* d_dc,
                         float* d_dgamma, float* d_dbeta, float* d_coef, double* d_sums, int B, int H, int W, int C, void* stream);
+/* d_out = GELU(d_hpre) (erf form), n bf16 elements (n % 8 == 0) */
+int msd_gelu_fwd_bf16(const void* d_hpre, void* d_out, long long n, void* stream);
 /* d_out = d_dh * gelu'(d_hpre), n bf16 elements (n % 8 == 0), in place allowed */
 int msd_gelu_bwd_bf16(const void* d_dh, const void* d_hpre, void* d_out, long long n, void* stream);
 /* LayerNorm backward over [M, D=768]: d_dy bf16 (or fp32 when dy_is_f32), d_x fp32 LN input; d_g fp32 [M,D] = (accumulate ?
@@ -231,6 +233,74 @@ int msd_head1x1_bwd(const float* d_dy, const float* d_w, void* d_dh, void* d_dyt
 int msd_batch_sum_f32(const float* d_in, float* d_out, int B, long long n, void* stream);
 /* attention backward: d_dqkv bf16 [B*T, 3*heads*64] from qkv and the gradient of the attention output */
 int msd_attention_bwd_bf16(const void* d_qkv, const void* d_dout, void* d_dqkv, int B, int T, int heads, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Training step of the restoration model (BASELINE config C4): forward in training mode (BatchNorm batch statistics,
+ * activations kept for the backward) and the full backward pass.  Replaces `output = self.model(noisy)` +
+ * `loss.backward()` in Trainer.train_epoch (src/training/trainer.py:141-146, 178-181) for the model part; the loss and
+ * its gradient come from msd_loss_fwd_bwd_f32.  Weights are NOT BatchNorm-folded here.
+ *   bf16 matrices as in msd_model_weights; additionally the transposed / tap-flipped copies the data-gradient GEMMs read.
+ *   Gradients are fp32 device buffers in the packed layouts noted below; NULL pointers are skipped (frozen parameters).
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct msd_bn_params {
+  const float *gamma, *beta;          /* [C] */
+  float *running_mean, *running_var;  /* [C], updated in place by the training forward (momentum 0.1, unbiased var) */
+} msd_bn_params;
+
+typedef struct msd_train_block {
+  const void *wT_qkv, *wT_proj, *wT_fc1, *wT_fc2; /* W^T: [768,2304], [768,768], [768,3072], [3072,768] bf16 */
+  int trainable;                                   /* 0 = frozen block (encoder.py:270-293): data gradients only */
+} msd_train_block;
+
+typedef struct msd_train_stage {
+  const void *w_up; const float *b_up;   /* [4*Cout, Kpad(Cin)] rows (di,dj,o), no BN fold; bias [4*Cout] */
+  const void *wT_up;                     /* [Cin, 4*Cout] = w_up^T (data gradient) */
+  msd_bn_params bn_up;
+  const void *w_conv[4];                 /* [Cout, 9*Kpad], no bias, no BN fold */
+  const void *wd_conv[4];                /* data-gradient weights [Cin, 9*Kpad(Cout)] with flipped taps; for the FIRST conv of
+                                            each ResidualBlock (index 0, 2) a tenth identity tap adds the skip gradient */
+  msd_bn_params bn_conv[4];
+} msd_train_stage;
+
+typedef struct msd_train_weights {
+  msd_model_weights enc;                 /* encoder fields as in the eval forward; decoder fields of `enc` are ignored */
+  const msd_train_block* blocks_t;       /* [depth] */
+  msd_train_stage stages[4];
+  const void *w_head3; const float *b_head3; const void *wd_head3; msd_bn_params bn_head;
+  const float *w_head1; const float *b_head1;
+  float bn_eps, bn_momentum;
+} msd_train_weights;
+
+typedef struct msd_block_grads {
+  float *ln1_g, *ln1_b, *ln2_g, *ln2_b, *w_qkv, *b_qkv, *w_proj, *b_proj, *w_fc1, *b_fc1, *w_fc2, *b_fc2;
+} msd_block_grads;
+
+typedef struct msd_stage_grads {
+  float *w_up;                           /* [4*Cout, Cin] rows (di,dj,o) */
+  float *bn_up_g, *bn_up_b;
+  float *w_conv[4];                      /* [9][Kpad(Cin)][Cout] tap-major */
+  float *bn_g[4], *bn_b[4];
+} msd_stage_grads;
+
+typedef struct msd_model_grads {
+  float *w_pe, *b_pe, *pe_ln_g, *pe_ln_b, *pos_embed;
+  const msd_block_grads* blocks;         /* [depth] host array */
+  float *norm_g, *norm_b;
+  msd_stage_grads stages[4];
+  float *w_head3;                        /* [9][Kpad][C] */
+  float *bn_head_g, *bn_head_b;
+  float *w_head1, *b_head1;              /* [out_channels, C], [out_channels] */
+} msd_model_grads;
+
+int msd_model_set_train_weights(msd_model* m, const msd_train_weights* w);
+/* byte offsets of the kept activations inside the training workspace (tests / debugging); see csrc/model.cu */
+int msd_model_train_layout(const msd_model* m, int B, size_t* out, int capacity);
+size_t msd_model_train_workspace_bytes(const msd_model* m, int B);
+/* d_x [B,C,S,S] fp32 -> d_y [B,out_channels,S,S] fp32; keeps every activation the backward needs inside d_ws */
+int msd_model_forward_train(msd_model* m, const float* d_x, int B, float* d_y, void* d_ws, size_t ws_bytes, void* stream);
+/* d_grad_y [B,out_channels,S,S] fp32; d_ws must be the workspace of the matching msd_model_forward_train call */
+int msd_model_backward(msd_model* m, const float* d_grad_y, int B, void* d_ws, size_t ws_bytes, const msd_model_grads* grads,
+                       void* stream);
 
 #ifdef __cplusplus
 }

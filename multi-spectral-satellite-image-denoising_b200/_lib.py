@@ -42,6 +42,41 @@ class ModelWeights(C.Structure):
     ]
 
 
+class BnParams(C.Structure):
+    _fields_ = [(n, c_void_p) for n in ("gamma", "beta", "running_mean", "running_var")]
+
+
+class TrainBlock(C.Structure):
+    _fields_ = [("wT_qkv", c_void_p), ("wT_proj", c_void_p), ("wT_fc1", c_void_p), ("wT_fc2", c_void_p), ("trainable", c_int)]
+
+
+class TrainStage(C.Structure):
+    _fields_ = [("w_up", c_void_p), ("b_up", c_void_p), ("wT_up", c_void_p), ("bn_up", BnParams), ("w_conv", c_void_p * 4),
+                ("wd_conv", c_void_p * 4), ("bn_conv", BnParams * 4)]
+
+
+class TrainWeights(C.Structure):
+    _fields_ = [("enc", ModelWeights), ("blocks_t", C.POINTER(TrainBlock)), ("stages", TrainStage * 4), ("w_head3", c_void_p),
+                ("b_head3", c_void_p), ("wd_head3", c_void_p), ("bn_head", BnParams), ("w_head1", c_void_p), ("b_head1", c_void_p),
+                ("bn_eps", c_float), ("bn_momentum", c_float)]
+
+
+class BlockGrads(C.Structure):
+    _fields_ = [(n, c_void_p) for n in (
+        "ln1_g", "ln1_b", "ln2_g", "ln2_b", "w_qkv", "b_qkv", "w_proj", "b_proj", "w_fc1", "b_fc1", "w_fc2", "b_fc2")]
+
+
+class StageGrads(C.Structure):
+    _fields_ = [("w_up", c_void_p), ("bn_up_g", c_void_p), ("bn_up_b", c_void_p), ("w_conv", c_void_p * 4), ("bn_g", c_void_p * 4),
+                ("bn_b", c_void_p * 4)]
+
+
+class ModelGrads(C.Structure):
+    _fields_ = [("w_pe", c_void_p), ("b_pe", c_void_p), ("pe_ln_g", c_void_p), ("pe_ln_b", c_void_p), ("pos_embed", c_void_p),
+                ("blocks", C.POINTER(BlockGrads)), ("norm_g", c_void_p), ("norm_b", c_void_p), ("stages", StageGrads * 4),
+                ("w_head3", c_void_p), ("bn_head_g", c_void_p), ("bn_head_b", c_void_p), ("w_head1", c_void_p), ("b_head1", c_void_p)]
+
+
 # name -> (restype, argtypes); must list every symbol include/msd.h declares (tests/test_abi.py checks this)
 SIGNATURES = {
     "msd_version": (c_int, []),
@@ -94,6 +129,12 @@ SIGNATURES = {
     "msd_head1x1_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "msd_batch_sum_f32": (c_int, [c_void_p, c_void_p, c_int, C.c_longlong, c_void_p]),
     "msd_attention_bwd_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "msd_gelu_fwd_bf16": (c_int, [c_void_p, c_void_p, C.c_longlong, c_void_p]),
+    "msd_model_set_train_weights": (c_int, [c_void_p, C.POINTER(TrainWeights)]),
+    "msd_model_train_layout": (c_int, [c_void_p, c_int, C.POINTER(c_size_t), c_int]),
+    "msd_model_train_workspace_bytes": (c_size_t, [c_void_p, c_int]),
+    "msd_model_forward_train": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "msd_model_backward": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_size_t, C.POINTER(ModelGrads), c_void_p]),
     "msd_wgrad_conv3x3_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                        c_void_p]),
 }

@@ -220,6 +220,8 @@ enum Epi : int {
   E_RM_F32_RESID,   // out fp32 = resid + acc + bias, in place                       (attention proj, fc2)
   E_CONV,           // haloed NHWC bf16 = GELU(acc + bias), halo rows zeroed         (every 3x3 conv; a ResidualBlock's skip is a 10th tap)
   E_CONVT,          // pixel-shuffle scatter of GELU(acc + bias)                     (ConvTranspose2d k2 s2)
+  E_CONV_RAW,       // haloed NHWC bf16 = acc + bias, halo rows zeroed               (training: pre-BatchNorm output, dgrad)
+  E_CONVT_RAW,      // pixel-shuffle scatter of acc + bias                            (training: pre-BatchNorm output)
   E_GENERIC         // any other combination of the Problem's flags (slower, runtime-branched)
 };
 
@@ -232,9 +234,9 @@ __host__ inline int classify(const Problem& p) {
     if (!p.out_f32 && p.resid == nullptr) return p.act ? E_RM_BF16_GELU : E_RM_BF16;
     return E_GENERIC;
   }
-  if (p.mode == EPI_CONV && p.act && !p.out_f32) return (p.skip && p.skip_tap < 0) ? E_GENERIC : E_CONV;   // epilogue-loaded skip: generic path
-  if (p.mode == EPI_CONVT && p.act && !p.out_f32 &&
-      (unsigned long long)(p.M / (int)p.in_plane.d + 1) * p.out_plane * p.ldo < (1ull << 31)) return E_CONVT;
+  if (p.mode == EPI_CONV && !p.out_f32 && !(p.skip && p.skip_tap < 0)) return p.act ? E_CONV : E_CONV_RAW;   // epilogue-loaded skip: generic path
+  if (p.mode == EPI_CONVT && !p.out_f32 &&
+      (unsigned long long)(p.M / (int)p.in_plane.d + 1) * p.out_plane * p.ldo < (1ull << 31)) return p.act ? E_CONVT : E_CONVT_RAW;
   return E_GENERIC;
 }
 
@@ -247,12 +249,13 @@ template <int BN, int EPI>
 __device__ __forceinline__ void epilogue_tile(const Problem& p, uint32_t stg_s, uint32_t bias_s, uint32_t taddr,
                                               uint64_t* tmem_empty_bar, int mrow0, int n0, int lane, int slab_begin, int slab_end) {
   using C = Cfg<BN>;
-  constexpr bool kConv = EPI == E_CONV;
+  constexpr bool kConv = EPI == E_CONV || EPI == E_CONV_RAW;
+  constexpr bool kConvT = EPI == E_CONVT || EPI == E_CONVT_RAW;
   constexpr bool kF32 = EPI == E_RM_F32 || EPI == E_RM_F32_RESID;
-  constexpr bool kGelu = EPI == E_RM_BF16_GELU || kConv || EPI == E_CONVT;
+  constexpr bool kGelu = EPI == E_RM_BF16_GELU || EPI == E_CONV || EPI == E_CONVT;
   constexpr int UPR = kF32 ? C::SC / 4 : C::SC / 8;        // 16-byte units per staged row (a power of two)
   constexpr uint32_t PITCH = (kF32 ? C::SC * 4 : C::SC * 2) + 16;
-  const uint32_t rowpix = (EPI == E_GENERIC || EPI == E_CONVT || kConv) ? row_info(p, mrow0 + lane) : 0u;
+  const uint32_t rowpix = (EPI == E_GENERIC || kConvT || kConv) ? row_info(p, mrow0 + lane) : 0u;
   const bool zero_row = kConv && (rowpix & kRowHalo) != 0;
   const int rows_valid = p.M - mrow0;   // rows rr < rows_valid exist (row-major / conv)
   const uint32_t ldo = (uint32_t)p.ldo;
@@ -320,7 +323,7 @@ __device__ __forceinline__ void epilogue_tile(const Problem& p, uint32_t stg_s, 
         const int rr = u / UPR, cu = u % UPR;
         v[j] = lds128(stg_s + rr * PITCH + cu * 16);
         const int n = n0 + nslab + cu * EPU;
-        if constexpr (EPI == E_CONVT) {
+        if constexpr (kConvT) {
           const uint32_t pix = __shfl_sync(0xffffffffu, rowpix, rr);
           uint32_t qq, o;
           fd_divmod((uint32_t)n, p.cout_div, qq, o);
@@ -586,6 +589,8 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         MSD_EPI_CASE(E_RM_F32_RESID)
         MSD_EPI_CASE(E_CONV)
         MSD_EPI_CASE(E_CONVT)
+        MSD_EPI_CASE(E_CONV_RAW)
+        MSD_EPI_CASE(E_CONVT_RAW)
         default: epilogue_tile<BN, E_GENERIC>(p, stg_s, bias_s, taddr, &tmem_empty[as], m0 + q * 32, n0, lane, slab_begin, slab_end); break;
       }
 #undef MSD_EPI_CASE

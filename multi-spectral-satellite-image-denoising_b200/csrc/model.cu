@@ -9,6 +9,7 @@
 //   qkv   bf16 [B*T, 3E], att bf16 [B*T, E], h bf16 [B*T, 4E]
 //   decoder stage s: three ping-pong buffers bf16 [B, H_s+2, W_s+2, C_s] (zero halo), H_s = 24,48,96,192
 #include "gemm.cuh"
+#include <algorithm>
 #include <new>
 #include <stdlib.h>
 #include <vector>
@@ -42,7 +43,7 @@ int make_linear(Problem& p, const void* a, const void* w, const float* bias, voi
 }
 
 int make_conv3x3(Problem& p, const void* x, const void* w, const float* bias, const void* skip, void* y, int B, int H,
-                 int W, int Cin, int Cout) {
+                 int W, int Cin, int Cout, int act = 1) {
   MSD_REQUIRE(x && w && y, "conv3x3: null pointer");
   MSD_REQUIRE(B > 0 && H > 0 && W > 0 && Cin % 8 == 0 && Cout % 16 == 0, "conv3x3: bad shape B=%d H=%d W=%d Cin=%d Cout=%d", B, H, W, Cin, Cout);
   const long long rows = (long long)B * (H + 2) * (W + 2);
@@ -55,7 +56,7 @@ int make_conv3x3(Problem& p, const void* x, const void* w, const float* bias, co
   p.kb_per_tap = round_up(Cin, 64) / 64; p.num_kb = 9 * p.kb_per_tap;
   for (int ky = 0; ky < 3; ++ky)
     for (int kx = 0; kx < 3; ++kx) p.tap_off[ky * 3 + kx] = (ky - 1) * (W + 2) + (kx - 1);
-  p.mode = gemm::EPI_CONV; p.act = 1; p.out_f32 = 0;
+  p.mode = gemm::EPI_CONV; p.act = act; p.out_f32 = 0;
   p.bias = bias; p.out = y; p.ldo = Cout;
   p.skip = reinterpret_cast<const __nv_bfloat16*>(skip);
   if (skip != nullptr) {
@@ -70,7 +71,7 @@ int make_conv3x3(Problem& p, const void* x, const void* w, const float* bias, co
 }
 
 int make_convt(Problem& p, const void* x, const void* w, const float* bias, void* y, int B, int Hin, int Win, int in_padded,
-               int Cin, int Cout) {
+               int Cin, int Cout, int act = 1) {
   MSD_REQUIRE(x && w && y, "convt: null pointer");
   MSD_REQUIRE(B > 0 && Hin > 0 && Win > 0 && Cin % 8 == 0 && Cout % 16 == 0, "convt: bad shape");
   const int ph = in_padded ? Hin + 2 : Hin, pw = in_padded ? Win + 2 : Win;
@@ -82,7 +83,7 @@ int make_convt(Problem& p, const void* x, const void* w, const float* bias, void
   p.M = (int)rows; p.N = 4 * Cout;
   p.a_rows = (int)rows; p.ldA = Cin; p.kvalid = Cin;
   p.kb_per_tap = round_up(Cin, 64) / 64; p.num_kb = p.kb_per_tap;
-  p.mode = gemm::EPI_CONVT; p.act = 1; p.out_f32 = 0;
+  p.mode = gemm::EPI_CONVT; p.act = act; p.out_f32 = 0;
   p.bias = bias; p.out = y; p.ldo = Cout;
   p.in_plane = make_fastdiv((uint32_t)(ph * pw));
   p.in_pitch = make_fastdiv((uint32_t)pw);
@@ -156,6 +157,11 @@ struct msd_model {
   msd_model_weights w;
   std::vector<msd_block_weights> blocks;
   bool has_weights = false;
+  // training step (msd_model_set_train_weights)
+  msd_train_weights tw;
+  std::vector<msd_block_weights> tblocks;
+  std::vector<msd_train_block> tblocks_t;
+  bool has_train_weights = false;
   int grid, tokens;
   // optional per-launch CUDA-event profile (bench.py's live roofline measurement)
   bool profile = false;
@@ -370,5 +376,380 @@ extern "C" int msd_model_forward(msd_model* m, const float* d_x, const void* d_p
     MSD_RUN(0, 2.0 * B * hw * hw * (double)c * 9.0 * c, gemm::launch(p, be, s));
     MSD_RUN(3, 2.0 * B * hw * hw * (double)c * d.out_channels, msd_head1x1_nchw_f32(Y, w.w_head1, w.b_head1, d_y, B, hw, hw, c, d.out_channels, stream));
   }
+  return MSD_OK;
+}
+
+// ==================================================================================================== training step
+// Forward in training mode + backward (BASELINE config C4; reference call sites src/training/trainer.py:141-146, 178-181).
+// Everything the backward needs stays in the caller's workspace:
+//   encoder : a_pe, x0pre (patch-embed GEMM output), per block l: xs[l] (block input, fp32), xn1, qkv, att, xm (fp32, after
+//             the attention residual), xn2, hpre, h; xs[depth] (encoder output before the final LayerNorm), xnf
+//   decoder : per stage the raw (pre-BatchNorm) and activated tensor of each of the five layers, BN statistics
+//   backward scratch: g (fp32 residual-stream gradient) + bf16 copy, dh, dxn, dqkv, datt, three decoder gradient buffers,
+//             the un-shuffled ConvTranspose gradient, fp64 / fp32 reduction scratch
+namespace {
+
+struct TrainLayout {
+  size_t a_pe, x0pre, xs, xm, xn1, qkv, att, xn2, hpre, h, xnf;            // per-block tensors are [depth] arrays of equal stride
+  size_t s_xs, s_xn, s_qkv, s_h;                                           // strides (bytes) of those arrays
+  size_t dec[4][10];                                                       // U_raw, X0, C1, Y1, C2, Z1, C3, Y2, C4, Z2
+  size_t head_c, head_h;
+  size_t stats;                                                            // 21 x [4][Cmax] fp32
+  size_t g, gbf, dh, dxn, dqkv, datt, gA, gB, gC, dys, dyt, sums, coef;
+  size_t total;
+};
+
+constexpr int kStatsStride = 4 * 1024;   // floats per BatchNorm layer in the stats area (C <= 1024)
+
+TrainLayout train_layout(const msd_model* m, int B) {
+  TrainLayout L;
+  const msd_model_desc& d = m->d;
+  const size_t M = (size_t)B * m->tokens, E = d.embed_dim, Hd = d.mlp_hidden;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += align256(bytes); return o; };
+  L.a_pe = take(M * (size_t)d.in_channels * d.patch_size * d.patch_size * 2);
+  L.x0pre = take(M * E * 4);
+  L.s_xs = align256(M * E * 4); L.s_xn = align256(M * E * 2); L.s_qkv = align256(M * 3 * E * 2); L.s_h = align256(M * Hd * 2);
+  L.xs = take(L.s_xs * (d.depth + 1));
+  L.xm = take(L.s_xs * d.depth);
+  L.xn1 = take(L.s_xn * d.depth);
+  L.qkv = take(L.s_qkv * d.depth);
+  L.att = take(L.s_xn * d.depth);
+  L.xn2 = take(L.s_xn * d.depth);
+  L.hpre = take(L.s_h * d.depth);
+  L.h = take(L.s_h * d.depth);
+  L.xnf = take(M * E * 2);
+  int hw = m->grid;
+  size_t big = 0, dys = 0;
+  for (int s = 0; s < 4; ++s) {
+    const size_t rows_in = (size_t)B * (s == 0 ? hw * hw : (hw + 2) * (hw + 2));
+    dys = std::max(dys, rows_in * 4 * d.dec_channels[s] * 2);
+    hw *= 2;
+    const size_t bytes = (size_t)B * (hw + 2) * (hw + 2) * d.dec_channels[s] * 2;
+    big = std::max(big, bytes);
+    for (int k = 0; k < 10; ++k) L.dec[s][k] = take(bytes);
+  }
+  {
+    const size_t bytes = (size_t)B * (hw + 2) * (hw + 2) * d.dec_channels[3] * 2;
+    L.head_c = take(bytes);
+    L.head_h = take(bytes);
+  }
+  L.stats = take((size_t)21 * kStatsStride * 4);
+  L.g = take(M * E * 4);
+  L.gbf = take(M * E * 2);
+  L.dh = take(M * Hd * 2);
+  L.dxn = take(M * E * 2);
+  L.dqkv = take(M * 3 * E * 2);
+  L.datt = take(M * E * 2);
+  L.gA = take(big); L.gB = take(big); L.gC = take(big);
+  L.dys = take(dys);
+  L.dyt = take((size_t)B * (hw + 2) * (hw + 2) * 16 * 2);
+  L.sums = take(2 * 4096 * sizeof(double));
+  L.coef = take(2 * 1024 * sizeof(float));
+  L.total = off;
+  return L;
+}
+
+// BatchNorm layer index in the stats area: stage s -> 5 layers (up, conv0..3), head = 20
+int bn_index(int stage, int k) { return stage * 5 + k; }
+
+int zero_f32(float* p, size_t n, cudaStream_t s) {
+  if (p != nullptr) MSD_CHECK_CUDA(cudaMemsetAsync(p, 0, n * sizeof(float), s));
+  return MSD_OK;
+}
+
+// bias gradient: column sums of a bf16 [rows, C] matrix -> fp32 [n_out] (n_out <= C)
+int bias_grad(const void* a, long long rows, int C, float* out, int n_out, double* sums, void* stream) {
+  if (out == nullptr) return MSD_OK;
+  MSD_TRY(msd_colsum_bf16(a, rows, C, sums, stream));
+  return msd_f64_to_f32(sums, out, n_out, stream);
+}
+
+}  // namespace
+
+extern "C" int msd_model_set_train_weights(msd_model* m, const msd_train_weights* w) {
+  MSD_REQUIRE(m && w && w->enc.blocks && w->blocks_t, "model_set_train_weights: null pointer");
+  m->tw = *w;
+  m->tblocks.assign(w->enc.blocks, w->enc.blocks + m->d.depth);
+  m->tblocks_t.assign(w->blocks_t, w->blocks_t + m->d.depth);
+  m->tw.enc.blocks = m->tblocks.data();
+  m->tw.blocks_t = m->tblocks_t.data();
+  m->has_train_weights = true;
+  return MSD_OK;
+}
+
+extern "C" size_t msd_model_train_workspace_bytes(const msd_model* m, int B) {
+  if (!m || B <= 0) return 0;
+  return train_layout(m, B).total;
+}
+
+extern "C" int msd_model_forward_train(msd_model* m, const float* d_x, int B, float* d_y, void* d_ws, size_t ws_bytes, void* stream) {
+  MSD_REQUIRE(m && m->has_train_weights, "model_forward_train: training weights not set");
+  MSD_REQUIRE(d_x && d_y && d_ws && B > 0, "model_forward_train: null pointer");
+  MSD_REQUIRE((reinterpret_cast<uintptr_t>(d_ws) & 255u) == 0, "model_forward_train: workspace must be 256-byte aligned");
+  const TrainLayout L = train_layout(m, B);
+  if (ws_bytes < L.total) {
+    msd_set_error("model_forward_train: workspace %zu < %zu bytes", ws_bytes, L.total);
+    return MSD_ERR_WORKSPACE;
+  }
+  const msd_model_desc& d = m->d;
+  const msd_train_weights& tw = m->tw;
+  const msd_model_weights& w = tw.enc;
+  cudaStream_t s = (cudaStream_t)stream;
+  unsigned char* ws = reinterpret_cast<unsigned char*>(d_ws);
+  const int M = B * m->tokens, E = d.embed_dim, Kpe = d.in_channels * d.patch_size * d.patch_size, Hd = d.mlp_hidden;
+  const int be = d.gemm_backend;
+  Problem p;
+  float* stats = reinterpret_cast<float*>(ws + L.stats);
+  double* sums = reinterpret_cast<double*>(ws + L.sums);
+
+  // ---- encoder (same arithmetic as the eval forward, every intermediate kept)
+  MSD_TRY(msd_patchify_bf16(d_x, ws + L.a_pe, B, d.in_channels, d.image_size, d.patch_size, stream));
+  float* x0pre = reinterpret_cast<float*>(ws + L.x0pre);
+  MSD_TRY(make_linear(p, ws + L.a_pe, w.w_pe, w.b_pe, x0pre, nullptr, M, E, Kpe, 0, 1));
+  MSD_TRY(gemm::launch(p, be, s));
+  float* x = reinterpret_cast<float*>(ws + L.xs);
+  MSD_CHECK_CUDA(cudaMemcpyAsync(x, x0pre, (size_t)M * E * 4, cudaMemcpyDeviceToDevice, s));
+  MSD_TRY(msd_layernorm_pos_f32(x, w.pe_ln_g, w.pe_ln_b, d.ln_eps_outer, w.pos_embed, m->tokens, M, E, stream));
+  for (int l = 0; l < d.depth; ++l) {
+    const msd_block_weights& bw = m->tblocks[l];
+    float* xin = reinterpret_cast<float*>(ws + L.xs + l * L.s_xs);
+    float* xmid = reinterpret_cast<float*>(ws + L.xm + l * L.s_xs);
+    float* xout = reinterpret_cast<float*>(ws + L.xs + (l + 1) * L.s_xs);
+    void *xn1 = ws + L.xn1 + l * L.s_xn, *qkv = ws + L.qkv + l * L.s_qkv, *att = ws + L.att + l * L.s_xn;
+    void *xn2 = ws + L.xn2 + l * L.s_xn, *hpre = ws + L.hpre + l * L.s_h, *h = ws + L.h + l * L.s_h;
+    MSD_TRY(msd_layernorm_f32_bf16(xin, bw.ln1_g, bw.ln1_b, d.ln_eps_block, xn1, M, E, stream));
+    MSD_TRY(make_linear(p, xn1, bw.w_qkv, bw.b_qkv, qkv, nullptr, M, 3 * E, E, 0, 0));
+    MSD_TRY(gemm::launch(p, be, s));
+    MSD_TRY(msd_attention_bf16(qkv, att, B, m->tokens, d.num_heads, stream));
+    MSD_TRY(make_linear(p, att, bw.w_proj, bw.b_proj, xmid, xin, M, E, E, 0, 1));
+    MSD_TRY(gemm::launch(p, be, s));
+    MSD_TRY(msd_layernorm_f32_bf16(xmid, bw.ln2_g, bw.ln2_b, d.ln_eps_block, xn2, M, E, stream));
+    MSD_TRY(make_linear(p, xn2, bw.w_fc1, bw.b_fc1, hpre, nullptr, M, Hd, E, 0, 0));
+    MSD_TRY(gemm::launch(p, be, s));
+    MSD_TRY(msd_gelu_fwd_bf16(hpre, h, (long long)M * Hd, stream));
+    MSD_TRY(make_linear(p, h, bw.w_fc2, bw.b_fc2, xout, xmid, M, E, Hd, 0, 1));
+    MSD_TRY(gemm::launch(p, be, s));
+  }
+  MSD_TRY(msd_layernorm_f32_bf16(reinterpret_cast<float*>(ws + L.xs + d.depth * L.s_xs), w.norm_g, w.norm_b, d.ln_eps_outer,
+                                 ws + L.xnf, M, E, stream));
+
+  // ---- decoder: conv -> raw bf16 -> batch statistics -> GELU(BN [+ skip])
+  const void* cur = ws + L.xnf;
+  int hw = m->grid, cin = E, in_pad = 0;
+  for (int st = 0; st < 4; ++st) {
+    const msd_train_stage& sw = tw.stages[st];
+    const int c = d.dec_channels[st];
+    unsigned char* T[10];
+    for (int k = 0; k < 10; ++k) T[k] = ws + L.dec[st][k];
+    MSD_TRY(zero_halo(T[0], B, 2 * hw, 2 * hw, c, s));
+    MSD_TRY(make_convt(p, cur, sw.w_up, sw.b_up, T[0], B, hw, hw, in_pad, cin, c, 0));
+    MSD_TRY(gemm::launch(p, be, s));
+    hw *= 2;
+    float* st_up = stats + (size_t)bn_index(st, 0) * kStatsStride;
+    MSD_TRY(msd_bn_stats_bf16(T[0], B, hw, hw, c, sw.bn_up.gamma, sw.bn_up.beta, tw.bn_eps, tw.bn_momentum, sw.bn_up.running_mean,
+                              sw.bn_up.running_var, st_up, sums, stream));
+    MSD_TRY(msd_bn_act_fwd_bf16(T[0], nullptr, st_up, T[1], B, hw, hw, c, stream));
+    // two ResidualBlocks: (in, raw1, act1, raw2, out) = (T1, T2, T3, T4, T5) and (T5, T6, T7, T8, T9)
+    for (int rb = 0; rb < 2; ++rb) {
+      unsigned char *in = T[1 + 4 * rb], *c1 = T[2 + 4 * rb], *y1 = T[3 + 4 * rb], *c2 = T[4 + 4 * rb], *out = T[5 + 4 * rb];
+      const msd_bn_params &b1 = sw.bn_conv[2 * rb], &b2 = sw.bn_conv[2 * rb + 1];
+      float* s1 = stats + (size_t)bn_index(st, 1 + 2 * rb) * kStatsStride;
+      float* s2 = stats + (size_t)bn_index(st, 2 + 2 * rb) * kStatsStride;
+      MSD_TRY(make_conv3x3(p, in, sw.w_conv[2 * rb], nullptr, nullptr, c1, B, hw, hw, c, c, 0));
+      MSD_TRY(gemm::launch(p, be, s));
+      MSD_TRY(msd_bn_stats_bf16(c1, B, hw, hw, c, b1.gamma, b1.beta, tw.bn_eps, tw.bn_momentum, b1.running_mean, b1.running_var, s1, sums, stream));
+      MSD_TRY(msd_bn_act_fwd_bf16(c1, nullptr, s1, y1, B, hw, hw, c, stream));
+      MSD_TRY(make_conv3x3(p, y1, sw.w_conv[2 * rb + 1], nullptr, nullptr, c2, B, hw, hw, c, c, 0));
+      MSD_TRY(gemm::launch(p, be, s));
+      MSD_TRY(msd_bn_stats_bf16(c2, B, hw, hw, c, b2.gamma, b2.beta, tw.bn_eps, tw.bn_momentum, b2.running_mean, b2.running_var, s2, sums, stream));
+      MSD_TRY(msd_bn_act_fwd_bf16(c2, in, s2, out, B, hw, hw, c, stream));
+    }
+    cur = T[9]; cin = c; in_pad = 1;
+  }
+  {
+    const int c = d.dec_channels[3];
+    float* sh = stats + (size_t)20 * kStatsStride;
+    MSD_TRY(make_conv3x3(p, cur, tw.w_head3, tw.b_head3, nullptr, ws + L.head_c, B, hw, hw, c, c, 0));
+    MSD_TRY(gemm::launch(p, be, s));
+    MSD_TRY(msd_bn_stats_bf16(ws + L.head_c, B, hw, hw, c, tw.bn_head.gamma, tw.bn_head.beta, tw.bn_eps, tw.bn_momentum,
+                              tw.bn_head.running_mean, tw.bn_head.running_var, sh, sums, stream));
+    MSD_TRY(msd_bn_act_fwd_bf16(ws + L.head_c, nullptr, sh, ws + L.head_h, B, hw, hw, c, stream));
+    MSD_TRY(msd_head1x1_nchw_f32(ws + L.head_h, tw.w_head1, tw.b_head1, d_y, B, hw, hw, c, d.out_channels, stream));
+  }
+  return MSD_OK;
+}
+
+extern "C" int msd_model_backward(msd_model* m, const float* d_grad_y, int B, void* d_ws, size_t ws_bytes, const msd_model_grads* gr,
+                                  void* stream) {
+  MSD_REQUIRE(m && m->has_train_weights, "model_backward: training weights not set");
+  MSD_REQUIRE(d_grad_y && d_ws && gr && gr->blocks && B > 0, "model_backward: null pointer");
+  const TrainLayout L = train_layout(m, B);
+  if (ws_bytes < L.total) {
+    msd_set_error("model_backward: workspace %zu < %zu bytes", ws_bytes, L.total);
+    return MSD_ERR_WORKSPACE;
+  }
+  const msd_model_desc& d = m->d;
+  const msd_train_weights& tw = m->tw;
+  const msd_model_weights& w = tw.enc;
+  cudaStream_t s = (cudaStream_t)stream;
+  unsigned char* ws = reinterpret_cast<unsigned char*>(d_ws);
+  const int M = B * m->tokens, E = d.embed_dim, Kpe = d.in_channels * d.patch_size * d.patch_size, Hd = d.mlp_hidden;
+  const int be = d.gemm_backend;
+  Problem p;
+  float* stats = reinterpret_cast<float*>(ws + L.stats);
+  double* sums = reinterpret_cast<double*>(ws + L.sums);
+  float* coef = reinterpret_cast<float*>(ws + L.coef);
+  unsigned char *gA = ws + L.gA, *gB = ws + L.gB, *gC = ws + L.gC;
+  const int S = d.image_size;
+
+  // ---- head: 1x1 conv, then conv3x3 + BN + GELU
+  {
+    const int c = d.dec_channels[3], kpad = round_up(c, 64);
+    const long long rows = (long long)B * (S + 2) * (S + 2);
+    MSD_TRY(msd_head1x1_bwd(d_grad_y, tw.w_head1, gA, ws + L.dyt, B, S, S, c, d.out_channels, stream));
+    if (gr->w_head1) {
+      MSD_TRY(zero_f32(gr->w_head1, (size_t)d.out_channels * c, s));
+      MSD_TRY(msd_wgrad_linear_bf16(ws + L.dyt, 16, ws + L.head_h, c, gr->w_head1, c, rows, d.out_channels, c, stream));
+    }
+    MSD_TRY(bias_grad(ws + L.dyt, rows, 16, gr->b_head1, d.out_channels, sums, stream));
+    MSD_TRY(msd_bn_act_bwd_bf16(gA, ws + L.head_c, nullptr, stats + (size_t)20 * kStatsStride, gA, gA, gr->bn_head_g, gr->bn_head_b, coef,
+                                sums, B, S, S, c, stream));
+    if (gr->w_head3) {
+      MSD_TRY(zero_f32(gr->w_head3, (size_t)9 * kpad * c, s));
+      MSD_TRY(msd_wgrad_conv3x3_bf16(ws + L.dec[3][9], gA, gr->w_head3, B, S, S, c, c, kpad, c, stream));
+    }
+    MSD_TRY(make_conv3x3(p, gA, tw.wd_head3, nullptr, nullptr, gB, B, S, S, c, c, 0));
+    MSD_TRY(gemm::launch(p, be, s));
+  }
+  // ---- decoder stages, last to first.  On entry gB holds the gradient of the stage output (haloed, halo zero).
+  int hw = S;
+  for (int st = 3; st >= 0; --st) {
+    const msd_train_stage& sw = tw.stages[st];
+    const msd_stage_grads& sg = gr->stages[st];
+    const int c = d.dec_channels[st], kpad = round_up(c, 64);
+    const int cin = st == 0 ? E : d.dec_channels[st - 1];
+    unsigned char* T[10];
+    for (int k = 0; k < 10; ++k) T[k] = ws + L.dec[st][k];
+    unsigned char *gin = gB, *t1 = gA;      // gin: gradient of the block output; t1: free buffer
+    for (int rb = 1; rb >= 0; --rb) {
+      unsigned char *in = T[1 + 4 * rb], *c1 = T[2 + 4 * rb], *y1 = T[3 + 4 * rb], *c2 = T[4 + 4 * rb];
+      float* s1 = stats + (size_t)bn_index(st, 1 + 2 * rb) * kStatsStride;
+      float* s2 = stats + (size_t)bn_index(st, 2 + 2 * rb) * kStatsStride;
+      // out = GELU(in + BN2(c2)):  dz -> gC (also the skip gradient), dc2 -> t1
+      MSD_TRY(msd_bn_act_bwd_bf16(gin, c2, in, s2, gC, t1, sg.bn_g[2 * rb + 1], sg.bn_b[2 * rb + 1], coef, sums, B, hw, hw, c, stream));
+      if (sg.w_conv[2 * rb + 1]) {
+        MSD_TRY(zero_f32(sg.w_conv[2 * rb + 1], (size_t)9 * kpad * c, s));
+        MSD_TRY(msd_wgrad_conv3x3_bf16(y1, t1, sg.w_conv[2 * rb + 1], B, hw, hw, c, c, kpad, c, stream));
+      }
+      MSD_TRY(make_conv3x3(p, t1, sw.wd_conv[2 * rb + 1], nullptr, nullptr, gin, B, hw, hw, c, c, 0));   // dy1 -> gin
+      MSD_TRY(gemm::launch(p, be, s));
+      // y1 = GELU(BN1(c1)):  dc1 in place
+      MSD_TRY(msd_bn_act_bwd_bf16(gin, c1, nullptr, s1, gin, gin, sg.bn_g[2 * rb], sg.bn_b[2 * rb], coef, sums, B, hw, hw, c, stream));
+      if (sg.w_conv[2 * rb]) {
+        MSD_TRY(zero_f32(sg.w_conv[2 * rb], (size_t)9 * kpad * c, s));
+        MSD_TRY(msd_wgrad_conv3x3_bf16(in, gin, sg.w_conv[2 * rb], B, hw, hw, c, c, kpad, c, stream));
+      }
+      // d(in) = dgrad(dc1) + skip gradient (identity tap, A = gC)
+      MSD_TRY(make_conv3x3(p, gin, sw.wd_conv[2 * rb], nullptr, gC, t1, B, hw, hw, c, c, 0));
+      MSD_TRY(gemm::launch(p, be, s));
+      std::swap(gin, t1);                    // gin now holds d(in)
+    }
+    // X0 = GELU(BN(U_raw)), U_raw = ConvT(stage input)
+    MSD_TRY(msd_bn_act_bwd_bf16(gin, T[0], nullptr, stats + (size_t)bn_index(st, 0) * kStatsStride, gin, gin, sg.bn_up_g, sg.bn_up_b, coef,
+                                sums, B, hw, hw, c, stream));
+    hw /= 2;
+    const int in_pad = st == 0 ? 0 : 1;
+    const long long rows_in = (long long)B * (in_pad ? (hw + 2) * (hw + 2) : hw * hw);
+    MSD_TRY(msd_convt_unshuffle_bf16(gin, ws + L.dys, B, hw, hw, in_pad, c, stream));
+    const void* stage_in = st == 0 ? (const void*)(ws + L.xnf) : (const void*)(ws + L.dec[st - 1][9]);
+    if (sg.w_up) {
+      MSD_TRY(zero_f32(sg.w_up, (size_t)4 * c * cin, s));
+      MSD_TRY(msd_wgrad_linear_bf16(ws + L.dys, 4 * c, stage_in, cin, sg.w_up, cin, rows_in, 4 * c, cin, stream));
+    }
+    // data gradient of the stage input: [rows_in, 4c] . W_up -> [rows_in, cin]  (halo rows of dys are zero -> stay zero)
+    void* dst = st == 0 ? (void*)(ws + L.dxn) : (void*)gB;   // the operand is dys, so gB (= gin after two swaps) is free again
+    MSD_TRY(make_linear(p, ws + L.dys, sw.wT_up, nullptr, dst, nullptr, (int)rows_in, cin, 4 * c, 0, 0));
+    MSD_TRY(gemm::launch(p, be, s));
+  }
+  // ---- encoder.  g: fp32 gradient of the residual stream, gbf its bf16 copy (operand of the GEMMs)
+  float* g = reinterpret_cast<float*>(ws + L.g);
+  void *gbf = ws + L.gbf, *dh = ws + L.dh, *dxn = ws + L.dxn, *dqkv = ws + L.dqkv, *datt = ws + L.datt;
+  MSD_TRY(zero_f32(gr->norm_g, E, s));
+  MSD_TRY(zero_f32(gr->norm_b, E, s));
+  MSD_TRY(msd_layernorm_bwd(dxn, 0, reinterpret_cast<const float*>(ws + L.xs + d.depth * L.s_xs), w.norm_g, d.ln_eps_outer, g, 0, gbf,
+                            gr->norm_g, gr->norm_b, M, E, stream));
+  for (int l = d.depth - 1; l >= 0; --l) {
+    const msd_block_weights& bw = m->tblocks[l];
+    const msd_train_block& bt = m->tblocks_t[l];
+    const msd_block_grads& bg = gr->blocks[l];
+    const bool tr = bt.trainable != 0;
+    const float* xin = reinterpret_cast<const float*>(ws + L.xs + l * L.s_xs);
+    const float* xmid = reinterpret_cast<const float*>(ws + L.xm + l * L.s_xs);
+    void *xn1 = ws + L.xn1 + l * L.s_xn, *qkv = ws + L.qkv + l * L.s_qkv, *att = ws + L.att + l * L.s_xn;
+    void *xn2 = ws + L.xn2 + l * L.s_xn, *hpre = ws + L.hpre + l * L.s_h, *h = ws + L.h + l * L.s_h;
+    // MLP branch: x_out = x_mid + fc2(GELU(fc1(LN2 x_mid)))
+    MSD_TRY(make_linear(p, gbf, bt.wT_fc2, nullptr, dh, nullptr, M, Hd, E, 0, 0));
+    MSD_TRY(gemm::launch(p, be, s));
+    if (tr) {
+      MSD_TRY(zero_f32(bg.w_fc2, (size_t)E * Hd, s));
+      MSD_TRY(msd_wgrad_linear_bf16(gbf, E, h, Hd, bg.w_fc2, Hd, M, E, Hd, stream));
+      MSD_TRY(bias_grad(gbf, M, E, bg.b_fc2, E, sums, stream));
+    }
+    MSD_TRY(msd_gelu_bwd_bf16(dh, hpre, dh, (long long)M * Hd, stream));
+    MSD_TRY(make_linear(p, dh, bt.wT_fc1, nullptr, dxn, nullptr, M, E, Hd, 0, 0));
+    MSD_TRY(gemm::launch(p, be, s));
+    if (tr) {
+      MSD_TRY(zero_f32(bg.w_fc1, (size_t)E * Hd, s));
+      MSD_TRY(msd_wgrad_linear_bf16(dh, Hd, xn2, E, bg.w_fc1, E, M, Hd, E, stream));
+      MSD_TRY(bias_grad(dh, M, Hd, bg.b_fc1, Hd, sums, stream));
+      MSD_TRY(zero_f32(bg.ln2_g, E, s));
+      MSD_TRY(zero_f32(bg.ln2_b, E, s));
+    }
+    MSD_TRY(msd_layernorm_bwd(dxn, 0, xmid, bw.ln2_g, d.ln_eps_block, g, 1, gbf, tr ? bg.ln2_g : nullptr, tr ? bg.ln2_b : nullptr, M, E, stream));
+    // attention branch: x_mid = x_in + proj(attn(LN1 x_in))
+    MSD_TRY(make_linear(p, gbf, bt.wT_proj, nullptr, datt, nullptr, M, E, E, 0, 0));
+    MSD_TRY(gemm::launch(p, be, s));
+    if (tr) {
+      MSD_TRY(zero_f32(bg.w_proj, (size_t)E * E, s));
+      MSD_TRY(msd_wgrad_linear_bf16(gbf, E, att, E, bg.w_proj, E, M, E, E, stream));
+      MSD_TRY(bias_grad(gbf, M, E, bg.b_proj, E, sums, stream));
+    }
+    MSD_TRY(msd_attention_bwd_bf16(qkv, datt, dqkv, B, m->tokens, d.num_heads, stream));
+    MSD_TRY(make_linear(p, dqkv, bt.wT_qkv, nullptr, dxn, nullptr, M, E, 3 * E, 0, 0));
+    MSD_TRY(gemm::launch(p, be, s));
+    if (tr) {
+      MSD_TRY(zero_f32(bg.w_qkv, (size_t)3 * E * E, s));
+      MSD_TRY(msd_wgrad_linear_bf16(dqkv, 3 * E, xn1, E, bg.w_qkv, E, M, 3 * E, E, stream));
+      MSD_TRY(bias_grad(dqkv, M, 3 * E, bg.b_qkv, 3 * E, sums, stream));
+      MSD_TRY(zero_f32(bg.ln1_g, E, s));
+      MSD_TRY(zero_f32(bg.ln1_b, E, s));
+    }
+    MSD_TRY(msd_layernorm_bwd(dxn, 0, xin, bw.ln1_g, d.ln_eps_block, g, 1, gbf, tr ? bg.ln1_g : nullptr, tr ? bg.ln1_b : nullptr, M, E, stream));
+  }
+  // ---- patch embedding: x0 = LN(pe) + pos_embed
+  if (gr->pos_embed) MSD_TRY(msd_batch_sum_f32(g, gr->pos_embed, B, (long long)m->tokens * E, stream));
+  MSD_TRY(zero_f32(gr->pe_ln_g, E, s));
+  MSD_TRY(zero_f32(gr->pe_ln_b, E, s));
+  MSD_TRY(msd_layernorm_bwd(g, 1, reinterpret_cast<const float*>(ws + L.x0pre), w.pe_ln_g, d.ln_eps_outer, g, 0, gbf, gr->pe_ln_g, gr->pe_ln_b,
+                            M, E, stream));
+  if (gr->w_pe) {
+    MSD_TRY(zero_f32(gr->w_pe, (size_t)E * Kpe, s));
+    MSD_TRY(msd_wgrad_linear_bf16(gbf, E, ws + L.a_pe, Kpe, gr->w_pe, Kpe, M, E, Kpe, stream));
+  }
+  MSD_TRY(bias_grad(gbf, M, E, gr->b_pe, E, sums, stream));
+  return MSD_OK;
+}
+
+// Byte offsets of the kept activations inside the training workspace, for tests and debugging:
+// out[0] = xnf, out[1 + 10*s + k] = decoder stage s tensor k (U_raw, X0, C1, Y1, C2, Z1, C3, Y2, C4, Z2), out[41] = head raw,
+// out[42] = head activated, out[43] = BatchNorm statistics (21 x [4][1024] fp32), out[44] = total bytes
+extern "C" int msd_model_train_layout(const msd_model* m, int B, size_t* out, int capacity) {
+  MSD_REQUIRE(m && out && B > 0 && capacity >= 45, "model_train_layout: need room for 45 offsets");
+  const TrainLayout L = train_layout(m, B);
+  out[0] = L.xnf;
+  for (int s = 0; s < 4; ++s)
+    for (int k = 0; k < 10; ++k) out[1 + 10 * s + k] = L.dec[s][k];
+  out[41] = L.head_c; out[42] = L.head_h; out[43] = L.stats; out[44] = L.total;
   return MSD_OK;
 }

@@ -244,6 +244,17 @@ __global__ void __launch_bounds__(kBlock) gelu_bwd_kernel(const __nv_bfloat16* _
   }
 }
 
+// h = GELU(h_pre), bf16 elementwise (the training forward keeps both: h_pre for the backward, h as the fc2 operand)
+__global__ void __launch_bounds__(kBlock) gelu_fwd_kernel(const __nv_bfloat16* __restrict__ hpre, __nv_bfloat16* __restrict__ out, long long nvec) {
+  for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < nvec; i += (long long)gridDim.x * kBlock) {
+    float z[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(hpre) + i), z);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) z[k] = gelu_fwd(z[k]);
+    reinterpret_cast<uint4*>(out)[i] = pack8(z);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // LayerNorm backward, one warp per row (D = 32 * 4 * NV):
 //   dxh = dy * gamma;  dx = rstd * (dxh - mean(dxh) - xhat * mean(dxh * xhat));  dgamma += dy * xhat;  dbeta += dy
@@ -500,6 +511,14 @@ extern "C" int msd_bn_act_bwd_bf16(const void* d_dy, const void* d_c, const void
   bn_act_bwd2_kernel<<<grid_for(rows * (C / 8)), kBlock, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(d_dz),
                                                                  reinterpret_cast<const __nv_bfloat16*>(d_c), d_stats, d_coef,
                                                                  reinterpret_cast<__nv_bfloat16*>(d_dc), rows, C, plane, pitch, H, W);
+  MSD_LAUNCH_CHECK();
+  return MSD_OK;
+}
+
+extern "C" int msd_gelu_fwd_bf16(const void* d_hpre, void* d_out, long long n, void* stream) {
+  MSD_REQUIRE(d_hpre && d_out && n > 0 && n % 8 == 0, "gelu_fwd: bad arguments");
+  gelu_fwd_kernel<<<grid_for(n / 8), kBlock, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(d_hpre),
+                                                                        reinterpret_cast<__nv_bfloat16*>(d_out), n / 8);
   MSD_LAUNCH_CHECK();
   return MSD_OK;
 }

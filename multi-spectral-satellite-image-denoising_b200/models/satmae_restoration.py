@@ -69,6 +69,54 @@ def pack_convt2x2(convt: nn.ConvTranspose2d, bn: nn.BatchNorm2d):
     return _bf16(w), bias.contiguous()
 
 
+def pack_conv3x3_raw(weight: torch.Tensor, with_identity: bool = False) -> torch.Tensor:
+    """[Cout,Cin,3,3] -> bf16 [Cout, 9*Kpad] tap-major, no BatchNorm fold (training step); with_identity appends the identity tap."""
+    w = weight.detach().float()
+    cout, cin = w.shape[:2]
+    kpad = (cin + 63) // 64 * 64
+    w = _pad_k(w.permute(0, 2, 3, 1).contiguous(), kpad).reshape(cout, 9 * kpad)
+    if with_identity:
+        assert cin == cout
+        w = torch.cat([w, _pad_k(torch.eye(cout, device=w.device, dtype=w.dtype), kpad)], dim=1)
+    return _bf16(w)
+
+
+def pack_conv3x3_dgrad(weight: torch.Tensor, with_identity: bool = False) -> torch.Tensor:
+    """Data-gradient operand of a 3x3 conv: the conv with flipped taps and swapped channel roles,
+    Wd[ci, tap, co] = W[co, ci, 8 - tap]  (dX = conv3x3(dY, Wd)).  with_identity: tenth tap = identity, adds the gradient
+    that reaches the same tensor through the ResidualBlock skip connection (blocks.py:85)."""
+    return pack_conv3x3_raw(weight.detach().flip(2, 3).permute(1, 0, 2, 3), with_identity)
+
+
+def pack_convt2x2_raw(weight: torch.Tensor, bias: torch.Tensor):
+    """[Cin,Cout,2,2] -> (bf16 [4*Cout, Kpad] rows (di,dj,o), fp32 bias [4*Cout], bf16 W^T [Cin, 4*Cout])."""
+    w = weight.detach().float()
+    cin, cout = w.shape[:2]
+    kpad = (cin + 63) // 64 * 64
+    m = w.permute(2, 3, 1, 0).contiguous().reshape(4 * cout, cin)
+    return _bf16(_pad_k(m, kpad)), bias.detach().float().repeat(4).contiguous(), _bf16(m.t())
+
+
+class _RestoreTrainFn(torch.autograd.Function):
+    """One training forward / backward of the whole network inside libmsd_b200 (csrc/model.cu, training step).  The
+    parameters are passed as inputs only so that autograd routes their gradients; the arithmetic reads the packed copies."""
+
+    @staticmethod
+    def forward(ctx, model, x, *params):
+        y, ws = model._forward_train(x)
+        ctx.model, ctx.ws, ctx.B = model, ws, x.shape[0]
+        ctx.needs = [p.requires_grad for p in params]
+        return y
+
+    @staticmethod
+    def backward(ctx, grad_y):
+        grads = ctx.model._backward_train(grad_y.detach().float().contiguous(), ctx.ws, ctx.B)
+        names = [n for n, _ in ctx.model.named_parameters()]
+        out = [grads.get(n) if need else None for n, need in zip(names, ctx.needs)]
+        ctx.ws = None
+        return (None, None, *out)
+
+
 class SatMAERestoration(nn.Module):
     """noisy [B,13,S,S] -> SatMAE ViT-B encoder -> CNN decoder -> restored [B,13,S,S] (fp32)."""
 
@@ -210,11 +258,15 @@ class SatMAERestoration(nn.Module):
             f"Expected {self.config['data']['num_bands']} bands, got {C_}"
         if not x.is_cuda:
             raise _lib.MsdError("SatMAERestoration.forward: CUDA tensor required (libmsd_b200 has no CPU path)")
-        if self.training or (torch.is_grad_enabled() and x.requires_grad):
-            raise _lib.MsdError("SatMAERestoration: the training forward/backward (batch-stat BatchNorm, dgrad/wgrad) is "
-                                "not built yet; call .eval() and run under torch.no_grad()")
         if next(self.parameters()).device != x.device:
             raise _lib.MsdError("SatMAERestoration: model and input are on different devices")
+        if self.training:
+            # training mode: BatchNorm batch statistics + the backward pass, both inside the library (csrc/model.cu)
+            if torch.is_grad_enabled():
+                return _RestoreTrainFn.apply(self, x.detach().float().contiguous(), *self.parameters())
+            return self._forward_train(x.detach().float().contiguous())[0]
+        if torch.is_grad_enabled() and x.requires_grad:
+            raise _lib.MsdError("SatMAERestoration: gradients with respect to the input image are not produced in eval mode")
         x = x.detach().float().contiguous()
         lib = self._ensure_ready(x.device)
         with torch.cuda.device(x.device):
@@ -229,6 +281,170 @@ class SatMAERestoration(nn.Module):
             _lib.check(lib.msd_model_forward(self._handle, _lib.ptr(x), _lib.ptr(patches), B, _lib.ptr(y), _lib.ptr(ws),
                                              ws.numel(), _lib.stream_ptr()))
         return y
+
+    # ------------------------------------------------------------------ training step
+    def _bn_params(self, bn: nn.BatchNorm2d, keep) -> _lib.BnParams:
+        b = _lib.BnParams()
+        g, be = bn.weight.detach().float().contiguous(), bn.bias.detach().float().contiguous()
+        keep.extend([g, be])
+        b.gamma, b.beta = _lib.ptr(g), _lib.ptr(be)
+        b.running_mean, b.running_var = _lib.ptr(bn.running_mean), _lib.ptr(bn.running_var)   # updated in place by the kernel
+        return b
+
+    @torch.no_grad()
+    def _pack_train(self):
+        """Un-folded bf16 weights + the transposed / tap-flipped copies the data-gradient GEMMs read (include/msd.h)."""
+        enc, dec = self.encoder, self.decoder
+        base, keep = self._pack(None)            # encoder part is shared with the eval packing; its decoder part is ignored
+        keep = list(keep)
+        tw = _lib.TrainWeights()
+        tw.enc = base
+        tb = (_lib.TrainBlock * enc.depth)()
+        for i, blk in enumerate(enc.blocks):
+            t = blk.tensors()
+            for name, wt in (("wT_qkv", t["qkv_w"]), ("wT_proj", t["proj_w"]), ("wT_fc1", t["fc1"].weight), ("wT_fc2", t["fc2"].weight)):
+                wT = _bf16(wt.detach().t())
+                keep.append(wT)
+                setattr(tb[i], name, _lib.ptr(wT))
+            tb[i].trainable = int(any(p.requires_grad for p in blk.parameters()))
+        keep.append(tb)
+        tw.blocks_t = C.cast(tb, C.POINTER(_lib.TrainBlock))
+        mods = list(dec.upsample_blocks)
+        per_stage = 1 + dec.num_residual_blocks
+        for s in range(4):
+            up = mods[s * per_stage]
+            ts = tw.stages[s]
+            w_up, b_up, wT_up = pack_convt2x2_raw(up.upsample[0].weight, up.upsample[0].bias)
+            keep.extend([w_up, b_up, wT_up])
+            ts.w_up, ts.b_up, ts.wT_up = _lib.ptr(w_up), _lib.ptr(b_up), _lib.ptr(wT_up)
+            ts.bn_up = self._bn_params(up.upsample[1], keep)
+            k = 0
+            for rb in mods[s * per_stage + 1:(s + 1) * per_stage]:
+                for conv, bn, first in ((rb.block[0], rb.block[1], True), (rb.block[3], rb.block[4], False)):
+                    wf, wd = pack_conv3x3_raw(conv.weight), pack_conv3x3_dgrad(conv.weight, with_identity=first)
+                    keep.extend([wf, wd])
+                    ts.w_conv[k], ts.wd_conv[k] = _lib.ptr(wf).value, _lib.ptr(wd).value
+                    ts.bn_conv[k] = self._bn_params(bn, keep)
+                    k += 1
+        h0, hbn, h3 = dec.head[0], dec.head[1], dec.head[3]
+        wf, wd = pack_conv3x3_raw(h0.weight), pack_conv3x3_dgrad(h0.weight)
+        hb = h0.bias.detach().float().contiguous()
+        w1, b1 = h3.weight.detach().float().reshape(dec.out_channels, -1).contiguous(), h3.bias.detach().float().contiguous()
+        keep.extend([wf, wd, hb, w1, b1])
+        tw.w_head3, tw.b_head3, tw.wd_head3 = _lib.ptr(wf), _lib.ptr(hb), _lib.ptr(wd)
+        tw.bn_head = self._bn_params(hbn, keep)
+        tw.w_head1, tw.b_head1 = _lib.ptr(w1), _lib.ptr(b1)
+        tw.bn_eps, tw.bn_momentum = float(hbn.eps), float(hbn.momentum if hbn.momentum is not None else 0.1)
+        return tw, keep
+
+    def _ensure_train_ready(self, device):
+        lib = _lib.load()
+        _lib.require_device(device)
+        if self._handle is None:
+            h = C.c_void_p()
+            d = self._desc()
+            _lib.check(lib.msd_model_create(C.byref(d), C.byref(h)))
+            self._handle = h
+        key = ("train",) + self._version_key(device)
+        if key != getattr(self, "_train_key", None):
+            tw, keep = self._pack_train()
+            _lib.check(lib.msd_model_set_train_weights(self._handle, C.byref(tw)))
+            self._train_packed, self._train_key = (tw, keep), key
+        return lib
+
+    def _forward_train(self, x: torch.Tensor):
+        lib = self._ensure_train_ready(x.device)
+        B = x.shape[0]
+        with torch.cuda.device(x.device):
+            need = lib.msd_model_train_workspace_bytes(self._handle, B)
+            ws = torch.empty(need, dtype=torch.uint8, device=x.device)   # owned by the autograd node until backward ran
+            y = torch.empty(B, self.decoder.out_channels, self.image_size, self.image_size, dtype=torch.float32, device=x.device)
+            _lib.check(lib.msd_model_forward_train(self._handle, _lib.ptr(x), B, _lib.ptr(y), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
+        for mod in self.decoder.modules():
+            if isinstance(mod, nn.BatchNorm2d) and mod.num_batches_tracked is not None:
+                mod.num_batches_tracked += 1
+        # the kernel changed the running statistics in place: the eval-mode packing must be rebuilt from them
+        self._packed_key = None
+        return y, ws
+
+    def _backward_train(self, grad_y: torch.Tensor, ws: torch.Tensor, B: int):
+        """Runs msd_model_backward and returns {parameter name: fp32 gradient in the parameter's own layout}."""
+        lib = _lib.load()
+        enc, dec = self.encoder, self.decoder
+        dev = grad_y.device
+        E, depth = enc.embed_dim, enc.depth
+        bufs = {}
+
+        def buf(name, *shape):
+            t = torch.empty(*shape, dtype=torch.float32, device=dev)
+            bufs[name] = t
+            return _lib.ptr(t)
+
+        def want(param):
+            return param.requires_grad
+
+        g = _lib.ModelGrads()
+        pe = enc.patch_embed
+        kpe = pe.proj.weight[0].numel()
+        if want(pe.proj.weight): g.w_pe = buf("encoder.patch_embed.proj.weight", E, kpe)
+        if want(pe.proj.bias): g.b_pe = buf("encoder.patch_embed.proj.bias", E)
+        if want(pe.norm.weight):
+            g.pe_ln_g, g.pe_ln_b = buf("encoder.patch_embed.norm.weight", E), buf("encoder.patch_embed.norm.bias", E)
+        if want(enc.pos_embed): g.pos_embed = buf("encoder.pos_embed", enc.pos_embed.shape[1], E)
+        bg = (_lib.BlockGrads * depth)()
+        names = {v: k for k, v in ((n, id(p)) for n, p in self.named_parameters())}
+        for i, blk in enumerate(enc.blocks):
+            if not any(p.requires_grad for p in blk.parameters()):
+                continue
+            t = blk.tensors()
+            hid = t["fc1"].weight.shape[0]
+            for field, param, shape in (
+                    ("ln1_g", t["ln1"].weight, (E,)), ("ln1_b", t["ln1"].bias, (E,)), ("ln2_g", t["ln2"].weight, (E,)),
+                    ("ln2_b", t["ln2"].bias, (E,)), ("w_qkv", t["qkv_w"], (3 * E, E)), ("b_qkv", t["qkv_b"], (3 * E,)),
+                    ("w_proj", t["proj_w"], (E, E)), ("b_proj", t["proj_b"], (E,)), ("w_fc1", t["fc1"].weight, (hid, E)),
+                    ("b_fc1", t["fc1"].bias, (hid,)), ("w_fc2", t["fc2"].weight, (E, hid)), ("b_fc2", t["fc2"].bias, (E,))):
+                setattr(bg[i], field, buf(names[id(param)], *shape))
+        g.blocks = C.cast(bg, C.POINTER(_lib.BlockGrads))
+        g.norm_g, g.norm_b = buf("encoder.norm.weight", E), buf("encoder.norm.bias", E)
+        mods = list(dec.upsample_blocks)
+        per_stage = 1 + dec.num_residual_blocks
+        post = []          # (parameter name, buffer name, unpack function)
+        cin = E
+        for s in range(4):
+            c = dec.channels[s]
+            kpad = (c + 63) // 64 * 64
+            up = mods[s * per_stage]
+            sg = g.stages[s]
+            pfx = f"decoder.upsample_blocks.{s * per_stage}.upsample."
+            sg.w_up = buf(pfx + "0.weight", 4 * c, cin)
+            post.append((pfx + "0.weight", lambda t, c=c, cin=cin: t.view(2, 2, c, cin).permute(3, 2, 0, 1).contiguous()))
+            sg.bn_up_g, sg.bn_up_b = buf(pfx + "1.weight", c), buf(pfx + "1.bias", c)
+            bufs[pfx + "0.bias"] = torch.zeros(c, dtype=torch.float32, device=dev)      # a bias in front of BatchNorm has zero gradient
+            k = 0
+            for j in range(dec.num_residual_blocks):
+                rp = f"decoder.upsample_blocks.{s * per_stage + 1 + j}.block."
+                for ci, bi in ((0, 1), (3, 4)):
+                    sg.w_conv[k] = buf(rp + f"{ci}.weight", 9, kpad, c).value
+                    post.append((rp + f"{ci}.weight", lambda t, c=c: t[:, :c, :].permute(2, 1, 0).reshape(c, c, 3, 3).contiguous()))
+                    sg.bn_g[k], sg.bn_b[k] = buf(rp + f"{bi}.weight", c).value, buf(rp + f"{bi}.bias", c).value
+                    k += 1
+            cin = c
+        c = dec.channels[-1]
+        kpad = (c + 63) // 64 * 64
+        g.w_head3 = buf("decoder.head.0.weight", 9, kpad, c)
+        post.append(("decoder.head.0.weight", lambda t, c=c: t[:, :c, :].permute(2, 1, 0).reshape(c, c, 3, 3).contiguous()))
+        bufs["decoder.head.0.bias"] = torch.zeros(c, dtype=torch.float32, device=dev)
+        g.bn_head_g, g.bn_head_b = buf("decoder.head.1.weight", c), buf("decoder.head.1.bias", c)
+        g.w_head1, g.b_head1 = buf("decoder.head.3.weight", dec.out_channels, c), buf("decoder.head.3.bias", dec.out_channels)
+        with torch.cuda.device(dev):
+            _lib.check(lib.msd_model_backward(self._handle, _lib.ptr(grad_y), B, _lib.ptr(ws), ws.numel(), C.byref(g), _lib.stream_ptr()))
+        for name, fn in post:
+            bufs[name] = fn(bufs[name])
+        out = {}
+        for name, param in self.named_parameters():
+            if name in bufs:
+                out[name] = bufs[name].reshape(param.shape)
+        return out
 
     # ------------------------------------------------------------------ reference helper API
     def count_parameters(self) -> Dict[str, int]:

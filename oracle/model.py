@@ -21,8 +21,11 @@ def _block_tensors(sd: dict, i: int):
             sd[p + "mlp.fc1.weight"], sd[p + "mlp.fc1.bias"], sd[p + "mlp.fc2.weight"], sd[p + "mlp.fc2.bias"])
 
 
-def _bn(x, sd, p, eps=1e-5):
-    return F.batch_norm(x, sd[p + "running_mean"], sd[p + "running_var"], sd[p + "weight"], sd[p + "bias"], False, 0.0, eps)
+def _bn(x, sd, p, eps=1e-5, training=False):
+    """eval: running statistics; training: batch statistics, running buffers updated in place with momentum 0.1
+    (nn.BatchNorm2d defaults, reference blocks.py:69)."""
+    return F.batch_norm(x, sd[p + "running_mean"], sd[p + "running_var"], sd[p + "weight"], sd[p + "bias"], training,
+                        0.1 if training else 0.0, eps)
 
 
 def encoder_forward(sd: dict, x: torch.Tensor, num_heads: int = 12, ln_eps_block: float = 1e-5, ln_eps_outer: float = 1e-5):
@@ -48,22 +51,23 @@ def encoder_forward(sd: dict, x: torch.Tensor, num_heads: int = 12, ln_eps_block
     return F.layer_norm(t, (D,), sd["encoder.norm.weight"], sd["encoder.norm.bias"], ln_eps_outer)  # encoder.py:322
 
 
-def decoder_forward(sd: dict, feat: torch.Tensor):
+def decoder_forward(sd: dict, feat: torch.Tensor, training: bool = False):
     x = feat
     i = 0
     while True:
         p = f"decoder.upsample_blocks.{i}."
         if p + "upsample.0.weight" in sd:                                           # blocks.py:113-120
             x = F.conv_transpose2d(x, sd[p + "upsample.0.weight"], sd[p + "upsample.0.bias"], stride=2)
-            x = F.gelu(_bn(x, sd, p + "upsample.1."))
+            x = F.gelu(_bn(x, sd, p + "upsample.1.", training=training))
         elif p + "block.0.weight" in sd:                                            # blocks.py:74-85
-            y = F.gelu(_bn(F.conv2d(x, sd[p + "block.0.weight"], None, padding=1), sd, p + "block.1."))
-            y = _bn(F.conv2d(y, sd[p + "block.3.weight"], None, padding=1), sd, p + "block.4.")
+            y = F.gelu(_bn(F.conv2d(x, sd[p + "block.0.weight"], None, padding=1), sd, p + "block.1.", training=training))
+            y = _bn(F.conv2d(y, sd[p + "block.3.weight"], None, padding=1), sd, p + "block.4.", training=training)
             x = F.gelu(x + y)
         else:
             break
         i += 1
-    x = F.gelu(_bn(F.conv2d(x, sd["decoder.head.0.weight"], sd["decoder.head.0.bias"], padding=1), sd, "decoder.head.1."))
+    x = F.gelu(_bn(F.conv2d(x, sd["decoder.head.0.weight"], sd["decoder.head.0.bias"], padding=1), sd, "decoder.head.1.",
+                  training=training))
     return F.conv2d(x, sd["decoder.head.3.weight"], sd["decoder.head.3.bias"])      # decoder.py:80
 
 
@@ -76,3 +80,13 @@ def restoration_forward(sd: dict, x: torch.Tensor, num_heads: int = 12, ln_eps_b
     feat = tok.transpose(1, 2).reshape(B, D, g, g)                                  # satmae_restoration.py:128-133
     y = decoder_forward(sd, feat)
     return (y, tok) if return_tokens else y
+
+
+def restoration_forward_train(sd: dict, x: torch.Tensor, num_heads: int = 12, ln_eps_block: float = 1e-5,
+                              ln_eps_outer: float = 1e-5):
+    """Training-mode forward (BatchNorm batch statistics; running buffers in `sd` are updated in place), differentiable:
+    what `self.model(noisy)` computes inside Trainer.train_epoch (reference src/training/trainer.py:141-143) in fp32."""
+    tok = encoder_forward(sd, x, num_heads, ln_eps_block, ln_eps_outer)
+    B, N, D = tok.shape
+    g = int(round(N ** 0.5))
+    return decoder_forward(sd, tok.transpose(1, 2).reshape(B, D, g, g), training=True)

@@ -238,3 +238,94 @@ def test_attention_bwd():
     _lib.check(lib.msd_attention_bwd_bf16(_lib.ptr(qkv_d), _lib.ptr(dout_d), _lib.ptr(dqkv), B, T, heads, _lib.stream_ptr()))
     for i, name in enumerate(("dq", "dk", "dv")):
         _close(dqkv[:, i * E:(i + 1) * E].cpu(), qkv.grad[:, i * E:(i + 1) * E], 2e-2)
+
+
+# ----------------------------------------------------------------------------------------------- whole training step
+def _close_rms(got, ref, rel_rms=6e-2, rel_max=0.1):
+    """Training-mode activations are O(1) after every BatchNorm, so bf16 rounding (two per layer: raw conv output and
+    activation) accumulates to a few percent over the 40 decoder tensors (measured 3.5% RMS at random init; layer-by-layer
+    growth is smooth, tools/train_debug.py).  Judged relative to the reference's own RMS / max."""
+    e = (got.float() - ref.float())
+    rms, ref_rms = e.pow(2).mean().sqrt().item(), ref.float().pow(2).mean().sqrt().item()
+    assert rms <= rel_rms * ref_rms, f"rms err {rms:.4g} vs ref rms {ref_rms:.4g}"
+    assert e.abs().max().item() <= rel_max * ref.abs().max().item(), f"max err {e.abs().max().item():.4g} vs ref max {ref.abs().max().item():.4g}"
+
+
+def _train_case(B=2, seed=42):
+    import recipes
+    from msd_b200.models import SatMAERestoration
+    torch.manual_seed(seed)
+    model = SatMAERestoration(recipes.base_config(), block_layout="fallback")      # blocks 0-5 frozen (configs/base.yaml:31)
+    sd = recipes.perturb_decoder_stats({k: v.clone() for k, v in model.state_dict().items()})
+    model.load_state_dict(sd)
+    x = recipes.model_input(B, seed=77)
+    target = torch.randn(B, 13, 192, 192, generator=torch.Generator().manual_seed(5)) * 0.5
+    return model, sd, x, target
+
+
+def test_train_forward_and_backward_vs_autograd():
+    from oracle import model as omodel
+    model, sd, x, target = _train_case()
+    frozen = {n for n, p in model.named_parameters() if not p.requires_grad}
+    # ---- oracle: torch fp32 autograd, training-mode BatchNorm
+    ref = {k: v.clone() for k, v in sd.items()}
+    for k, v in ref.items():
+        if v.is_floating_point() and "running_" not in k and k not in frozen:
+            v.requires_grad_(True)
+    y_ref = omodel.restoration_forward_train(ref, x)
+    loss_ref = ((y_ref - target) ** 2).mean()
+    loss_ref.backward()
+    # ---- CUDA path
+    model.cuda().train()
+    y = model(x.cuda())
+    assert y.requires_grad
+    loss = ((y - target.cuda()) ** 2).mean()
+    loss.backward()
+    _close_rms(y.detach().cpu(), y_ref.detach())
+    # running statistics follow nn.BatchNorm2d (momentum 0.1, unbiased variance)
+    for k, v in model.state_dict().items():
+        if "running_" in k:
+            assert torch.allclose(v.cpu(), ref[k], rtol=2e-2, atol=2e-3), k
+        if k.endswith("num_batches_tracked"):
+            assert int(v) == 1
+    worst = []
+    for n, p in model.named_parameters():
+        if n in frozen:
+            assert p.grad is None, n
+            continue
+        assert p.grad is not None, n
+        gref = ref[n].grad
+        scale = gref.abs().max().item()
+        e = (p.grad.cpu() - gref).abs().max().item()
+        if n.endswith(("upsample.0.bias", "head.0.bias")):      # a bias in front of BatchNorm: exactly zero gradient
+            assert p.grad.abs().max().item() == 0 and scale < 1e-6
+            continue
+        rms = (p.grad.cpu() - gref).pow(2).mean().sqrt().item() / (gref.pow(2).mean().sqrt().item() + 1e-20)
+        worst.append((rms, e / (scale + 1e-20), n, scale))
+    worst.sort(reverse=True)
+    print("worst gradient errors (rel rms, rel max, name, |grad|max):", *worst[:12], sep="\n  ")
+    import os
+    if os.environ.get("MSD_TRAIN_VERBOSE"):
+        for w_ in sorted(worst, key=lambda t: t[2]):
+            print(f"   {w_[2]:60s} rms {w_[0]:.4f} max {w_[1]:.4f} scale {w_[3]:.3g}")
+    # bf16 activations/gradients vs fp32 autograd: torch's own bf16 autocast on the same model, input and loss deviates from
+    # fp32 by 0.7% (head) ... 5.6% (stage 2) ... 11% (stage 0 and the whole encoder) relative RMS -- the same profile this path
+    # shows (0.6% ... 4.7% ... 9-10%); recorded in DESIGN.md.  The bound below is that mixed-precision envelope.
+    assert worst[0][0] <= 0.15 and max(w[1] for w in worst) <= 0.15, worst[:8]
+
+
+def test_train_mode_no_grad_forward_matches_and_eval_still_works():
+    from oracle import model as omodel
+    model, sd, x, _ = _train_case(B=2, seed=7)
+    model.cuda().train()
+    with torch.no_grad():
+        y = model(x.cuda())
+    ref = {k: v.clone() for k, v in sd.items()}
+    with torch.no_grad():
+        y_ref = omodel.restoration_forward_train(ref, x)
+    _close_rms(y.cpu(), y_ref)
+    model.eval()
+    with torch.no_grad():
+        y2 = model(x.cuda())
+    y2_ref = omodel.restoration_forward(ref, x)                 # eval forward with the UPDATED running statistics
+    assert (y2.cpu() - y2_ref).abs().max().item() <= 2e-2
