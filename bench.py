@@ -137,6 +137,57 @@ def run_reference(args):
     return 0
 
 
+# ------------------------------------------------------------------------------------------------ training step (C4)
+def train_step_bench(dev, world, steps=5, warmup=2, micro=64):
+    """BASELINE config C4: one data-parallel training step per rank on `micro` tiles: corrupt -> training forward (batch-stat
+    BatchNorm) -> MSE + 0.1 (1-SSIM) -> backward (blocks 0-5 frozen) -> gradient all-reduce -> clip 1.0 -> AdamW.  Everything
+    except the optimizer update (torch fused AdamW) runs in libmsd_b200."""
+    import torch.distributed as dist
+    from msd_b200.data import AddSensorNoise
+    from msd_b200.models import SatMAERestoration
+    from msd_b200.training import CombinedLoss
+    from msd_b200.training.distributed import allreduce_gradients
+    torch.manual_seed(42)
+    model = SatMAERestoration(recipes.base_config(), block_layout="fallback").to(dev).train()
+    noise = AddSensorNoise(*recipes.NOISE_CONFIGS["base"])
+    crit = CombinedLoss(1.0, 0.1)
+    opt = torch.optim.AdamW(model.get_optimizer_param_groups(1e-4, 0.05), betas=(0.9, 0.999), fused=True)
+    clean, _ = recipes.eurosat_tiles(32, seed=200 + int(os.environ.get("RANK", "0")))
+    clean = clean.repeat(micro // 32 + 1, 1, 1, 1)[:micro].contiguous().to(dev)
+
+    def step():
+        out = model(noise(clean))
+        loss = crit(out, clean)
+        loss.backward()
+        allreduce_gradients(model.parameters())
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        return loss
+
+    for _ in range(warmup):
+        step()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0.record()
+    for _ in range(steps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_step = ms.item() / steps
+    del model, opt
+    torch.cuda.empty_cache()
+    return {"value": world * micro / ms_step * 1e3, "unit": "img/s", "ms_per_step": ms_step, "micro_batch_per_gpu": micro,
+            "steps": steps, "algorithmic_gflop_per_img": 146.4, "tflops_per_gpu": 146.4 * micro / ms_step,
+            "loss": float(loss.detach()), "frozen_blocks": [0, 1, 2, 3, 4, 5],
+            "note": "fwd+bwd+loss in libmsd_b200 (bf16 tensor cores, fp32 accumulate); optimizer = torch fused AdamW"}
+
+
 # ------------------------------------------------------------------------------------------------ CUDA arm
 def main():
     ap = argparse.ArgumentParser()
@@ -147,6 +198,7 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--backend", type=int, default=0, help="0 tcgen05 (product), 1 legacy mma.sync (A/B)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the C4 training-step measurement")
     ap.add_argument("--profile-out", default=None, help="write the per-launch event profile (json) here")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -302,6 +354,10 @@ def main():
         "clocks": clk.summary(),
         "quality": {k: float(v) for k, v in metrics_dev.items()},
     }
+    if not args.no_train and args.backend == 0:
+        del model
+        torch.cuda.empty_cache()
+        line["train_step"] = train_step_bench(dev, world)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r = cpu_port_run(steps=8, warmup=1)
         line["cpu_baseline"] = {"value": r["value"], "unit": "img/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}

@@ -165,8 +165,9 @@ class SatMAERestoration(nn.Module):
         return d
 
     @torch.no_grad()
-    def _pack(self, device):
-        """bf16 / BN-folded copies of the parameters in the layouts include/msd.h documents."""
+    def _pack(self, device, encoder_only: bool = False):
+        """bf16 / BN-folded copies of the parameters in the layouts include/msd.h documents.
+        encoder_only: skip the BatchNorm-folded decoder (the training step packs its own un-folded decoder weights)."""
         enc, dec = self.encoder, self.decoder
         keep = []  # tensors that must outlive the C struct
 
@@ -198,6 +199,8 @@ class SatMAERestoration(nn.Module):
         keep.append(blocks)
         w.blocks = C.cast(blocks, C.POINTER(_lib.BlockWeights))
         w.norm_g, w.norm_b = f32(enc.norm.weight), f32(enc.norm.bias)
+        if encoder_only:
+            return w, keep
         mods = list(dec.upsample_blocks)
         per_stage = 1 + dec.num_residual_blocks
         for s in range(4):
@@ -295,7 +298,7 @@ class SatMAERestoration(nn.Module):
     def _pack_train(self):
         """Un-folded bf16 weights + the transposed / tap-flipped copies the data-gradient GEMMs read (include/msd.h)."""
         enc, dec = self.encoder, self.decoder
-        base, keep = self._pack(None)            # encoder part is shared with the eval packing; its decoder part is ignored
+        base, keep = self._pack(None, encoder_only=True)   # encoder part is shared with the eval packing
         keep = list(keep)
         tw = _lib.TrainWeights()
         tw.enc = base

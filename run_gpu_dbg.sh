@@ -1,2 +1,2 @@
 mkdir -p gpurun_out
-python tools/bn_cancel_probe.py > gpurun_out/bn_probe.log 2>&1; tail -20 gpurun_out/bn_probe.log
+python tools/train_bench.py > gpurun_out/train_bench.log 2>&1; tail -5 gpurun_out/train_bench.log

@@ -66,3 +66,33 @@ def test_launcher_rebinds_reference_names():
             "assert e.MetricsTracker is M.MetricsTracker and d.AddSensorNoise is D.AddSensorNoise and len(done) >= 20") % str(Path(__file__).resolve().parent.parent)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-2000:]
+
+
+def _grad_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from msd_b200.training.distributed import allreduce_gradients
+    torch.manual_seed(0)
+    params = [torch.nn.Parameter(torch.zeros(s)) for s in ((7, 5), (1000,), (3, 3, 3, 3), (2,))]
+    params[1].requires_grad_(False)                           # a frozen parameter: no gradient on any rank
+    for i, p in enumerate(params):
+        if p.requires_grad:
+            p.grad = torch.full_like(p, float(rank + 1) * (i + 1))
+    n = allreduce_gradients(params, bucket_mb=1)
+    out[rank] = (n, [None if p.grad is None else p.grad.clone() for p in params])
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_world2():
+    """C4 data-parallel step: gradients are averaged in place, frozen parameters are skipped, shapes survive the bucketing."""
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_grad_worker, args=(world, 29519, out), nprocs=world, join=True)
+    for rank in range(world):
+        n, grads = out[rank]
+        assert n >= 1 and grads[1] is None
+        for i in (0, 2, 3):
+            assert grads[i].shape == [(7, 5), (1000,), (3, 3, 3, 3), (2,)][i]
+            assert torch.allclose(grads[i], torch.full_like(grads[i], 1.5 * (i + 1)))
