@@ -302,6 +302,22 @@ int msd_model_forward_train(msd_model* m, const float* d_x, int B, float* d_y, v
 int msd_model_backward(msd_model* m, const float* d_grad_y, int B, void* d_ws, size_t ws_bytes, const msd_model_grads* grads,
                        void* stream);
 
+/* ---------------------------------------------------------------------------------------------------
+ * Data formats either side of the path (csrc/ingest.cu).
+ * msd_ingest_u16_f32: EuroSATMultiSpectral.__getitem__ preprocessing (src/data/dataset.py:160-186) for a batch of raw tiles:
+ *   d_dn uint16 [B,C,h,w] -> per-image scale (max > 10: /10000, max > 1.5: /255, else 1) -> bilinear SxS (align_corners=False)
+ *   -> clamp(0,1) -> (x-0.5)/0.25 -> d_out fp32 [B,C,S,S]; d_scale_ws fp32 [B] scratch.
+ * msd_tile_extract_f32 / msd_tile_blend_f32: full-scene tiling (BASELINE config C5; no reference semantics):
+ *   tiles[t] = scene[:, ty0[t]:+S, tx0[t]:+S];  out = sum_t w_t restored_t / sum_t w_t over scene rows [row0,row1) with the
+ *   separable weight w(y,x) = r(y) r(x), r(i) = min(i+1, S-i, ramp)/ramp; gy[ny], gx[nx] = sorted tile-grid origins,
+ *   tile_index[ny*nx] = slot of grid tile (r,k) in d_restored or -1.
+ * ------------------------------------------------------------------------------------------------- */
+int msd_ingest_u16_f32(const uint16_t* d_dn, float* d_out, float* d_scale_ws, int B, int C, int h, int w, int S, void* stream);
+int msd_tile_extract_f32(const float* d_scene, const int* d_ty0, const int* d_tx0, float* d_tiles, int n_tiles, int C, int H, int W,
+                         int S, void* stream);
+int msd_tile_blend_f32(const float* d_restored, const int* d_gy, const int* d_gx, const int* d_tile_index, int ny, int nx, float* d_out,
+                       int C, int H, int W, int S, int ramp, int row0, int row1, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

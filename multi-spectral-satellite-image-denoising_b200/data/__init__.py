@@ -1,5 +1,7 @@
-"""Mirror of the reference's ``src.data`` for the hot path (src/data/__init__.py:7-15): only AddSensorNoise is
-re-implemented; dataset / dataloader I/O stays with the reference."""
+"""Mirror of the reference's ``src.data`` for the hot path (src/data/__init__.py:7-15): AddSensorNoise is
+re-implemented, plus the batched GPU form of the dataset's per-sample preprocessing (ingest_tiles);
+file I/O and the DataLoader stay with the reference."""
 from .transforms import AddSensorNoise
+from .ingest import ingest_tiles
 
-__all__ = ["AddSensorNoise"]
+__all__ = ["AddSensorNoise", "ingest_tiles"]

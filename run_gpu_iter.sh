@@ -1,2 +1,2 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_train.py -q -p no:cacheprovider ${PYTEST_ARGS:-} > gpurun_out/t_train.log 2>&1; echo "train rc=$?"; tail -n 25 gpurun_out/t_train.log
+timeout 600 python -m pytest ${PYTEST_FILES:-tests/test_gpu_scene.py} -q -p no:cacheprovider ${PYTEST_ARGS:-} > gpurun_out/t_iter.log 2>&1; echo "rc=$?"; tail -n 30 gpurun_out/t_iter.log
