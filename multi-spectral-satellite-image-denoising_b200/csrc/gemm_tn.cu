@@ -57,6 +57,10 @@ __host__ __device__ constexpr uint32_t make_idesc_mn(int m, int n) {
 __device__ __forceinline__ void red_add_f32(float* addr, float v) {
   asm volatile("red.global.add.f32 [%0], %1;\n" ::"l"(addr), "f"(v) : "memory");
 }
+// four consecutive fp32 adds in one 16-byte reduction (sm_90+): a quarter of the L2 atomic transactions
+__device__ __forceinline__ void red_add_v4_f32(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 
 template <int MODE, int NB>   // MODE 0 = linear (NB 64-column atoms of B per tile), 1 = conv3x3 (NB = 1)
 struct TnCfg {
@@ -173,6 +177,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     mbar_wait(acc_full, 0);
     tcgen05_fence_after();
     const int r = q * 32 + lane;
+    const bool vec_ok = (p.ldo & 3) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15u) == 0;
 #pragma unroll 1
     for (int g = 0; g < C::NACC; ++g) {
       long long orow;
@@ -192,9 +197,15 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tmem_ld_wait();
         if (row_ok) {
           float* dst = p.out + orow * p.ldo + b_col0 + c * 16;
+          if (vec_ok && b_col0 + c * 16 + 16 <= p.out_cols) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (b_col0 + c * 16 + j < p.out_cols) red_add_f32(dst + j, __uint_as_float(v[j]));
+            for (int j = 0; j < 16; j += 4)
+              red_add_v4_f32(dst + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (b_col0 + c * 16 + j < p.out_cols) red_add_f32(dst + j, __uint_as_float(v[j]));
+          }
         }
       }
     }
@@ -221,10 +232,19 @@ int launch_tn(TnProblem& p, cudaStream_t s) {
   }
   p.num_kb = (int)((p.rows + KB - 1) / KB);
   const int tiles = p.tiles_m * p.tiles_n;
-  // split the contraction so that the grid covers the machine about twice (fp32 atomics merge the partial sums)
-  int splitk = (2 * num_sms() + tiles - 1) / tiles;
-  if (splitk > p.num_kb) splitk = p.num_kb;
-  if (splitk < 1) splitk = 1;
+  // Split the contraction across CTAs (fp32 atomics merge the partial sums).  Every CTA pays a fixed prologue (TMA latency)
+  // and epilogue (its whole tile goes out through atomics), so the split is chosen to fill WHOLE waves of the machine with
+  // as few, as long CTAs as possible: the smallest number of waves whose CTAs still contract >= 48 k-blocks each wins,
+  // else one wave.
+  const int sms = num_sms();
+  int splitk = 1;
+  for (int waves = 1; waves <= 4; ++waves) {
+    int sk = (waves * sms) / tiles;
+    if (sk < 1) sk = 1;
+    if (sk > p.num_kb) sk = p.num_kb;
+    splitk = sk;
+    if (tiles * sk >= (waves * sms * 9) / 10 || p.num_kb / sk < 48) break;   // this wave count is (nearly) full, or CTAs get short
+  }
   p.kb_per_split = (p.num_kb + splitk - 1) / splitk;
   p.splitk = (p.num_kb + p.kb_per_split - 1) / p.kb_per_split;
   gemm_tn_kernel<MODE, NB><<<tiles * p.splitk, kThreadsTn, C::SMEM_BYTES, s>>>(tmA, tmB, p);

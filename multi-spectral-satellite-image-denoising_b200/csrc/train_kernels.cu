@@ -37,6 +37,25 @@ __device__ __forceinline__ float gelu_grad(float z) {
   const float erf_abs = fmaf(-poly * t, e, 1.0f);
   return fmaf(0.5f, copysignf(erf_abs, z), 0.5f) + z * 0.3989422804014327f * e;
 }
+// dy * gelu'(z) for two elements at a time in half2 (tanh form, MUFU.TANH.F16x2):
+//   u = z (c0 + c1 z^2), t = tanh(u), gelu'(z) = 0.5 (1 + t) + 0.5 z (1 - t^2) (c0 + 3 c1 z^2)
+// |tanh form - erf form| <= 1e-3 on the derivative and fp16 evaluation (1e-3 relative) are both below the bf16 rounding of
+// the product that follows; z is clamped to +-8 (the derivative is 0 / 1 beyond, and fp16 z^2 must not overflow).
+__device__ __forceinline__ float2 gelu_grad2(float z0, float z1) {
+  const __half2 z = __floats2half2_rn(fminf(fmaxf(z0, -8.f), 8.f), fminf(fmaxf(z1, -8.f), 8.f));
+  const __half2 c0 = __float2half2_rn(0.7978845608f), c1 = __float2half2_rn(0.0356774081f), c3 = __float2half2_rn(0.1070322243f);
+  const __half2 half = __float2half2_rn(0.5f), one = __float2half2_rn(1.0f);
+  const __half2 z2 = __hmul2(z, z);
+  const __half2 u = __hmul2(z, __hfma2(z2, c1, c0));
+  uint32_t ui = *reinterpret_cast<const uint32_t*>(&u), ti;
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(ti) : "r"(ui));
+  const __half2 t = *reinterpret_cast<const __half2*>(&ti);
+  const __half2 sech2 = __hfma2(__hneg2(t), t, one);                          // 1 - t^2
+  const __half2 inner = __hmul2(__hmul2(half, z), __hfma2(z2, c3, c0));       // 0.5 z (c0 + 3 c1 z^2)
+  const __half2 g = __hfma2(sech2, inner, __hfma2(half, t, half));
+  return __half22float2(g);
+}
+
 __device__ __forceinline__ bool interior_row(uint32_t p, const FastDiv& plane, const FastDiv& pitch, int H, int W) {
   uint32_t img, rem, yy, xx;
   fd_divmod(p, plane, img, rem);
@@ -117,15 +136,19 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, double count
   }
 }
 
-// y = GELU(scale * c + shift [+ skip]) on interior pixels, 0 on the halo
+// y = GELU(scale * c + shift [+ skip]) on interior pixels, 0 on the halo.  Thread t owns the 8-channel vector t % VPR of rows
+// t / VPR, + RPI, ... (no per-element division; scale / shift live in registers)
 __global__ void __launch_bounds__(kBlock) bn_act_fwd_kernel(const __nv_bfloat16* __restrict__ c, const __nv_bfloat16* __restrict__ skip,
                                                             const float* __restrict__ stats, __nv_bfloat16* __restrict__ y,
                                                             long long rows, int C, FastDiv plane, FastDiv pitch, int H, int W) {
   const int vpr = C >> 3;
-  const long long total = rows * vpr;
-  for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < total; i += (long long)gridDim.x * kBlock) {
-    const long long row = i / vpr;
-    const int v = (int)(i - row * vpr);
+  const int rpi = kBlock / vpr;
+  const int v = threadIdx.x % vpr, r0 = threadIdx.x / vpr;
+  if (r0 >= rpi) return;
+  float sc[8], sf[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { sc[k] = stats[v * 8 + k]; sf[k] = stats[C + v * 8 + k]; }
+  for (long long row = (long long)blockIdx.x * rpi + r0; row < rows; row += (long long)gridDim.x * rpi) {
     uint4 o = make_uint4(0u, 0u, 0u, 0u);
     if (interior_row((uint32_t)row, plane, pitch, H, W)) {
       float f[8], s[8];
@@ -133,7 +156,7 @@ __global__ void __launch_bounds__(kBlock) bn_act_fwd_kernel(const __nv_bfloat16*
       if (skip != nullptr) unpack8(__ldg(reinterpret_cast<const uint4*>(skip + row * C + v * 8)), s);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        float z = fmaf(f[k], __ldg(stats + v * 8 + k), __ldg(stats + C + v * 8 + k));
+        float z = fmaf(f[k], sc[k], sf[k]);
         if (skip != nullptr) z += s[k];
         f[k] = gelu_fwd(z);
       }
@@ -169,13 +192,15 @@ __global__ void __launch_bounds__(kBlock) bn_act_bwd1_kernel(const __nv_bfloat16
         unpack8(__ldg(reinterpret_cast<const uint4*>(c + row * C + v * 8)), f);
         if (skip != nullptr) unpack8(__ldg(reinterpret_cast<const uint4*>(skip + row * C + v * 8)), s);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          float z = fmaf(f[k], sc[k], sf[k]);
-          if (skip != nullptr) z += s[k];
-          const float d = g[k] * gelu_grad(z);
-          g[k] = d;
-          s1[k] += d;
-          s2[k] = fmaf(d, (f[k] - mean[k]) * rstd[k], s2[k]);
+        for (int k = 0; k < 8; k += 2) {
+          float z0 = fmaf(f[k], sc[k], sf[k]), z1 = fmaf(f[k + 1], sc[k + 1], sf[k + 1]);
+          if (skip != nullptr) { z0 += s[k]; z1 += s[k + 1]; }
+          const float2 gg = gelu_grad2(z0, z1);
+          const float d0 = g[k] * gg.x, d1 = g[k + 1] * gg.y;
+          g[k] = d0; g[k + 1] = d1;
+          s1[k] += d0; s1[k + 1] += d1;
+          s2[k] = fmaf(d0, (f[k] - mean[k]) * rstd[k], s2[k]);
+          s2[k + 1] = fmaf(d1, (f[k + 1] - mean[k + 1]) * rstd[k + 1], s2[k + 1]);
         }
         o = pack8(g);
       }
@@ -208,27 +233,31 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums, double c
   coef[C + c] = (float)(sums[C + c] / count);
 }
 
-// pass 2: dc = gamma*rstd * (dz - k1 - xhat * k2) on interior pixels, 0 on the halo
+// pass 2: dc = gamma*rstd * (dz - k1 - xhat * k2) on interior pixels, 0 on the halo (same thread layout as the forward)
 __global__ void __launch_bounds__(kBlock) bn_act_bwd2_kernel(const __nv_bfloat16* __restrict__ dz, const __nv_bfloat16* __restrict__ c,
                                                              const float* __restrict__ stats, const float* __restrict__ coef,
                                                              __nv_bfloat16* __restrict__ dc, long long rows, int C, FastDiv plane,
                                                              FastDiv pitch, int H, int W) {
   const int vpr = C >> 3;
-  const long long total = rows * vpr;
-  for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < total; i += (long long)gridDim.x * kBlock) {
-    const long long row = i / vpr;
-    const int v = (int)(i - row * vpr);
+  const int rpi = kBlock / vpr;
+  const int v = threadIdx.x % vpr, r0 = threadIdx.x / vpr;
+  if (r0 >= rpi) return;
+  // dc = a * dz + b * c + d  with  a = scale, b = -scale*rstd*k2, d = scale * (mean*rstd*k2 - k1)
+  float ca[8], cb[8], cd[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int ch = v * 8 + k;
+    const float sc = stats[ch], mean = stats[2 * C + ch], rstd = stats[3 * C + ch], k1 = coef[ch], k2 = coef[C + ch];
+    ca[k] = sc; cb[k] = -sc * rstd * k2; cd[k] = sc * (mean * rstd * k2 - k1);
+  }
+  for (long long row = (long long)blockIdx.x * rpi + r0; row < rows; row += (long long)gridDim.x * rpi) {
     uint4 o = make_uint4(0u, 0u, 0u, 0u);
     if (interior_row((uint32_t)row, plane, pitch, H, W)) {
       float g[8], f[8];
       unpack8(__ldg(reinterpret_cast<const uint4*>(dz + row * C + v * 8)), g);
       unpack8(__ldg(reinterpret_cast<const uint4*>(c + row * C + v * 8)), f);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int ch = v * 8 + k;
-        const float xh = (f[k] - __ldg(stats + 2 * C + ch)) * __ldg(stats + 3 * C + ch);
-        g[k] = __ldg(stats + ch) * (g[k] - __ldg(coef + ch) - xh * __ldg(coef + C + ch));
-      }
+      for (int k = 0; k < 8; ++k) g[k] = fmaf(ca[k], g[k], fmaf(cb[k], f[k], cd[k]));
       o = pack8(g);
     }
     *reinterpret_cast<uint4*>(dc + row * C + v * 8) = o;
@@ -249,7 +278,10 @@ __global__ void __launch_bounds__(kBlock) gelu_bwd_kernel(const __nv_bfloat16* _
     unpack8(__ldg(reinterpret_cast<const uint4*>(dh) + i), g);
     unpack8(__ldg(reinterpret_cast<const uint4*>(hpre) + i), z);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) g[k] *= gelu_grad(z[k]);
+    for (int k = 0; k < 8; k += 2) {
+      const float2 gg = gelu_grad2(z[k], z[k + 1]);
+      g[k] *= gg.x; g[k + 1] *= gg.y;
+    }
     reinterpret_cast<uint4*>(out)[i] = pack8(g);
   }
 }
@@ -489,10 +521,10 @@ extern "C" int msd_bn_stats_bf16(const void* d_c, int B, int H, int W, int C, co
 
 extern "C" int msd_bn_act_fwd_bf16(const void* d_c, const void* d_skip, const float* d_stats, void* d_y, int B, int H, int W, int C,
                                    void* stream) {
-  MSD_REQUIRE(d_c && d_stats && d_y && C % 8 == 0, "bn_act_fwd: bad arguments");
+  MSD_REQUIRE(d_c && d_stats && d_y && C % 8 == 0 && C / 8 <= kBlock, "bn_act_fwd: bad arguments");
   const long long rows = (long long)B * (H + 2) * (W + 2);
   MSD_REQUIRE(rows < (1ll << 31), "bn_act_fwd: too many pixels");
-  bn_act_fwd_kernel<<<grid_for(rows * (C / 8)), kBlock, 0, (cudaStream_t)stream>>>(
+  bn_act_fwd_kernel<<<grid_for((rows + kBlock / (C / 8) - 1) / (kBlock / (C / 8)) * kBlock, 16), kBlock, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(d_c), reinterpret_cast<const __nv_bfloat16*>(d_skip), d_stats,
       reinterpret_cast<__nv_bfloat16*>(d_y), rows, C, make_fastdiv((uint32_t)((H + 2) * (W + 2))), make_fastdiv((uint32_t)(W + 2)), H, W);
   MSD_LAUNCH_CHECK();
@@ -512,13 +544,13 @@ extern "C" int msd_bn_act_bwd_bf16(const void* d_dy, const void* d_c, const void
   const FastDiv plane = make_fastdiv((uint32_t)((H + 2) * (W + 2))), pitch = make_fastdiv((uint32_t)(W + 2));
   MSD_CHECK_CUDA(cudaMemsetAsync(d_sums, 0, sizeof(double) * 2 * C, s));
   const int rpi = kBlock / (C / 8);
-  bn_act_bwd1_kernel<<<grid_for((rows + rpi - 1) / rpi * kBlock, 8), kBlock, 2 * kBlock * 8 * sizeof(float), s>>>(
+  bn_act_bwd1_kernel<<<grid_for((rows + rpi - 1) / rpi * kBlock, 16), kBlock, 2 * kBlock * 8 * sizeof(float), s>>>(
       reinterpret_cast<const __nv_bfloat16*>(d_dy), reinterpret_cast<const __nv_bfloat16*>(d_c),
       reinterpret_cast<const __nv_bfloat16*>(d_skip), d_stats, reinterpret_cast<__nv_bfloat16*>(d_dz), d_sums, rows, C, plane, pitch, H, W);
   MSD_LAUNCH_CHECK();
   bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(d_sums, (double)B * H * W, d_dgamma, d_dbeta, d_coef, C);
   MSD_LAUNCH_CHECK();
-  bn_act_bwd2_kernel<<<grid_for(rows * (C / 8)), kBlock, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(d_dz),
+  bn_act_bwd2_kernel<<<grid_for((rows + rpi - 1) / rpi * kBlock, 16), kBlock, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(d_dz),
                                                                  reinterpret_cast<const __nv_bfloat16*>(d_c), d_stats, d_coef,
                                                                  reinterpret_cast<__nv_bfloat16*>(d_dc), rows, C, plane, pitch, H, W);
   MSD_LAUNCH_CHECK();

@@ -11,6 +11,7 @@ from __future__ import annotations
 
 import ctypes as C
 import logging
+import os
 from typing import Dict
 
 import torch
@@ -177,7 +178,7 @@ class SatMAERestoration(nn.Module):
             return _lib.ptr(t)
 
         def b16(t):
-            t = _bf16(t.detach())
+            t = self._cached_cast(t, "b16", lambda a: _bf16(a.detach()))
             keep.append(t)
             return _lib.ptr(t)
 
@@ -222,6 +223,17 @@ class SatMAERestoration(nn.Module):
         w.w_head1 = f32(dec.head[3].weight.reshape(dec.out_channels, -1))
         w.b_head1 = f32(dec.head[3].bias)
         return w, keep
+
+    def _cached_cast(self, t: torch.Tensor, tag: str, fn):
+        """Packed copy of `t`; copies of frozen parameters (requires_grad False) are made once and reused."""
+        if t.requires_grad:
+            return fn(t)
+        cache = self.__dict__.setdefault("_frozen_cache", {})
+        key = (t.data_ptr(), tuple(t.shape), t._version, tag)
+        hit = cache.get(key)
+        if hit is None:
+            hit = cache[key] = fn(t)
+        return hit
 
     def _ensure_ready(self, device):
         lib = _lib.load()
@@ -306,7 +318,7 @@ class SatMAERestoration(nn.Module):
         for i, blk in enumerate(enc.blocks):
             t = blk.tensors()
             for name, wt in (("wT_qkv", t["qkv_w"]), ("wT_proj", t["proj_w"]), ("wT_fc1", t["fc1"].weight), ("wT_fc2", t["fc2"].weight)):
-                wT = _bf16(wt.detach().t())
+                wT = self._cached_cast(wt, "b16T", lambda a: _bf16(a.detach().t()))
                 keep.append(wT)
                 setattr(tb[i], name, _lib.ptr(wT))
             tb[i].trainable = int(any(p.requires_grad for p in blk.parameters()))
@@ -348,11 +360,37 @@ class SatMAERestoration(nn.Module):
             d = self._desc()
             _lib.check(lib.msd_model_create(C.byref(d), C.byref(h)))
             self._handle = h
-        key = ("train",) + self._version_key(device)
-        if key != getattr(self, "_train_key", None):
-            tw, keep = self._pack_train()
+        # The packed copies (bf16 casts, transposes, tap-flipped conv weights) must follow every optimizer step.  They are
+        # ~100 small device ops on fixed addresses, so they are captured ONCE into a CUDA graph and replayed per step: one
+        # launch instead of a host-bound stream of tiny kernels.  Copies of frozen parameters are cached outside the graph.
+        params, bufs = list(self.parameters()), list(self.buffers())
+        static_key = (str(device), self.gemm_backend, tuple(p.data_ptr() for p in params), tuple(p.requires_grad for p in params),
+                      tuple(b.data_ptr() for b in bufs))
+        versions = tuple(p._version for p in params)
+        if static_key != getattr(self, "_train_static_key", None):
+            self._train_graph = None
+            tw, keep = self._pack_train()                      # eager: warms up every op and fills the frozen-parameter cache
+            try:
+                if os.environ.get("MSD_NO_PACK_GRAPH"):
+                    raise RuntimeError("disabled by MSD_NO_PACK_GRAPH")
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    tw, keep = self._pack_train()
+                graph.replay()
+                self._train_graph = graph
+            except Exception as exc:  # pragma: no cover - capture is an optimisation of the plumbing only
+                logger.warning("weight-packing graph capture failed (%s); packing eagerly every step", exc)
+                tw, keep = self._pack_train()
             _lib.check(lib.msd_model_set_train_weights(self._handle, C.byref(tw)))
-            self._train_packed, self._train_key = (tw, keep), key
+            self._train_packed, self._train_static_key, self._train_versions = (tw, keep), static_key, versions
+        elif versions != self._train_versions:
+            if self._train_graph is not None:
+                self._train_graph.replay()
+            else:
+                tw, keep = self._pack_train()
+                _lib.check(lib.msd_model_set_train_weights(self._handle, C.byref(tw)))
+                self._train_packed = (tw, keep)
+            self._train_versions = versions
         return lib
 
     def _forward_train(self, x: torch.Tensor):

@@ -48,3 +48,12 @@ if args.only in (None, "loss"):
     timeit(fwd_bwd, 3 * nbytes, "loss fwd+bwd")
     with torch.no_grad():
         timeit(lambda: crit(b, a), 2 * nbytes, "loss fwd")
+if args.only in (None, "attention"):
+    from msd_b200 import _lib
+    lib = _lib.load()
+    qkv = torch.randn(B * 144, 2304, device="cuda").to(torch.bfloat16)
+    out = torch.empty(B * 144, 768, device="cuda", dtype=torch.bfloat16)
+    def att():
+        _lib.check(lib.msd_attention_bf16(_lib.ptr(qkv), _lib.ptr(out), B, 144, 12, _lib.stream_ptr()))
+    timeit(att, qkv.numel() * 2 + out.numel() * 2, "attention fwd")
+    print(f"   attention: {4.0 * B * 12 * 144 * 144 * 64 / 1e9:.1f} GFLOP per launch")
