@@ -64,18 +64,34 @@ extern template int launch_bn<16>(const Problem&, cudaStream_t);
 
 }  // namespace tc5
 
-int pick_bn_tc5(int N) {
-  // largest tile that divides N; 2*BN fp32 accumulator columns must fit the 512 TMEM columns
+int pick_bn_tc5(int N, int M, bool wave_aware) {
+  // Tile width: a divisor of N (2*BN fp32 accumulator columns must fit the 512 TMEM columns).  Wider tiles amortise the A
+  // operand better, but the persistent grid runs whole waves of 148 CTAs: for the small GEMMs of the training step
+  // (M = 9,216 rows at micro-batch 64) a narrower tile that fills its last wave beats a wider one that leaves it half empty.
   const int cand[] = {256, 192, 128, 96, 64, 48, 32, 16};
-  for (int c : cand)
-    if (N % c == 0) return c;
-  return 0;
+  const double speed[] = {1.00, 0.97, 0.90, 0.84, 0.74, 0.62, 0.45, 0.25};   // relative per-tile efficiency (tools/gemm_bench.py)
+  const int sms = tc5::num_sms();
+  const long long tiles_m = (M + BLOCK_M - 1) / BLOCK_M;
+  int best = 0;
+  double best_score = -1.0;
+  for (int i = 0; i < 8; ++i) {
+    const int c = cand[i];
+    if (N % c != 0) continue;
+    if (!wave_aware) return c;                                 // largest divisor
+    const long long tiles = tiles_m * (N / c);
+    const long long waves = (tiles + sms - 1) / sms;
+    const double score = speed[i] * (double)tiles / (double)(waves * sms);
+    if (score > best_score + 1e-9) { best_score = score; best = c; }
+  }
+  return best;
 }
 
 int launch_tc5(const Problem& p, cudaStream_t s) {
   MSD_REQUIRE(p.N % 16 == 0, "gemm_tc5: N=%d must be a multiple of 16", p.N);
   MSD_REQUIRE(p.ldA % 8 == 0 && msd_aligned16(p.A) && msd_aligned16(p.Wt), "gemm_tc5: operands must be 16-byte aligned / pitched");
-  switch (pick_bn_tc5(p.N)) {
+  // multi-tap (3x3 conv) problems keep the largest tile: their summation order (tap-major vs dx-merged) depends on the tile
+  // width through the kernel mode, and results must not depend on the batch size (sharding invariance is tested bit-exactly)
+  switch (pick_bn_tc5(p.N, p.M, p.num_kb == p.kb_per_tap)) {
     case 256: return tc5::launch_bn<256>(p, s);
     case 192: return tc5::launch_bn<192>(p, s);
     case 128: return tc5::launch_bn<128>(p, s);

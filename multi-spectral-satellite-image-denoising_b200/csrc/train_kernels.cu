@@ -156,11 +156,12 @@ __global__ void __launch_bounds__(kBlock) bn_act_fwd_kernel(const __nv_bfloat16*
       if (skip != nullptr) unpack8(__ldg(reinterpret_cast<const uint4*>(skip + row * C + v * 8)), s);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        float z = fmaf(f[k], sc[k], sf[k]);
-        if (skip != nullptr) z += s[k];
-        f[k] = gelu_fwd(z);
+        f[k] = fmaf(f[k], sc[k], sf[k]);
+        if (skip != nullptr) f[k] += s[k];
       }
-      o = pack8(f);
+      // the same half2 tanh-form GELU the eval-path GEMM epilogues apply (common.cuh), so train and eval activations agree
+      const uint2 a = gelu4_to_bf16(make_float4(f[0], f[1], f[2], f[3])), b = gelu4_to_bf16(make_float4(f[4], f[5], f[6], f[7]));
+      o = make_uint4(a.x, a.y, b.x, b.y);
     }
     *reinterpret_cast<uint4*>(y + row * C + v * 8) = o;
   }
@@ -291,9 +292,8 @@ __global__ void __launch_bounds__(kBlock) gelu_fwd_kernel(const __nv_bfloat16* _
   for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < nvec; i += (long long)gridDim.x * kBlock) {
     float z[8];
     unpack8(__ldg(reinterpret_cast<const uint4*>(hpre) + i), z);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) z[k] = gelu_fwd(z[k]);
-    reinterpret_cast<uint4*>(out)[i] = pack8(z);
+    const uint2 a = gelu4_to_bf16(make_float4(z[0], z[1], z[2], z[3])), b = gelu4_to_bf16(make_float4(z[4], z[5], z[6], z[7]));
+    reinterpret_cast<uint4*>(out)[i] = make_uint4(a.x, a.y, b.x, b.y);
   }
 }
 
