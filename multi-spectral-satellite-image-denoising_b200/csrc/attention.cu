@@ -11,7 +11,7 @@
 namespace {
 
 constexpr int HD = 64;       // head dim
-constexpr int LDS = HD + 8;  // padded smem row (144 B): conflict-free ldmatrix
+constexpr int LDS = HD;      // dense 128-byte rows; the 16-byte chunk index is XOR-swizzled with (row & 7): conflict-free ldmatrix
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
@@ -33,42 +33,52 @@ __device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], 
 
 template <int kT>
 __global__ void __launch_bounds__(kT * 2) attention_kernel(const __nv_bfloat16* __restrict__ qkv,
-                                                           __nv_bfloat16* __restrict__ out, int heads) {
+                                                           __nv_bfloat16* __restrict__ out, int heads, int problems) {
   static_assert(kT % 16 == 0, "token count must be a multiple of 16");
   constexpr int NT = kT / 8;    // key tiles of 8
   constexpr int KS = kT / 16;   // key steps of 16 for P.V
   constexpr int kThreads = kT * 2;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __nv_bfloat16(*Qs)[LDS] = reinterpret_cast<__nv_bfloat16(*)[LDS]>(smem_raw);
-  __nv_bfloat16(*Ks)[LDS] = Qs + kT;
-  __nv_bfloat16(*Vs)[LDS] = Ks + kT;
-
-  const int b = blockIdx.x / heads, h = blockIdx.x - b * heads;
+  // Persistent CTA with two q/k/v buffers: the next (image, head) problem streams in through cp.async while the current
+  // one is being computed, so the load latency (the kernel used to sit in the barrier behind it) is off the critical path.
+  typedef __nv_bfloat16 (*Tile)[LDS];
   const int E = heads * HD;
-  const __nv_bfloat16* base = qkv + (size_t)b * kT * 3 * E + h * HD;
-  // stage q, k, v: 3 * kT rows of 128 B, 16-byte chunks
-  for (int i = threadIdx.x; i < 3 * kT * 8; i += kThreads) {
-    const int which = i / (kT * 8), rem = i - which * kT * 8, row = rem >> 3, ch = rem & 7;
-    cp_async16(&Qs[which * kT + row][ch * 8], base + (size_t)row * 3 * E + which * E + ch * 8);
-  }
-  asm volatile("cp.async.commit_group;\n" ::);
+  auto issue_load = [&](int problem, int buf) {
+    Tile dst = reinterpret_cast<Tile>(smem_raw) + buf * 3 * kT;
+    const int bb = problem / heads, hh = problem - bb * heads;
+    const __nv_bfloat16* base = qkv + (size_t)bb * kT * 3 * E + hh * HD;
+    // q, k, v: 3 * kT rows of 128 B, 16-byte chunks
+    for (int i = threadIdx.x; i < 3 * kT * 8; i += kThreads) {
+      const int which = i / (kT * 8), rem = i - which * kT * 8, row = rem >> 3, ch = rem & 7;
+      cp_async16(&dst[which * kT + row][(ch ^ (row & 7)) * 8], base + (size_t)row * 3 * E + which * E + ch * 8);
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
+  };
+  if ((int)blockIdx.x < problems) issue_load(blockIdx.x, 0);
+  int it = 0;
+  for (int problem = blockIdx.x; problem < problems; problem += gridDim.x, ++it) {
   asm volatile("cp.async.wait_group 0;\n" ::);
-  __syncthreads();
+  __syncthreads();              // this problem's tile has landed AND every warp is done with the buffer about to be refilled
+  if (problem + (int)gridDim.x < problems) issue_load(problem + gridDim.x, (it + 1) & 1);
+  Tile Qs = reinterpret_cast<Tile>(smem_raw) + (it & 1) * 3 * kT;
+  Tile Ks = Qs + kT;
+  Tile Vs = Ks + kT;
+  const int b = problem / heads, h = problem - b * heads;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row0 = warp * 16;
 
   uint32_t qa[4][4];
 #pragma unroll
-  for (int kk = 0; kk < 4; ++kk) ldmatrix_x4(qa[kk], &Qs[row0 + (lane & 15)][kk * 16 + (lane >> 4) * 8]);
+  for (int kk = 0; kk < 4; ++kk) ldmatrix_x4(qa[kk], &Qs[row0 + (lane & 15)][((kk * 2 + (lane >> 4)) ^ (lane & 7)) * 8]);
 
   float s[NT][4];
 #pragma unroll
   for (int j = 0; j < NT; ++j) {
     s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.0f;
     uint32_t kb0[4], kb1[4];
-    ldmatrix_x4(kb0, &Ks[8 * j + (lane & 7)][(lane >> 3) * 8]);
-    ldmatrix_x4(kb1, &Ks[8 * j + (lane & 7)][32 + (lane >> 3) * 8]);
+    ldmatrix_x4(kb0, &Ks[8 * j + (lane & 7)][((lane >> 3) ^ (lane & 7)) * 8]);
+    ldmatrix_x4(kb1, &Ks[8 * j + (lane & 7)][((4 + (lane >> 3)) ^ (lane & 7)) * 8]);
     mma_bf16(s[j], qa[0], kb0[0], kb0[1]);
     mma_bf16(s[j], qa[1], kb0[2], kb0[3]);
     mma_bf16(s[j], qa[2], kb1[0], kb1[1]);
@@ -109,7 +119,7 @@ __global__ void __launch_bounds__(kT * 2) attention_kernel(const __nv_bfloat16* 
 #pragma unroll
     for (int n2 = 0; n2 < 4; ++n2) {  // two 8-wide dim tiles per ldmatrix.x4.trans
       uint32_t vb[4];
-      ldmatrix_x4_trans(vb, &Vs[16 * kk + (lane & 7) + ((lane >> 3) & 1) * 8][16 * n2 + (lane >> 4) * 8]);
+      ldmatrix_x4_trans(vb, &Vs[16 * kk + (lane & 7) + ((lane >> 3) & 1) * 8][((2 * n2 + (lane >> 4)) ^ (lane & 7)) * 8]);
       mma_bf16(o[2 * n2], pa, vb[0], vb[1]);
       mma_bf16(o[2 * n2 + 1], pa, vb[2], vb[3]);
     }
@@ -122,6 +132,7 @@ __global__ void __launch_bounds__(kT * 2) attention_kernel(const __nv_bfloat16* 
     *reinterpret_cast<uint32_t*>(ob + (size_t)r0 * E + n * 8 + c0) = pack_bf16x2(o[n][0] * inv0, o[n][1] * inv0);
     *reinterpret_cast<uint32_t*>(ob + (size_t)(r0 + 8) * E + n * 8 + c0) = pack_bf16x2(o[n][2] * inv1, o[n][3] * inv1);
   }
+  }   // problem loop
 }
 
 }  // namespace
@@ -131,14 +142,16 @@ extern "C" int msd_attention_bf16(const void* d_qkv, void* d_out, int B, int T, 
   MSD_REQUIRE(msd_aligned16(d_qkv) && msd_aligned16(d_out), "attention: pointers must be 16-byte aligned");
   MSD_REQUIRE(T == 144, "attention: only T=144 tokens (192x192 images, patch 16) is built; got T=%d", T);
   constexpr int kT = 144;
-  const size_t smem = 3 * kT * LDS * sizeof(__nv_bfloat16);
+  const size_t smem = 2 * 3 * kT * LDS * sizeof(__nv_bfloat16);   // two q/k/v buffers (double-buffered persistent CTAs)
   static bool attr_set = false;
   if (!attr_set) {
     MSD_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<kT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  attention_kernel<kT><<<(unsigned)(B * heads), kT * 2, smem, (cudaStream_t)stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(d_qkv), reinterpret_cast<__nv_bfloat16*>(d_out), heads);
+  const int problems = B * heads;
+  const int grid = problems < 2 * 148 ? problems : 2 * 148;       // two resident CTAs per SM (2 x 108 KB of shared memory)
+  attention_kernel<kT><<<(unsigned)grid, kT * 2, smem, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(d_qkv), reinterpret_cast<__nv_bfloat16*>(d_out), heads, problems);
   MSD_LAUNCH_CHECK();
   return MSD_OK;
 }

@@ -105,48 +105,80 @@ template <int CIN, int COUT>   // compile-time upper bounds of Cin (multiple of 
 __global__ void __launch_bounds__(256) head1x1_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
                                                       const float* __restrict__ bias, float* __restrict__ y, int B, int H,
                                                       int W, int Cin, int Cout) {
+  // Two pixels per thread: every broadcast 128-bit weight load feeds 8 FMAs.  With one pixel per thread the kernel was bound
+  // by the shared-memory return path (an LDS.128 occupies it for 4 cycles, the same as the 4 FMAs it fed), not by HBM or FMA.
+  constexpr int PPT = 2;
   __shared__ __align__(16) float sw[COUT * CIN];
   __shared__ float sb[16];
-  for (int i = threadIdx.x; i < Cout * Cin; i += 256) sw[i] = w[i];
+  for (int i = threadIdx.x; i < COUT * CIN; i += 256) {
+    const int o = i / CIN, c = i - o * CIN;
+    sw[i] = (o < Cout && c < Cin) ? w[o * Cin + c] : 0.0f;
+  }
   if (threadIdx.x < 16) sb[threadIdx.x] = threadIdx.x < Cout ? bias[threadIdx.x] : 0.0f;
   __syncthreads();
-  const size_t npix = (size_t)B * H * W;
-  for (size_t p = (size_t)blockIdx.x * 256 + threadIdx.x; p < npix; p += (size_t)gridDim.x * 256) {
-    const int b = (int)(p / ((size_t)H * W));
-    const int rem = (int)(p - (size_t)b * H * W);
-    const int yy = rem / W, xx = rem - yy * W;
-    const __nv_bfloat16* src = x + (((size_t)b * (H + 2) + (yy + 1)) * (W + 2) + (xx + 1)) * Cin;
-    float in[CIN];
+  const uint32_t npix = (uint32_t)B * H * W, hw = (uint32_t)H * W, step = gridDim.x * (256 * PPT);
+  // software pipeline: the raw bf16 rows of the NEXT pair of pixels are requested before the current pair is computed
+  // (a thread holds ~1000 instructions of work per pair; only 8 warps fit per SM, too few to hide HBM latency otherwise)
+  uint4 raw[PPT][CIN / 8], nxt[PPT][CIN / 8];
+  auto fetch = [&](uint32_t p0, uint4 (&dst)[PPT][CIN / 8]) {
 #pragma unroll
-    for (int c8 = 0; c8 < CIN / 8; ++c8) {
-      if (c8 * 8 < Cin) {
-        const uint4 u = __ldg(reinterpret_cast<const uint4*>(src + c8 * 8));
+    for (int q = 0; q < PPT; ++q) {
+      const uint32_t p = p0 + q * 256u;
+      const uint32_t pp = p < npix ? p : 0u;
+      const uint32_t b = pp / hw, rem = pp - b * hw;
+      const uint32_t yy = rem / (uint32_t)W, xx = rem - yy * (uint32_t)W;
+      const __nv_bfloat16* src = x + (((size_t)b * (H + 2) + (yy + 1)) * (W + 2) + (xx + 1)) * Cin;
+#pragma unroll
+      for (int c8 = 0; c8 < CIN / 8; ++c8)
+        dst[q][c8] = (p < npix && c8 * 8 < Cin) ? __ldg(reinterpret_cast<const uint4*>(src + c8 * 8)) : make_uint4(0u, 0u, 0u, 0u);
+    }
+  };
+  uint32_t p0 = blockIdx.x * (256u * PPT) + threadIdx.x;
+  if (p0 < npix) fetch(p0, raw);
+  for (; p0 < npix; p0 += step) {
+    if (p0 + step < npix) fetch(p0 + step, nxt);
+    float in[PPT][CIN];
+#pragma unroll
+    for (int q = 0; q < PPT; ++q)
+#pragma unroll
+      for (int c8 = 0; c8 < CIN / 8; ++c8) {
+        const uint4 u = raw[q][c8];
         float2 f;
-        f = unpack_bf16x2(u.x); in[c8 * 8 + 0] = f.x; in[c8 * 8 + 1] = f.y;
-        f = unpack_bf16x2(u.y); in[c8 * 8 + 2] = f.x; in[c8 * 8 + 3] = f.y;
-        f = unpack_bf16x2(u.z); in[c8 * 8 + 4] = f.x; in[c8 * 8 + 5] = f.y;
-        f = unpack_bf16x2(u.w); in[c8 * 8 + 6] = f.x; in[c8 * 8 + 7] = f.y;
+        f = unpack_bf16x2(u.x); in[q][c8 * 8 + 0] = f.x; in[q][c8 * 8 + 1] = f.y;
+        f = unpack_bf16x2(u.y); in[q][c8 * 8 + 2] = f.x; in[q][c8 * 8 + 3] = f.y;
+        f = unpack_bf16x2(u.z); in[q][c8 * 8 + 4] = f.x; in[q][c8 * 8 + 5] = f.y;
+        f = unpack_bf16x2(u.w); in[q][c8 * 8 + 6] = f.x; in[q][c8 * 8 + 7] = f.y;
       }
-    }
-    // weights are read as broadcast 128-bit shared loads (one per 4 FMAs): the FMA pipe, not the LSU, sets the pace
-    float acc[COUT];
-#pragma unroll
-    for (int o = 0; o < COUT; ++o) acc[o] = sb[o];
-#pragma unroll
-    for (int c4 = 0; c4 < CIN / 4; ++c4) {
-      if (c4 * 4 < Cin) {
-#pragma unroll
-        for (int o = 0; o < COUT; ++o) {
-          if (o < Cout) {
-            const float4 w4 = *reinterpret_cast<const float4*>(&sw[o * Cin + c4 * 4]);
-            acc[o] = fmaf(in[c4 * 4 + 3], w4.w, fmaf(in[c4 * 4 + 2], w4.z, fmaf(in[c4 * 4 + 1], w4.y, fmaf(in[c4 * 4], w4.x, acc[o]))));
-          }
-        }
-      }
-    }
+    float acc[PPT][COUT];
 #pragma unroll
     for (int o = 0; o < COUT; ++o)
-      if (o < Cout) y[(((size_t)b * Cout + o) * H + yy) * W + xx] = acc[o];
+#pragma unroll
+      for (int q = 0; q < PPT; ++q) acc[q][o] = sb[o];
+#pragma unroll
+    for (int c4 = 0; c4 < CIN / 4; ++c4) {
+#pragma unroll
+      for (int o = 0; o < COUT; ++o) {
+        const float4 w4 = *reinterpret_cast<const float4*>(&sw[o * CIN + c4 * 4]);
+#pragma unroll
+        for (int q = 0; q < PPT; ++q)
+          acc[q][o] = fmaf(in[q][c4 * 4 + 3], w4.w, fmaf(in[q][c4 * 4 + 2], w4.z, fmaf(in[q][c4 * 4 + 1], w4.y, fmaf(in[q][c4 * 4], w4.x, acc[q][o]))));
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < PPT; ++q) {
+      const uint32_t p = p0 + q * 256u;
+      if (p < npix) {
+        const uint32_t b = p / hw, rem = p - b * hw;
+        float* dst = y + (size_t)b * Cout * hw + rem;
+#pragma unroll
+        for (int o = 0; o < COUT; ++o)
+          if (o < Cout) dst[(size_t)o * hw] = acc[q][o];
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < PPT; ++q)
+#pragma unroll
+      for (int c8 = 0; c8 < CIN / 8; ++c8) raw[q][c8] = nxt[q][c8];
   }
 }
 
@@ -182,7 +214,8 @@ extern "C" int msd_head1x1_nchw_f32(const void* d_x, const float* d_w, const flo
   MSD_REQUIRE(d_x && d_w && d_b && d_y, "head1x1: null pointer");
   MSD_REQUIRE(Cin % 8 == 0 && Cin <= 64 && Cout <= 16 && Cout > 0, "head1x1: Cin=%d (<=64, %%8) Cout=%d (<=16)", Cin, Cout);
   const size_t npix = (size_t)B * H * W;
-  const unsigned blocks = (unsigned)((npix + 255) / 256 < 148u * 8u ? (npix + 255) / 256 : 148u * 8u);
+  MSD_REQUIRE(npix < (1ull << 30), "head1x1: too many pixels");
+  const unsigned blocks = (unsigned)((npix + 511) / 512 < 148u * 8u ? (npix + 511) / 512 : 148u * 8u);
   if (Cin == 48 && Cout == 13)
     head1x1_kernel<48, 13><<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(d_x), d_w, d_b, d_y, B, H, W, Cin, Cout);
   else

@@ -16,7 +16,7 @@ using namespace ssim;
 
 struct SsimSmem {
   RawTile<2> raw;
-  HBlur<5> hb;
+  HBlur<4> hb;
   double red[3][kThreads / 32];
 };
 
@@ -34,13 +34,14 @@ ssim_mse_kernel(const float* __restrict__ pred, const float* __restrict__ target
   load_raw_plane(sm.raw.v[0], pred + poff, y0, x0, H, W);
   load_raw_plane(sm.raw.v[1], target + poff, y0, x0, H, W);
   __syncthreads();
-  // maps: p, t, p*p, t*t, p*t   (metrics.py:105-117)
-  hpass<2, 5>(sm.raw, sm.hb, [](int m, const float (&px)[2]) -> float {
-    return m == 0 ? px[0] : m == 1 ? px[1] : m == 2 ? px[0] * px[0] : m == 3 ? px[1] * px[1] : px[0] * px[1];
+  // maps: p, t, p*p + t*t, p*t.  The reference blurs p*p and t*t separately (metrics.py:105-117) but its ssim_map only uses
+  // sigma1_sq + sigma2_sq (:118-121), and the blur is linear: one map of the sum saves a fifth of the stencil work.
+  hpass<2, 4>(sm.raw, sm.hb, [](int m, const float (&px)[2]) -> float {
+    return m == 0 ? px[0] : m == 1 ? px[1] : m == 2 ? fmaf(px[0], px[0], px[1] * px[1]) : px[0] * px[1];
   });
   __syncthreads();
-  float res[5][8];
-  vpass<5>(sm.hb, res);
+  float res[4][8];
+  vpass<4>(sm.hb, res);
 
   const int x = threadIdx.x & 63, h = threadIdx.x >> 6;
   float s_ssim = 0.0f, s_sq = 0.0f, s_abs = 0.0f;
@@ -49,7 +50,7 @@ ssim_mse_kernel(const float* __restrict__ pred, const float* __restrict__ target
     for (int o = 0; o < 8; ++o) {
       int yy = y0 + 8 * h + o;
       if (yy < H) {
-        s_ssim += ssim_value(res[0][o], res[1][o], res[2][o], res[3][o], res[4][o], consts);
+        s_ssim += ssim_value_sum(res[0][o], res[1][o], res[2][o], res[3][o], consts);
         float d = sm.raw.v[0][8 * h + o + R][x + R] - sm.raw.v[1][8 * h + o + R][x + R];
         s_sq = fmaf(d, d, s_sq);
         s_abs += fabsf(d);

@@ -126,4 +126,13 @@ __device__ __forceinline__ float ssim_value(float mu1, float mu2, float e11, flo
   return num / den;
 }
 
+// same map from the blurred statistics mu1, mu2, E[p^2 + t^2], E[pt]
+__device__ __forceinline__ float ssim_value_sum(float mu1, float mu2, float esum, float e12, const SsimConsts& c) {
+  const float mu1_sq = mu1 * mu1, mu2_sq = mu2 * mu2, mu1_mu2 = mu1 * mu2;
+  const float s12 = e12 - mu1_mu2;
+  const float num = (2.0f * mu1_mu2 + c.C1) * (2.0f * s12 + c.C2);
+  const float den = (mu1_sq + mu2_sq + c.C1) * ((esum - mu1_sq - mu2_sq) + c.C2);
+  return num / den;
+}
+
 }  // namespace ssim
