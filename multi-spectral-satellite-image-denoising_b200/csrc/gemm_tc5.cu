@@ -53,6 +53,9 @@ int num_sms() {
   return n;
 }
 
+template <int BN> int launch_pair(const Problem&, cudaStream_t);   // gemm_tc5_pair.cu (cta_group::2)
+extern template int launch_pair<256>(const Problem&, cudaStream_t);
+extern template int launch_pair<192>(const Problem&, cudaStream_t);
 extern template int launch_bn<256>(const Problem&, cudaStream_t);
 extern template int launch_bn<192>(const Problem&, cudaStream_t);
 extern template int launch_bn<128>(const Problem&, cudaStream_t);
@@ -91,7 +94,13 @@ int launch_tc5(const Problem& p, cudaStream_t s) {
   MSD_REQUIRE(p.ldA % 8 == 0 && msd_aligned16(p.A) && msd_aligned16(p.Wt), "gemm_tc5: operands must be 16-byte aligned / pitched");
   // multi-tap (3x3 conv) problems keep the largest tile: their summation order (tap-major vs dx-merged) depends on the tile
   // width through the kernel mode, and results must not depend on the batch size (sharding invariance is tested bit-exactly)
-  switch (pick_bn_tc5(p.N, p.M, p.num_kb == p.kb_per_tap)) {
+  const int bn = pick_bn_tc5(p.N, p.M, p.num_kb == p.kb_per_tap);
+  // wide tiles of large problems run on CTA pairs (cta_group::2): half the W traffic per CTA, deeper ring
+  static const bool no_pair = getenv("MSD_NO_PAIR") != nullptr;
+  if (!no_pair && (bn == 256 || bn == 192) && p.M >= 2048 && p.mode != EPI_CONVT && p.dbg_shift == 0 && p.dbg_bo == 0 &&
+      !(p.mode == EPI_CONV && p.skip != nullptr && p.skip_tap < 0))
+    return bn == 256 ? tc5::launch_pair<256>(p, s) : tc5::launch_pair<192>(p, s);
+  switch (bn) {
     case 256: return tc5::launch_bn<256>(p, s);
     case 192: return tc5::launch_bn<192>(p, s);
     case 128: return tc5::launch_bn<128>(p, s);

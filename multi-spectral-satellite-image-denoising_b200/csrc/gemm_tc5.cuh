@@ -245,7 +245,12 @@ __host__ inline int classify(const Problem& p) {
 //            -> padded shared-memory row; the TMEM buffer is handed back as soon as the warp's last slab is in registers
 //   phase B (lanes run along the columns): 16-byte units are read back and stored as coalesced row segments; the fp32
 //            residual variant loads its operand there (batched, all loads in flight before the first add)
-template <int BN, int EPI>
+// arrive on the barrier at the same shared-memory offset in the EVEN CTA of a cta_group::2 pair (cute::Sm100MmaPeerBitMask)
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];\n" ::"r"(smem_u32(bar) & 0xFEFFFFFFu) : "memory");
+}
+
+template <int BN, int EPI, bool PAIR = false>
 __device__ __forceinline__ void epilogue_tile(const Problem& p, uint32_t stg_s, uint32_t bias_s, uint32_t taddr,
                                               uint64_t* tmem_empty_bar, int mrow0, int n0, int lane, int slab_begin, int slab_end) {
   using C = Cfg<BN>;
@@ -262,7 +267,7 @@ __device__ __forceinline__ void epilogue_tile(const Problem& p, uint32_t stg_s, 
   if (slab_begin >= slab_end) {          // a one-slab tile leaves the second column half idle: just release the buffer
     tcgen05_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(tmem_empty_bar);
+    if (lane == 0) { if (PAIR) mbar_arrive_leader(tmem_empty_bar); else mbar_arrive(tmem_empty_bar); }
     return;
   }
 #pragma unroll 1
@@ -274,7 +279,7 @@ __device__ __forceinline__ void epilogue_tile(const Problem& p, uint32_t stg_s, 
     if (slab == slab_end - 1) {
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tmem_empty_bar);
+      if (lane == 0) { if (PAIR) mbar_arrive_leader(tmem_empty_bar); else mbar_arrive(tmem_empty_bar); }
     }
     const int nslab = slab * C::SC;
     if constexpr (EPI == E_GENERIC) {

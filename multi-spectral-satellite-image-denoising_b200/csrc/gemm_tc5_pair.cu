@@ -1,0 +1,243 @@
+// CTA-pair (tcgen05 cta_group::2) variant of the plain-mode GEMM / tap-major conv kernel of gemm_tc5.cuh.
+//
+// Why: the single-CTA kernel moves (128 + BN) x 64 bf16 through L2 -> shared memory per k-block for a 128 x BN tile, and
+// ncu puts its wide GEMMs at the TMA / L2 delivery rate (~50 B/clk/SM, tensor pipe 58-61 % active).  Two CTAs of a cluster
+// (same TPC) compute one 256 x BN tile with ONE instruction stream: each CTA loads its own 128 rows of A and only HALF of
+// the W tile (BN/2 rows); `tcgen05.mma.cta_group::2` (M = 256) reads the other half from the peer's shared memory.  Operand
+// bytes per CTA per k-block drop from 48 KB to 32 KB (BN = 256) and the ring gets deeper.
+//
+// Roles per CTA: warp 0 TMA producer (both CTAs; transaction bytes land on the LEADER's full barrier), warps 1 / 3 MMA
+// issuers (leader CTA only; even / odd tiles, one TMEM accumulator buffer each), warp 2 TMEM allocator (cta_group::2 in both
+// CTAs), warps 4-19 epilogue (both CTAs, own 128 rows; the fused epilogues of gemm_tc5.cuh unchanged).  `tcgen05.commit ...
+// multicast::cluster` frees a stage / publishes an accumulator in both CTAs at once; the epilogue warps of both CTAs hand a
+// TMEM buffer back by arriving on the leader's barrier through the cluster shared-memory window.
+#include "gemm_tc5.cuh"
+
+namespace gemm {
+namespace tc5 {
+
+template <int BN>
+struct PairCfg {
+  static constexpr uint32_t A_BOX_BYTES = BLOCK_M * BLOCK_K * 2;          // own 128 rows
+  static constexpr uint32_t W_BOX_BYTES = (BN / 2) * BLOCK_K * 2;         // own half of the W tile
+  static constexpr uint32_t STAGE_BYTES = A_BOX_BYTES + W_BOX_BYTES;
+  using E = Cfg<BN, MODE_PLAIN>;                                          // epilogue staging geometry
+  static constexpr int kStagesRaw = (int)((227u * 1024u - 1024u - 256u - E::STG_BYTES) / STAGE_BYTES);
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr uint32_t SMEM_BYTES = kStages * STAGE_BYTES + E::STG_BYTES + 1024 + 256;
+  static constexpr uint32_t TMEM_COLS = 512;
+  static_assert(BN % 32 == 0 && 2 * BN <= 512 && W_BOX_BYTES % 1024 == 0, "pair tile width");
+  static_assert(kStages >= 3, "pipeline too shallow");
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+// 2-SM TMA load: the data lands in THIS CTA's shared memory, the transaction bytes on the LEADER CTA's mbarrier
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* tm, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tcgen05_mma_bf16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((Cfg<BN, MODE_PLAIN>::THREADS), 1)
+gemm_tc5_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     const __grid_constant__ CUtensorMap tmS, const Problem p, int tiles_m2, int tiles_n, int epi) {
+  using C = PairCfg<BN>;
+  using E = Cfg<BN, MODE_PLAIN>;
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  unsigned char* smem_a = smem;
+  unsigned char* smem_b = smem + C::kStages * C::A_BOX_BYTES;
+  unsigned char* smem_stg = smem + C::kStages * C::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_stg + E::STG_BYTES);
+  uint64_t* empty = bars + 2 * C::kStages;        // bars[0 .. 2*kStages): full[issuer][stage] (used in the leader CTA)
+  uint64_t* tmem_full = bars + 3 * C::kStages;
+  uint64_t* tmem_empty = tmem_full + 2;           // used in the leader CTA
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < C::kStages; ++i) { mbar_init(&bars[i], 1); mbar_init(&bars[C::kStages + i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], E::EPI_WARPS); }   // both CTAs' warps of one buffer
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_ptr)), "r"(C::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::: "memory");
+  }
+  tcgen05_fence_before();
+  cluster_sync_all();                              // barrier inits + TMEM of both CTAs visible before any cross-CTA traffic
+  tcgen05_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
+  const int num_tiles = tiles_m2 * tiles_n;        // 256-row pair tiles
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  const int kbpt = p.kb_per_tap;
+  const int nk_last = min(BLOCK_K / 16, (p.kvalid - (kbpt - 1) * BLOCK_K + 15) / 16);
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs) =====
+    int stage = 0; uint32_t phase = 0;
+    uint32_t it = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+      const int tm = tile / tiles_n;
+      const int m0 = tm * (2 * BLOCK_M) + (int)rank * BLOCK_M, n0 = (tile - tm * tiles_n) * BN + (int)rank * (BN / 2);
+      uint64_t* full = bars + (it & 1u) * C::kStages;
+      int tap = 0, kc = 0;
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        if (elect_one()) {
+          if (leader) mbar_arrive_expect_tx(&full[stage], 2 * C::STAGE_BYTES);      // both CTAs' boxes of this stage
+          tma_load_2d_pair(tap == p.skip_tap ? &tmS : &tmA, &full[stage], smem_a + stage * C::A_BOX_BYTES, kc * BLOCK_K, m0 + p.tap_off[tap]);
+          tma_load_2d_pair(&tmB, &full[stage], smem_b + stage * C::W_BOX_BYTES, kb * BLOCK_K, n0);
+        }
+        __syncwarp();
+        if (++kc == kbpt) { kc = 0; ++tap; }
+        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if ((warp == 1 || warp == 3) && leader) {
+    // ===== MMA issuers (leader CTA only) =====
+    constexpr uint32_t idesc = make_idesc(2 * BLOCK_M, BN);
+    constexpr uint32_t HI = (1024u >> 4) | (1u << 14) | (2u << 29);
+    const uint32_t par = warp == 1 ? 0u : 1u;
+    const uint32_t a_lo0 = (smem_u32(smem_a) & 0x3FFFFu) >> 4, b_lo0 = (smem_u32(smem_b) & 0x3FFFFu) >> 4;
+    const uint32_t tmem_d = tmem_base + par * BN;
+    uint64_t* full = bars + par * C::kStages;
+    uint32_t pmask = 0, it = 0;
+    int gstep = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it, gstep += p.num_kb) {
+      if ((it & 1u) != par) continue;
+      int stage = gstep % C::kStages;
+      mbar_wait(&tmem_empty[par], ((it >> 1) & 1u) ^ 1u);
+      tcgen05_fence_after();
+      uint32_t acc = 0;
+      int kc = 0;
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        mbar_wait(&full[stage], (pmask >> stage) & 1u);
+        pmask ^= 1u << stage;
+        tcgen05_fence_after();
+        const int nk = (kc == kbpt - 1) ? nk_last : BLOCK_K / 16;
+        if (elect_one()) {
+          const uint64_t da = ((uint64_t)HI << 32) | (a_lo0 + stage * (C::A_BOX_BYTES >> 4));
+          const uint64_t db = ((uint64_t)HI << 32) | (b_lo0 + stage * (C::W_BOX_BYTES >> 4));
+          for (int k = 0; k < nk; ++k) tcgen05_mma_bf16_pair(tmem_d, da + 2u * k, db + 2u * k, idesc, k == 0 ? acc : 1u);
+          tcgen05_commit_pair(&empty[stage]);
+          if (kb == p.num_kb - 1) tcgen05_commit_pair(&tmem_full[par]);
+        }
+        __syncwarp();
+        acc = 1;
+        if (++kc == kbpt) kc = 0;
+        if (++stage == C::kStages) stage = 0;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue (both CTAs, own 128 rows) =====
+    const int e = warp - 4;
+    const int q = warp & 3, grp = (e >> 2) & 1, half = e >> 3;
+    const uint32_t stg_s = smem_u32(smem_stg + e * E::STG_WARP_BYTES);
+    const uint32_t bias_s = stg_s + 32 * E::STG_PITCH;
+    const int slab_begin = half ? E::SLAB_SPLIT : 0, slab_end = half ? E::NSLAB : E::SLAB_SPLIT;
+    const int ncols = (slab_end - slab_begin) * E::SC;
+    int it = 0, bias_n0 = -1;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+      if ((it & 1) != grp) continue;
+      const uint32_t as = it & 1, aphase = (it >> 1) & 1;
+      const int tm = tile / tiles_n;
+      const int m0 = tm * (2 * BLOCK_M) + (int)rank * BLOCK_M, n0 = (tile - tm * tiles_n) * BN;
+      if (n0 != bias_n0) {
+        bias_n0 = n0;
+        float b[(E::SLAB_SPLIT * E::SC + 31) / 32];
+#pragma unroll
+        for (int k = 0; k < (E::SLAB_SPLIT * E::SC + 31) / 32; ++k) {
+          const int i = k * 32 + lane;
+          b[k] = (p.bias != nullptr && i < ncols) ? __ldg(p.bias + n0 + slab_begin * E::SC + i) : 0.0f;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < (E::SLAB_SPLIT * E::SC + 31) / 32; ++k) {
+          const int i = k * 32 + lane;
+          if (i < ncols) asm volatile("st.shared.f32 [%0], %1;\n" ::"r"(bias_s + 4u * i), "f"(b[k]) : "memory");
+        }
+        __syncwarp();
+      }
+      mbar_wait(&tmem_full[as], aphase);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
+#define MSD_EPI_CASE(EE) case EE: epilogue_tile<BN, EE, true>(p, stg_s, bias_s, taddr, &tmem_empty[as], m0 + q * 32, n0, lane, slab_begin, slab_end); break;
+      switch (epi) {
+        MSD_EPI_CASE(E_RM_F32)
+        MSD_EPI_CASE(E_RM_BF16)
+        MSD_EPI_CASE(E_RM_BF16_GELU)
+        MSD_EPI_CASE(E_RM_F32_RESID)
+        MSD_EPI_CASE(E_CONV)
+        MSD_EPI_CASE(E_CONV_RAW)
+        default: epilogue_tile<BN, E_GENERIC, true>(p, stg_s, bias_s, taddr, &tmem_empty[as], m0 + q * 32, n0, lane, slab_begin, slab_end); break;
+      }
+#undef MSD_EPI_CASE
+    }
+  }
+  tcgen05_fence_before();
+  cluster_sync_all();                              // no CTA may free TMEM / exit while its peer still reads its shared memory
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(C::TMEM_COLS) : "memory");
+  }
+}
+
+template <int BN>
+int launch_pair(const Problem& p, cudaStream_t s) {
+  using C = PairCfg<BN>;
+  CUtensorMap tmA, tmB;
+  int rc = make_map(&tmA, p.A, (uint64_t)p.kvalid, (uint64_t)p.a_rows, (uint64_t)p.ldA, BLOCK_M);
+  if (rc) return rc;
+  rc = make_map(&tmB, p.Wt, (uint64_t)p.num_kb * BLOCK_K, (uint64_t)p.N, (uint64_t)p.num_kb * BLOCK_K, BN / 2);
+  if (rc) return rc;
+  CUtensorMap tmS = tmA;
+  if (p.skip_tap >= 0) {
+    rc = make_map(&tmS, p.skip, (uint64_t)p.kvalid, (uint64_t)p.a_rows, (uint64_t)p.ldA, BLOCK_M);
+    if (rc) return rc;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    MSD_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc5_pair_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int tiles_m2 = (p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M), tiles_n = p.N / BN;
+  const int tiles = tiles_m2 * tiles_n;
+  const int clusters = tiles < num_sms() / 2 ? tiles : num_sms() / 2;
+  gemm_tc5_pair_kernel<BN><<<2 * clusters, Cfg<BN, MODE_PLAIN>::THREADS, C::SMEM_BYTES, s>>>(tmA, tmB, tmS, p, tiles_m2, tiles_n, classify(p));
+  MSD_LAUNCH_CHECK();
+  return MSD_OK;
+}
+
+template int launch_pair<256>(const Problem&, cudaStream_t);
+template int launch_pair<192>(const Problem&, cudaStream_t);
+
+}  // namespace tc5
+}  // namespace gemm

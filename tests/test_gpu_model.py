@@ -37,7 +37,9 @@ def _close(got, ref, rel=2e-2):
 # ----------------------------------------------------------------------------------------------- GEMM
 @pytest.mark.parametrize("backend", BACKENDS)
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (1152, 768, 768), (288, 2304, 768), (1296, 3072, 768), (200, 768, 3072),
-                                   (144, 768, 3328), (130, 48, 128), (576, 16, 64), (1000, 96, 192), (384, 192, 320)])
+                                   (144, 768, 3328), (130, 48, 128), (576, 16, 64), (1000, 96, 192), (384, 192, 320),
+                                   # >= 2048 rows with a 256- or 192-wide tile: the cta_group::2 pair kernel (ragged last pair tile too)
+                                   (2304, 768, 768), (4000, 2304, 768), (2177, 3072, 768), (2560, 768, 3072), (2500, 192, 320)])
 def test_linear_vs_fp32(backend, M, N, K):
     g = torch.Generator().manual_seed(M + N + K)
     a = _bf(torch.randn(M, K, generator=g)).cuda()
@@ -57,16 +59,16 @@ def test_linear_exact_on_small_integers(backend):
     """integer-valued operands: every product and partial sum is exact in bf16 x bf16 -> fp32, so any indexing or
     descriptor mistake (swizzle, K advance, tile origin) shows up as an exact mismatch."""
     g = torch.Generator().manual_seed(0)
-    M, N, K = 400, 320, 256
-    a = torch.randint(-3, 4, (M, K), generator=g).float()
-    w = torch.randint(-3, 4, (N, K), generator=g).float()
-    out = gh.linear(_bf(a).cuda(), _bf(w).cuda(), None, out_f32=True, backend=backend)
-    assert torch.equal(out.cpu(), a @ w.t())
+    for M, N, K in ((400, 320, 256), (2400, 768, 320)):          # single-CTA tiles; CTA-pair tiles (M >= 2048, BN = 256)
+        a = torch.randint(-3, 4, (M, K), generator=g).float()
+        w = torch.randint(-3, 4, (N, K), generator=g).float()
+        out = gh.linear(_bf(a).cuda(), _bf(w).cuda(), None, out_f32=True, backend=backend)
+        assert torch.equal(out.cpu(), a @ w.t())
 
 
 @pytest.mark.parametrize("backend", BACKENDS)
 @pytest.mark.parametrize("cin,cout,H,W,B", [(48, 48, 20, 12, 2), (96, 96, 10, 14, 3), (192, 192, 8, 8, 1), (384, 384, 24, 24, 1),
-                                            (64, 16, 5, 7, 2)])
+                                            (64, 16, 5, 7, 2), (192, 192, 30, 33, 2), (384, 384, 24, 24, 4)])   # last two: CTA-pair tiles
 def test_conv3x3_vs_torch(backend, cin, cout, H, W, B):
     torch.manual_seed(cin + H)
     conv = nn.Conv2d(cin, cout, 3, padding=1, bias=False)
