@@ -56,6 +56,8 @@ int num_sms() {
 template <int BN> int launch_pair(const Problem&, cudaStream_t);   // gemm_tc5_pair.cu (cta_group::2)
 extern template int launch_pair<256>(const Problem&, cudaStream_t);
 extern template int launch_pair<192>(const Problem&, cudaStream_t);
+extern template int launch_pair<96>(const Problem&, cudaStream_t);
+extern template int launch_pair<48>(const Problem&, cudaStream_t);
 extern template int launch_bn<256>(const Problem&, cudaStream_t);
 extern template int launch_bn<192>(const Problem&, cudaStream_t);
 extern template int launch_bn<128>(const Problem&, cudaStream_t);
@@ -97,9 +99,17 @@ int launch_tc5(const Problem& p, cudaStream_t s) {
   const int bn = pick_bn_tc5(p.N, p.M, p.num_kb == p.kb_per_tap);
   // wide tiles of large problems run on CTA pairs (cta_group::2): half the W traffic per CTA, deeper ring
   static const bool no_pair = getenv("MSD_NO_PAIR") != nullptr;
-  if (!no_pair && (bn == 256 || bn == 192) && p.M >= 2048 && p.mode != EPI_CONVT && p.dbg_shift == 0 && p.dbg_bo == 0 &&
-      !(p.mode == EPI_CONV && p.skip != nullptr && p.skip_tap < 0))
+  const bool pair_ok = !no_pair && p.M >= 2048 && p.dbg_shift == 0 && p.dbg_bo == 0 &&
+                       !(p.mode == EPI_CONV && p.skip != nullptr && p.skip_tap < 0);
+  if (pair_ok && (bn == 256 || bn == 192))
     return bn == 256 ? tc5::launch_pair<256>(p, s) : tc5::launch_pair<192>(p, s);
+  // 3x3 convs with 96 / 48 channels: dx-merged windows + the weight matrix resident in shared memory, split over the pair
+  static const bool no_merge = getenv("MSD_NO_MERGE3") != nullptr;
+  // (the 48-channel stage measures slightly FASTER on single CTAs -- 0.555 vs 0.586 ms at B = 256 -- and stays there;
+  //  MSD_PAIR48 switches it for A/B runs)
+  static const bool pair48 = getenv("MSD_PAIR48") != nullptr;
+  if (pair_ok && !no_merge && (bn == 96 || (bn == 48 && pair48)) && p.N == bn && tc5::is_conv3x3(p) && p.num_kb <= 20)
+    return bn == 96 ? tc5::launch_pair<96>(p, s) : tc5::launch_pair<48>(p, s);
   switch (bn) {
     case 256: return tc5::launch_bn<256>(p, s);
     case 192: return tc5::launch_bn<192>(p, s);

@@ -16,17 +16,32 @@
 namespace gemm {
 namespace tc5 {
 
-template <int BN>
+// MERGED = the dx-merged 3x3 conv mode of gemm_tc5.cuh with the packed weight matrix RESIDENT in shared memory, split over the
+// pair: each CTA keeps its BN/2 output channels of all taps (96 channels: 2 x 120 KB), so a stage is one 136-row A box only.
+template <int BN, bool MERGED>
 struct PairCfg {
-  static constexpr uint32_t A_BOX_BYTES = BLOCK_M * BLOCK_K * 2;          // own 128 rows
-  static constexpr uint32_t W_BOX_BYTES = (BN / 2) * BLOCK_K * 2;         // own half of the W tile
-  static constexpr uint32_t STAGE_BYTES = A_BOX_BYTES + W_BOX_BYTES;
-  using E = Cfg<BN, MODE_PLAIN>;                                          // epilogue staging geometry
-  static constexpr int kStagesRaw = (int)((227u * 1024u - 1024u - 256u - E::STG_BYTES) / STAGE_BYTES);
+  static constexpr uint32_t A_BOX_BYTES = (MERGED ? MERGE_ROWS : BLOCK_M) * BLOCK_K * 2;   // own 128 (+8) rows
+  static constexpr uint32_t W_BOX_BYTES = (BN / 2) * BLOCK_K * 2;                           // own half of one W k-block
+  static constexpr uint32_t STAGE_BYTES = A_BOX_BYTES + (MERGED ? 0u : W_BOX_BYTES);
+  static constexpr int MAX_RES_KB = 20;                                                     // 10 taps x 2 k-blocks
+  static constexpr uint32_t RESIDENT_BYTES = MERGED ? MAX_RES_KB * W_BOX_BYTES : 0u;
+  using E = Cfg<BN, (MERGED ? MODE_MERGE3 : MODE_PLAIN)>;                                   // epilogue slab geometry
+  // merged (narrow) tiles: 8 epilogue warps, each owning all slabs of its rows (the shared memory goes to the resident weights
+  // and a deeper A ring instead of 16 staging buffers), and FOUR TMEM accumulator buffers: with one instruction stream feeding
+  // two SMs the issue work per tile halves, and what bounds a narrow tile is the commit -> drain -> remote-arrive round trip of
+  // its accumulator buffer, which two extra buffers hide.
+  static constexpr int EPI_WARPS = MERGED ? 8 : E::EPI_WARPS;
+  static constexpr int THREADS = 128 + 32 * EPI_WARPS;
+  static constexpr int SLAB_SPLIT = MERGED ? E::NSLAB : E::SLAB_SPLIT;
+  static constexpr uint32_t STG_WARP_BYTES = 32 * E::STG_PITCH + SLAB_SPLIT * E::SC * 4;
+  static constexpr uint32_t STG_BYTES = EPI_WARPS * STG_WARP_BYTES;
+  static constexpr int NBUF = (4 * BN <= 512) ? 4 : 2;
+  static constexpr uint32_t BAR_BYTES = 512;
+  static constexpr int kStagesRaw = (int)((227u * 1024u - 1024u - BAR_BYTES - STG_BYTES - RESIDENT_BYTES) / STAGE_BYTES);
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
-  static constexpr uint32_t SMEM_BYTES = kStages * STAGE_BYTES + E::STG_BYTES + 1024 + 256;
+  static constexpr uint32_t SMEM_BYTES = kStages * STAGE_BYTES + RESIDENT_BYTES + STG_BYTES + 1024 + BAR_BYTES;
   static constexpr uint32_t TMEM_COLS = 512;
-  static_assert(BN % 32 == 0 && 2 * BN <= 512 && W_BOX_BYTES % 1024 == 0, "pair tile width");
+  static_assert(BN % 16 == 0 && 2 * BN <= 512 && W_BOX_BYTES % 1024 == 0 && A_BOX_BYTES % 1024 == 0, "pair tile geometry");
   static_assert(kStages >= 3, "pipeline too shallow");
 };
 
@@ -59,22 +74,24 @@ __device__ __forceinline__ void tcgen05_mma_bf16_pair(uint32_t tmem_d, uint64_t 
       : "memory");
 }
 
-template <int BN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((Cfg<BN, MODE_PLAIN>::THREADS), 1)
+template <int BN, bool MERGED>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((PairCfg<BN, MERGED>::THREADS), 1)
 gemm_tc5_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmS, const Problem p, int tiles_m2, int tiles_n, int epi) {
-  using C = PairCfg<BN>;
-  using E = Cfg<BN, MODE_PLAIN>;
+  using C = PairCfg<BN, MERGED>;
+  using E = typename C::E;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
   unsigned char* smem_a = smem;
-  unsigned char* smem_b = smem + C::kStages * C::A_BOX_BYTES;
-  unsigned char* smem_stg = smem + C::kStages * C::STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_stg + E::STG_BYTES);
+  unsigned char* smem_b = smem + C::kStages * C::A_BOX_BYTES;                  // per-stage W halves (plain mode)
+  unsigned char* smem_res = smem + C::kStages * C::STAGE_BYTES;                // resident W half (merged mode)
+  unsigned char* smem_stg = smem_res + C::RESIDENT_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_stg + C::STG_BYTES);
   uint64_t* empty = bars + 2 * C::kStages;        // bars[0 .. 2*kStages): full[issuer][stage] (used in the leader CTA)
-  uint64_t* tmem_full = bars + 3 * C::kStages;
-  uint64_t* tmem_empty = tmem_full + 2;           // used in the leader CTA
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* tmem_full = bars + 3 * C::kStages;    // [NBUF]
+  uint64_t* tmem_empty = tmem_full + C::NBUF;     // [NBUF], used in the leader CTA
+  uint64_t* res_full = tmem_empty + C::NBUF;      // used in the leader CTA
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -85,7 +102,8 @@ gemm_tc5_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < C::kStages; ++i) { mbar_init(&bars[i], 1); mbar_init(&bars[C::kStages + i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], E::EPI_WARPS); }   // both CTAs' warps of one buffer
+    for (int i = 0; i < C::NBUF; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], C::EPI_WARPS); }   // both CTAs' warps of one group
+    mbar_init(res_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (warp == 2) {
@@ -100,15 +118,44 @@ gemm_tc5_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
   const int kbpt = p.kb_per_tap;
   const int nk_last = min(BLOCK_K / 16, (p.kvalid - (kbpt - 1) * BLOCK_K + 15) / 16);
+  const int n_dy = 3, has_skip = p.skip_tap >= 0 ? 1 : 0;
+  const int steps_per_tile = MERGED ? (n_dy + has_skip) * kbpt : p.num_kb;
 
   if (warp == 0) {
     // ===== TMA producer (both CTAs) =====
     int stage = 0; uint32_t phase = 0;
     uint32_t it = 0;
+    if constexpr (MERGED) {
+      // this CTA's half (BN/2 output channels) of the whole packed weight matrix stays resident; both halves are counted on the
+      // leader's barrier, which its MMA issuers wait for once
+      if (elect_one()) {
+        if (leader) mbar_arrive_expect_tx(res_full, 2u * (uint32_t)p.num_kb * C::W_BOX_BYTES);
+        for (int kb = 0; kb < p.num_kb; ++kb) tma_load_2d_pair(&tmB, res_full, smem_res + kb * C::W_BOX_BYTES, kb * BLOCK_K, (int)rank * (BN / 2));
+      }
+      __syncwarp();
+    }
+    const int tap0 = p.tap_off[0], tap3 = p.tap_off[3], tap6 = p.tap_off[6];
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
       const int tm = tile / tiles_n;
       const int m0 = tm * (2 * BLOCK_M) + (int)rank * BLOCK_M, n0 = (tile - tm * tiles_n) * BN + (int)rank * (BN / 2);
       uint64_t* full = bars + (it & 1u) * C::kStages;
+      if constexpr (MERGED) {
+        // rows m0 + off(dy, dx=-1) .. +135: windows at +0 / +1 / +2 rows are the dx taps; the skip tensor is read through the middle one
+        for (int dy = 0; dy < n_dy + has_skip; ++dy) {
+          const bool is_skip = dy == n_dy;
+          const int row = is_skip ? m0 - 1 : m0 + (dy == 0 ? tap0 : dy == 1 ? tap3 : tap6);
+          for (int kc = 0; kc < kbpt; ++kc) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            if (elect_one()) {
+              if (leader) mbar_arrive_expect_tx(&full[stage], 2 * C::A_BOX_BYTES);
+              tma_load_2d_pair(is_skip ? &tmS : &tmA, &full[stage], smem_a + stage * C::A_BOX_BYTES, kc * BLOCK_K, row);
+            }
+            __syncwarp();
+            if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+          }
+        }
+        continue;
+      }
       int tap = 0, kc = 0;
       for (int kb = 0; kb < p.num_kb; ++kb) {
         mbar_wait(&empty[stage], phase ^ 1);
@@ -128,16 +175,50 @@ gemm_tc5_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     constexpr uint32_t HI = (1024u >> 4) | (1u << 14) | (2u << 29);
     const uint32_t par = warp == 1 ? 0u : 1u;
     const uint32_t a_lo0 = (smem_u32(smem_a) & 0x3FFFFu) >> 4, b_lo0 = (smem_u32(smem_b) & 0x3FFFFu) >> 4;
-    const uint32_t tmem_d = tmem_base + par * BN;
+    const uint32_t r_lo0 = (smem_u32(smem_res) & 0x3FFFFu) >> 4;
     uint64_t* full = bars + par * C::kStages;
     uint32_t pmask = 0, it = 0;
     int gstep = 0;
-    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it, gstep += p.num_kb) {
+    if constexpr (MERGED) { mbar_wait(res_full, 0); tcgen05_fence_after(); }
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it, gstep += steps_per_tile) {
       if ((it & 1u) != par) continue;
       int stage = gstep % C::kStages;
-      mbar_wait(&tmem_empty[par], ((it >> 1) & 1u) ^ 1u);
+      // this issuer's n-th tile goes to accumulator buffer par (+2 on odd n when there are four buffers)
+      const uint32_t n = it >> 1;
+      const uint32_t buf = C::NBUF == 4 ? par + 2u * (n & 1u) : par;
+      const uint32_t uses = C::NBUF == 4 ? n >> 1 : n;
+      mbar_wait(&tmem_empty[buf], (uses & 1u) ^ 1u);
       tcgen05_fence_after();
+      const uint32_t tmem_d = tmem_base + buf * BN;
       uint32_t acc = 0;
+      if constexpr (MERGED) {
+        for (int dy = 0; dy < n_dy + has_skip; ++dy) {
+          const bool is_skip = dy == n_dy;
+          for (int kc = 0; kc < kbpt; ++kc) {
+            mbar_wait(&full[stage], (pmask >> stage) & 1u);
+            pmask ^= 1u << stage;
+            tcgen05_fence_after();
+            const int nk = (kc == kbpt - 1) ? nk_last : BLOCK_K / 16;
+            const bool last = (dy == n_dy + has_skip - 1) && (kc == kbpt - 1);
+            if (elect_one()) {
+              const uint32_t a_lo = a_lo0 + stage * (C::A_BOX_BYTES >> 4);
+              const int j0 = is_skip ? 1 : 0, j1 = is_skip ? 2 : 3;                       // window j = rows +j = tap dx = j - 1
+              for (int j = j0; j < j1; ++j) {
+                const int tap = is_skip ? p.skip_tap : 3 * dy + j;
+                const uint64_t da = ((uint64_t)HI << 32) | (a_lo + 8u * j);
+                const uint64_t db = ((uint64_t)HI << 32) | (r_lo0 + (uint32_t)(tap * kbpt + kc) * (C::W_BOX_BYTES >> 4));
+                for (int k = 0; k < nk; ++k) { tcgen05_mma_bf16_pair(tmem_d, da + 2u * k, db + 2u * k, idesc, acc); acc = 1; }
+              }
+              tcgen05_commit_pair(&empty[stage]);
+              if (last) tcgen05_commit_pair(&tmem_full[buf]);
+            }
+            __syncwarp();
+            acc = 1;
+            if (++stage == C::kStages) stage = 0;
+          }
+        }
+        continue;
+      }
       int kc = 0;
       for (int kb = 0; kb < p.num_kb; ++kb) {
         mbar_wait(&full[stage], (pmask >> stage) & 1u);
@@ -149,7 +230,7 @@ gemm_tc5_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           const uint64_t db = ((uint64_t)HI << 32) | (b_lo0 + stage * (C::W_BOX_BYTES >> 4));
           for (int k = 0; k < nk; ++k) tcgen05_mma_bf16_pair(tmem_d, da + 2u * k, db + 2u * k, idesc, k == 0 ? acc : 1u);
           tcgen05_commit_pair(&empty[stage]);
-          if (kb == p.num_kb - 1) tcgen05_commit_pair(&tmem_full[par]);
+          if (kb == p.num_kb - 1) tcgen05_commit_pair(&tmem_full[buf]);
         }
         __syncwarp();
         acc = 1;
@@ -161,27 +242,29 @@ gemm_tc5_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     // ===== epilogue (both CTAs, own 128 rows) =====
     const int e = warp - 4;
     const int q = warp & 3, grp = (e >> 2) & 1, half = e >> 3;
-    const uint32_t stg_s = smem_u32(smem_stg + e * E::STG_WARP_BYTES);
+    const uint32_t stg_s = smem_u32(smem_stg + e * C::STG_WARP_BYTES);
     const uint32_t bias_s = stg_s + 32 * E::STG_PITCH;
-    const int slab_begin = half ? E::SLAB_SPLIT : 0, slab_end = half ? E::NSLAB : E::SLAB_SPLIT;
+    const int slab_begin = half ? C::SLAB_SPLIT : 0, slab_end = half ? E::NSLAB : C::SLAB_SPLIT;
     const int ncols = (slab_end - slab_begin) * E::SC;
     int it = 0, bias_n0 = -1;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
       if ((it & 1) != grp) continue;
-      const uint32_t as = it & 1, aphase = (it >> 1) & 1;
+      const uint32_t n = (uint32_t)it >> 1;
+      const uint32_t as = C::NBUF == 4 ? (uint32_t)grp + 2u * (n & 1u) : (uint32_t)grp;
+      const uint32_t aphase = (C::NBUF == 4 ? n >> 1 : n) & 1u;
       const int tm = tile / tiles_n;
       const int m0 = tm * (2 * BLOCK_M) + (int)rank * BLOCK_M, n0 = (tile - tm * tiles_n) * BN;
       if (n0 != bias_n0) {
         bias_n0 = n0;
-        float b[(E::SLAB_SPLIT * E::SC + 31) / 32];
+        float b[(C::SLAB_SPLIT * E::SC + 31) / 32];
 #pragma unroll
-        for (int k = 0; k < (E::SLAB_SPLIT * E::SC + 31) / 32; ++k) {
+        for (int k = 0; k < (C::SLAB_SPLIT * E::SC + 31) / 32; ++k) {
           const int i = k * 32 + lane;
           b[k] = (p.bias != nullptr && i < ncols) ? __ldg(p.bias + n0 + slab_begin * E::SC + i) : 0.0f;
         }
         __syncwarp();
 #pragma unroll
-        for (int k = 0; k < (E::SLAB_SPLIT * E::SC + 31) / 32; ++k) {
+        for (int k = 0; k < (C::SLAB_SPLIT * E::SC + 31) / 32; ++k) {
           const int i = k * 32 + lane;
           if (i < ncols) asm volatile("st.shared.f32 [%0], %1;\n" ::"r"(bias_s + 4u * i), "f"(b[k]) : "memory");
         }
@@ -198,6 +281,8 @@ gemm_tc5_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         MSD_EPI_CASE(E_RM_F32_RESID)
         MSD_EPI_CASE(E_CONV)
         MSD_EPI_CASE(E_CONV_RAW)
+        MSD_EPI_CASE(E_CONVT)
+        MSD_EPI_CASE(E_CONVT_RAW)
         default: epilogue_tile<BN, E_GENERIC, true>(p, stg_s, bias_s, taddr, &tmem_empty[as], m0 + q * 32, n0, lane, slab_begin, slab_end); break;
       }
 #undef MSD_EPI_CASE
@@ -210,34 +295,43 @@ gemm_tc5_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   }
 }
 
-template <int BN>
-int launch_pair(const Problem& p, cudaStream_t s) {
-  using C = PairCfg<BN>;
+template <int BN, bool MERGED>
+int launch_pair_mode(const Problem& p, cudaStream_t s) {
+  using C = PairCfg<BN, MERGED>;
   CUtensorMap tmA, tmB;
-  int rc = make_map(&tmA, p.A, (uint64_t)p.kvalid, (uint64_t)p.a_rows, (uint64_t)p.ldA, BLOCK_M);
+  const uint32_t a_box_rows = MERGED ? MERGE_ROWS : BLOCK_M;
+  int rc = make_map(&tmA, p.A, (uint64_t)p.kvalid, (uint64_t)p.a_rows, (uint64_t)p.ldA, a_box_rows);
   if (rc) return rc;
   rc = make_map(&tmB, p.Wt, (uint64_t)p.num_kb * BLOCK_K, (uint64_t)p.N, (uint64_t)p.num_kb * BLOCK_K, BN / 2);
   if (rc) return rc;
   CUtensorMap tmS = tmA;
   if (p.skip_tap >= 0) {
-    rc = make_map(&tmS, p.skip, (uint64_t)p.kvalid, (uint64_t)p.a_rows, (uint64_t)p.ldA, BLOCK_M);
+    rc = make_map(&tmS, p.skip, (uint64_t)p.kvalid, (uint64_t)p.a_rows, (uint64_t)p.ldA, a_box_rows);
     if (rc) return rc;
   }
   static bool attr_set = false;
   if (!attr_set) {
-    MSD_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc5_pair_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
+    MSD_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc5_pair_kernel<BN, MERGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
     attr_set = true;
   }
   const int tiles_m2 = (p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M), tiles_n = p.N / BN;
   const int tiles = tiles_m2 * tiles_n;
   const int clusters = tiles < num_sms() / 2 ? tiles : num_sms() / 2;
-  gemm_tc5_pair_kernel<BN><<<2 * clusters, Cfg<BN, MODE_PLAIN>::THREADS, C::SMEM_BYTES, s>>>(tmA, tmB, tmS, p, tiles_m2, tiles_n, classify(p));
+  gemm_tc5_pair_kernel<BN, MERGED><<<2 * clusters, C::THREADS, C::SMEM_BYTES, s>>>(tmA, tmB, tmS, p, tiles_m2, tiles_n, classify(p));
   MSD_LAUNCH_CHECK();
   return MSD_OK;
 }
 
+template <int BN>
+int launch_pair(const Problem& p, cudaStream_t s) {
+  if constexpr (BN == 96 || BN == 48) return launch_pair_mode<BN, true>(p, s);
+  else return launch_pair_mode<BN, false>(p, s);
+}
+
 template int launch_pair<256>(const Problem&, cudaStream_t);
 template int launch_pair<192>(const Problem&, cudaStream_t);
+template int launch_pair<96>(const Problem&, cudaStream_t);
+template int launch_pair<48>(const Problem&, cudaStream_t);
 
 }  // namespace tc5
 }  // namespace gemm

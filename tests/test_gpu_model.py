@@ -68,7 +68,7 @@ def test_linear_exact_on_small_integers(backend):
 
 @pytest.mark.parametrize("backend", BACKENDS)
 @pytest.mark.parametrize("cin,cout,H,W,B", [(48, 48, 20, 12, 2), (96, 96, 10, 14, 3), (192, 192, 8, 8, 1), (384, 384, 24, 24, 1),
-                                            (64, 16, 5, 7, 2), (192, 192, 30, 33, 2), (384, 384, 24, 24, 4)])   # last two: CTA-pair tiles
+                                            (64, 16, 5, 7, 2), (192, 192, 30, 33, 2), (384, 384, 24, 24, 4), (48, 48, 40, 41, 2), (96, 96, 30, 31, 3)])   # last four: CTA-pair tiles
 def test_conv3x3_vs_torch(backend, cin, cout, H, W, B):
     torch.manual_seed(cin + H)
     conv = nn.Conv2d(cin, cout, 3, padding=1, bias=False)
