@@ -140,18 +140,18 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------ training step (C4)
 def train_step_bench(dev, world, steps=5, warmup=2, micro=64):
     """BASELINE config C4: one data-parallel training step per rank on `micro` tiles: corrupt -> training forward (batch-stat
-    BatchNorm) -> MSE + 0.1 (1-SSIM) -> backward (blocks 0-5 frozen) -> gradient all-reduce -> clip 1.0 -> AdamW.  Everything
-    except the optimizer update (torch fused AdamW) runs in libmsd_b200."""
+    BatchNorm) -> MSE + 0.1 (1-SSIM) -> backward (blocks 0-5 frozen) -> gradient all-reduce -> clip 1.0 + AdamW.  All of it runs
+    in libmsd_b200 (the all-reduce is NCCL through torch.distributed)."""
     import torch.distributed as dist
     from msd_b200.data import AddSensorNoise
     from msd_b200.models import SatMAERestoration
-    from msd_b200.training import CombinedLoss
+    from msd_b200.training import CombinedLoss, FusedAdamW
     from msd_b200.training.distributed import allreduce_gradients
     torch.manual_seed(42)
     model = SatMAERestoration(recipes.base_config(), block_layout="fallback").to(dev).train()
     noise = AddSensorNoise(*recipes.NOISE_CONFIGS["base"])
     crit = CombinedLoss(1.0, 0.1)
-    opt = torch.optim.AdamW(model.get_optimizer_param_groups(1e-4, 0.05), betas=(0.9, 0.999), fused=True)
+    opt = FusedAdamW(model.get_optimizer_param_groups(1e-4, 0.05), betas=(0.9, 0.999), max_grad_norm=1.0)
     clean, _ = recipes.eurosat_tiles(32, seed=200 + int(os.environ.get("RANK", "0")))
     clean = clean.repeat(micro // 32 + 1, 1, 1, 1)[:micro].contiguous().to(dev)
 
@@ -160,8 +160,7 @@ def train_step_bench(dev, world, steps=5, warmup=2, micro=64):
         loss = crit(out, clean)
         loss.backward()
         allreduce_gradients(model.parameters())
-        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
-        opt.step()
+        opt.step()                                       # global-norm clip (1.0) + AdamW, one fused pass (csrc/optim.cu)
         opt.zero_grad(set_to_none=True)
         return loss
 
@@ -185,7 +184,7 @@ def train_step_bench(dev, world, steps=5, warmup=2, micro=64):
     return {"value": world * micro / ms_step * 1e3, "unit": "img/s", "ms_per_step": ms_step, "micro_batch_per_gpu": micro,
             "steps": steps, "algorithmic_gflop_per_img": 146.4, "tflops_per_gpu": 146.4 * micro / ms_step,
             "loss": float(loss.detach()), "frozen_blocks": [0, 1, 2, 3, 4, 5],
-            "note": "fwd+bwd+loss in libmsd_b200 (bf16 tensor cores, fp32 accumulate); optimizer = torch fused AdamW"}
+            "note": "corrupt + fwd + loss + bwd + clip/AdamW all in libmsd_b200 (bf16 tensor cores, fp32 accumulate / master weights)"}
 
 
 # ------------------------------------------------------------------------------------------------ CUDA arm

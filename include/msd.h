@@ -318,6 +318,23 @@ int msd_tile_extract_f32(const float* d_scene, const int* d_ty0, const int* d_tx
 int msd_tile_blend_f32(const float* d_restored, const int* d_gy, const int* d_gx, const int* d_tile_index, int ny, int nx, float* d_out,
                        int C, int H, int W, int S, int ramp, int row0, int row1, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------
+ * Optimizer step.  Replaces torch.nn.utils.clip_grad_norm_ + torch.optim.AdamW.step in
+ * Trainer.train_epoch (src/training/trainer.py:188-213; optimizer built in scripts/train.py:144-160).
+ * `tensors` is a HOST array of n entries whose pointers are device fp32 buffers of `numel` elements.
+ *   msd_grad_sqnorm_f32: *d_sqnorm (device fp64) = sum over all tensors of sum g^2
+ *   msd_adamw_step_f32 : decoupled weight decay, bias-corrected moments (step is 1-based); when max_grad_norm > 0 the gradient
+ *                        is multiplied by min(1, max_grad_norm / (sqrt(*d_sqnorm) + 1e-6)) on the fly (gradients are not modified)
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct msd_adamw_tensor {
+  float* param; const float* grad; float* exp_avg; float* exp_avg_sq;
+  long long numel;
+  float lr, weight_decay;
+} msd_adamw_tensor;
+int msd_grad_sqnorm_f32(const msd_adamw_tensor* tensors, int n, double* d_sqnorm, void* stream);
+int msd_adamw_step_f32(const msd_adamw_tensor* tensors, int n, float beta1, float beta2, float eps, int step, float max_grad_norm,
+                       const double* d_sqnorm, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -77,6 +77,11 @@ class ModelGrads(C.Structure):
                 ("w_head3", c_void_p), ("bn_head_g", c_void_p), ("bn_head_b", c_void_p), ("w_head1", c_void_p), ("b_head1", c_void_p)]
 
 
+class AdamWTensor(C.Structure):
+    _fields_ = [("param", c_void_p), ("grad", c_void_p), ("exp_avg", c_void_p), ("exp_avg_sq", c_void_p), ("numel", C.c_longlong),
+                ("lr", c_float), ("weight_decay", c_float)]
+
+
 # name -> (restype, argtypes); must list every symbol include/msd.h declares (tests/test_abi.py checks this)
 SIGNATURES = {
     "msd_version": (c_int, []),
@@ -139,6 +144,8 @@ SIGNATURES = {
     "msd_tile_extract_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "msd_tile_blend_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int,
                                    c_int, c_int, c_int, c_void_p]),
+    "msd_grad_sqnorm_f32": (c_int, [C.POINTER(AdamWTensor), c_int, c_void_p, c_void_p]),
+    "msd_adamw_step_f32": (c_int, [C.POINTER(AdamWTensor), c_int, c_float, c_float, c_float, c_int, c_float, c_void_p, c_void_p]),
     "msd_wgrad_conv3x3_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                        c_void_p]),
 }

@@ -363,3 +363,25 @@ def test_train_step_at_larger_batch_vs_oracle_on_device():
         g, r = p.grad, ref[n].grad
         errs.append(((g - r).pow(2).mean().sqrt() / (r.pow(2).mean().sqrt() + 1e-30)).item())
     assert max(errs) <= 0.2 and sorted(errs)[len(errs) // 2] <= 0.15, (max(errs), sorted(errs)[len(errs) // 2])
+
+
+def test_fused_adamw_with_clip_matches_torch():
+    from msd_b200.training import FusedAdamW
+    g = torch.Generator().manual_seed(0)
+    shapes = [(768, 3328), (13, 48, 1, 1), (7,), (384, 384, 3, 3), (1, 144, 768), (5, 3)]
+    ref = [torch.nn.Parameter(torch.randn(*s, generator=g).cuda()) for s in shapes]
+    mine = [torch.nn.Parameter(p.detach().clone()) for p in ref]
+    groups = lambda ps: [{"params": ps[:3], "lr": 1e-3, "weight_decay": 0.05}, {"params": ps[3:], "lr": 1e-2, "weight_decay": 0.0}]
+    o_ref = torch.optim.AdamW(groups(ref), betas=(0.9, 0.999), eps=1e-8)
+    o_mine = FusedAdamW(groups(mine), betas=(0.9, 0.999), eps=1e-8, max_grad_norm=1.0)
+    for step in range(4):
+        for a, b in zip(ref, mine):
+            gr = torch.randn(a.shape, generator=g).cuda() * (0.01 if step == 3 else 1.0)    # last step: norm < 1, clip inactive
+            a.grad, b.grad = gr.clone(), gr.clone()
+        norm = torch.nn.utils.clip_grad_norm_(ref, 1.0)
+        o_ref.step(); o_mine.step()
+        assert abs(o_mine.last_grad_sqnorm.item() ** 0.5 - norm.item()) <= 1e-4 * norm.item()
+        for a, b in zip(ref, mine):
+            assert torch.allclose(a, b, rtol=1e-5, atol=1e-6)
+    sd = o_mine.state_dict()
+    assert set(sd["state"][0].keys()) == {"step", "exp_avg", "exp_avg_sq"}

@@ -10,7 +10,7 @@ import torch
 import recipes
 from msd_b200.data import AddSensorNoise
 from msd_b200.models import SatMAERestoration
-from msd_b200.training import CombinedLoss
+from msd_b200.training import CombinedLoss, FusedAdamW
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=64)
@@ -22,7 +22,7 @@ torch.manual_seed(42)
 model = SatMAERestoration(recipes.base_config(), block_layout="fallback").to(dev).train()
 noise = AddSensorNoise(*recipes.NOISE_CONFIGS["base"])
 crit = CombinedLoss(1.0, 0.1)
-opt = torch.optim.AdamW(model.get_optimizer_param_groups(1e-4, 0.05), betas=(0.9, 0.999), fused=True)
+opt = FusedAdamW(model.get_optimizer_param_groups(1e-4, 0.05), betas=(0.9, 0.999), max_grad_norm=1.0)
 clean, _ = recipes.eurosat_tiles(32, seed=3)
 clean = clean.repeat(args.batch // 32 + 1, 1, 1, 1)[:args.batch].contiguous().to(dev)
 ev = lambda: torch.cuda.Event(enable_timing=True)
@@ -39,7 +39,6 @@ for it in range(args.steps + 2):
     loss.backward()
     e[4].record()
     if not args.no_opt:
-        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
         opt.step()
     opt.zero_grad(set_to_none=True)
     e[5].record()
