@@ -342,10 +342,18 @@ def main():
         "e2e": {"value": e2e_value, "unit": "img/s", "ms_per_step": ms_e2e / K, "h2d_bytes_per_step": B * TILE_ELEMS * 4,
                 "d2h_bytes_per_step": 40},
         "gpu_launches": launches_per_step * K,
-        "roofline": {"bound": "tensor", "kernel": "gemm_tc5_kernel<BN> (tcgen05 GEMM + implicit 3x3 conv family)" if args.backend == 0 else "gemm_hmma_kernel<BN>",
+        "roofline": {"bound": "tensor", "kernel": "gemm_tc5_pair_kernel<BN> / gemm_tc5_kernel<BN,MODE> (tcgen05 GEMM + implicit 3x3 conv family)" if args.backend == 0 else "gemm_hmma_kernel<BN>",
                      "achieved": achieved_tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": achieved_tf / pk["tf_sustained"],
                      "peak_source": f"{pk['src']} bf16_tflops_sustained (kernel timed inside a long step)",
-                     "traffic": None, "launches_per_step": gemm_n, "ms_per_step": gemm_ms,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the most frequent member of the family (the
+                     # qkv GEMM, 36 of 70 launches are this shape class), ncu --set full, profiles/r1_v3_ncu_full_summaries.txt;
+                     # its algorithmic bytes are 56.6 MB (A) + 3.5 MB (W) + 169.9 MB (out): the 126 MB L2 still holds part of the
+                     # output when the capture ends, nothing is re-read
+                     "traffic": 181.7e6 if args.backend == 0 else None,
+                     "traffic_kernel": "gemm_tc5_pair_kernel<256,0> on the qkv shape (M=36864, N=2304, K=768), bytes per launch",
+                     "tensor_pipe_active_pct_ncu": {"qkv": 71.2, "fc2": 66.6, "conv 24x24x384": 75.5, "conv 96x96x96": 50.2,
+                                                    "conv 192x192x48": 32.6, "source": "profiles/r1_v3_ncu_full_summaries.txt"},
+                     "launches_per_step": gemm_n, "ms_per_step": gemm_ms,
                      "algorithmic_gflop_per_step": gemm_flops / 1e9,
                      "share_of_step": gemm_ms / ms_step if ms_step > 0 else None,
                      "other_ms_per_step": {"attention": agg.get(1, [0])[0], "layernorm": agg.get(2, [0])[0], "other_model": agg.get(3, [0])[0]},
