@@ -162,6 +162,9 @@ struct msd_model {
   std::vector<msd_block_weights> tblocks;
   std::vector<msd_train_block> tblocks_t;
   bool has_train_weights = false;
+  // weight gradients run on a second stream, under the bandwidth-bound passes of the main stream (msd_model_backward)
+  cudaStream_t side = nullptr;
+  std::vector<cudaEvent_t> side_ev;
   int grid, tokens;
   // optional per-launch CUDA-event profile (bench.py's live roofline measurement)
   bool profile = false;
@@ -243,6 +246,8 @@ extern "C" int msd_model_launch_count(const msd_model* m) {
 extern "C" void msd_model_destroy(msd_model* m) {
   if (!m) return;
   for (cudaEvent_t e : m->ev) cudaEventDestroy(e);
+  for (cudaEvent_t e : m->side_ev) cudaEventDestroy(e);
+  if (m->side) cudaStreamDestroy(m->side);
   delete m;
 }
 
@@ -467,6 +472,56 @@ int bias_grad(const void* a, long long rows, int C, float* out, int n_out, doubl
 
 }  // namespace
 
+namespace {
+
+// Fork / join bookkeeping for the weight-gradient stream.  A weight gradient only feeds the optimizer, never the rest of the
+// backward, and it is tensor-bound, while the main stream spends a third of the backward in HBM-bound BatchNorm / LayerNorm /
+// GELU passes: run concurrently they fill each other's idle unit.  fork(): the side stream waits for everything enqueued on
+// the main stream so far (its operands exist).  done(): an event after the side-stream work; the main stream waits on it right
+// before the first kernel that overwrites one of that work's operands.
+struct SideStream {
+  msd_model* m;
+  cudaStream_t main_s, side_s;
+  int next = 0;
+  bool enabled;
+  int init(msd_model* model, cudaStream_t s) {
+    m = model; main_s = s;
+    static const bool off = getenv("MSD_NO_SIDE_STREAM") != nullptr;
+    enabled = !off;
+    if (!enabled) { side_s = s; return MSD_OK; }
+    if (m->side == nullptr) MSD_CHECK_CUDA(cudaStreamCreateWithFlags(&m->side, cudaStreamNonBlocking));
+    if (m->side_ev.empty()) {
+      m->side_ev.resize(512);
+      for (auto& e : m->side_ev) MSD_CHECK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    side_s = m->side;
+    return MSD_OK;
+  }
+  cudaEvent_t ev() { cudaEvent_t e = m->side_ev[next]; next = (next + 1) % (int)m->side_ev.size(); return e; }
+  int fork() {
+    if (!enabled) return MSD_OK;
+    cudaEvent_t e = ev();
+    MSD_CHECK_CUDA(cudaEventRecord(e, main_s));
+    MSD_CHECK_CUDA(cudaStreamWaitEvent(side_s, e, 0));
+    return MSD_OK;
+  }
+  int done(cudaEvent_t* out) {
+    *out = nullptr;
+    if (!enabled) return MSD_OK;
+    cudaEvent_t e = ev();
+    MSD_CHECK_CUDA(cudaEventRecord(e, side_s));
+    *out = e;
+    return MSD_OK;
+  }
+  int wait(cudaEvent_t& e) {                         // main stream must not pass this point before the side work is finished
+    if (enabled && e != nullptr) MSD_CHECK_CUDA(cudaStreamWaitEvent(main_s, e, 0));
+    e = nullptr;
+    return MSD_OK;
+  }
+};
+
+}  // namespace
+
 extern "C" int msd_model_set_train_weights(msd_model* m, const msd_train_weights* w) {
   MSD_REQUIRE(m && w && w->enc.blocks && w->blocks_t, "model_set_train_weights: null pointer");
   m->tw = *w;
@@ -602,6 +657,12 @@ extern "C" int msd_model_backward(msd_model* m, const float* d_grad_y, int B, vo
   float* coef = reinterpret_cast<float*>(ws + L.coef);
   unsigned char *gA = ws + L.gA, *gB = ws + L.gB, *gC = ws + L.gC;
   const int S = d.image_size;
+  SideStream ss;
+  MSD_TRY(ss.init(m, s));
+  void* side = (void*)ss.side_s;
+  // events of side-stream work still reading a buffer the main stream will overwrite later
+  cudaEvent_t e_gA = nullptr, e_gB = nullptr, e_dys = nullptr, e_gbf = nullptr, e_dh = nullptr, e_dqkv = nullptr;
+  auto ev_of = [&](unsigned char* buf) -> cudaEvent_t& { return buf == gA ? e_gA : e_gB; };
 
   // ---- head: 1x1 conv, then conv3x3 + BN + GELU
   {
@@ -609,15 +670,18 @@ extern "C" int msd_model_backward(msd_model* m, const float* d_grad_y, int B, vo
     const long long rows = (long long)B * (S + 2) * (S + 2);
     MSD_TRY(msd_head1x1_bwd(d_grad_y, tw.w_head1, gA, ws + L.dyt, B, S, S, c, d.out_channels, stream));
     if (gr->w_head1) {
-      MSD_TRY(zero_f32(gr->w_head1, (size_t)d.out_channels * c, s));
-      MSD_TRY(msd_wgrad_linear_bf16(ws + L.dyt, 16, ws + L.head_h, c, gr->w_head1, c, rows, d.out_channels, c, stream));
+      MSD_TRY(ss.fork());
+      MSD_TRY(zero_f32(gr->w_head1, (size_t)d.out_channels * c, ss.side_s));
+      MSD_TRY(msd_wgrad_linear_bf16(ws + L.dyt, 16, ws + L.head_h, c, gr->w_head1, c, rows, d.out_channels, c, side));
     }
     MSD_TRY(bias_grad(ws + L.dyt, rows, 16, gr->b_head1, d.out_channels, sums, stream));
     MSD_TRY(msd_bn_act_bwd_bf16(gA, ws + L.head_c, nullptr, stats + (size_t)20 * kStatsStride, gA, gA, gr->bn_head_g, gr->bn_head_b, coef,
                                 sums, B, S, S, c, stream));
     if (gr->w_head3) {
-      MSD_TRY(zero_f32(gr->w_head3, (size_t)9 * kpad * c, s));
-      MSD_TRY(msd_wgrad_conv3x3_bf16(ws + L.dec[3][9], gA, gr->w_head3, B, S, S, c, c, kpad, c, stream));
+      MSD_TRY(ss.fork());
+      MSD_TRY(zero_f32(gr->w_head3, (size_t)9 * kpad * c, ss.side_s));
+      MSD_TRY(msd_wgrad_conv3x3_bf16(ws + L.dec[3][9], gA, gr->w_head3, B, S, S, c, c, kpad, c, side));
+      MSD_TRY(ss.done(&e_gA));
     }
     MSD_TRY(make_conv3x3(p, gA, tw.wd_head3, nullptr, nullptr, gB, B, S, S, c, c, 0));
     MSD_TRY(gemm::launch(p, be, s));
@@ -637,38 +701,49 @@ extern "C" int msd_model_backward(msd_model* m, const float* d_grad_y, int B, vo
       float* s1 = stats + (size_t)bn_index(st, 1 + 2 * rb) * kStatsStride;
       float* s2 = stats + (size_t)bn_index(st, 2 + 2 * rb) * kStatsStride;
       // out = GELU(in + BN2(c2)):  dz -> gC (also the skip gradient), dc2 -> t1
+      MSD_TRY(ss.wait(ev_of(t1)));
       MSD_TRY(msd_bn_act_bwd_bf16(gin, c2, in, s2, gC, t1, sg.bn_g[2 * rb + 1], sg.bn_b[2 * rb + 1], coef, sums, B, hw, hw, c, stream));
       if (sg.w_conv[2 * rb + 1]) {
-        MSD_TRY(zero_f32(sg.w_conv[2 * rb + 1], (size_t)9 * kpad * c, s));
-        MSD_TRY(msd_wgrad_conv3x3_bf16(y1, t1, sg.w_conv[2 * rb + 1], B, hw, hw, c, c, kpad, c, stream));
+        MSD_TRY(ss.fork());
+        MSD_TRY(zero_f32(sg.w_conv[2 * rb + 1], (size_t)9 * kpad * c, ss.side_s));
+        MSD_TRY(msd_wgrad_conv3x3_bf16(y1, t1, sg.w_conv[2 * rb + 1], B, hw, hw, c, c, kpad, c, side));
+        MSD_TRY(ss.done(&ev_of(t1)));
       }
       MSD_TRY(make_conv3x3(p, t1, sw.wd_conv[2 * rb + 1], nullptr, nullptr, gin, B, hw, hw, c, c, 0));   // dy1 -> gin
       MSD_TRY(gemm::launch(p, be, s));
       // y1 = GELU(BN1(c1)):  dc1 in place
       MSD_TRY(msd_bn_act_bwd_bf16(gin, c1, nullptr, s1, gin, gin, sg.bn_g[2 * rb], sg.bn_b[2 * rb], coef, sums, B, hw, hw, c, stream));
       if (sg.w_conv[2 * rb]) {
-        MSD_TRY(zero_f32(sg.w_conv[2 * rb], (size_t)9 * kpad * c, s));
-        MSD_TRY(msd_wgrad_conv3x3_bf16(in, gin, sg.w_conv[2 * rb], B, hw, hw, c, c, kpad, c, stream));
+        MSD_TRY(ss.fork());
+        MSD_TRY(zero_f32(sg.w_conv[2 * rb], (size_t)9 * kpad * c, ss.side_s));
+        MSD_TRY(msd_wgrad_conv3x3_bf16(in, gin, sg.w_conv[2 * rb], B, hw, hw, c, c, kpad, c, side));
+        MSD_TRY(ss.done(&ev_of(gin)));
       }
-      // d(in) = dgrad(dc1) + skip gradient (identity tap, A = gC)
+      // d(in) = dgrad(dc1) + skip gradient (identity tap, A = gC); it overwrites t1, which the conv-2 weight gradient reads
+      MSD_TRY(ss.wait(ev_of(t1)));
       MSD_TRY(make_conv3x3(p, gin, sw.wd_conv[2 * rb], nullptr, gC, t1, B, hw, hw, c, c, 0));
       MSD_TRY(gemm::launch(p, be, s));
       std::swap(gin, t1);                    // gin now holds d(in)
     }
     // X0 = GELU(BN(U_raw)), U_raw = ConvT(stage input)
+    MSD_TRY(ss.wait(ev_of(gin)));
     MSD_TRY(msd_bn_act_bwd_bf16(gin, T[0], nullptr, stats + (size_t)bn_index(st, 0) * kStatsStride, gin, gin, sg.bn_up_g, sg.bn_up_b, coef,
                                 sums, B, hw, hw, c, stream));
     hw /= 2;
     const int in_pad = st == 0 ? 0 : 1;
     const long long rows_in = (long long)B * (in_pad ? (hw + 2) * (hw + 2) : hw * hw);
+    MSD_TRY(ss.wait(e_dys));
     MSD_TRY(msd_convt_unshuffle_bf16(gin, ws + L.dys, B, hw, hw, in_pad, c, stream));
     const void* stage_in = st == 0 ? (const void*)(ws + L.xnf) : (const void*)(ws + L.dec[st - 1][9]);
     if (sg.w_up) {
-      MSD_TRY(zero_f32(sg.w_up, (size_t)4 * c * cin, s));
-      MSD_TRY(msd_wgrad_linear_bf16(ws + L.dys, 4 * c, stage_in, cin, sg.w_up, cin, rows_in, 4 * c, cin, stream));
+      MSD_TRY(ss.fork());
+      MSD_TRY(zero_f32(sg.w_up, (size_t)4 * c * cin, ss.side_s));
+      MSD_TRY(msd_wgrad_linear_bf16(ws + L.dys, 4 * c, stage_in, cin, sg.w_up, cin, rows_in, 4 * c, cin, side));
+      MSD_TRY(ss.done(&e_dys));
     }
     // data gradient of the stage input: [rows_in, 4c] . W_up -> [rows_in, cin]  (halo rows of dys are zero -> stay zero)
     void* dst = st == 0 ? (void*)(ws + L.dxn) : (void*)gB;   // the operand is dys, so gB (= gin after two swaps) is free again
+    if (st != 0) MSD_TRY(ss.wait(e_gB));
     MSD_TRY(make_linear(p, ws + L.dys, sw.wT_up, nullptr, dst, nullptr, (int)rows_in, cin, 4 * c, 0, 0));
     MSD_TRY(gemm::launch(p, be, s));
   }
@@ -689,42 +764,54 @@ extern "C" int msd_model_backward(msd_model* m, const float* d_grad_y, int B, vo
     void *xn1 = ws + L.xn1 + l * L.s_xn, *qkv = ws + L.qkv + l * L.s_qkv, *att = ws + L.att + l * L.s_xn;
     void *xn2 = ws + L.xn2 + l * L.s_xn, *hpre = ws + L.hpre + l * L.s_h, *h = ws + L.h + l * L.s_h;
     // MLP branch: x_out = x_mid + fc2(GELU(fc1(LN2 x_mid)))
+    MSD_TRY(ss.wait(e_dh));                     // the previous block's fc1 weight gradient still reads dh
     MSD_TRY(make_linear(p, gbf, bt.wT_fc2, nullptr, dh, nullptr, M, Hd, E, 0, 0));
     MSD_TRY(gemm::launch(p, be, s));
     if (tr) {
-      MSD_TRY(zero_f32(bg.w_fc2, (size_t)E * Hd, s));
-      MSD_TRY(msd_wgrad_linear_bf16(gbf, E, h, Hd, bg.w_fc2, Hd, M, E, Hd, stream));
+      MSD_TRY(ss.fork());
+      MSD_TRY(zero_f32(bg.w_fc2, (size_t)E * Hd, ss.side_s));
+      MSD_TRY(msd_wgrad_linear_bf16(gbf, E, h, Hd, bg.w_fc2, Hd, M, E, Hd, side));
+      MSD_TRY(ss.done(&e_gbf));
       MSD_TRY(bias_grad(gbf, M, E, bg.b_fc2, E, sums, stream));
     }
     MSD_TRY(msd_gelu_bwd_bf16(dh, hpre, dh, (long long)M * Hd, stream));
     MSD_TRY(make_linear(p, dh, bt.wT_fc1, nullptr, dxn, nullptr, M, E, Hd, 0, 0));
     MSD_TRY(gemm::launch(p, be, s));
     if (tr) {
-      MSD_TRY(zero_f32(bg.w_fc1, (size_t)E * Hd, s));
-      MSD_TRY(msd_wgrad_linear_bf16(dh, Hd, xn2, E, bg.w_fc1, E, M, Hd, E, stream));
+      MSD_TRY(ss.fork());
+      MSD_TRY(zero_f32(bg.w_fc1, (size_t)E * Hd, ss.side_s));
+      MSD_TRY(msd_wgrad_linear_bf16(dh, Hd, xn2, E, bg.w_fc1, E, M, Hd, E, side));
+      MSD_TRY(ss.done(&e_dh));
       MSD_TRY(bias_grad(dh, M, Hd, bg.b_fc1, Hd, sums, stream));
       MSD_TRY(zero_f32(bg.ln2_g, E, s));
       MSD_TRY(zero_f32(bg.ln2_b, E, s));
     }
+    MSD_TRY(ss.wait(e_gbf));                    // LayerNorm backward rewrites gbf, which the fc2 weight gradient reads
     MSD_TRY(msd_layernorm_bwd(dxn, 0, xmid, bw.ln2_g, d.ln_eps_block, g, 1, gbf, tr ? bg.ln2_g : nullptr, tr ? bg.ln2_b : nullptr, M, E, stream));
     // attention branch: x_mid = x_in + proj(attn(LN1 x_in))
     MSD_TRY(make_linear(p, gbf, bt.wT_proj, nullptr, datt, nullptr, M, E, E, 0, 0));
     MSD_TRY(gemm::launch(p, be, s));
     if (tr) {
-      MSD_TRY(zero_f32(bg.w_proj, (size_t)E * E, s));
-      MSD_TRY(msd_wgrad_linear_bf16(gbf, E, att, E, bg.w_proj, E, M, E, E, stream));
+      MSD_TRY(ss.fork());
+      MSD_TRY(zero_f32(bg.w_proj, (size_t)E * E, ss.side_s));
+      MSD_TRY(msd_wgrad_linear_bf16(gbf, E, att, E, bg.w_proj, E, M, E, E, side));
+      MSD_TRY(ss.done(&e_gbf));
       MSD_TRY(bias_grad(gbf, M, E, bg.b_proj, E, sums, stream));
     }
+    MSD_TRY(ss.wait(e_dqkv));                   // the previous block's qkv weight gradient still reads dqkv
     MSD_TRY(msd_attention_bwd_bf16(qkv, datt, dqkv, B, m->tokens, d.num_heads, stream));
     MSD_TRY(make_linear(p, dqkv, bt.wT_qkv, nullptr, dxn, nullptr, M, E, 3 * E, 0, 0));
     MSD_TRY(gemm::launch(p, be, s));
     if (tr) {
-      MSD_TRY(zero_f32(bg.w_qkv, (size_t)3 * E * E, s));
-      MSD_TRY(msd_wgrad_linear_bf16(dqkv, 3 * E, xn1, E, bg.w_qkv, E, M, 3 * E, E, stream));
+      MSD_TRY(ss.fork());
+      MSD_TRY(zero_f32(bg.w_qkv, (size_t)3 * E * E, ss.side_s));
+      MSD_TRY(msd_wgrad_linear_bf16(dqkv, 3 * E, xn1, E, bg.w_qkv, E, M, 3 * E, E, side));
+      MSD_TRY(ss.done(&e_dqkv));
       MSD_TRY(bias_grad(dqkv, M, 3 * E, bg.b_qkv, 3 * E, sums, stream));
       MSD_TRY(zero_f32(bg.ln1_g, E, s));
       MSD_TRY(zero_f32(bg.ln1_b, E, s));
     }
+    MSD_TRY(ss.wait(e_gbf));                    // ... and the proj weight gradient
     MSD_TRY(msd_layernorm_bwd(dxn, 0, xin, bw.ln1_g, d.ln_eps_block, g, 1, gbf, tr ? bg.ln1_g : nullptr, tr ? bg.ln1_b : nullptr, M, E, stream));
   }
   // ---- patch embedding: x0 = LN(pe) + pos_embed
@@ -734,10 +821,15 @@ extern "C" int msd_model_backward(msd_model* m, const float* d_grad_y, int B, vo
   MSD_TRY(msd_layernorm_bwd(g, 1, reinterpret_cast<const float*>(ws + L.x0pre), w.pe_ln_g, d.ln_eps_outer, g, 0, gbf, gr->pe_ln_g, gr->pe_ln_b,
                             M, E, stream));
   if (gr->w_pe) {
-    MSD_TRY(zero_f32(gr->w_pe, (size_t)E * Kpe, s));
-    MSD_TRY(msd_wgrad_linear_bf16(gbf, E, ws + L.a_pe, Kpe, gr->w_pe, Kpe, M, E, Kpe, stream));
+    MSD_TRY(ss.fork());
+    MSD_TRY(zero_f32(gr->w_pe, (size_t)E * Kpe, ss.side_s));
+    MSD_TRY(msd_wgrad_linear_bf16(gbf, E, ws + L.a_pe, Kpe, gr->w_pe, Kpe, M, E, Kpe, side));
   }
   MSD_TRY(bias_grad(gbf, M, E, gr->b_pe, E, sums, stream));
+  // join: everything the side stream produced is ordered before whatever the caller enqueues next on `stream`
+  cudaEvent_t e_all = nullptr;
+  MSD_TRY(ss.done(&e_all));
+  MSD_TRY(ss.wait(e_all));
   return MSD_OK;
 }
 

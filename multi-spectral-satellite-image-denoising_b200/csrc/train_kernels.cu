@@ -185,27 +185,44 @@ __global__ void __launch_bounds__(kBlock) bn_act_bwd1_kernel(const __nv_bfloat16
     for (int i = 0; i < 8; ++i) {
       sc[i] = stats[v * 8 + i]; sf[i] = stats[C + v * 8 + i]; mean[i] = stats[2 * C + v * 8 + i]; rstd[i] = stats[3 * C + v * 8 + i];
     }
-    for (long long row = (long long)blockIdx.x * rpi + r0; row < rows; row += (long long)gridDim.x * rpi) {
-      uint4 o = make_uint4(0u, 0u, 0u, 0u);
-      if (interior_row((uint32_t)row, plane, pitch, H, W)) {
-        float g[8], f[8], s[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(dy + row * C + v * 8)), g);
-        unpack8(__ldg(reinterpret_cast<const uint4*>(c + row * C + v * 8)), f);
-        if (skip != nullptr) unpack8(__ldg(reinterpret_cast<const uint4*>(skip + row * C + v * 8)), s);
+    // two rows per iteration, every load issued before the first use (the pass is latency-bound otherwise)
+    const long long stride = (long long)gridDim.x * rpi;
+    for (long long row = (long long)blockIdx.x * rpi + r0; row < rows; row += 2 * stride) {
+      uint4 rg[2], rc[2], rs[2];
+      bool in[2];
 #pragma unroll
-        for (int k = 0; k < 8; k += 2) {
-          float z0 = fmaf(f[k], sc[k], sf[k]), z1 = fmaf(f[k + 1], sc[k + 1], sf[k + 1]);
-          if (skip != nullptr) { z0 += s[k]; z1 += s[k + 1]; }
-          const float2 gg = gelu_grad2(z0, z1);
-          const float d0 = g[k] * gg.x, d1 = g[k + 1] * gg.y;
-          g[k] = d0; g[k + 1] = d1;
-          s1[k] += d0; s1[k + 1] += d1;
-          s2[k] = fmaf(d0, (f[k] - mean[k]) * rstd[k], s2[k]);
-          s2[k + 1] = fmaf(d1, (f[k + 1] - mean[k + 1]) * rstd[k + 1], s2[k + 1]);
+      for (int u = 0; u < 2; ++u) {
+        const long long r = row + u * stride;
+        in[u] = r < rows && interior_row((uint32_t)r, plane, pitch, H, W);
+        rg[u] = rc[u] = rs[u] = make_uint4(0u, 0u, 0u, 0u);
+        if (in[u]) {
+          rg[u] = __ldg(reinterpret_cast<const uint4*>(dy + r * C + v * 8));
+          rc[u] = __ldg(reinterpret_cast<const uint4*>(c + r * C + v * 8));
+          if (skip != nullptr) rs[u] = __ldg(reinterpret_cast<const uint4*>(skip + r * C + v * 8));
         }
-        o = pack8(g);
       }
-      *reinterpret_cast<uint4*>(dz + row * C + v * 8) = o;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const long long r = row + u * stride;
+        if (r >= rows) break;
+        uint4 o = make_uint4(0u, 0u, 0u, 0u);
+        if (in[u]) {
+          float g[8], f[8], s[8];
+          unpack8(rg[u], g); unpack8(rc[u], f); unpack8(rs[u], s);
+#pragma unroll
+          for (int k = 0; k < 8; k += 2) {
+            const float z0 = fmaf(f[k], sc[k], sf[k]) + s[k], z1 = fmaf(f[k + 1], sc[k + 1], sf[k + 1]) + s[k + 1];
+            const float2 gg = gelu_grad2(z0, z1);
+            const float d0 = g[k] * gg.x, d1 = g[k + 1] * gg.y;
+            g[k] = d0; g[k + 1] = d1;
+            s1[k] += d0; s1[k + 1] += d1;
+            s2[k] = fmaf(d0, (f[k] - mean[k]) * rstd[k], s2[k]);
+            s2[k + 1] = fmaf(d1, (f[k + 1] - mean[k + 1]) * rstd[k + 1], s2[k + 1]);
+          }
+          o = pack8(g);
+        }
+        *reinterpret_cast<uint4*>(dz + r * C + v * 8) = o;
+      }
     }
   }
 #pragma unroll
