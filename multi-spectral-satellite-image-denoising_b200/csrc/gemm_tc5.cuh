@@ -361,6 +361,39 @@ __device__ __forceinline__ void epilogue_tile(const Problem& p, uint32_t stg_s, 
   }
 }
 
+// One whole tile of the resident-weight 3x3 conv mode with one k-block per tap (<= 64 channels), issued as straight-line code:
+// STEPS = 3 (dy) or 4 (+ identity skip tap) pipeline stages, NK valid 16-wide K slices, windows dx = -1, 0, +1 at +0 / +128 /
+// +256 bytes of the stage's A box, weights at tap * W_BOX in the resident matrix.  a_base / r_lo are (address >> 4).
+template <int BN, int STEPS, int NK, uint32_t A_STAGE_BYTES_>
+__device__ __forceinline__ void issue_tile_resident(uint32_t tmem_d, uint32_t a_base, uint32_t r_lo, uint32_t idesc, uint64_t* full,
+                                                    uint64_t* empty, uint64_t* tmem_full_bar, uint32_t parity, int skip_tap) {
+  constexpr uint32_t HI = (1024u >> 4) | (1u << 14) | (2u << 29);
+  constexpr uint32_t WB = (BN * BLOCK_K * 2) >> 4;
+  const uint64_t da0 = ((uint64_t)HI << 32) | a_base, db0 = ((uint64_t)HI << 32) | r_lo;
+#pragma unroll
+  for (int st = 0; st < STEPS; ++st) {
+    mbar_wait(&full[st], parity);
+    tcgen05_fence_after();
+    if (elect_one()) {
+      const uint64_t da = da0 + (uint64_t)(st * (A_STAGE_BYTES_ >> 4));
+      if (st < 3) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+#pragma unroll
+          for (int k = 0; k < NK; ++k)
+            tcgen05_mma_bf16(tmem_d, da + (uint64_t)(8 * j + 2 * k), db0 + (uint64_t)((3 * st + j) * WB + 2 * k), idesc, (st | j | k) != 0 ? 1u : 0u);
+      } else {                                           // identity skip tap through the middle window
+        const uint64_t db = db0 + (uint64_t)((uint32_t)skip_tap * WB);
+#pragma unroll
+        for (int k = 0; k < NK; ++k) tcgen05_mma_bf16(tmem_d, da + (uint64_t)(8 + 2 * k), db + (uint64_t)(2 * k), idesc, 1u);
+      }
+      tcgen05_commit(&empty[st]);
+      if (st == STEPS - 1) tcgen05_commit(tmem_full_bar);
+    }
+    __syncwarp();
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ kernel
 template <int BN, int MODE>
 __global__ void __launch_bounds__((Cfg<BN, MODE>::THREADS), 1)
@@ -408,6 +441,10 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int n_dy = 3, has_skip = p.skip_tap >= 0 ? 1 : 0;
   // 16-wide K slices of the last k-block of a tap that hold valid channels (K = 48 or 96 does not fill it)
   const int nk_last = min(BLOCK_K / 16, (p.kvalid - (kbpt - 1) * BLOCK_K + 15) / 16);
+  // Ring length.  The resident-weight mode uses exactly TWO tiles' worth of stages (6 or 8 <= kStages): tile `it` then always
+  // occupies stages (it & 1) * steps .. + steps, i.e. each MMA issuer (even / odd tiles) sees the SAME stages every tile and its
+  // whole per-tile instruction stream has loop-invariant descriptors (issue_tile_resident below).
+  const int ring = (MODE == MODE_MERGE3_RESIDENT) ? min(C::kStages, 2 * (n_dy + has_skip) * kbpt) : C::kStages;
 
   // Producer and MMA warps run their loops with all 32 lanes converged and let one elected lane issue the
   // asynchronous instructions.  Both loops are the serial critical path of a CTA (one warp each, nothing to hide
@@ -468,7 +505,7 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               tma_load_2d(is_skip ? &tmS : &tmA, &full[stage], smem_a + stage * A_STAGE_BYTES, kc * BLOCK_K, row);
             }
             __syncwarp();
-            if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+            if (++stage == ring) { stage = 0; phase ^= 1; }
           }
         }
       }
@@ -493,7 +530,7 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if constexpr (MODE == MODE_MERGE3_RESIDENT) { mbar_wait(res_full, 0); tcgen05_fence_after(); }
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it, gstep += steps_per_tile) {
       if ((it & 1u) != par) continue;
-      int stage = gstep % C::kStages;
+      int stage = gstep % ring;
       mbar_wait(&tmem_empty[par], ((it >> 1) & 1u) ^ 1u);
       tcgen05_fence_after();
       uint32_t acc = 0;                                   // first MMA of the tile overwrites the accumulator
@@ -517,6 +554,19 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           if (++stage == C::kStages) stage = 0;
         }
       } else {
+        if constexpr (MODE == MODE_MERGE3_RESIDENT) {
+          if (kbpt == 1 && nk_last == 3 && ring == 2 * (n_dy + has_skip)) {
+            // 48-channel stage: straight-line issue, every descriptor = a per-issuer base + a compile-time offset
+            const uint32_t a_base = a_lo0 + par * (uint32_t)(n_dy + has_skip) * (A_STAGE_BYTES >> 4);
+            uint64_t* fullp = full + par * (n_dy + has_skip);
+            uint64_t* emptyp = empty + par * (n_dy + has_skip);
+            const uint32_t parity = (it >> 1) & 1u;
+            if (has_skip) issue_tile_resident<BN, 4, 3, A_STAGE_BYTES>(tmem_d, a_base, r_lo0, idesc, fullp, emptyp, &tmem_full[par], parity, p.skip_tap);
+            else issue_tile_resident<BN, 3, 3, A_STAGE_BYTES>(tmem_d, a_base, r_lo0, idesc, fullp, emptyp, &tmem_full[par], parity, 0);
+            pmask ^= ((1u << (n_dy + has_skip)) - 1u) << (par * (n_dy + has_skip));
+            continue;
+          }
+        }
         for (int dy = 0; dy < n_dy + has_skip; ++dy) {
           const bool is_skip = dy == n_dy;
           for (int kc = 0; kc < kbpt; ++kc) {
@@ -544,7 +594,7 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
             __syncwarp();
             acc = 1;
-            if (++stage == C::kStages) stage = 0;
+            if (++stage == ring) stage = 0;
           }
         }
       }
