@@ -218,6 +218,9 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # stdout carries exactly ONE JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION writes it to stdout) off it
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     W = max(3, args.warmup)
     K, B = args.steps, args.batch

@@ -1,0 +1,4 @@
+mkdir -p gpurun_out
+N=${NGPU:-8}
+python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29543 bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err; echo "n$N rc=$?"
+head -c 600 gpurun_out/bench_n$N.json; echo; grep -v "^\*\|OMP_NUM" gpurun_out/bench_n$N.err | tail -25 | cut -c1-250
