@@ -313,6 +313,8 @@ int msd_model_backward(msd_model* m, const float* d_grad_y, int B, void* d_ws, s
  *   tile_index[ny*nx] = slot of grid tile (r,k) in d_restored or -1.
  * ------------------------------------------------------------------------------------------------- */
 int msd_ingest_u16_f32(const uint16_t* d_dn, float* d_out, float* d_scale_ws, int B, int C, int h, int w, int S, void* stream);
+/* inverse of the ingest normalisation (the writer side): d_dn uint16 = round(clamp(x*0.25 + 0.5, 0, 1) * 10000) */
+int msd_export_u16(const float* d_x, uint16_t* d_dn, long long numel, void* stream);
 int msd_tile_extract_f32(const float* d_scene, const int* d_ty0, const int* d_tx0, float* d_tiles, int n_tiles, int C, int H, int W,
                          int S, void* stream);
 int msd_tile_blend_f32(const float* d_restored, const int* d_gy, const int* d_gx, const int* d_tile_index, int ny, int nx, float* d_out,

@@ -131,6 +131,18 @@ __global__ void __launch_bounds__(kBlock) tile_blend_kernel(const float* __restr
   }
 }
 
+// inverse of the ingest normalisation: restored fp32 in [-2, 2] -> Sentinel-2 digital numbers (reflectance x 10000, uint16)
+__global__ void __launch_bounds__(kBlock) export_kernel(const float* __restrict__ x, uint16_t* __restrict__ dn, long long n4) {
+  for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < n4; i += (long long)gridDim.x * kBlock) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+    auto q = [](float t) -> uint32_t {
+      t = fminf(fmaxf(fmaf(t, 0.25f, 0.5f), 0.0f), 1.0f);       // (x - 0.5) / 0.25 undone, clamp as dataset.py:182 does
+      return (uint32_t)__float2int_rn(t * 10000.0f);
+    };
+    reinterpret_cast<uint2*>(dn)[i] = make_uint2(q(v.x) | (q(v.y) << 16), q(v.z) | (q(v.w) << 16));
+  }
+}
+
 unsigned grid_for(long long items) {
   const long long blocks = (items + kBlock - 1) / kBlock;
   return (unsigned)(blocks < 1 ? 1 : blocks < 148ll * 16 ? blocks : 148ll * 16);
@@ -165,6 +177,14 @@ extern "C" int msd_tile_blend_f32(const float* d_restored, const int* d_gy, cons
   const long long total = (long long)C * (row1 - row0) * W;
   tile_blend_kernel<<<grid_for(total), kBlock, 0, (cudaStream_t)stream>>>(d_restored, d_gy, d_gx, d_tile_index, ny, nx, d_out, C, H, W, S,
                                                                          ramp, row0, row1, total);
+  MSD_LAUNCH_CHECK();
+  return MSD_OK;
+}
+
+extern "C" int msd_export_u16(const float* d_x, uint16_t* d_dn, long long numel, void* stream) {
+  MSD_REQUIRE(d_x && d_dn && numel > 0 && numel % 4 == 0, "export: bad arguments");
+  MSD_REQUIRE(msd_aligned16(d_x) && (reinterpret_cast<uintptr_t>(d_dn) & 7u) == 0, "export: pointers must be 16- / 8-byte aligned");
+  export_kernel<<<grid_for(numel / 4), kBlock, 0, (cudaStream_t)stream>>>(d_x, d_dn, numel / 4);
   MSD_LAUNCH_CHECK();
   return MSD_OK;
 }

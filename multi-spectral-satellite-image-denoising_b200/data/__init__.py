@@ -2,6 +2,6 @@
 re-implemented, plus the batched GPU form of the dataset's per-sample preprocessing (ingest_tiles, SURVEY 8f row N1);
 file I/O and the DataLoader stay with the reference."""
 from .transforms import AddSensorNoise
-from .ingest import ingest_tiles
+from .ingest import export_tiles, ingest_tiles
 
-__all__ = ["AddSensorNoise", "ingest_tiles"]
+__all__ = ["AddSensorNoise", "ingest_tiles", "export_tiles"]

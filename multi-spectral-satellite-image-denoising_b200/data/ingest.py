@@ -29,3 +29,19 @@ def ingest_tiles(dn: torch.Tensor, target_size: int = 192) -> torch.Tensor:
         scale = torch.empty(B, dtype=torch.float32, device=dn.device)
         _lib.check(lib.msd_ingest_u16_f32(_lib.ptr(dn), _lib.ptr(out), _lib.ptr(scale), B, C, h, w, target_size, _lib.stream_ptr()))
     return out
+
+
+def export_tiles(x: torch.Tensor) -> torch.Tensor:
+    """Restored tiles in the model's normalisation ([-2, 2], fp32 CUDA) -> Sentinel-2 digital numbers (uint16, reflectance x
+    10000): the inverse of `ingest_tiles`' scaling, for writing results back in the source product's units."""
+    if not x.is_cuda or x.dtype != torch.float32:
+        raise _lib.MsdError("export_tiles: fp32 CUDA tensor required (libmsd_b200 has no CPU path)")
+    x = x.contiguous()
+    if x.numel() % 4:
+        raise _lib.MsdError("export_tiles: element count must be a multiple of 4")
+    lib = _lib.load()
+    _lib.require_device(x.device)
+    with torch.cuda.device(x.device):
+        out = torch.empty(x.shape, dtype=torch.uint16, device=x.device)
+        _lib.check(lib.msd_export_u16(_lib.ptr(x), _lib.ptr(out), x.numel(), _lib.stream_ptr()))
+    return out

@@ -76,3 +76,16 @@ def test_scene_restoration_with_the_real_model_is_shard_invariant():
     parts = [restore_scene(model, scene, overlap=32, batch=4, rank=r, world=2) for r in range(2)]
     glued = torch.cat([p[0] for p in parts], dim=1)
     assert parts[0][1][1] == parts[1][1][0] and torch.equal(glued, full)     # same tiles, same gather order: bit-identical
+
+
+def test_export_is_the_inverse_of_the_ingest_scaling():
+    from msd_b200.data import export_tiles
+    gen = torch.Generator().manual_seed(4)
+    x = torch.rand(3, 13, 192, 192, generator=gen) * 5 - 2.5            # beyond [-2, 2] on both sides: clamped
+    got = export_tiles(x.cuda()).cpu().to(torch.int32)
+    want = torch.round((x * 0.25 + 0.5).clamp(0, 1) * 10000).to(torch.int32)
+    assert (got - want).abs().max().item() <= 1                          # rounding ties at fp32 resolution
+    assert (got != want).float().mean().item() < 1e-3
+    dn = torch.randint(0, 10001, (2, 13, 192, 192), generator=gen)
+    back = export_tiles(ingest_tiles(dn.to(torch.int32).cuda(), 192)).cpu().to(torch.int32)   # same size: no resampling
+    assert (back - dn).abs().max().item() <= 1
