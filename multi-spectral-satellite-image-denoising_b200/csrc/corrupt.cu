@@ -158,10 +158,11 @@ __global__ void __launch_bounds__(kThreads) corrupt_kernel(const CorruptParams p
     p.noisy[e] = v;
     if (p.patch != nullptr) {
       // A[(b*gh + py)*gw + px][c*P*P + ky*P + kx]                (encoder.py:48-50)
-      uint32_t py = yy / p.P, ky = yy - py * p.P, px = xx / p.P, kx = xx - px * p.P;
-      size_t row = ((size_t)b * p.gridw + py) * p.gridw + px;
-      size_t col = ((size_t)c * p.P + ky) * p.P + kx;
-      p.patch[row * ((size_t)p.C * p.P * p.P) + col] = __float2bfloat16_rn(v);
+      // patch size is 16 (the only one the model supports): shifts instead of runtime integer divisions, 32-bit offsets
+      const uint32_t py = yy >> 4, ky = yy & 15u, px = xx >> 4, kx = xx & 15u;
+      const uint32_t row = (b * (uint32_t)p.gridw + py) * (uint32_t)p.gridw + px;
+      const uint32_t col = (c << 8) + (ky << 4) + kx;
+      p.patch[(size_t)row * ((size_t)p.C << 8) + col] = __float2bfloat16_rn(v);
     }
   }
 }

@@ -1,2 +1,2 @@
-timeout 300 python -m pytest tests/test_gpu_model.py -q -p no:cacheprovider -x -k "conv3x3" 2>&1 | tail -15
-python tools/gemm_bench.py --only conv3; python tools/gemm_bench.py --only conv3_skip; python tools/gemm_bench.py --only conv4; python tools/gemm_bench.py --only conv4_skip
+python -m pytest tests/test_gpu_elementwise.py -q -p no:cacheprovider -x 2>&1 | tail -2
+python tools/elem_bench.py --only corrupt --iters 10 2>&1 | tail -2
