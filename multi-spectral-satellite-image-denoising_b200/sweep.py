@@ -5,7 +5,7 @@ One process per GPU.  The sweep is cut into fixed global batches; rank r takes a
 generated and corrupted from seed `seed + k` whatever rank runs it, so the result is independent of the GPU count.
 The only collective is one NCCL all_reduce(SUM) of the tracker's fp64[5] running sums at the end.
 
-    torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 -m msd_b200.sweep --tiles 27000 --batch 250
+    torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 -m msd_b200.sweep --tiles 27000 --batch 256
 """
 from __future__ import annotations
 
@@ -33,13 +33,14 @@ def batch_sizes(n_tiles: int, batch: int):
 
 
 def synthetic_tiles(n: int, seed: int, device) -> torch.Tensor:
-    """EuroSAT-shaped clean tiles: U[0,0.52] 64x64 reflectance -> bilinear 192 -> clamp -> (x-0.5)/0.25,
-    i.e. src/data/dataset.py:168-186 applied to synthetic digital numbers; generated on the device from `seed`."""
+    """EuroSAT-shaped clean tiles: 64x64 Sentinel-2 digital numbers in [0, 5200) (reflectance 0..0.52) ->
+    the dataset's preprocessing (/10000, bilinear 192, clamp, (x-0.5)/0.25; src/data/dataset.py:160-186) as ONE ingest kernel.
+    Generated on the device from `seed`, so batch k is the same whatever rank produces it."""
+    from .data import ingest_tiles
     g = torch.Generator(device=device)
     g.manual_seed(seed)
-    raw = torch.rand(n, 13, 64, 64, generator=g, device=device) * 0.52
-    x = torch.nn.functional.interpolate(raw, size=192, mode="bilinear", align_corners=False).clamp_(0, 1)
-    return ((x - 0.5) / 0.25).contiguous()
+    dn = torch.randint(0, 5200, (n, 13, 64, 64), generator=g, device=device, dtype=torch.int32).to(torch.uint16)
+    return ingest_tiles(dn, 192)
 
 
 @torch.no_grad()
@@ -51,11 +52,14 @@ def evaluation_sweep(model, noise, n_tiles: int, batch: int, rank: int = 0, worl
     lo, hi = shard_batches(len(sizes), rank, world)
     tracker = tracker or MetricsTracker()
     model.eval()
+    patches = None
     for k in range(lo, hi):
         clean = tile_fn(sizes[k], seed + k, device)
         torch.manual_seed(seed + k)                 # corruption of batch k does not depend on who runs it
-        noisy = noise(clean)
-        tracker.update(model(noisy), clean)
+        if patches is None or patches.shape[0] != clean.shape[0] * 144:
+            patches = torch.empty(clean.shape[0] * 144, 13 * 256, dtype=torch.bfloat16, device=device)
+        noisy = noise(clean, patch_out=patches)     # the corruption kernel also emits the patch-embedding operand
+        tracker.update(model(noisy, patches=patches), clean)
     if world > 1 and all_reduce:
         if tracker._acc is None:                    # a rank with no batches still joins the collective
             tracker._acc = torch.zeros(5, dtype=torch.float64, device=device)
@@ -69,7 +73,7 @@ def main():
     from .models import SatMAERestoration
     ap = argparse.ArgumentParser()
     ap.add_argument("--tiles", type=int, default=27000)
-    ap.add_argument("--batch", type=int, default=250)
+    ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--seed", type=int, default=42)
     ap.add_argument("--checkpoint", default=None)
     args = ap.parse_args()

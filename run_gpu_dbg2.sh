@@ -1,2 +1,2 @@
-python -m pytest tests/test_gpu_elementwise.py -q -p no:cacheprovider -x 2>&1 | tail -2
-python tools/elem_bench.py --only corrupt --iters 10 2>&1 | tail -2
+python -m msd_b200.sweep --tiles 27000 --batch 250 2>/dev/null | tail -1
+python -m msd_b200.sweep --tiles 27000 --batch 256 2>/dev/null | tail -1
