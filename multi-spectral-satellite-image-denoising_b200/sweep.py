@@ -91,8 +91,12 @@ def main():
         model.load_state_dict(torch.load(args.checkpoint, map_location="cpu")["model_state_dict"])
     model = model.eval().cuda()
     noise = AddSensorNoise(0.015, 0.008, 0.08, 0.005)      # configs/base.yaml:20-24
+    # one untimed batch: library / driver one-time initialisation (module load, kernel attributes, allocator) is not sweep time
+    evaluation_sweep(model, noise, min(args.batch, args.tiles), args.batch, 0, 1, args.seed, all_reduce=False)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     e0.record()
     metrics = evaluation_sweep(model, noise, args.tiles, args.batch, rank, world, args.seed)
     e1.record()
