@@ -66,6 +66,9 @@ class AddSensorNoise(nn.Module):
             raise _lib.MsdError(f"AddSensorNoise: expected [C,H,W] or [B,C,H,W], got {tuple(x.shape)}")
         x = x.contiguous()
         B, C_, H, W = x.shape
+        if x.numel() == 0:                      # empty batch: the reference's clone / randn_like chain returns an empty tensor
+            self.last_dead_mask = torch.zeros(B, C_, dtype=torch.bool, device=x.device) if self.dead_band_prob > 0 else None
+            return x.clone() if is_batched else x.clone().squeeze(0)
         lib = _lib.load()
         _lib.require_device(x.device)
         with torch.cuda.device(x.device):

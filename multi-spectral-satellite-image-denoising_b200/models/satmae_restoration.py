@@ -275,6 +275,8 @@ class SatMAERestoration(nn.Module):
             raise _lib.MsdError("SatMAERestoration.forward: CUDA tensor required (libmsd_b200 has no CPU path)")
         if next(self.parameters()).device != x.device:
             raise _lib.MsdError("SatMAERestoration: model and input are on different devices")
+        if B == 0:                              # empty batch: nothing to launch
+            return x.new_zeros(0, self.decoder.out_channels, H, W, dtype=torch.float32)
         if self.training:
             # training mode: BatchNorm batch statistics + the backward pass, both inside the library (csrc/model.cu)
             if torch.is_grad_enabled():

@@ -107,6 +107,8 @@ class MetricsTracker:
     @torch.no_grad()
     def update(self, pred: torch.Tensor, target: torch.Tensor):
         """pred, target: [B, C, H, W]; no host synchronisation."""
+        if pred.shape[0] == 0:                  # empty batch: the reference's per-sample loop (metrics.py:247-256) adds nothing
+            return
         _, sums, _ = fused_metrics(pred, target, self.data_range)
         if self._acc is None:
             self._acc = sums

@@ -209,3 +209,20 @@ def test_loss_weights_and_data_range():
         total, _, _, ograd = oloss.combined_loss_and_grad(b, a, wm, wsm, dr, dtype=torch.float64)
         assert loss.item() == pytest.approx(total, rel=1e-5)
         assert (p.grad.cpu().double() - ograd).abs().max().item() < 2e-4 * ograd.abs().max().item() + 1e-12
+
+
+def test_empty_batches_behave_like_the_reference():
+    """B = 0: AddSensorNoise returns an empty tensor, MetricsTracker.update adds nothing, the model returns [0,13,S,S]."""
+    import recipes
+    from msd_b200.data import AddSensorNoise
+    from msd_b200.models import SatMAERestoration
+    from msd_b200.training import MetricsTracker
+    x = torch.zeros(0, 13, 192, 192, device="cuda")
+    assert AddSensorNoise()(x).shape == (0, 13, 192, 192)
+    t = MetricsTracker()
+    t.update(x, x)
+    assert t.compute() == {"psnr": 0.0, "ssim": 0.0, "sam": 0.0, "rmse": 0.0}
+    torch.manual_seed(0)
+    m = SatMAERestoration(recipes.base_config(), block_layout="fallback").eval().cuda()
+    with torch.no_grad():
+        assert m(x).shape == (0, 13, 192, 192)
