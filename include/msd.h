@@ -181,6 +181,8 @@ int msd_layernorm_pos_f32(float* d_x, const float* d_g, const float* d_b, float 
                           int M, int D, void* stream);
 /* qkv bf16 [B*T, 3*heads*64] -> out bf16 [B*T, heads*64]; softmax(q k^T / 8) v per (image, head); T <= 256. */
 int msd_attention_bf16(const void* d_qkv, void* d_out, int B, int T, int heads, void* stream);
+/* the same contraction on tcgen05 / TMEM / TMA (product path; msd_attention_bf16 is the mma.sync baseline): T == 144 */
+int msd_attention_tc5_bf16(const void* d_qkv, void* d_out, int B, int T, int heads, void* stream);
 /* x [B,C,S,S] fp32 -> A [B*(S/P)^2, C*P*P] bf16, column order (c,ky,kx), token n = (S/P)*py + px. */
 int msd_patchify_bf16(const float* d_x, void* d_a, int B, int C, int S, int P, void* stream);
 /* head 1x1: x haloed NHWC bf16 [B,H+2,W+2,Cin] -> y NCHW fp32 [B,Cout,H,W]; w fp32 [Cout,Cin]. */

@@ -337,7 +337,7 @@ extern "C" int msd_model_forward(msd_model* m, const float* d_x, const void* d_p
     MSD_RUN(2, 0.0, msd_layernorm_f32_bf16(x, bw.ln1_g, bw.ln1_b, d.ln_eps_block, xn, M, E, stream));
     MSD_TRY(make_linear(p, xn, bw.w_qkv, bw.b_qkv, qkv, nullptr, M, 3 * E, E, 0, 0));
     MSD_RUN(0, linear_flops(M, 3 * E, E), gemm::launch(p, be, s));
-    MSD_RUN(1, 4.0 * B * d.num_heads * (double)m->tokens * m->tokens * 64, msd_attention_bf16(qkv, att, B, m->tokens, d.num_heads, stream));
+    MSD_RUN(1, 4.0 * B * d.num_heads * (double)m->tokens * m->tokens * 64, (be == 0 ? msd_attention_tc5_bf16 : msd_attention_bf16)(qkv, att, B, m->tokens, d.num_heads, stream));
     MSD_TRY(make_linear(p, att, bw.w_proj, bw.b_proj, x, x, M, E, E, 0, 1));
     MSD_RUN(0, linear_flops(M, E, E), gemm::launch(p, be, s));
     MSD_RUN(2, 0.0, msd_layernorm_f32_bf16(x, bw.ln2_g, bw.ln2_b, d.ln_eps_block, xn, M, E, stream));
@@ -576,7 +576,7 @@ extern "C" int msd_model_forward_train(msd_model* m, const float* d_x, int B, fl
     MSD_TRY(msd_layernorm_f32_bf16(xin, bw.ln1_g, bw.ln1_b, d.ln_eps_block, xn1, M, E, stream));
     MSD_TRY(make_linear(p, xn1, bw.w_qkv, bw.b_qkv, qkv, nullptr, M, 3 * E, E, 0, 0));
     MSD_TRY(gemm::launch(p, be, s));
-    MSD_TRY(msd_attention_bf16(qkv, att, B, m->tokens, d.num_heads, stream));
+    MSD_TRY((be == 0 ? msd_attention_tc5_bf16 : msd_attention_bf16)(qkv, att, B, m->tokens, d.num_heads, stream));
     MSD_TRY(make_linear(p, att, bw.w_proj, bw.b_proj, xmid, xin, M, E, E, 0, 1));
     MSD_TRY(gemm::launch(p, be, s));
     MSD_TRY(msd_layernorm_f32_bf16(xmid, bw.ln2_g, bw.ln2_b, d.ln_eps_block, xn2, M, E, stream));

@@ -1,5 +1,3 @@
 mkdir -p gpurun_out
-python tools/gemm_bench.py --only qkv --iters 2 > gpurun_out/plain_qkv.log 2>&1 && \
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_tc5 -s 2 -c 1 -o gpurun_out/prof_qkv python tools/gemm_bench.py --only qkv --iters 2 > gpurun_out/ncu_qkv.log 2>&1; echo "ncu qkv rc=$?"
-python tools/gemm_bench.py --only conv4 --iters 2 > gpurun_out/plain_c4.log 2>&1 && \
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_tc5 -s 2 -c 1 -o gpurun_out/prof_conv4 python tools/gemm_bench.py --only conv4 --iters 2 > gpurun_out/ncu_c4.log 2>&1; echo "ncu conv4 rc=$?"
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:attention_tc5 -s 2 -c 1 -o gpurun_out/prof_attn -f python tools/attn_bench.py > gpurun_out/ncu_attn.log 2>&1; echo "ncu rc=$?"
+tail -3 gpurun_out/ncu_attn.log

@@ -129,17 +129,38 @@ def test_layernorm_and_pos():
     torch.testing.assert_close(x2, ref, rtol=1e-5, atol=1e-5)
 
 
-@pytest.mark.parametrize("B", [1, 5])
-def test_attention_vs_sdpa(B):
+@pytest.mark.parametrize("B", [1, 5, 40])
+@pytest.mark.parametrize("entry", ["msd_attention_tc5_bf16", "msd_attention_bf16"])
+def test_attention_vs_sdpa(entry, B):
+    """tcgen05 attention (product path) and the mma.sync baseline vs fp32 SDPA; B = 40 -> 480 problems on 148 persistent
+    CTAs (3-4 problems each: the stage ring, both TMEM tiles and every barrier phase wrap), rows 128..143 come from the
+    shifted second tile."""
     lib = _lib.load()
     g = torch.Generator().manual_seed(B)
     T, H, E = 144, 12, 768
     qkv = _bf(torch.randn(B * T, 3 * E, generator=g) * 1.5).cuda()
-    out = torch.empty(B * T, E, dtype=torch.bfloat16, device="cuda")
-    _lib.check(lib.msd_attention_bf16(_lib.ptr(qkv), _lib.ptr(out), B, T, H, _lib.stream_ptr()))
+    out = torch.full((B * T, E), float("nan"), dtype=torch.bfloat16, device="cuda")
+    _lib.check(getattr(lib, entry)(_lib.ptr(qkv), _lib.ptr(out), B, T, H, _lib.stream_ptr()))
     q, k, v = qkv.float().reshape(B, T, 3, H, 64).permute(2, 0, 3, 1, 4)
     ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B * T, E)
     _close(out, ref, 1.5e-2)
+
+
+def test_attention_tc5_matches_the_baseline_kernel_on_peaked_rows():
+    """Large logits (near one-hot softmax rows) and a zero head: both kernels round P to bf16 after the same max-subtracted
+    exp2, so they agree to a bf16 ulp of the output."""
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(7)
+    B, T, H, E = 3, 144, 12, 768
+    qkv = torch.randn(B * T, 3 * E, generator=g) * 4.0
+    qkv[:, :64] = 0.0
+    qkv = _bf(qkv).cuda()
+    a = torch.empty(B * T, E, dtype=torch.bfloat16, device="cuda")
+    b = torch.empty_like(a)
+    _lib.check(lib.msd_attention_tc5_bf16(_lib.ptr(qkv), _lib.ptr(a), B, T, H, _lib.stream_ptr()))
+    _lib.check(lib.msd_attention_bf16(_lib.ptr(qkv), _lib.ptr(b), B, T, H, _lib.stream_ptr()))
+    assert torch.isfinite(a.float()).all()
+    assert (a.float() - b.float()).abs().max().item() <= 2 ** -7 * b.float().abs().max().item()
 
 
 # ----------------------------------------------------------------------------------------------- whole model
