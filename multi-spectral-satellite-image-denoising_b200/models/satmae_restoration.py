@@ -12,6 +12,7 @@ from __future__ import annotations
 import ctypes as C
 import logging
 import os
+import weakref
 from typing import Dict
 
 import torch
@@ -225,15 +226,32 @@ class SatMAERestoration(nn.Module):
         return w, keep
 
     def _cached_cast(self, t: torch.Tensor, tag: str, fn):
-        """Packed copy of `t`; copies of frozen parameters (requires_grad False) are made once and reused."""
+        """Packed copy of `t`; copies of frozen parameters (requires_grad False) are made once and reused.
+        An entry belongs to one parameter OBJECT (held by weak reference) at one address and version: after
+        `.cpu()` / `.cuda()` the allocator may hand a parameter the address another same-shaped one had before, so the
+        address alone does not identify the tensor (twelve blocks share every shape)."""
         if t.requires_grad:
             return fn(t)
+        src = t._base if t._is_view() and t._base is not None else t
         cache = self.__dict__.setdefault("_frozen_cache", {})
-        key = (t.data_ptr(), tuple(t.shape), t._version, tag)
+        key = (id(src), t.data_ptr(), tuple(t.shape), tuple(t.stride()), src._version, tag)
         hit = cache.get(key)
-        if hit is None:
-            hit = cache[key] = fn(t)
-        return hit
+        if hit is not None and hit[0]() is src:
+            return hit[1]
+        out = fn(t)
+        cache[key] = (weakref.ref(src), out)
+        return out
+
+    def _apply(self, fn, recurse=True):
+        """Moving / casting the module re-homes every parameter: drop the packed copies made from the old storage."""
+        out = super()._apply(fn, recurse)
+        self.__dict__.pop("_frozen_cache", None)
+        self._packed, self._packed_key = None, None
+        for k in ("_train_packed", "_train_static_key", "_train_versions", "_train_graph"):
+            if k in self.__dict__:
+                self.__dict__[k] = None
+        self._workspaces.clear()
+        return out
 
     def _ensure_ready(self, device):
         lib = _lib.load()

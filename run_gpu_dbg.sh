@@ -1,3 +1,2 @@
-mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_train.py -q -p no:cacheprovider -x > gpurun_out/t_train.log 2>&1; echo "train tests rc=$?"; tail -n 2 gpurun_out/t_train.log
-python tools/train_bench.py > gpurun_out/train_bench.log 2>&1; grep -v "^$" gpurun_out/train_bench.log | grep "ms/step\|bn_\|colsum" | awk '{print substr($0,1,72), substr($0,150,62)}' | head -12
+timeout 600 python -m pytest tests/test_gpu_model.py -q -p no:cacheprovider 2>&1 | tail -3
+timeout 900 python -m pytest tests -q -p no:cacheprovider -m gpu 2>&1 | tail -3

@@ -239,3 +239,22 @@ def test_model_batch_independence_and_ragged_tiles(seeded_model):
     assert prof["batch_size"] == 2 and prof["peak_vram_gb"] > 0
     assert m.launches_per_forward() == 114
     m.cpu()
+
+
+def test_forward_is_unchanged_after_moving_the_model_off_and_back_onto_the_device():
+    """base.yaml freezes blocks 0..5, whose packed weights are cached: after .cpu() / .cuda() the parameters sit at other
+    addresses (often the ones a sibling block had) and the cached copies must not be matched by address."""
+    torch.manual_seed(42)
+    m = SatMAERestoration(recipes.base_config(), block_layout="fallback").eval()
+    x = recipes.model_input(2).cuda()
+    outs = []
+    for backend in (0, 0, 1, 0):
+        m.gemm_backend = backend
+        m.cuda()
+        with torch.no_grad():
+            outs.append(m(x).cpu())
+        m.cpu()
+        junk = [torch.empty(n, device="cuda") for n in (768 * 3072, 768 * 768, 2304 * 768)]   # shuffle the allocator's free lists
+        del junk
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[3])
+    assert (outs[2] - outs[0]).abs().max().item() <= 2e-2

@@ -158,3 +158,28 @@ def test_pretrained_checkpoint_surgery_matches_reference(tmp_path):
     rsd = ref.state_dict()
     for k in ("patch_embed.proj.weight", "patch_embed.proj.bias", "pos_embed", "norm.weight", "norm.bias"):
         assert torch.equal(sd[k], rsd[k]), k
+
+
+def test_frozen_parameter_cache_follows_the_parameter_not_the_address():
+    """The packed copies of frozen parameters are cached; twelve blocks share every shape, so a cache keyed by address
+    alone hands block i the copy of block j once `.cpu()` / `.cuda()` has re-homed the parameters."""
+    m = SatMAERestoration(recipes.base_config(), block_layout="fallback")
+    a = m.encoder.blocks[0].mlp[0].weight
+    b = m.encoder.blocks[1].mlp[0].weight
+    assert not a.requires_grad and not b.requires_grad and a.shape == b.shape      # base.yaml freezes blocks 0..5
+    calls = []
+    cast = lambda t: (calls.append(1), t.detach().clone())[1]
+    ca = m._cached_cast(a, "b16", cast)
+    assert m._cached_cast(a, "b16", cast) is ca and len(calls) == 1                # same parameter, same version: reused
+    with torch.no_grad():
+        b.data = a.data                                                           # b now lives at a's address
+    cb = m._cached_cast(b, "b16", cast)
+    assert cb is not ca and len(calls) == 2                                        # another parameter object: not a's copy
+    with torch.no_grad():
+        a.add_(1.0)                                                                # in-place update bumps the version
+    assert m._cached_cast(a, "b16", cast) is not ca
+    v = a.reshape(-1)                                                              # views are cached under their base parameter
+    cv = m._cached_cast(v, "flat", cast)
+    assert m._cached_cast(a.reshape(-1), "flat", cast) is cv
+    m.double()                                                                     # any _apply drops the packed copies
+    assert "_frozen_cache" not in m.__dict__ and m._packed_key is None
