@@ -42,6 +42,26 @@ int make_map(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t rows, u
   return MSD_OK;
 }
 
+// 3-D fp32 tensor map over [planes, H, W] (W contiguous), box {box_w, box_h, 1}, no swizzle: halo tiles of an image plane;
+// out-of-image coordinates (negative or >= extent) read as zero, which is exactly the zero padding of the SSIM window
+int make_map_planes_f32(CUtensorMap* tm, const void* base, uint64_t W, uint64_t H, uint64_t planes, uint32_t box_w, uint32_t box_h) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return MSD_ERR_CUDA;
+  cuuint64_t dims[3] = {W, H, planes};
+  cuuint64_t strides[2] = {W * 4, W * H * 4};
+  cuuint32_t box[3] = {box_w, box_h, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    msd_set_error("cuTensorMapEncodeTiled (fp32 planes) failed (%d): W=%llu H=%llu planes=%llu base=%p", (int)r,
+                  (unsigned long long)W, (unsigned long long)H, (unsigned long long)planes, base);
+    return MSD_ERR_CUDA;
+  }
+  return MSD_OK;
+}
+
 int num_sms() {
   static int n = 0;
   if (n == 0) {

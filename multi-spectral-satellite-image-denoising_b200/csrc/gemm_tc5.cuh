@@ -661,6 +661,7 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
 // host: launch one BN instantiation (instantiated per BN in gemm_tc5_bn*.cu)
 int make_map(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t rows, uint64_t ld, uint32_t box_rows);
+int make_map_planes_f32(CUtensorMap* tm, const void* base, uint64_t W, uint64_t H, uint64_t planes, uint32_t box_w, uint32_t box_h);
 int num_sms();
 
 template <int BN, int MODE>

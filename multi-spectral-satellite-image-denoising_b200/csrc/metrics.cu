@@ -4,10 +4,14 @@
 //   sums in fp64, a third turns them into {psnr, ssim, sam, rmse} per image and the tracker's running sums,
 //   all on the device; the host reads 5 doubles once per batch.
 //
-//   ssim_mse_kernel: one CTA per (plane b*C+c, 32x64 tile): sum (p-t)^2 and sum ssim_map     (:39, :105-121)
-//   sam_kernel     : one thread per pixel, 13-band dot / norms / acos                         (:155-170)
-// Algorithmic HBM bytes: 2 tensors * 4 B per element per kernel.
-#include "common.cuh"
+//   metrics_fused_kernel (W % 4 == 0, the product path): one CTA per (image, 32x64 tile) walks the C bands.  The halo tiles
+//                    of pred / target arrive by TMA (3-D tensor map, out-of-image = zero = the window's zero padding) into a
+//                    two-deep shared-memory ring, band c+1 in flight while band c is blurred; the SSIM map, (p-t)^2, |p-t| of
+//                    the band and the per-pixel spectral dot / norms of SAM come from the same tile, so pred and target
+//                    cross HBM exactly once (algorithmic bytes: 2 tensors * 4 B per element) and a CTA does one fp64
+//                    reduction per 13 bands.
+//   ssim_mse_kernel + sam_kernel: the same sums for any W, one CTA per (plane, tile) / one thread per pixel (two passes).
+#include "gemm_tc5.cuh"
 #include "ssim_tile.cuh"
 
 namespace {
@@ -66,6 +70,116 @@ ssim_mse_kernel(const float* __restrict__ pred, const float* __restrict__ target
     for (int w = 0; w < kThreads / 32; ++w) t += sm.red[threadIdx.x][w];
     // scratch slots: 0 = sum (p-t)^2, 1 = sum ssim_map, 2 = sum SAM degrees (sam_kernel), 3 = sum |p-t|
     atomicAdd(acc + (size_t)(plane / C) * 4 + (threadIdx.x == 2 ? 3 : threadIdx.x), t);
+  }
+}
+
+// ---- fused product path -----------------------------------------------------------------------------------------
+struct FusedSmem {
+  RawTile<2> raw[2];          // ring of two bands: [buf].v[0] = pred halo tile, .v[1] = target halo tile  (TMA destinations)
+  HBlur<4> hb;
+  double red[4][kThreads / 32];
+  uint64_t bar[2];
+};
+constexpr uint32_t kTileBytes = IH * PW * 4;     // one TMA box: 42 rows x 80 floats
+// A TMA box must start on a 16-byte boundary of the row (an inner coordinate of x0 - 5 floats raises an illegal-instruction
+// fault): the box starts at x0 - 8 and the stencil reads it three columns further in.
+constexpr int kXoff = 3;
+
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* tm, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n"
+      ::"r"(gemm::tc5::smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(gemm::tc5::smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(kThreads, 2)
+metrics_fused_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmT, int C, int H, int W,
+                     int tiles_x, int tiles_y, SsimConsts consts, float eps, double* __restrict__ acc /*[B][4]*/) {
+  using gemm::tc5::mbar_init; using gemm::tc5::mbar_wait; using gemm::tc5::mbar_arrive_expect_tx;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  FusedSmem& sm = *reinterpret_cast<FusedSmem*>(smem_raw);
+  const int tile = blockIdx.x % (tiles_x * tiles_y);
+  const int b = blockIdx.x / (tiles_x * tiles_y);
+  const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+  const int y0 = ty * TH, x0 = tx * TW;
+  if (threadIdx.x == 0) {
+    mbar_init(&sm.bar[0], 1); mbar_init(&sm.bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+  // warp 0 issues the loads, one elected lane, the warp converged around it (as the GEMM producers do)
+#define MSD_ISSUE_BAND(c_)                                                                                            \
+  do {                                                                                                                 \
+    if (threadIdx.x < 32) {                                                                                            \
+      if (gemm::tc5::elect_one()) {                                                                                    \
+        const int buf_ = (c_) & 1;                                                                                     \
+        mbar_arrive_expect_tx(&sm.bar[buf_], 2 * kTileBytes);                                                          \
+        tma_load_3d(&tmP, &sm.bar[buf_], &sm.raw[buf_].v[0][0][0], x0 - R - kXoff, y0 - R, b * C + (c_));                     \
+        tma_load_3d(&tmT, &sm.bar[buf_], &sm.raw[buf_].v[1][0][0], x0 - R - kXoff, y0 - R, b * C + (c_));                     \
+      }                                                                                                                \
+      __syncwarp();                                                                                                    \
+    }                                                                                                                  \
+  } while (0)
+  MSD_ISSUE_BAND(0);
+
+  const int x = threadIdx.x & 63, h = threadIdx.x >> 6;
+  const bool col_ok = x0 + x < W;
+  float dot[8], pp[8], tt[8];
+#pragma unroll
+  for (int o = 0; o < 8; ++o) dot[o] = pp[o] = tt[o] = 0.0f;
+  double d_ssim = 0.0, d_sq = 0.0, d_abs = 0.0;
+
+  for (int c = 0; c < C; ++c) {
+    const int buf = c & 1;
+    // ring slot (c+1)&1 was last read for band c-1; every thread passed the barrier that closes that iteration
+    if (c + 1 < C) MSD_ISSUE_BAND(c + 1);
+    mbar_wait(&sm.bar[buf], (uint32_t)(c >> 1) & 1u);
+    const RawTile<2>& raw = sm.raw[buf];
+    // maps: p, t, p*p + t*t, p*t.  The reference blurs p*p and t*t separately (metrics.py:105-117) but its ssim_map only uses
+    // sigma1_sq + sigma2_sq (:118-121), and the blur is linear: one map of the sum saves a fifth of the stencil work.
+    hpass<2, 4, kXoff>(raw, sm.hb, [](int m, const float (&px)[2]) -> float {
+      return m == 0 ? px[0] : m == 1 ? px[1] : m == 2 ? fmaf(px[0], px[0], px[1] * px[1]) : px[0] * px[1];
+    });
+    __syncthreads();
+    float res[4][8];
+    vpass<4>(sm.hb, res);
+    float s_ssim = 0.0f, s_sq = 0.0f, s_abs = 0.0f;
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {
+      const float a = raw.v[0][8 * h + o + R][x + R + kXoff], bb = raw.v[1][8 * h + o + R][x + R + kXoff];
+      dot[o] = fmaf(a, bb, dot[o]);            // SAM: spectral dot product and norms, band by band (metrics.py:155-160)
+      pp[o] = fmaf(a, a, pp[o]);
+      tt[o] = fmaf(bb, bb, tt[o]);
+      if (col_ok && y0 + 8 * h + o < H) {
+        s_ssim += ssim_value_sum(res[0][o], res[1][o], res[2][o], res[3][o], consts);
+        const float d = a - bb;
+        s_sq = fmaf(d, d, s_sq);
+        s_abs += fabsf(d);
+      }
+    }
+    d_ssim += (double)s_ssim; d_sq += (double)s_sq; d_abs += (double)s_abs;
+    __syncthreads();                           // hb and ring slot `buf` are free again
+  }
+#undef MSD_ISSUE_BAND
+  // SAM angle of this thread's pixels (metrics.py:161-170)
+  float sum_deg = 0.0f;
+#pragma unroll
+  for (int o = 0; o < 8; ++o) {
+    if (col_ok && y0 + 8 * h + o < H) {
+      const float pn = sqrtf(pp[o]) + eps, tn = sqrtf(tt[o]) + eps;
+      float cosang = dot[o] / (pn * tn);
+      cosang = fminf(fmaxf(cosang, -1.0f), 1.0f);
+      sum_deg += acosf(cosang) * 57.29577951308232f;  // torch.rad2deg
+    }
+  }
+  const double r_sq = warp_sum_d(d_sq), r_ssim = warp_sum_d(d_ssim), r_sam = warp_sum_d((double)sum_deg), r_abs = warp_sum_d(d_abs);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { sm.red[0][warp] = r_sq; sm.red[1][warp] = r_ssim; sm.red[2][warp] = r_sam; sm.red[3][warp] = r_abs; }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double t = 0.0;
+    for (int w = 0; w < kThreads / 32; ++w) t += sm.red[threadIdx.x][w];
+    atomicAdd(acc + (size_t)b * 4 + threadIdx.x, t);   // slots: sum (p-t)^2, sum ssim_map, sum SAM degrees, sum |p-t|
   }
 }
 
@@ -144,18 +258,35 @@ extern "C" int msd_metrics_f32(const float* d_pred, const float* d_target, int B
   SsimConsts consts;
   consts.C1 = (float)((0.01 * (double)data_range) * (0.01 * (double)data_range));
   consts.C2 = (float)((0.03 * (double)data_range) * (0.03 * (double)data_range));
-  static bool attr_set = false;
-  if (!attr_set) {
-    MSD_CHECK_CUDA(cudaFuncSetAttribute(ssim_mse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SsimSmem)));
-    attr_set = true;
-  }
-  const unsigned blocks = (unsigned)B * C * tiles_x * tiles_y;
-  ssim_mse_kernel<<<blocks, kThreads, sizeof(SsimSmem), s>>>(d_pred, d_target, C, H, W, tiles_x, tiles_y, consts, d_scratch);
-  MSD_LAUNCH_CHECK();
   const int HW = H * W;
-  const int chunks = (HW + 1023) / 1024;
-  sam_kernel<<<(unsigned)B * chunks, 256, 0, s>>>(d_pred, d_target, C, HW, chunks, 1e-8f, d_scratch);
-  MSD_LAUNCH_CHECK();
+  CUtensorMap tmP, tmT;
+  // TMA needs 16-byte aligned rows; anything else (and a driver that refuses the map) takes the two-pass kernels below
+  const bool fused = W % 4 == 0 && msd_aligned16(d_pred) && msd_aligned16(d_target) &&
+                     gemm::tc5::make_map_planes_f32(&tmP, d_pred, (uint64_t)W, (uint64_t)H, (uint64_t)B * C, PW, IH) == MSD_OK &&
+                     gemm::tc5::make_map_planes_f32(&tmT, d_target, (uint64_t)W, (uint64_t)H, (uint64_t)B * C, PW, IH) == MSD_OK;
+  if (fused) {
+    // product path: TMA-staged, one pass over pred and target
+    static bool fused_attr_set = false;
+    if (!fused_attr_set) {
+      MSD_CHECK_CUDA(cudaFuncSetAttribute(metrics_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem)));
+      fused_attr_set = true;
+    }
+    metrics_fused_kernel<<<(unsigned)B * tiles_x * tiles_y, kThreads, sizeof(FusedSmem), s>>>(tmP, tmT, C, H, W, tiles_x, tiles_y, consts,
+                                                                                             1e-8f, d_scratch);
+    MSD_LAUNCH_CHECK();
+  } else {
+    static bool attr_set = false;
+    if (!attr_set) {
+      MSD_CHECK_CUDA(cudaFuncSetAttribute(ssim_mse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SsimSmem)));
+      attr_set = true;
+    }
+    const unsigned blocks = (unsigned)B * C * tiles_x * tiles_y;
+    ssim_mse_kernel<<<blocks, kThreads, sizeof(SsimSmem), s>>>(d_pred, d_target, C, H, W, tiles_x, tiles_y, consts, d_scratch);
+    MSD_LAUNCH_CHECK();
+    const int chunks = (HW + 1023) / 1024;
+    sam_kernel<<<(unsigned)B * chunks, 256, 0, s>>>(d_pred, d_target, C, HW, chunks, 1e-8f, d_scratch);
+    MSD_LAUNCH_CHECK();
+  }
   metrics_finalize_kernel<<<1, 256, 0, s>>>(d_scratch, B, C, HW, (double)data_range, d_per_image, d_sums);
   MSD_LAUNCH_CHECK();
   return MSD_OK;

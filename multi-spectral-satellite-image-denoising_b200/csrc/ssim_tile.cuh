@@ -69,16 +69,20 @@ __device__ __forceinline__ void fir8(const float (&in)[18], float (&out)[8]) {
 }
 
 // Horizontal pass.  MapFn(m, raw values at one pixel) -> value of map m at that pixel.
-template <int NRAW, int NMAPS, typename MapFn>
+// XOFF: tile column of the first halo pixel (0 when the tile starts at x0 - R; 3 when it starts at x0 - 8, the 16-byte
+// aligned start a TMA box needs).
+template <int NRAW, int NMAPS, int XOFF = 0, typename MapFn>
 __device__ __forceinline__ void hpass(const RawTile<NRAW>& raw, HBlur<NMAPS>& hb, MapFn mapfn) {
+  constexpr int NV = (18 + XOFF + 3) / 4;      // float4 loads covering the 18 inputs of 8 adjacent outputs
+  static_assert(8 * (TW / 8 - 1) + 4 * NV <= PW, "padded raw row too short");
   for (int item = threadIdx.x; item < IH * (TW / 8); item += kThreads) {
     const int r = item >> 3, g = item & 7;
-    float in[NRAW][20];
+    float in[NRAW][4 * NV];
 #pragma unroll
     for (int i = 0; i < NRAW; ++i) {
       const float4* src = reinterpret_cast<const float4*>(&raw.v[i][r][8 * g]);
 #pragma unroll
-      for (int q = 0; q < 5; ++q) {
+      for (int q = 0; q < NV; ++q) {
         float4 t = src[q];
         in[i][4 * q + 0] = t.x; in[i][4 * q + 1] = t.y; in[i][4 * q + 2] = t.z; in[i][4 * q + 3] = t.w;
       }
@@ -90,7 +94,7 @@ __device__ __forceinline__ void hpass(const RawTile<NRAW>& raw, HBlur<NMAPS>& hb
       for (int j = 0; j < 18; ++j) {
         float px[NRAW];
 #pragma unroll
-        for (int i = 0; i < NRAW; ++i) px[i] = in[i][j];
+        for (int i = 0; i < NRAW; ++i) px[i] = in[i][XOFF + j];
         cur[j] = mapfn(m, px);
       }
       fir8(cur, out);
