@@ -171,6 +171,10 @@ int msd_linear_bf16(const void* d_a, const void* d_w, const float* d_bias, void*
  * result is GELU(conv + bias + skip) -- the skip connection is accumulated by the tensor cores like any other tap. */
 int msd_conv3x3_nhwc_bf16(const void* d_x, const void* d_w, const float* d_bias, const void* d_skip, void* d_y,
                           int B, int H, int W, int Cin, int Cout, int backend, void* stream);
+/* The decoder head in one kernel (decoder.py:76-81): y NCHW fp32 [B,Cout,H,W] = head_w . GELU(conv3x3(x) + bias) + head_b with
+ * x haloed NHWC bf16 [B,H+2,W+2,48], w [48, 9*64] (BN folded), head_w fp32 [Cout,48], Cout <= 16; tcgen05 path only. */
+int msd_conv3x3_head_nchw_f32(const void* d_x, const void* d_w, const float* d_bias, const float* d_head_w,
+                              const float* d_head_b, float* d_y, int B, int H, int W, int Cin, int Cout, void* stream);
 /* ConvTranspose2d k2 s2 + bias + GELU: x [B,Hin(+2p),Win(+2p),Cin] bf16 -> y [B,2Hin+2,2Win+2,Cout] haloed. */
 int msd_convt2x2_nhwc_bf16(const void* d_x, const void* d_w, const float* d_bias, void* d_y, int B, int Hin, int Win,
                            int in_padded, int Cin, int Cout, int backend, void* stream);

@@ -44,6 +44,13 @@ struct Problem {
   FastDiv in_plane, in_pitch, cout_div;
   int in_pad, Hin, Win;
   int out_plane, out_pitch; // (2Hin+2)*(2Win+2), 2Win+2
+  // EPI_CONV with the decoder's 1x1 head fused behind it (decoder.py:76-81; tcgen05 resident-weight conv mode only):
+  // the GELU'd tile never goes to HBM -- each epilogue lane contracts its accumulator row (rounded to bf16, as the two-kernel
+  // path stores it) with the fp32 1x1 weights and stores NCHW fp32 straight into the model output.  `out` is unused then.
+  const float* head_w;      // [head_cout, N] fp32, or null
+  const float* head_b;      // [head_cout]
+  float* head_out;          // [B, head_cout, H, W]
+  int head_cout;            // <= 16
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) { return act ? gelu_erf(v) : v; }
@@ -140,6 +147,7 @@ __device__ __forceinline__ void epilogue_store(const Problem& p, int m, int n, f
 // host launchers (one per backend)
 int launch_tc5(const Problem& p, cudaStream_t s);
 int launch_hmma(const Problem& p, cudaStream_t s);
+bool tc5_can_fuse_head(const Problem& p, int head_cout);   // may this 3x3 conv carry the 1x1 head in its epilogue?
 
 inline int launch(const Problem& p, int backend, cudaStream_t s) { return backend == 1 ? launch_hmma(p, s) : launch_tc5(p, s); }
 

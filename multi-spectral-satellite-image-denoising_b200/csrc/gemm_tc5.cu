@@ -111,6 +111,8 @@ int pick_bn_tc5(int N, int M, bool wave_aware) {
   return best;
 }
 
+bool tc5_can_fuse_head(const Problem& p, int head_cout) { return tc5::can_fuse_head(p, head_cout); }
+
 int launch_tc5(const Problem& p, cudaStream_t s) {
   MSD_REQUIRE(p.N % 16 == 0, "gemm_tc5: N=%d must be a multiple of 16", p.N);
   MSD_REQUIRE(p.ldA % 8 == 0 && msd_aligned16(p.A) && msd_aligned16(p.Wt), "gemm_tc5: operands must be 16-byte aligned / pitched");
@@ -128,7 +130,7 @@ int launch_tc5(const Problem& p, cudaStream_t s) {
   // (the 48-channel stage measures slightly FASTER on single CTAs -- 0.555 vs 0.586 ms at B = 256 -- and stays there;
   //  MSD_PAIR48 switches it for A/B runs)
   static const bool pair48 = getenv("MSD_PAIR48") != nullptr;
-  if (pair_ok && !no_merge && (bn == 96 || (bn == 48 && pair48)) && p.N == bn && tc5::is_conv3x3(p) && p.num_kb <= 20)
+  if (pair_ok && !no_merge && p.head_out == nullptr && (bn == 96 || (bn == 48 && pair48)) && p.N == bn && tc5::is_conv3x3(p) && p.num_kb <= 20)
     return bn == 96 ? tc5::launch_pair<96>(p, s) : tc5::launch_pair<48>(p, s);
   switch (bn) {
     case 256: return tc5::launch_bn<256>(p, s);

@@ -170,6 +170,57 @@ __device__ __forceinline__ uint32_t row_info(const Problem& p, int m) {
   return img * (uint32_t)p.out_plane + (2 * yy + 1) * (uint32_t)p.out_pitch + (2 * xx + 1);
 }
 
+// E_CONV_HEAD: NCHW offset of channel 0 of the output pixel of accumulator row m (a padded pixel of [B, H+2, W+2]), or kRowSkip
+__device__ __forceinline__ uint32_t row_info_head(const Problem& p, int m) {
+  if (m >= p.M) return kRowSkip;
+  uint32_t img, rem, yy, xx;
+  fd_divmod((uint32_t)m, p.plane, img, rem);
+  fd_divmod(rem, p.pitch, yy, xx);
+  if (!(yy >= 1 && yy <= (uint32_t)p.H && xx >= 1 && xx <= (uint32_t)p.W)) return kRowSkip;
+  return (img * (uint32_t)p.head_cout * (uint32_t)p.H + (yy - 1)) * (uint32_t)p.W + (xx - 1);
+}
+// Weights of the fused 1x1 head in shared memory: fp32 [16][48] (rows >= head_cout are zero) followed by 16 biases.
+// Measured alternatives, all 0.78-1.12 ms for the fused kernel against ~0.5 ms for the conv alone (tools/head_bench.py): mma.sync
+// tiles in the epilogue (the legacy HMMA queues behind the in-flight tcgen05 MMAs of the next tile, ~900 cycles per epilogue);
+// packed FFMA2; weights as a kernel parameter (one LDCU per weight).  The epilogue warps' issue slots are the limit.
+constexpr uint32_t HEAD_TABLE_BYTES = 16 * 48 * 4 + 16 * 4;
+__device__ __forceinline__ void build_head_table(const Problem& p, uint32_t table_s, int tid, int nthreads) {
+  for (int i = tid; i < 16 * 48 + 16; i += nthreads) {
+    float v = 0.0f;
+    if (i < 16 * 48) {
+      const int n = i / 48, k = i - n * 48;
+      if (n < p.head_cout) v = __ldg(p.head_w + (size_t)n * p.N + k);
+    } else if (i - 16 * 48 < p.head_cout && p.head_b != nullptr) {
+      v = __ldg(p.head_b + (i - 16 * 48));
+    }
+    asm volatile("st.shared.f32 [%0], %1;\n" ::"r"(table_s + 4u * i), "f"(v) : "memory");
+  }
+}
+// out[n] = bias[n] + sum_k a[k] * w[n][k] for this lane's pixel; NOUT accumulators advance together (independent FMA chains),
+// every 128-bit weight load is a warp-wide broadcast
+template <int NOUT>
+__device__ __forceinline__ void head_rows(const float (&a)[48], uint32_t table_s, float* __restrict__ out, uint32_t pix, uint32_t hw, int cout) {
+  float acc[NOUT];
+#pragma unroll
+  for (int n = 0; n < NOUT; ++n) asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(acc[n]) : "r"(table_s + 16u * 48u * 4u + 4u * n));
+#pragma unroll
+  for (int k = 0; k < 48; k += 4) {
+#pragma unroll
+    for (int n = 0; n < NOUT; ++n) {
+      const uint4 w = lds128(table_s + 4u * (uint32_t)(n * 48 + k));
+      acc[n] = fmaf(a[k], __uint_as_float(w.x), acc[n]);
+      acc[n] = fmaf(a[k + 1], __uint_as_float(w.y), acc[n]);
+      acc[n] = fmaf(a[k + 2], __uint_as_float(w.z), acc[n]);
+      acc[n] = fmaf(a[k + 3], __uint_as_float(w.w), acc[n]);
+    }
+  }
+  if (pix != kRowSkip) {
+#pragma unroll
+    for (int n = 0; n < NOUT; ++n)
+      if (n < cout) out[pix + (uint32_t)n * hw] = acc[n];       // lanes = consecutive pixels: 128-byte rows per channel plane
+  }
+}
+
 // K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
 //   [0,14) start address >> 4, [16,30) leading byte offset >> 4 (unused for one swizzle atom along K),
 //   [32,46) stride byte offset >> 4 = 8 rows * 128 B, [46,48) version = 1 (sm_100), [61,64) layout = 2 (128B swizzle)
@@ -222,6 +273,7 @@ enum Epi : int {
   E_CONVT,          // pixel-shuffle scatter of GELU(acc + bias)                     (ConvTranspose2d k2 s2)
   E_CONV_RAW,       // haloed NHWC bf16 = acc + bias, halo rows zeroed               (training: pre-BatchNorm output, dgrad)
   E_CONVT_RAW,      // pixel-shuffle scatter of acc + bias                            (training: pre-BatchNorm output)
+  E_CONV_HEAD,      // NCHW fp32 = head_w . GELU(acc + bias) + head_b                 (head conv3x3 + 1x1, one kernel)
   E_GENERIC         // any other combination of the Problem's flags (slower, runtime-branched)
 };
 
@@ -234,6 +286,7 @@ __host__ inline int classify(const Problem& p) {
     if (!p.out_f32 && p.resid == nullptr) return p.act ? E_RM_BF16_GELU : E_RM_BF16;
     return E_GENERIC;
   }
+  if (p.mode == EPI_CONV && p.head_out != nullptr) return E_CONV_HEAD;
   if (p.mode == EPI_CONV && !p.out_f32 && !(p.skip && p.skip_tap < 0)) return p.act ? E_CONV : E_CONV_RAW;   // epilogue-loaded skip: generic path
   if (p.mode == EPI_CONVT && !p.out_f32 &&
       (unsigned long long)(p.M / (int)p.in_plane.d + 1) * p.out_plane * p.ldo < (1ull << 31)) return p.act ? E_CONVT : E_CONVT_RAW;
@@ -252,15 +305,18 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
 
 template <int BN, int EPI, bool PAIR = false>
 __device__ __forceinline__ void epilogue_tile(const Problem& p, uint32_t stg_s, uint32_t bias_s, uint32_t taddr,
-                                              uint64_t* tmem_empty_bar, int mrow0, int n0, int lane, int slab_begin, int slab_end) {
+                                              uint64_t* tmem_empty_bar, int mrow0, int n0, int lane, int slab_begin, int slab_end,
+                                              uint32_t head_s = 0) {
   using C = Cfg<BN>;
+  constexpr bool kHead = EPI == E_CONV_HEAD;
+  static_assert(!kHead || (C::NSLAB == 1 && C::SC == 48), "the fused head epilogue is built for one 48-column slab");
   constexpr bool kConv = EPI == E_CONV || EPI == E_CONV_RAW;
   constexpr bool kConvT = EPI == E_CONVT || EPI == E_CONVT_RAW;
   constexpr bool kF32 = EPI == E_RM_F32 || EPI == E_RM_F32_RESID;
-  constexpr bool kGelu = EPI == E_RM_BF16_GELU || EPI == E_CONV || EPI == E_CONVT;
+  constexpr bool kGelu = EPI == E_RM_BF16_GELU || EPI == E_CONV || EPI == E_CONVT || kHead;
   constexpr int UPR = kF32 ? C::SC / 4 : C::SC / 8;        // 16-byte units per staged row (a power of two)
   constexpr uint32_t PITCH = (kF32 ? C::SC * 4 : C::SC * 2) + 16;
-  const uint32_t rowpix = (EPI == E_GENERIC || kConvT || kConv) ? row_info(p, mrow0 + lane) : 0u;
+  const uint32_t rowpix = kHead ? row_info_head(p, mrow0 + lane) : (EPI == E_GENERIC || kConvT || kConv) ? row_info(p, mrow0 + lane) : 0u;
   const bool zero_row = kConv && (rowpix & kRowHalo) != 0;
   const int rows_valid = p.M - mrow0;   // rows rr < rows_valid exist (row-major / conv)
   const uint32_t ldo = (uint32_t)p.ldo;
@@ -301,6 +357,23 @@ __device__ __forceinline__ void epilogue_tile(const Problem& p, uint32_t stg_s, 
         r[4 * c + 1] = __float_as_uint(__uint_as_float(r[4 * c + 1]) + __uint_as_float(b.y));
         r[4 * c + 2] = __float_as_uint(__uint_as_float(r[4 * c + 2]) + __uint_as_float(b.z));
         r[4 * c + 3] = __float_as_uint(__uint_as_float(r[4 * c + 3]) + __uint_as_float(b.w));
+      }
+      if constexpr (kHead) {
+        // fused 1x1 head: GELU, round to bf16 (the activation precision of the two-kernel path), contract with head_w on the lane
+        float a[48];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+          const float4 v0 = make_float4(__uint_as_float(r[8 * c]), __uint_as_float(r[8 * c + 1]), __uint_as_float(r[8 * c + 2]), __uint_as_float(r[8 * c + 3]));
+          const float4 v1 = make_float4(__uint_as_float(r[8 * c + 4]), __uint_as_float(r[8 * c + 5]), __uint_as_float(r[8 * c + 6]), __uint_as_float(r[8 * c + 7]));
+          const uint2 o0 = gelu4_to_bf16(v0), o1 = gelu4_to_bf16(v1);
+          const float2 f0 = unpack_bf16x2(o0.x), f1 = unpack_bf16x2(o0.y), f2 = unpack_bf16x2(o1.x), f3 = unpack_bf16x2(o1.y);
+          a[8 * c] = f0.x; a[8 * c + 1] = f0.y; a[8 * c + 2] = f1.x; a[8 * c + 3] = f1.y;
+          a[8 * c + 4] = f2.x; a[8 * c + 5] = f2.y; a[8 * c + 6] = f3.x; a[8 * c + 7] = f3.y;
+        }
+        const uint32_t hw = (uint32_t)p.H * (uint32_t)p.W;
+        if (p.head_cout == 13) head_rows<13>(a, head_s, p.head_out, rowpix, hw, 13);
+        else head_rows<16>(a, head_s, p.head_out, rowpix, hw, p.head_cout);
+        continue;
       }
       if constexpr (kF32) {
 #pragma unroll
@@ -608,6 +681,15 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const uint32_t bias_s = stg_s + 32 * C::STG_PITCH;
     const int slab_begin = half ? C::SLAB_SPLIT : 0, slab_end = half ? C::NSLAB : C::SLAB_SPLIT;
     const int ncols = (slab_end - slab_begin) * C::SC;
+    uint32_t head_s = 0;
+    if constexpr (MODE == MODE_MERGE3_RESIDENT && BN == 48) {
+      if (epi == E_CONV_HEAD) {
+        // the head conv has nine taps: the tenth (skip) slot of the resident weight area holds the 1x1 head's weights
+        head_s = smem_u32(smem_res + 9 * C::W_BOX_BYTES);
+        build_head_table(p, head_s, (int)threadIdx.x - 128, C::EPI_WARPS * 32);
+        asm volatile("bar.sync 1, %0;\n" ::"n"(C::EPI_WARPS * 32) : "memory");
+      }
+    }
     int it = 0, bias_n0 = -1;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       if ((it & 1) != grp) continue;
@@ -635,6 +717,12 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       mbar_wait(&tmem_full[as], aphase);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
+      if constexpr (MODE == MODE_MERGE3_RESIDENT && BN == 48) {
+        if (epi == E_CONV_HEAD) {
+          epilogue_tile<BN, E_CONV_HEAD>(p, stg_s, bias_s, taddr, &tmem_empty[as], m0 + q * 32, n0, lane, slab_begin, slab_end, head_s);
+          continue;
+        }
+      }
       // one specialised instruction stream per fused epilogue (the switch is per tile, the loops inside are branch-free)
 #define MSD_EPI_CASE(E) case E: epilogue_tile<BN, E>(p, stg_s, bias_s, taddr, &tmem_empty[as], m0 + q * 32, n0, lane, slab_begin, slab_end); break;
       switch (epi) {
@@ -699,8 +787,23 @@ __host__ inline bool is_conv3x3(const Problem& p) {
   return p.tap_off[4] == 0 && p.dbg_shift == 0;
 }
 
+// can the 1x1 head ride in this conv's epilogue?  (48-channel 3x3 conv without skip in the resident-weight mode)
+__host__ inline bool can_fuse_head(const Problem& p, int head_cout) {
+  static const bool off = getenv("MSD_NO_MERGE3") != nullptr || getenv("MSD_NO_HEAD_FUSION") != nullptr;
+  return !off && is_conv3x3(p) && p.N == 48 && p.kb_per_tap == 1 && p.num_kb == 9 && p.skip_tap < 0 && p.act && head_cout >= 1 &&
+         head_cout <= 16 && (unsigned long long)(p.M / (int)p.plane.d + 1) * head_cout * p.H * p.W < (1ull << 31);
+}
+
 template <int BN>
 int launch_bn(const Problem& p, cudaStream_t s) {
+  if constexpr (BN == 48) {
+    if (p.head_out != nullptr) {
+      MSD_REQUIRE(can_fuse_head(p, p.head_cout) && p.head_w != nullptr, "gemm_tc5: this conv cannot carry the fused 1x1 head");
+      return launch_mode<BN, MODE_MERGE3_RESIDENT>(p, s);
+    }
+  } else {
+    MSD_REQUIRE(p.head_out == nullptr, "gemm_tc5: the fused 1x1 head needs the 48-channel conv kernel");
+  }
   if constexpr (BN == 48 || BN == 96) {
     static const bool no_merge = getenv("MSD_NO_MERGE3") != nullptr;     // A/B switch for the profiles
     if (!no_merge && is_conv3x3(p)) {

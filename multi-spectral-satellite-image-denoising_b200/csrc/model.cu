@@ -141,6 +141,17 @@ extern "C" int msd_conv3x3_nhwc_bf16(const void* d_x, const void* d_w, const flo
   return gemm::launch(p, backend, (cudaStream_t)stream);
 }
 
+extern "C" int msd_conv3x3_head_nchw_f32(const void* d_x, const void* d_w, const float* d_bias, const float* d_head_w,
+                                        const float* d_head_b, float* d_y, int B, int H, int W, int Cin, int Cout, void* stream) {
+  Problem p;
+  MSD_REQUIRE(d_y != nullptr && d_head_w != nullptr, "conv3x3_head: null pointer");
+  int rc = make_conv3x3(p, d_x, d_w, d_bias, nullptr, d_y /*unused by the kernel*/, B, H, W, Cin, Cin);
+  if (rc) return rc;
+  MSD_REQUIRE(gemm::tc5_can_fuse_head(p, Cout), "conv3x3_head: only the 48-channel head conv (<= 16 outputs) carries the fused 1x1");
+  p.head_w = d_head_w; p.head_b = d_head_b; p.head_out = d_y; p.head_cout = Cout;
+  return gemm::launch(p, 0, (cudaStream_t)stream);
+}
+
 extern "C" int msd_convt2x2_nhwc_bf16(const void* d_x, const void* d_w, const float* d_bias, void* d_y, int B, int Hin,
                                       int Win, int in_padded, int Cin, int Cout, int backend, void* stream) {
   Problem p;
@@ -169,6 +180,7 @@ struct msd_model {
   // optional per-launch CUDA-event profile (bench.py's live roofline measurement)
   bool profile = false;
   std::vector<cudaEvent_t> ev;      // 2 per launch
+  bool head_fused = false;          // last forward ran the 1x1 head inside the head conv's epilogue
   std::vector<int> prof_kind;       // 0 gemm/conv (tensor path), 1 attention, 2 layernorm, 3 other
   std::vector<double> prof_flops;   // algorithmic FLOPs of the launch (2*M*N*K on unpadded shapes)
   int prof_count = 0;
@@ -218,6 +230,7 @@ extern "C" int msd_model_create(const msd_model_desc* desc, msd_model** out) {
   m->d = *desc;
   m->grid = desc->image_size / desc->patch_size;
   m->tokens = m->grid * m->grid;
+  m->head_fused = desc->gemm_backend == 0 && desc->dec_channels[3] == 48 && getenv("MSD_NO_MERGE3") == nullptr && getenv("MSD_NO_HEAD_FUSION") == nullptr;
   *out = m;
   return MSD_OK;
 }
@@ -239,8 +252,8 @@ extern "C" size_t msd_model_workspace_bytes(const msd_model* m, int B) {
 extern "C" int msd_model_launch_count(const msd_model* m) {
   if (!m) return 0;
   // patchify + pe gemm + ln_pos + depth*(ln, qkv, attn, proj, ln, fc1, fc2) + final ln
-  // + 4*(zero_halo + convT + 4 conv) + head conv + head 1x1
-  return 3 + 7 * m->d.depth + 1 + 4 * 6 + 2;
+  // + 4*(zero_halo + convT + 4 conv) + head conv (the 1x1 head rides in its epilogue on the tcgen05 path, else + head 1x1)
+  return 3 + 7 * m->d.depth + 1 + 4 * 6 + (m->head_fused ? 1 : 2);
 }
 
 extern "C" void msd_model_destroy(msd_model* m) {
@@ -378,8 +391,17 @@ extern "C" int msd_model_forward(msd_model* m, const float* d_x, const void* d_p
     const int c = d.dec_channels[3];
     void* Y = ws + L.stage[3][1];
     MSD_TRY(make_conv3x3(p, cur, w.w_head3, w.b_head3, nullptr, Y, B, hw, hw, c, c));
-    MSD_RUN(0, 2.0 * B * hw * hw * (double)c * 9.0 * c, gemm::launch(p, be, s));
-    MSD_RUN(3, 2.0 * B * hw * hw * (double)c * d.out_channels, msd_head1x1_nchw_f32(Y, w.w_head1, w.b_head1, d_y, B, hw, hw, c, d.out_channels, stream));
+    const double f3 = 2.0 * B * hw * hw * (double)c * 9.0 * c, f1 = 2.0 * B * hw * hw * (double)c * d.out_channels;
+    if (be == 0 && gemm::tc5_can_fuse_head(p, d.out_channels)) {
+      // conv3x3 + BN + GELU + conv1x1 in one kernel: the 48-channel activation of the head never reaches HBM
+      p.head_w = w.w_head1; p.head_b = w.b_head1; p.head_out = d_y; p.head_cout = d.out_channels;
+      m->head_fused = true;
+      MSD_RUN(0, f3 + f1, gemm::launch(p, be, s));
+    } else {
+      m->head_fused = false;
+      MSD_RUN(0, f3, gemm::launch(p, be, s));
+      MSD_RUN(3, f1, msd_head1x1_nchw_f32(Y, w.w_head1, w.b_head1, d_y, B, hw, hw, c, d.out_channels, stream));
+    }
   }
   return MSD_OK;
 }

@@ -93,6 +93,39 @@ def test_conv3x3_vs_torch(backend, cin, cout, H, W, B):
         _close(emulate.unhalo_nchw(y.cpu().float()), F.gelu(bn(conv(x))), 3e-2)     # and against the real conv
 
 
+@pytest.mark.parametrize("H,W,B,cout", [(20, 12, 2, 13), (40, 41, 3, 13), (9, 7, 1, 16), (33, 30, 2, 5)])
+def test_head_conv_with_fused_1x1_vs_separate_kernels(H, W, B, cout):
+    """decoder head (decoder.py:76-81) in one kernel: conv3x3 + BN + GELU stays in the epilogue's registers (rounded to bf16 as
+    the two-kernel path stores it) and is contracted with the fp32 1x1 weights there.  Same activation as the two-kernel
+    path, so the two agree to fp32 rounding of a 48-term dot product; ragged last tiles and every halo row are covered."""
+    torch.manual_seed(H * W)
+    conv = nn.Conv2d(48, 48, 3, padding=1, bias=True)
+    bn = nn.BatchNorm2d(48).eval()
+    bn.running_mean.normal_(0, 0.2); bn.running_var.uniform_(0.5, 1.5); bn.weight.data.normal_(1, 0.1); bn.bias.data.normal_(0, 0.1)
+    w1 = (torch.randn(cout, 48) * 0.3).cuda()
+    b1 = torch.randn(cout).cuda()
+    x = _bf(torch.randn(B, 48, H, W)).float()
+    with torch.no_grad():
+        w, b = pack_conv3x3(conv, bn)
+    xh = _bf(emulate.halo_nhwc(x)).cuda()
+    lib = _lib.load()
+    wc, bc = w.cuda(), b.cuda()                       # named: the library only sees raw pointers
+    y = torch.full((B, cout, H, W), float("nan"), device="cuda")
+    _lib.check(lib.msd_conv3x3_head_nchw_f32(_lib.ptr(xh), _lib.ptr(wc), _lib.ptr(bc), _lib.ptr(w1), _lib.ptr(b1), _lib.ptr(y),
+                                             B, H, W, 48, cout, _lib.stream_ptr()))
+    mid = gh.conv3x3(xh, wc, bc, None, B, H, W, 48, 48, 0)              # haloed NHWC bf16, the tile the fused kernel keeps on chip
+    y2 = torch.empty(B, cout, H, W, device="cuda")
+    _lib.check(lib.msd_head1x1_nchw_f32(_lib.ptr(mid), _lib.ptr(w1), _lib.ptr(b1), _lib.ptr(y2), B, H, W, 48, cout, _lib.stream_ptr()))
+    assert torch.isfinite(y).all()
+    ref = torch.einsum("bhwc,oc->bohw", mid[:, 1:-1, 1:-1].float(), w1) + b1.view(1, -1, 1, 1)
+    scale = ref.abs().max().item()
+    assert (y - ref).abs().max().item() <= 2e-5 * scale
+    assert (y - y2).abs().max().item() <= 2e-5 * scale
+    with torch.no_grad():
+        full = F.conv2d(F.gelu(bn(conv(x))), w1.cpu().view(cout, 48, 1, 1), b1.cpu())
+    _close(y.cpu(), full, 3e-2)
+
+
 @pytest.mark.parametrize("backend", BACKENDS)
 @pytest.mark.parametrize("cin,cout,Hin,Win,padded,B", [(768, 384, 12, 12, False, 2), (96, 48, 9, 7, True, 2), (192, 96, 6, 6, True, 1)])
 def test_convt_vs_torch(backend, cin, cout, Hin, Win, padded, B):
@@ -237,7 +270,7 @@ def test_model_batch_independence_and_ragged_tiles(seeded_model):
     assert c["total"] == 96_371_197
     prof = m.profile_memory(batch_size=2)
     assert prof["batch_size"] == 2 and prof["peak_vram_gb"] > 0
-    assert m.launches_per_forward() == 114
+    assert m.launches_per_forward() == 113      # the 1x1 head rides in the head conv
     m.cpu()
 
 
