@@ -179,47 +179,42 @@ __device__ __forceinline__ uint32_t row_info_head(const Problem& p, int m) {
   if (!(yy >= 1 && yy <= (uint32_t)p.H && xx >= 1 && xx <= (uint32_t)p.W)) return kRowSkip;
   return (img * (uint32_t)p.head_cout * (uint32_t)p.H + (yy - 1)) * (uint32_t)p.W + (xx - 1);
 }
-// Weights of the fused 1x1 head in shared memory: fp32 [16][48] (rows >= head_cout are zero) followed by 16 biases.
-// Measured alternatives, all 0.78-1.12 ms for the fused kernel against ~0.5 ms for the conv alone (tools/head_bench.py): mma.sync
-// tiles in the epilogue (the legacy HMMA queues behind the in-flight tcgen05 MMAs of the next tile, ~900 cycles per epilogue);
-// packed FFMA2; weights as a kernel parameter (one LDCU per weight).  The epilogue warps' issue slots are the limit.
-constexpr uint32_t HEAD_TABLE_BYTES = 16 * 48 * 4 + 16 * 4;
-__device__ __forceinline__ void build_head_table(const Problem& p, uint32_t table_s, int tid, int nthreads) {
-  for (int i = tid; i < 16 * 48 + 16; i += nthreads) {
-    float v = 0.0f;
-    if (i < 16 * 48) {
-      const int n = i / 48, k = i - n * 48;
-      if (n < p.head_cout) v = __ldg(p.head_w + (size_t)n * p.N + k);
-    } else if (i - 16 * 48 < p.head_cout && p.head_b != nullptr) {
-      v = __ldg(p.head_b + (i - 16 * 48));
-    }
-    asm volatile("st.shared.f32 [%0], %1;\n" ::"r"(table_s + 4u * i), "f"(v) : "memory");
+// Fused 1x1 head = a second, tiny tcgen05 contraction per tile:  D2[128 x 16] = A2[128 x 48] . W2^T, fp32 in 16 spare TMEM columns.
+//   A2 : the tile's GELU'd activation, bf16, written by the epilogue lanes (one row each) as the K-major SWIZZLE_128B operand into
+//        ring stage 6 + buffer (the nine-tap head conv cycles through stages 0..5 only)
+//   W2 : the fp32 1x1 weights split into hi + lo bf16 (two MMAs per K step: ~16 mantissa bits of every weight), built once per CTA
+//        in the free tenth-tap slot of the resident weight area, followed by the mbarriers of the hand-off and the 16 biases
+// The issuer of a tile waits for its A2 (a2_full), issues the six M128 x N16 x K16 MMAs and commits d2_full; the epilogue lanes
+// then read 16 columns and store NCHW fp32.  Measured alternatives for the same contraction in the epilogue warps -- FMA pipe with
+// broadcast ld.shared weights (0.78 ms for the fused kernel vs ~0.5 for the conv alone), packed FFMA2 (0.81), mma.sync tiles (0.78:
+// the legacy HMMA queues behind the in-flight tcgen05 MMAs), weights as kernel parameters (1.12: one LDCU per weight) -- all made
+// the epilogue warps the bottleneck of the kernel.
+constexpr uint32_t HEAD_W2_LO = 2048, HEAD_BARS = 4096, HEAD_BIAS = 4160, HEAD_SLOT_BYTES = 4224;
+__device__ __forceinline__ void build_head_operand(const Problem& p, uint32_t slot_s, int tid, int nthreads) {
+  // W2 as two [16 rows x 64 k] K-major SWIZZLE_128B tiles (rows >= head_cout and k >= N are zero)
+  for (int i = tid; i < 16 * 32; i += nthreads) {
+    const int n = i >> 5, kp = i & 31, k = 2 * kp;
+    float w0 = 0.0f, w1 = 0.0f;
+    if (n < p.head_cout && k < p.N) { w0 = __ldg(p.head_w + (size_t)n * p.N + k); w1 = __ldg(p.head_w + (size_t)n * p.N + k + 1); }
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(w0), h1 = __float2bfloat16_rn(w1);
+    const uint32_t hi = pack_bf16x2(w0, w1), lo = pack_bf16x2(w0 - __bfloat162float(h0), w1 - __bfloat162float(h1));
+    const uint32_t off = (uint32_t)(n >> 3) * 1024u + (uint32_t)(n & 7) * 128u + ((((uint32_t)k >> 3) ^ (uint32_t)(n & 7)) << 4) + ((uint32_t)k & 7u) * 2u;
+    asm volatile("st.shared.u32 [%0], %1;\n" ::"r"(slot_s + off), "r"(hi) : "memory");
+    asm volatile("st.shared.u32 [%0], %1;\n" ::"r"(slot_s + HEAD_W2_LO + off), "r"(lo) : "memory");
+  }
+  for (int i = tid; i < 16; i += nthreads) {
+    const float b = (i < p.head_cout && p.head_b != nullptr) ? __ldg(p.head_b + i) : 0.0f;
+    asm volatile("st.shared.f32 [%0], %1;\n" ::"r"(slot_s + HEAD_BIAS + 4u * i), "f"(b) : "memory");
   }
 }
-// out[n] = bias[n] + sum_k a[k] * w[n][k] for this lane's pixel; NOUT accumulators advance together (independent FMA chains),
-// every 128-bit weight load is a warp-wide broadcast
-template <int NOUT>
-__device__ __forceinline__ void head_rows(const float (&a)[48], uint32_t table_s, float* __restrict__ out, uint32_t pix, uint32_t hw, int cout) {
-  float acc[NOUT];
-#pragma unroll
-  for (int n = 0; n < NOUT; ++n) asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(acc[n]) : "r"(table_s + 16u * 48u * 4u + 4u * n));
-#pragma unroll
-  for (int k = 0; k < 48; k += 4) {
-#pragma unroll
-    for (int n = 0; n < NOUT; ++n) {
-      const uint4 w = lds128(table_s + 4u * (uint32_t)(n * 48 + k));
-      acc[n] = fmaf(a[k], __uint_as_float(w.x), acc[n]);
-      acc[n] = fmaf(a[k + 1], __uint_as_float(w.y), acc[n]);
-      acc[n] = fmaf(a[k + 2], __uint_as_float(w.z), acc[n]);
-      acc[n] = fmaf(a[k + 3], __uint_as_float(w.w), acc[n]);
-    }
-  }
-  if (pix != kRowSkip) {
-#pragma unroll
-    for (int n = 0; n < NOUT; ++n)
-      if (n < cout) out[pix + (uint32_t)n * hw] = acc[n];       // lanes = consecutive pixels: 128-byte rows per channel plane
-  }
-}
+struct HeadCtx {
+  uint32_t a2_s;        // shared address of this accumulator buffer's A2 tile
+  uint32_t bias_s;      // 16 fp32 biases
+  uint32_t taddr_d2;    // TMEM address of D2 for this warp's lane quadrant
+  uint64_t* a2_full;    // epilogue -> issuer: the A2 tile is written
+  uint64_t* d2_full;    // issuer -> epilogue: D2 is complete
+  uint32_t parity;
+};
 
 // K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
 //   [0,14) start address >> 4, [16,30) leading byte offset >> 4 (unused for one swizzle atom along K),
@@ -306,7 +301,7 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
 template <int BN, int EPI, bool PAIR = false>
 __device__ __forceinline__ void epilogue_tile(const Problem& p, uint32_t stg_s, uint32_t bias_s, uint32_t taddr,
                                               uint64_t* tmem_empty_bar, int mrow0, int n0, int lane, int slab_begin, int slab_end,
-                                              uint32_t head_s = 0) {
+                                              const HeadCtx* hc = nullptr) {
   using C = Cfg<BN>;
   constexpr bool kHead = EPI == E_CONV_HEAD;
   static_assert(!kHead || (C::NSLAB == 1 && C::SC == 48), "the fused head epilogue is built for one 48-column slab");
@@ -359,20 +354,38 @@ __device__ __forceinline__ void epilogue_tile(const Problem& p, uint32_t stg_s, 
         r[4 * c + 3] = __float_as_uint(__uint_as_float(r[4 * c + 3]) + __uint_as_float(b.w));
       }
       if constexpr (kHead) {
-        // fused 1x1 head: GELU, round to bf16 (the activation precision of the two-kernel path), contract with head_w on the lane
-        float a[48];
+        // fused 1x1 head: GELU, round to bf16, write this lane's row of the A2 operand (16-byte chunk c of row r sits at chunk
+        // position c ^ (r & 7) of the row's 128 bytes: the SWIZZLE_128B pattern, conflict-free for row-per-lane stores)
+        const uint32_t rr = (uint32_t)(mrow0 & 127) + (uint32_t)lane;          // row inside the 128-row tile
+        const uint32_t row_s = hc->a2_s + (rr >> 3) * 1024u + (rr & 7u) * 128u;
 #pragma unroll
         for (int c = 0; c < 6; ++c) {
           const float4 v0 = make_float4(__uint_as_float(r[8 * c]), __uint_as_float(r[8 * c + 1]), __uint_as_float(r[8 * c + 2]), __uint_as_float(r[8 * c + 3]));
           const float4 v1 = make_float4(__uint_as_float(r[8 * c + 4]), __uint_as_float(r[8 * c + 5]), __uint_as_float(r[8 * c + 6]), __uint_as_float(r[8 * c + 7]));
           const uint2 o0 = gelu4_to_bf16(v0), o1 = gelu4_to_bf16(v1);
-          const float2 f0 = unpack_bf16x2(o0.x), f1 = unpack_bf16x2(o0.y), f2 = unpack_bf16x2(o1.x), f3 = unpack_bf16x2(o1.y);
-          a[8 * c] = f0.x; a[8 * c + 1] = f0.y; a[8 * c + 2] = f1.x; a[8 * c + 3] = f1.y;
-          a[8 * c + 4] = f2.x; a[8 * c + 5] = f2.y; a[8 * c + 6] = f3.x; a[8 * c + 7] = f3.y;
+          sts128(row_s + ((((uint32_t)c) ^ (rr & 7u)) << 4), make_uint4(o0.x, o0.y, o1.x, o1.y));
         }
-        const uint32_t hw = (uint32_t)p.H * (uint32_t)p.W;
-        if (p.head_cout == 13) head_rows<13>(a, head_s, p.head_out, rowpix, hw, 13);
-        else head_rows<16>(a, head_s, p.head_out, rowpix, hw, p.head_cout);
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");       // generic-proxy stores -> visible to the MMA's async proxy
+        __syncwarp();
+        if (lane == 0) mbar_arrive(hc->a2_full);
+        mbar_wait(hc->d2_full, hc->parity);
+        tcgen05_fence_after();
+        uint32_t d2[16];
+        tmem_ld16(hc->taddr_d2, d2);
+        tmem_ld_wait();
+        tcgen05_fence_before();
+        if (rowpix != kRowSkip) {
+          const uint32_t hw = (uint32_t)p.H * (uint32_t)p.W;
+          float* outp = p.head_out + rowpix;
+#pragma unroll
+          for (int n = 0; n < 16; ++n) {
+            if (n < p.head_cout) {
+              float bsc;
+              asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(bsc) : "r"(hc->bias_s + 4u * n));
+              outp[(uint32_t)n * hw] = __uint_as_float(d2[n]) + bsc;         // lanes = consecutive pixels: 128-byte rows per channel plane
+            }
+          }
+        }
         continue;
       }
       if constexpr (kF32) {
@@ -497,6 +510,14 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     for (int i = 0; i < C::kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&full[C::kStages + i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], C::EPI_WARPS / 2); }
     mbar_init(res_full, 1);
+    if constexpr (MODE == MODE_MERGE3_RESIDENT && BN == 48) {
+      static_assert(C::kStages >= 8 && 2 * BN + 32 <= (int)C::TMEM_COLS && HEAD_SLOT_BYTES <= C::W_BOX_BYTES, "fused head: needs ring stages 6/7, 32 spare TMEM columns and the tenth-tap slot");
+      if (epi == E_CONV_HEAD) {          // hand-off barriers of the fused 1x1 head (in the free tenth-tap slot, see HeadCtx)
+        uint64_t* hb = reinterpret_cast<uint64_t*>(smem_res + 9 * C::W_BOX_BYTES + HEAD_BARS);
+        mbar_init(&hb[0], 4); mbar_init(&hb[1], 4);      // a2_full[buf]: the four epilogue warps of the buffer's group
+        mbar_init(&hb[2], 1); mbar_init(&hb[3], 1);      // d2_full[buf]: tcgen05.commit
+      }
+    }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (warp == 2) {
@@ -601,6 +622,31 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     uint64_t* full = bars + par * C::kStages;
     uint32_t pmask = 0;
     if constexpr (MODE == MODE_MERGE3_RESIDENT) { mbar_wait(res_full, 0); tcgen05_fence_after(); }
+    // fused 1x1 head (E_CONV_HEAD): D2 = A2 . (W2hi + W2lo)^T into 16 spare TMEM columns once the tile's epilogue lanes wrote A2
+    bool head_pending = false;
+    uint32_t head_parity = 0;
+    auto issue_head = [&](uint32_t hpar) {
+      if constexpr (MODE == MODE_MERGE3_RESIDENT && BN == 48) {
+        uint64_t* hb = reinterpret_cast<uint64_t*>(smem_res + 9 * C::W_BOX_BYTES + HEAD_BARS);
+        mbar_wait(&hb[par], hpar);
+        tcgen05_fence_after();
+        if (elect_one()) {
+          constexpr uint32_t HI = (1024u >> 4) | (1u << 14) | (2u << 29);
+          constexpr uint32_t idesc2 = make_idesc(BLOCK_M, 16);
+          const uint32_t a2_lo = a_lo0 + (6u + par) * (A_STAGE_BYTES >> 4);
+          const uint32_t w2_lo = r_lo0 + 9u * (C::W_BOX_BYTES >> 4);
+          const uint32_t d2 = tmem_base + 2 * BN + par * 16;
+#pragma unroll
+          for (int kk = 0; kk < 3; ++kk) {
+            const uint64_t da = ((uint64_t)HI << 32) | (a2_lo + 2u * kk);
+            tcgen05_mma_bf16(d2, da, ((uint64_t)HI << 32) | (w2_lo + 2u * kk), idesc2, kk ? 1u : 0u);
+            tcgen05_mma_bf16(d2, da, ((uint64_t)HI << 32) | (w2_lo + (HEAD_W2_LO >> 4) + 2u * kk), idesc2, 1u);
+          }
+          tcgen05_commit(&hb[2 + par]);
+        }
+        __syncwarp();
+      }
+    };
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it, gstep += steps_per_tile) {
       if ((it & 1u) != par) continue;
       int stage = gstep % ring;
@@ -636,6 +682,15 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const uint32_t parity = (it >> 1) & 1u;
             if (has_skip) issue_tile_resident<BN, 4, 3, A_STAGE_BYTES>(tmem_d, a_base, r_lo0, idesc, fullp, emptyp, &tmem_full[par], parity, p.skip_tap);
             else issue_tile_resident<BN, 3, 3, A_STAGE_BYTES>(tmem_d, a_base, r_lo0, idesc, fullp, emptyp, &tmem_full[par], parity, 0);
+            if constexpr (BN == 48) {
+              if (epi == E_CONV_HEAD) {
+                // fused 1x1 head of this issuer's PREVIOUS tile: its epilogue lanes wrote A2 while this tile's MMAs were being
+                // queued, so the conv MMAs never wait on an epilogue (issuing head(t) before tile t+2 put phase A of the epilogue,
+                // ~2,300 cycles, on the tensor core's critical path: 0.79 ms instead of 0.5)
+                if (head_pending) issue_head(head_parity);
+                head_pending = true; head_parity = parity;
+              }
+            }
             pmask ^= ((1u << (n_dy + has_skip)) - 1u) << (par * (n_dy + has_skip));
             continue;
           }
@@ -672,6 +727,7 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
       }
     }
+    if (head_pending) issue_head(head_parity);           // the last tile of this issuer
   } else if (warp >= 4) {
     // ===== epilogue: warp w may only read TMEM lanes 32*(w%4).. (hardware rule).  e = w-4: bit 2 selects the accumulator
     // buffer (even / odd tiles of this CTA), bit 3 the column half of the tile =====
@@ -681,12 +737,11 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const uint32_t bias_s = stg_s + 32 * C::STG_PITCH;
     const int slab_begin = half ? C::SLAB_SPLIT : 0, slab_end = half ? C::NSLAB : C::SLAB_SPLIT;
     const int ncols = (slab_end - slab_begin) * C::SC;
-    uint32_t head_s = 0;
     if constexpr (MODE == MODE_MERGE3_RESIDENT && BN == 48) {
       if (epi == E_CONV_HEAD) {
-        // the head conv has nine taps: the tenth (skip) slot of the resident weight area holds the 1x1 head's weights
-        head_s = smem_u32(smem_res + 9 * C::W_BOX_BYTES);
-        build_head_table(p, head_s, (int)threadIdx.x - 128, C::EPI_WARPS * 32);
+        // the head conv has nine taps: the tenth (skip) slot of the resident weight area holds the 1x1 head's W2 operand
+        build_head_operand(p, smem_u32(smem_res + 9 * C::W_BOX_BYTES), (int)threadIdx.x - 128, C::EPI_WARPS * 32);
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
         asm volatile("bar.sync 1, %0;\n" ::"n"(C::EPI_WARPS * 32) : "memory");
       }
     }
@@ -719,7 +774,13 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
       if constexpr (MODE == MODE_MERGE3_RESIDENT && BN == 48) {
         if (epi == E_CONV_HEAD) {
-          epilogue_tile<BN, E_CONV_HEAD>(p, stg_s, bias_s, taddr, &tmem_empty[as], m0 + q * 32, n0, lane, slab_begin, slab_end, head_s);
+          uint64_t* hb = reinterpret_cast<uint64_t*>(smem_res + 9 * C::W_BOX_BYTES + HEAD_BARS);
+          HeadCtx hc;
+          hc.a2_s = smem_u32(smem_a + (6 + as) * A_STAGE_BYTES);
+          hc.bias_s = smem_u32(smem_res + 9 * C::W_BOX_BYTES + HEAD_BIAS);
+          hc.taddr_d2 = tmem_base + ((uint32_t)(q * 32) << 16) + 2 * BN + as * 16;
+          hc.a2_full = &hb[as]; hc.d2_full = &hb[2 + as]; hc.parity = aphase;
+          epilogue_tile<BN, E_CONV_HEAD>(p, stg_s, bias_s, taddr, &tmem_empty[as], m0 + q * 32, n0, lane, slab_begin, slab_end, &hc);
           continue;
         }
       }

@@ -32,7 +32,13 @@ def separate():
     _lib.check(lib.msd_conv3x3_nhwc_bf16(_lib.ptr(xh), _lib.ptr(wc), _lib.ptr(bc), None, _lib.ptr(mid), B, H, W, 48, 48, 0, st))
     _lib.check(lib.msd_head1x1_nchw_f32(_lib.ptr(mid), _lib.ptr(w1), _lib.ptr(b1), _lib.ptr(y), B, H, W, 48, 13, st))
 
-for name, fn in (("fused conv3x3+1x1", fused), ("conv3x3 + head1x1", separate)):
+def conv_only():
+    _lib.check(lib.msd_conv3x3_nhwc_bf16(_lib.ptr(xh), _lib.ptr(wc), _lib.ptr(bc), None, _lib.ptr(mid), B, H, W, 48, 48, 0, st))
+
+def head_only():
+    _lib.check(lib.msd_head1x1_nchw_f32(_lib.ptr(mid), _lib.ptr(w1), _lib.ptr(b1), _lib.ptr(y), B, H, W, 48, 13, st))
+
+for name, fn in (("fused conv3x3+1x1", fused), ("conv3x3 + head1x1", separate), ("conv3x3 alone", conv_only), ("head1x1 alone", head_only)):
     for _ in range(3):
         fn()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
