@@ -212,15 +212,17 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE JSON line.  NCCL writes its version banner (and anything NCCL_DEBUG asks for) to file descriptor 1
+    # from C, so descriptor 1 is pointed at stderr for the whole run and the JSON line is written to the saved descriptor.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- libmsd_b200 has no CPU path (use --impl reference for the CPU baseline)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # stdout carries exactly ONE JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION writes it to stdout) off it
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     W = max(3, args.warmup)
     K, B = args.steps, args.batch
@@ -380,7 +382,8 @@ def main():
                 {"ms_per_step": ms_step, "launches": [{"i": i, "kind": names[k], "ms": ms, "gflop": fl / 1e9,
                                                        "tflops": (fl / ms / 1e9) if ms > 0 and fl > 0 else None}
                                                       for i, (ms, k, fl) in enumerate(per_launch)]}, indent=1))
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
     return 0
