@@ -292,7 +292,7 @@ def main():
             for b in range(2):
                 freed[b].record()
             prefetch(0)
-            out = None
+            out, prev = None, None
             for i in range(steps):
                 if i + 1 < steps:
                     prefetch(i + 1)
@@ -302,8 +302,12 @@ def main():
                 noisy = noise(c, patch_out=patches)
                 restored = model(noisy, patches=patches)
                 t.update(restored, c)
+                t.prefetch()                                # D2H of the 5 fp64 sums of THIS step, behind its kernels
                 freed[i % 2].record()
-                out = t.compute()                           # D2H of the 5 fp64 sums (synchronises the compute stream)
+                if prev is not None:
+                    out = prev.compute()                    # read step i-1's result while step i runs (its launches are queued)
+                prev = t
+            out = prev.compute()
             return out
 
         e2e_run(2)

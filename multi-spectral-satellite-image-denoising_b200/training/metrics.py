@@ -103,6 +103,7 @@ class MetricsTracker:
         self._acc = None        # fp64 [5] on the device: sum psnr, sum ssim, sum sam, sum rmse, count
         self._host = [0.0, 0.0, 0.0, 0.0, 0.0]
         self._dirty = False
+        self._pending = None    # event of an in-flight prefetch()
 
     @torch.no_grad()
     def update(self, pred: torch.Tensor, target: torch.Tensor):
@@ -117,6 +118,7 @@ class MetricsTracker:
                 sums = sums.to(self._acc.device)
             self._acc += sums
         self._dirty = True
+        self._pending = None
 
     def all_reduce(self, group=None):
         """Sum the running sums over all ranks (NCCL; the only collective of the evaluation sweep)."""
@@ -126,8 +128,28 @@ class MetricsTracker:
         dist.all_reduce(self._acc, op=dist.ReduceOp.SUM, group=group)
         self._dirty = True
 
+    def prefetch(self):
+        """Start the device -> host copy of the running sums on the current stream (pinned buffer + event).  A later compute()
+        / *_sum then waits for that 40-byte copy only, not for whatever the stream was given afterwards: an evaluation loop
+        can enqueue batch i+1 before it reads the result of batch i."""
+        if self._acc is None or not self._dirty:
+            return self
+        if getattr(self, "_pinned", None) is None:
+            self._pinned = torch.empty(5, dtype=torch.float64, pin_memory=True)
+        with torch.cuda.device(self._acc.device):
+            self._pinned.copy_(self._acc, non_blocking=True)
+            self._pending = torch.cuda.Event()
+            self._pending.record()
+        return self
+
     def _sync(self):
-        if self._dirty:
+        pending = getattr(self, "_pending", None)
+        if pending is not None:
+            pending.synchronize()
+            self._host = self._pinned.tolist()
+            self._pending = None
+            self._dirty = False
+        elif self._dirty:
             self._host = self._acc.cpu().tolist()
             self._dirty = False
         return self._host

@@ -226,3 +226,20 @@ def test_empty_batches_behave_like_the_reference():
     m = SatMAERestoration(recipes.base_config(), block_layout="fallback").eval().cuda()
     with torch.no_grad():
         assert m(x).shape == (0, 13, 192, 192)
+
+
+def test_tracker_prefetch_reads_the_same_sums_without_draining_the_stream():
+    """prefetch() copies the running sums behind the kernels of the batch it follows; compute() then returns exactly what a
+    blocking read would have, also when more work (another tracker's batch) was queued after the prefetch, and an update()
+    after a prefetch invalidates the pending copy."""
+    from msd_b200.training import MetricsTracker
+    a, b = recipes.metric_cases()["small_c4"]
+    a, b = a.cuda(), b.cuda()
+    t1, t2 = MetricsTracker(), MetricsTracker()
+    t1.update(b, a); t1.prefetch()
+    t2.update(b * 0.5, a)                     # queued after t1's prefetch
+    ref = MetricsTracker(); ref.update(b, a)
+    assert t1.compute() == ref.compute()
+    t1.update(b * 0.5, a)                     # pending copy is stale now
+    ref.update(b * 0.5, a)
+    assert t1.compute() == ref.compute() and t1.count == 2 * a.shape[0]
