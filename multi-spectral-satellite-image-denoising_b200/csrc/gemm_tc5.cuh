@@ -213,8 +213,30 @@ struct HeadCtx {
   uint32_t taddr_d2;    // TMEM address of D2 for this warp's lane quadrant
   uint64_t* a2_full;    // epilogue -> issuer: the A2 tile is written
   uint64_t* d2_full;    // issuer -> epilogue: D2 is complete
-  uint32_t parity;
+  uint32_t parity;      // phase parity of THIS tile on both barriers
+  // software pipeline of the epilogue lanes: D2 of this buffer's previous tile is read while this tile is handled
+  bool has_prev;
+  uint32_t prev_rowpix; // output offset of this lane's pixel in the previous tile (kRowSkip: none)
 };
+// read D2 of the pending tile of this accumulator buffer and store the lane's pixel (NCHW fp32, + bias)
+__device__ __forceinline__ void head_store(const Problem& p, const HeadCtx& hc, uint32_t pix) {
+  uint32_t d2[16];
+  tmem_ld16(hc.taddr_d2, d2);
+  tmem_ld_wait();
+  tcgen05_fence_before();
+  if (pix != kRowSkip) {
+    const uint32_t hw = (uint32_t)p.H * (uint32_t)p.W;
+    float* outp = p.head_out + pix;
+#pragma unroll
+    for (int n = 0; n < 16; ++n) {
+      if (n < p.head_cout) {
+        float bsc;
+        asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(bsc) : "r"(hc.bias_s + 4u * n));
+        outp[(uint32_t)n * hw] = __uint_as_float(d2[n]) + bsc;         // lanes = consecutive pixels: 128-byte rows per channel plane
+      }
+    }
+  }
+}
 
 // K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
 //   [0,14) start address >> 4, [16,30) leading byte offset >> 4 (unused for one swizzle atom along K),
@@ -301,7 +323,7 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
 template <int BN, int EPI, bool PAIR = false>
 __device__ __forceinline__ void epilogue_tile(const Problem& p, uint32_t stg_s, uint32_t bias_s, uint32_t taddr,
                                               uint64_t* tmem_empty_bar, int mrow0, int n0, int lane, int slab_begin, int slab_end,
-                                              const HeadCtx* hc = nullptr) {
+                                              HeadCtx* hc = nullptr) {
   using C = Cfg<BN>;
   constexpr bool kHead = EPI == E_CONV_HEAD;
   static_assert(!kHead || (C::NSLAB == 1 && C::SC == 48), "the fused head epilogue is built for one 48-column slab");
@@ -354,38 +376,33 @@ __device__ __forceinline__ void epilogue_tile(const Problem& p, uint32_t stg_s, 
         r[4 * c + 3] = __float_as_uint(__uint_as_float(r[4 * c + 3]) + __uint_as_float(b.w));
       }
       if constexpr (kHead) {
-        // fused 1x1 head: GELU, round to bf16, write this lane's row of the A2 operand (16-byte chunk c of row r sits at chunk
-        // position c ^ (r & 7) of the row's 128 bytes: the SWIZZLE_128B pattern, conflict-free for row-per-lane stores)
+        // fused 1x1 head: GELU, round to bf16 (registers); once the head MMAs of this buffer's PREVIOUS tile have finished with A2
+        // and D2 (d2_full, normally long complete: they run right behind this tile's conv MMAs), write this lane's row of the A2
+        // operand (16-byte chunk c of row r at chunk position c ^ (r & 7) of the row's 128 bytes: the SWIZZLE_128B pattern,
+        // conflict-free for row-per-lane stores), store the previous tile's pixel from D2, then hand A2 to the issuer.  The lanes
+        // never wait for the D2 of the tile they just produced.
         const uint32_t rr = (uint32_t)(mrow0 & 127) + (uint32_t)lane;          // row inside the 128-row tile
         const uint32_t row_s = hc->a2_s + (rr >> 3) * 1024u + (rr & 7u) * 128u;
+        uint4 q[6];
 #pragma unroll
         for (int c = 0; c < 6; ++c) {
           const float4 v0 = make_float4(__uint_as_float(r[8 * c]), __uint_as_float(r[8 * c + 1]), __uint_as_float(r[8 * c + 2]), __uint_as_float(r[8 * c + 3]));
           const float4 v1 = make_float4(__uint_as_float(r[8 * c + 4]), __uint_as_float(r[8 * c + 5]), __uint_as_float(r[8 * c + 6]), __uint_as_float(r[8 * c + 7]));
           const uint2 o0 = gelu4_to_bf16(v0), o1 = gelu4_to_bf16(v1);
-          sts128(row_s + ((((uint32_t)c) ^ (rr & 7u)) << 4), make_uint4(o0.x, o0.y, o1.x, o1.y));
+          q[c] = make_uint4(o0.x, o0.y, o1.x, o1.y);
         }
+        if (hc->has_prev) {
+          mbar_wait(hc->d2_full, hc->parity ^ 1u);
+          tcgen05_fence_after();
+        }
+#pragma unroll
+        for (int c = 0; c < 6; ++c) sts128(row_s + ((((uint32_t)c) ^ (rr & 7u)) << 4), q[c]);
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");       // generic-proxy stores -> visible to the MMA's async proxy
+        if (hc->has_prev) head_store(p, *hc, hc->prev_rowpix);                // before the arrive: head(t) may then overwrite D2
         __syncwarp();
         if (lane == 0) mbar_arrive(hc->a2_full);
-        mbar_wait(hc->d2_full, hc->parity);
-        tcgen05_fence_after();
-        uint32_t d2[16];
-        tmem_ld16(hc->taddr_d2, d2);
-        tmem_ld_wait();
-        tcgen05_fence_before();
-        if (rowpix != kRowSkip) {
-          const uint32_t hw = (uint32_t)p.H * (uint32_t)p.W;
-          float* outp = p.head_out + rowpix;
-#pragma unroll
-          for (int n = 0; n < 16; ++n) {
-            if (n < p.head_cout) {
-              float bsc;
-              asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(bsc) : "r"(hc->bias_s + 4u * n));
-              outp[(uint32_t)n * hw] = __uint_as_float(d2[n]) + bsc;         // lanes = consecutive pixels: 128-byte rows per channel plane
-            }
-          }
-        }
+        hc->has_prev = true;
+        hc->prev_rowpix = rowpix;
         continue;
       }
       if constexpr (kF32) {
@@ -746,6 +763,8 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
     }
     int it = 0, bias_n0 = -1;
+    HeadCtx hc;                       // fused 1x1 head: this warp's pending tile (E_CONV_HEAD only)
+    hc.has_prev = false; hc.prev_rowpix = kRowSkip; hc.parity = 0; hc.d2_full = nullptr;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       if ((it & 1) != grp) continue;
       const uint32_t as = it & 1, aphase = (it >> 1) & 1;
@@ -775,7 +794,6 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       if constexpr (MODE == MODE_MERGE3_RESIDENT && BN == 48) {
         if (epi == E_CONV_HEAD) {
           uint64_t* hb = reinterpret_cast<uint64_t*>(smem_res + 9 * C::W_BOX_BYTES + HEAD_BARS);
-          HeadCtx hc;
           hc.a2_s = smem_u32(smem_a + (6 + as) * A_STAGE_BYTES);
           hc.bias_s = smem_u32(smem_res + 9 * C::W_BOX_BYTES + HEAD_BIAS);
           hc.taddr_d2 = tmem_base + ((uint32_t)(q * 32) << 16) + 2 * BN + as * 16;
@@ -798,6 +816,13 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         default: epilogue_tile<BN, E_GENERIC>(p, stg_s, bias_s, taddr, &tmem_empty[as], m0 + q * 32, n0, lane, slab_begin, slab_end); break;
       }
 #undef MSD_EPI_CASE
+    }
+    if constexpr (MODE == MODE_MERGE3_RESIDENT && BN == 48) {
+      if (epi == E_CONV_HEAD && hc.has_prev) {           // the last tile of this warp's accumulator buffer
+        mbar_wait(hc.d2_full, hc.parity);
+        tcgen05_fence_after();
+        head_store(p, hc, hc.prev_rowpix);
+      }
     }
   }
   tcgen05_fence_before();
