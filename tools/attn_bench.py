@@ -6,6 +6,7 @@ import torch
 from msd_b200 import _lib
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+FLUSH = "--noflush" not in sys.argv      # --noflush with a small B: operands stay in L2 (compute-side time per problem)
 T, H, E = 144, 12, 768
 lib = _lib.load()
 qkv = (torch.randn(B * T, 3 * E, device="cuda") * 1.5).bfloat16()
@@ -17,7 +18,8 @@ for name in ("msd_attention_tc5_bf16", "msd_attention_bf16"):
         _lib.check(fn(_lib.ptr(qkv), _lib.ptr(out), B, T, H, _lib.stream_ptr()))
     ts = []
     for _ in range(20):
-        flush.zero_()
+        if FLUSH:
+            flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         _lib.check(fn(_lib.ptr(qkv), _lib.ptr(out), B, T, H, _lib.stream_ptr()))
@@ -28,4 +30,4 @@ for name in ("msd_attention_tc5_bf16", "msd_attention_bf16"):
     ms = ts[len(ts) // 2]
     gflop = 4.0 * B * H * T * T * 64 / 1e9
     gbytes = B * T * 4 * E * 2 / 1e9
-    print(f"{name}: {ms:.4f} ms  {gflop / ms:.0f} TFLOP/s  {gbytes / ms * 1e3:.0f} GB/s (q,k,v in + out)")
+    print(f"B={B} flush={FLUSH} {name}: {ms:.4f} ms  {gflop / ms:.0f} TFLOP/s  {gbytes / ms * 1e3:.0f} GB/s (q,k,v in + out)")

@@ -1,4 +1,3 @@
 mkdir -p gpurun_out
-python -m msd_b200.sweep --tiles 27000 2>/dev/null | tail -1
-python -m msd_b200.sweep --tiles 27000 2>/dev/null | tail -1
-python tools/scene_bench.py 2>/dev/null | tail -1
+timeout 300 python -m pytest tests/test_gpu_model.py -q -p no:cacheprovider -x -k "attention" > gpurun_out/t_attn.log 2>&1; echo "attn rc=$?"; tail -n 5 gpurun_out/t_attn.log
+timeout 120 python tools/attn_bench.py 2>&1 | tail -3
