@@ -370,7 +370,7 @@ def main():
                      "traffic": 181.7e6 if args.backend == 0 else None,
                      "traffic_kernel": "gemm_tc5_pair_kernel<256,0> on the qkv shape (M=36864, N=2304, K=768), bytes per launch",
                      "tensor_pipe_active_pct_ncu": {"qkv": 71.2, "fc2": 66.6, "conv 24x24x384": 75.5, "conv 96x96x96": 50.2,
-                                                    "conv 192x192x48": 32.6, "attention (tcgen05)": 22.5, "head conv + fused 1x1": 22.3,
+                                                    "conv 192x192x48": 32.6, "attention (tcgen05)": 22.5, "head conv + fused 1x1": 37.6,
                                                    "source": "profiles/r1_v3_ncu_full_summaries.txt (GEMM kernels, unchanged since) + profiles/r1_v4_ncu_full_summaries.txt"},
                      "launches_per_step": enc_n, "ms_per_step": enc_ms,
                      "algorithmic_gflop_per_step": enc_flops / 1e9,
