@@ -143,10 +143,9 @@ extern "C" int msd_attention_bf16(const void* d_qkv, void* d_out, int B, int T, 
   MSD_REQUIRE(T == 144, "attention: only T=144 tokens (192x192 images, patch 16) is built; got T=%d", T);
   constexpr int kT = 144;
   const size_t smem = 2 * 3 * kT * LDS * sizeof(__nv_bfloat16);   // two q/k/v buffers (double-buffered persistent CTAs)
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_set;
+  if (attr_set.first()) {
     MSD_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<kT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
   }
   const int problems = B * heads;
   const int grid = problems < 2 * 148 ? problems : 2 * 148;       // two resident CTAs per SM (2 x 108 KB of shared memory)

@@ -196,10 +196,9 @@ extern "C" int msd_attention_bwd_bf16(const void* d_qkv, const void* d_dout, voi
   MSD_REQUIRE(msd_aligned16(d_qkv) && msd_aligned16(d_dout) && msd_aligned16(d_dqkv), "attention_bwd: pointers must be 16-byte aligned");
   MSD_REQUIRE(T == kT, "attention_bwd: only T=144 tokens is built; got T=%d", T);
   const size_t smem = (size_t)4 * kT * LDS * sizeof(__nv_bfloat16) + (size_t)2 * kT * LDP * sizeof(__nv_bfloat16);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_set;
+  if (attr_set.first()) {
     MSD_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
   }
   attention_bwd_kernel<<<(unsigned)(B * heads), kThreads, smem, (cudaStream_t)stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(d_qkv), reinterpret_cast<const __nv_bfloat16*>(d_dout),

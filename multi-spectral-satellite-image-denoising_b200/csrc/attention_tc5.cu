@@ -254,10 +254,9 @@ extern "C" int msd_attention_tc5_bf16(const void* d_qkv, void* d_out, int B, int
   const int E = heads * HD;
   int rc = make_map(&tm, d_qkv, (uint64_t)3 * E, (uint64_t)B * T, (uint64_t)3 * E, (uint32_t)T);
   if (rc) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_set;
+  if (attr_set.first()) {
     MSD_CHECK_CUDA(cudaFuncSetAttribute(attention_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_A));
-    attr_set = true;
   }
   const int problems = B * heads;
   const int grid = problems < num_sms() ? problems : num_sms();

@@ -34,6 +34,20 @@ void msd_set_error(const char* fmt, ...);
 
 static inline bool msd_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// cudaFuncSetAttribute belongs to a function ON A DEVICE: a process that drives several GPUs has to set it once per device,
+// not once per process.  `static PerDeviceOnce guard; if (guard.first()) cudaFuncSetAttribute(...)`.
+struct PerDeviceOnce {
+  bool done[64] = {};
+  bool first() {
+    int d = 0;
+    cudaGetDevice(&d);
+    d &= 63;
+    if (done[d]) return false;
+    done[d] = true;
+    return true;
+  }
+};
+
 // ---------------------------------------------------------------------------------------------------
 // exact unsigned division by a runtime constant (n < 2^31): q = (umulhi(n, m) + n) >> s
 // ---------------------------------------------------------------------------------------------------

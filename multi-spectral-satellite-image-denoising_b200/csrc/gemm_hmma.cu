@@ -100,10 +100,9 @@ __global__ void __launch_bounds__(kThreads) gemm_hmma_kernel(const Problem p, in
 template <int BN>
 int launch_bn(const Problem& p, cudaStream_t s) {
   const size_t smem = 2 * (size_t)(BLOCK_M + BN) * LDSM * sizeof(__nv_bfloat16);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_set;
+  if (attr_set.first()) {
     MSD_CHECK_CUDA(cudaFuncSetAttribute(gemm_hmma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
   }
   const int tiles_m = (p.M + BLOCK_M - 1) / BLOCK_M, tiles_n = p.N / BN;
   gemm_hmma_kernel<BN><<<(unsigned)(tiles_m * tiles_n), kThreads, smem, s>>>(p, tiles_n);

@@ -852,10 +852,9 @@ int launch_mode(const Problem& p, cudaStream_t s) {
     rc = make_map(&tmS, p.skip, (uint64_t)p.kvalid, (uint64_t)p.a_rows, (uint64_t)p.ldA, a_box_rows);
     if (rc) return rc;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_set;
+  if (attr_set.first()) {
     MSD_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc5_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
-    attr_set = true;
   }
   const int tiles_m = (p.M + BLOCK_M - 1) / BLOCK_M, tiles_n = p.N / BN;
   const int tiles = tiles_m * tiles_n;

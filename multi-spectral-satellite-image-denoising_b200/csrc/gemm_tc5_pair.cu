@@ -309,10 +309,9 @@ int launch_pair_mode(const Problem& p, cudaStream_t s) {
     rc = make_map(&tmS, p.skip, (uint64_t)p.kvalid, (uint64_t)p.a_rows, (uint64_t)p.ldA, a_box_rows);
     if (rc) return rc;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_set;
+  if (attr_set.first()) {
     MSD_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc5_pair_kernel<BN, MERGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
-    attr_set = true;
   }
   const int tiles_m2 = (p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M), tiles_n = p.N / BN;
   const int tiles = tiles_m2 * tiles_n;

@@ -225,10 +225,9 @@ int launch_tn(TnProblem& p, cudaStream_t s) {
   if (rc) return rc;
   rc = make_map(&tmB, p.B, (uint64_t)p.b_cols, (uint64_t)p.rows, (uint64_t)p.ldB, KB);
   if (rc) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_set;
+  if (attr_set.first()) {
     MSD_CHECK_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<MODE, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
-    attr_set = true;
   }
   p.num_kb = (int)((p.rows + KB - 1) / KB);
   const int tiles = p.tiles_m * p.tiles_n;

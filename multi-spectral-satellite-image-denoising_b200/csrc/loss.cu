@@ -153,12 +153,11 @@ extern "C" int msd_loss_fwd_bwd_f32(const float* d_pred, const float* d_target, 
   SsimConsts consts;
   consts.C1 = (float)((0.01 * (double)data_range) * (0.01 * (double)data_range));
   consts.C2 = (float)((0.03 * (double)data_range) * (0.03 * (double)data_range));
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_set;
+  if (attr_set.first()) {
     MSD_CHECK_CUDA(cudaFuncSetAttribute(loss_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FwdSmem)));
     MSD_CHECK_CUDA(cudaFuncSetAttribute(loss_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FwdSmem)));
     MSD_CHECK_CUDA(cudaFuncSetAttribute(loss_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdSmem)));
-    attr_set = true;
   }
   const int tiles_x = (W + TW - 1) / TW, tiles_y = (H + TH - 1) / TH;
   const unsigned blocks = (unsigned)B * C * tiles_x * tiles_y;

@@ -266,19 +266,17 @@ extern "C" int msd_metrics_f32(const float* d_pred, const float* d_target, int B
                      gemm::tc5::make_map_planes_f32(&tmT, d_target, (uint64_t)W, (uint64_t)H, (uint64_t)B * C, PW, IH) == MSD_OK;
   if (fused) {
     // product path: TMA-staged, one pass over pred and target
-    static bool fused_attr_set = false;
-    if (!fused_attr_set) {
+    static PerDeviceOnce fused_attr_set;
+    if (fused_attr_set.first()) {
       MSD_CHECK_CUDA(cudaFuncSetAttribute(metrics_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem)));
-      fused_attr_set = true;
     }
     metrics_fused_kernel<<<(unsigned)B * tiles_x * tiles_y, kThreads, sizeof(FusedSmem), s>>>(tmP, tmT, C, H, W, tiles_x, tiles_y, consts,
                                                                                              1e-8f, d_scratch);
     MSD_LAUNCH_CHECK();
   } else {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_set;
+    if (attr_set.first()) {
       MSD_CHECK_CUDA(cudaFuncSetAttribute(ssim_mse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SsimSmem)));
-      attr_set = true;
     }
     const unsigned blocks = (unsigned)B * C * tiles_x * tiles_y;
     ssim_mse_kernel<<<blocks, kThreads, sizeof(SsimSmem), s>>>(d_pred, d_target, C, H, W, tiles_x, tiles_y, consts, d_scratch);

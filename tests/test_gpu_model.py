@@ -291,3 +291,22 @@ def test_forward_is_unchanged_after_moving_the_model_off_and_back_onto_the_devic
         del junk
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[3])
     assert (outs[2] - outs[0]).abs().max().item() <= 2e-2
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_second_device_in_the_same_process_gives_the_same_result():
+    """One process driving two GPUs: kernel attributes (opt-in shared memory) are per device, tensor maps and workspaces
+    per call -- the second device must produce exactly what the first one did."""
+    from msd_b200.training import MetricsTracker
+    outs = []
+    x = recipes.model_input(2)
+    for dev in ("cuda:0", "cuda:1"):
+        torch.manual_seed(42)
+        m = SatMAERestoration(recipes.base_config(), block_layout="fallback").eval().to(dev)
+        with torch.no_grad():
+            y = m(x.to(dev))
+        t = MetricsTracker()
+        t.update(y, x.to(dev))
+        outs.append((y.cpu(), t.compute()))
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert outs[0][1] == outs[1][1]

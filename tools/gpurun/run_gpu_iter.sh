@@ -1,4 +1,2 @@
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_gpu_model.py -q -p no:cacheprovider -x -k "attention" > gpurun_out/t_attn.log 2>&1; echo "attn rc=$?"; tail -n 5 gpurun_out/t_attn.log
-timeout 120 python tools/attn_bench.py 2>&1 | tail -2
-timeout 120 python tools/attn_bench.py 64 2>&1 | tail -2
+timeout 900 python -m pytest tests -q -p no:cacheprovider -m gpu -x > gpurun_out/t_gpu.log 2>&1; echo "gpu tests rc=$?"; tail -n 3 gpurun_out/t_gpu.log
