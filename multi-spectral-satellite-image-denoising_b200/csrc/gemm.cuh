@@ -27,6 +27,7 @@ struct Problem {
   int M, N;                 // output rows / cols (N % 16 == 0)
   int a_rows, ldA, kvalid;  // A extent; kvalid = valid K per tap (<= kb_per_tap*64), the rest reads as zero
   int num_kb, kb_per_tap;
+  int w_ld_kb;              // row pitch of Wt in 64-wide k-blocks (0: num_kb) -- a packed matrix may hold more taps than are contracted
   int tap_off[10];
   int dbg_shift, dbg_bo;    // experiment knobs (tools/desc_probe.py): unaligned A window start / descriptor base offset
   int skip_tap;             // >= 0: tap whose A operand is `skip` (same shape as A) and whose weights are the identity

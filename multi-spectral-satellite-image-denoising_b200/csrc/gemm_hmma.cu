@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(kThreads) gemm_hmma_kernel(const Problem p, in
 
   const int m0 = (blockIdx.x / tiles_n) * BLOCK_M, n0 = (blockIdx.x % tiles_n) * BN;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int ldB = p.num_kb * BLOCK_K;
+  const int ldB = (p.w_ld_kb ? p.w_ld_kb : p.num_kb) * BLOCK_K;
 
   auto load_stage = [&](int kb, int buf) {
     const int tap = kb / p.kb_per_tap, kc = kb - tap * p.kb_per_tap;

@@ -122,7 +122,7 @@ int launch_tc5(const Problem& p, cudaStream_t s) {
   // wide tiles of large problems run on CTA pairs (cta_group::2): half the W traffic per CTA, deeper ring
   static const bool no_pair = getenv("MSD_NO_PAIR") != nullptr;
   const bool pair_ok = !no_pair && p.M >= 2048 && p.dbg_shift == 0 && p.dbg_bo == 0 &&
-                       !(p.mode == EPI_CONV && p.skip != nullptr && p.skip_tap < 0);
+                       !(p.mode == EPI_CONV && p.skip != nullptr && p.skip_tap < 0 && !p.act);   // raw + epilogue skip: generic single-CTA path
   if (pair_ok && (bn == 256 || bn == 192))
     return bn == 256 ? tc5::launch_pair<256>(p, s) : tc5::launch_pair<192>(p, s);
   // 3x3 convs with 96 / 48 channels: dx-merged windows + the weight matrix resident in shared memory, split over the pair

@@ -291,6 +291,7 @@ enum Epi : int {
   E_CONV_RAW,       // haloed NHWC bf16 = acc + bias, halo rows zeroed               (training: pre-BatchNorm output, dgrad)
   E_CONVT_RAW,      // pixel-shuffle scatter of acc + bias                            (training: pre-BatchNorm output)
   E_CONV_HEAD,      // NCHW fp32 = head_w . GELU(acc + bias) + head_b                 (head conv3x3 + 1x1, one kernel)
+  E_CONV_SKIPADD,   // haloed NHWC bf16 = GELU(acc + bias + skip), skip read in the epilogue (ResidualBlock's second conv, 9 taps)
   E_GENERIC         // any other combination of the Problem's flags (slower, runtime-branched)
 };
 
@@ -304,7 +305,8 @@ __host__ inline int classify(const Problem& p) {
     return E_GENERIC;
   }
   if (p.mode == EPI_CONV && p.head_out != nullptr) return E_CONV_HEAD;
-  if (p.mode == EPI_CONV && !p.out_f32 && !(p.skip && p.skip_tap < 0)) return p.act ? E_CONV : E_CONV_RAW;   // epilogue-loaded skip: generic path
+  if (p.mode == EPI_CONV && !p.out_f32 && p.skip && p.skip_tap < 0 && p.act) return E_CONV_SKIPADD;
+  if (p.mode == EPI_CONV && !p.out_f32 && !(p.skip && p.skip_tap < 0)) return p.act ? E_CONV : E_CONV_RAW;   // raw + epilogue skip: generic path
   if (p.mode == EPI_CONVT && !p.out_f32 &&
       (unsigned long long)(p.M / (int)p.in_plane.d + 1) * p.out_plane * p.ldo < (1ull << 31)) return p.act ? E_CONVT : E_CONVT_RAW;
   return E_GENERIC;
@@ -327,14 +329,15 @@ __device__ __forceinline__ void epilogue_tile(const Problem& p, uint32_t stg_s, 
   using C = Cfg<BN>;
   constexpr bool kHead = EPI == E_CONV_HEAD;
   static_assert(!kHead || (C::NSLAB == 1 && C::SC == 48), "the fused head epilogue is built for one 48-column slab");
-  constexpr bool kConv = EPI == E_CONV || EPI == E_CONV_RAW;
+  constexpr bool kSkipAdd = EPI == E_CONV_SKIPADD;
+  constexpr bool kConv = EPI == E_CONV || EPI == E_CONV_RAW || kSkipAdd;
   constexpr bool kConvT = EPI == E_CONVT || EPI == E_CONVT_RAW;
   constexpr bool kF32 = EPI == E_RM_F32 || EPI == E_RM_F32_RESID;
   constexpr bool kGelu = EPI == E_RM_BF16_GELU || EPI == E_CONV || EPI == E_CONVT || kHead;
   constexpr int UPR = kF32 ? C::SC / 4 : C::SC / 8;        // 16-byte units per staged row (a power of two)
   constexpr uint32_t PITCH = (kF32 ? C::SC * 4 : C::SC * 2) + 16;
   const uint32_t rowpix = kHead ? row_info_head(p, mrow0 + lane) : (EPI == E_GENERIC || kConvT || kConv) ? row_info(p, mrow0 + lane) : 0u;
-  const bool zero_row = kConv && (rowpix & kRowHalo) != 0;
+  const bool zero_row = kConv && !kSkipAdd && (rowpix & kRowHalo) != 0;      // (the skip-add variant zeroes halo rows in phase B)
   const int rows_valid = p.M - mrow0;   // rows rr < rows_valid exist (row-major / conv)
   const uint32_t ldo = (uint32_t)p.ldo;
   if (slab_begin >= slab_end) {          // a one-slab tile leaves the second column half idle: just release the buffer
@@ -413,8 +416,16 @@ __device__ __forceinline__ void epilogue_tile(const Problem& p, uint32_t stg_s, 
         for (int c = 0; c < UPR; ++c) {
           const float4 v0 = make_float4(__uint_as_float(r[8 * c]), __uint_as_float(r[8 * c + 1]), __uint_as_float(r[8 * c + 2]), __uint_as_float(r[8 * c + 3]));
           const float4 v1 = make_float4(__uint_as_float(r[8 * c + 4]), __uint_as_float(r[8 * c + 5]), __uint_as_float(r[8 * c + 6]), __uint_as_float(r[8 * c + 7]));
-          uint2 o0 = kGelu ? gelu4_to_bf16(v0) : make_uint2(pack_bf16x2(v0.x, v0.y), pack_bf16x2(v0.z, v0.w));
-          uint2 o1 = kGelu ? gelu4_to_bf16(v1) : make_uint2(pack_bf16x2(v1.x, v1.y), pack_bf16x2(v1.z, v1.w));
+          uint2 o0, o1;
+          if constexpr (kSkipAdd) {
+            // pre-activation staged as fp16 (the precision GELU is evaluated in anyway); skip + GELU follow in phase B
+            const __half2 h0 = __floats2half2_rn(v0.x, v0.y), h1 = __floats2half2_rn(v0.z, v0.w), h2 = __floats2half2_rn(v1.x, v1.y), h3 = __floats2half2_rn(v1.z, v1.w);
+            o0 = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+            o1 = make_uint2(*reinterpret_cast<const uint32_t*>(&h2), *reinterpret_cast<const uint32_t*>(&h3));
+          } else {
+            o0 = kGelu ? gelu4_to_bf16(v0) : make_uint2(pack_bf16x2(v0.x, v0.y), pack_bf16x2(v0.z, v0.w));
+            o1 = kGelu ? gelu4_to_bf16(v1) : make_uint2(pack_bf16x2(v1.x, v1.y), pack_bf16x2(v1.z, v1.w));
+          }
           if (zero_row) { o0 = make_uint2(0u, 0u); o1 = o0; }
           sts128(stg_s + lane * PITCH + c * 16, make_uint4(o0.x, o0.y, o1.x, o1.y));
         }
@@ -440,6 +451,31 @@ __device__ __forceinline__ void epilogue_tile(const Problem& p, uint32_t stg_s, 
         } else {
           live[j] = rr < rows_valid;
           off[j] = (uint32_t)(mrow0 + rr) * ldo + (uint32_t)n;
+        }
+      }
+      if constexpr (kSkipAdd) {
+        // ResidualBlock (blocks.py:85): GELU(x + block(x)).  The skip tensor is read here, coalesced, instead of riding through the
+        // tensor cores as a tenth identity tap (one A box and 1/9 of the MMAs less per tile); halo rows are stored as zeros.
+        uint4 sk[UPR];
+        bool halo[UPR];
+#pragma unroll
+        for (int j = 0; j < UPR; ++j) {
+          const int rr = (j * 32 + lane) / UPR;
+          halo[j] = (__shfl_sync(0xffffffffu, rowpix, rr) & kRowHalo) != 0;
+          sk[j] = (live[j] && !halo[j]) ? __ldg(reinterpret_cast<const uint4*>(p.skip + off[j])) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int j = 0; j < UPR; ++j) {
+          uint32_t w[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+          const uint32_t k4[4] = {sk[j].x, sk[j].y, sk[j].z, sk[j].w};
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const float2 sf = unpack_bf16x2(k4[t]);
+            const __half2 z = __hadd2(*reinterpret_cast<const __half2*>(&w[t]), __floats2half2_rn(sf.x, sf.y));
+            const float2 g = __half22float2(gelu_h2(z));
+            w[t] = halo[j] ? 0u : pack_bf16x2(g.x, g.y);
+          }
+          v[j] = make_uint4(w[0], w[1], w[2], w[3]);
         }
       }
       if constexpr (EPI == E_RM_F32_RESID) {
@@ -813,6 +849,7 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         MSD_EPI_CASE(E_CONVT)
         MSD_EPI_CASE(E_CONV_RAW)
         MSD_EPI_CASE(E_CONVT_RAW)
+        MSD_EPI_CASE(E_CONV_SKIPADD)
         default: epilogue_tile<BN, E_GENERIC>(p, stg_s, bias_s, taddr, &tmem_empty[as], m0 + q * 32, n0, lane, slab_begin, slab_end); break;
       }
 #undef MSD_EPI_CASE
@@ -845,7 +882,7 @@ int launch_mode(const Problem& p, cudaStream_t s) {
   CUtensorMap tmA, tmB;
   int rc = make_map(&tmA, p.A, (uint64_t)p.kvalid, (uint64_t)p.a_rows, (uint64_t)p.ldA, a_box_rows);
   if (rc) return rc;
-  rc = make_map(&tmB, p.Wt, (uint64_t)p.num_kb * BLOCK_K, (uint64_t)p.N, (uint64_t)p.num_kb * BLOCK_K, BN);
+  rc = make_map(&tmB, p.Wt, (uint64_t)p.num_kb * BLOCK_K, (uint64_t)p.N, (uint64_t)(p.w_ld_kb ? p.w_ld_kb : p.num_kb) * BLOCK_K, BN);
   if (rc) return rc;
   CUtensorMap tmS = tmA;
   if (p.skip_tap >= 0) {

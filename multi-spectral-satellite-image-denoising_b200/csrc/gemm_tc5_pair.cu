@@ -283,6 +283,7 @@ gemm_tc5_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         MSD_EPI_CASE(E_CONV_RAW)
         MSD_EPI_CASE(E_CONVT)
         MSD_EPI_CASE(E_CONVT_RAW)
+        MSD_EPI_CASE(E_CONV_SKIPADD)
         default: epilogue_tile<BN, E_GENERIC, true>(p, stg_s, bias_s, taddr, &tmem_empty[as], m0 + q * 32, n0, lane, slab_begin, slab_end); break;
       }
 #undef MSD_EPI_CASE
@@ -302,7 +303,7 @@ int launch_pair_mode(const Problem& p, cudaStream_t s) {
   const uint32_t a_box_rows = MERGED ? MERGE_ROWS : BLOCK_M;
   int rc = make_map(&tmA, p.A, (uint64_t)p.kvalid, (uint64_t)p.a_rows, (uint64_t)p.ldA, a_box_rows);
   if (rc) return rc;
-  rc = make_map(&tmB, p.Wt, (uint64_t)p.num_kb * BLOCK_K, (uint64_t)p.N, (uint64_t)p.num_kb * BLOCK_K, BN / 2);
+  rc = make_map(&tmB, p.Wt, (uint64_t)p.num_kb * BLOCK_K, (uint64_t)p.N, (uint64_t)(p.w_ld_kb ? p.w_ld_kb : p.num_kb) * BLOCK_K, BN / 2);
   if (rc) return rc;
   CUtensorMap tmS = tmA;
   if (p.skip_tap >= 0) {

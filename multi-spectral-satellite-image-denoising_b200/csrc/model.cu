@@ -42,8 +42,10 @@ int make_linear(Problem& p, const void* a, const void* w, const float* bias, voi
   return MSD_OK;
 }
 
+// skip_in_epilogue: the skip tensor is added by the epilogue warps (E_CONV_SKIPADD) and only nine taps are contracted; the
+// weight matrix keeps its ten-tap packing (row pitch 10 * Kpad), the identity tap is simply not used
 int make_conv3x3(Problem& p, const void* x, const void* w, const float* bias, const void* skip, void* y, int B, int H,
-                 int W, int Cin, int Cout, int act = 1) {
+                 int W, int Cin, int Cout, int act = 1, bool skip_in_epilogue = false) {
   MSD_REQUIRE(x && w && y, "conv3x3: null pointer");
   MSD_REQUIRE(B > 0 && H > 0 && W > 0 && Cin % 8 == 0 && Cout % 16 == 0, "conv3x3: bad shape B=%d H=%d W=%d Cin=%d Cout=%d", B, H, W, Cin, Cout);
   const long long rows = (long long)B * (H + 2) * (W + 2);
@@ -62,7 +64,11 @@ int make_conv3x3(Problem& p, const void* x, const void* w, const float* bias, co
   if (skip != nullptr) {
     // skip connection = a tenth tap: A = skip tensor at row shift 0, W block = identity (packed by the host shim)
     MSD_REQUIRE(Cin == Cout, "conv3x3: a skip connection needs Cin == Cout (got %d, %d)", Cin, Cout);
-    p.skip_tap = 9; p.tap_off[9] = 0; p.num_kb = 10 * p.kb_per_tap;
+    if (skip_in_epilogue && act) {
+      p.w_ld_kb = 10 * p.kb_per_tap;
+    } else {
+      p.skip_tap = 9; p.tap_off[9] = 0; p.num_kb = 10 * p.kb_per_tap;
+    }
   }
   p.plane = make_fastdiv((uint32_t)((H + 2) * (W + 2)));
   p.pitch = make_fastdiv((uint32_t)(W + 2));
@@ -133,10 +139,20 @@ extern "C" int msd_linear_bf16(const void* d_a, const void* d_w, const float* d_
   return gemm::launch(p, backend, (cudaStream_t)stream);
 }
 
+// ResidualBlock skip connection on the tcgen05 path: added by the epilogue warps for >= 96 channels (the conv is bound by its
+// operand loads there: 0.574 -> 0.445 ms at 96 channels, 0.371 -> 0.35 at 192 / 384), as a tenth identity tap through the tensor
+// cores for 48 channels (that conv is bound by its epilogue warps: 0.633 vs 0.669 ms).  MSD_SKIP_TAP=1 / MSD_SKIP_EPI=1 force one
+// way for A/B runs; the mma.sync baseline always takes the identity tap.
+static bool skip_in_epilogue(int backend, int channels) {
+  static const bool tap = getenv("MSD_SKIP_TAP") != nullptr, epi = getenv("MSD_SKIP_EPI") != nullptr;
+  if (backend != 0 || tap) return false;
+  return epi || channels >= 96;
+}
+
 extern "C" int msd_conv3x3_nhwc_bf16(const void* d_x, const void* d_w, const float* d_bias, const void* d_skip, void* d_y,
                                      int B, int H, int W, int Cin, int Cout, int backend, void* stream) {
   Problem p;
-  int rc = make_conv3x3(p, d_x, d_w, d_bias, d_skip, d_y, B, H, W, Cin, Cout);
+  int rc = make_conv3x3(p, d_x, d_w, d_bias, d_skip, d_y, B, H, W, Cin, Cout, 1, skip_in_epilogue(backend, Cout));
   if (rc) return rc;
   return gemm::launch(p, backend, (cudaStream_t)stream);
 }
@@ -377,12 +393,12 @@ extern "C" int msd_model_forward(msd_model* m, const float* d_x, const void* d_p
     // ResidualBlock 1: Z = GELU(X + BN(conv(GELU(BN(conv X)))))   (blocks.py:74-85)
     MSD_TRY(make_conv3x3(p, X, sw.w_conv[0], sw.b_conv[0], nullptr, Y, B, hw, hw, cout, cout));
     MSD_RUN(0, cf, gemm::launch(p, be, s));
-    MSD_TRY(make_conv3x3(p, Y, sw.w_conv[1], sw.b_conv[1], X, Z, B, hw, hw, cout, cout));
+    MSD_TRY(make_conv3x3(p, Y, sw.w_conv[1], sw.b_conv[1], X, Z, B, hw, hw, cout, cout, 1, skip_in_epilogue(be, cout)));
     MSD_RUN(0, cf, gemm::launch(p, be, s));
     // ResidualBlock 2: X = GELU(Z + ...)
     MSD_TRY(make_conv3x3(p, Z, sw.w_conv[2], sw.b_conv[2], nullptr, Y, B, hw, hw, cout, cout));
     MSD_RUN(0, cf, gemm::launch(p, be, s));
-    MSD_TRY(make_conv3x3(p, Y, sw.w_conv[3], sw.b_conv[3], Z, X, B, hw, hw, cout, cout));
+    MSD_TRY(make_conv3x3(p, Y, sw.w_conv[3], sw.b_conv[3], Z, X, B, hw, hw, cout, cout, 1, skip_in_epilogue(be, cout)));
     MSD_RUN(0, cf, gemm::launch(p, be, s));
     cur = X; cin = cout; in_pad = 1;
   }
