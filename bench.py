@@ -346,7 +346,7 @@ def main():
     achieved_tf = enc_flops / (enc_ms / 1e3) / 1e12 if enc_ms > 0 else 0.0
     if args.backend != 0:
         achieved_tf, enc_ms, enc_flops, enc_n = family_tf, gemm_ms, gemm_flops, gemm_n
-    launches_per_step = 2 + (model.launches_per_forward() - 1) + 3      # corrupt(2) + forward (patchify fused away) + metrics(3)
+    launches_per_step = 2 + (model.launches_per_forward() - 1) + 2      # corrupt(2) + forward (patchify fused away) + metrics(fused pass + finalize)
 
     line = {
         "metric": METRIC, "value": value, "unit": "img/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_step,
