@@ -124,6 +124,13 @@ typedef struct msd_block_weights {
   const void *w_proj; const float *b_proj;  /* [768,768]   */
   const void *w_fc1;  const float *b_fc1;   /* [3072,768]  */
   const void *w_fc2;  const float *b_fc2;   /* [768,3072]  */
+  /* LayerNorm folded into the GEMM behind it (optional; all six set or all NULL; tcgen05 backend only):
+   *   w_*_ln bf16 [N,768] = bf16(gamma[k] * W[n,k]),  s_* fp32 [N] = sum_k float(w_*_ln[n,k]),
+   *   b_*_ln fp32 [N] = b[n] + sum_k beta[k] * W[n,k]   (gamma, beta = norm1 for qkv, norm2 for fc1).
+   * When present the eval forward runs no per-block LayerNorm kernel: proj / fc2 emit the bf16 copy of the residual row and
+   * its partial {sum, sum of squares}, qkv / fc1 apply rstd * (acc - mean * s) + b_ln in their epilogues (encoder.py:154-176). */
+  const void *w_qkv_ln; const float *s_qkv; const float *b_qkv_ln;
+  const void *w_fc1_ln; const float *s_fc1; const float *b_fc1_ln;
 } msd_block_weights;
 
 typedef struct msd_stage_weights {
@@ -183,6 +190,19 @@ int msd_layernorm_f32_bf16(const float* d_x, const float* d_g, const float* d_b,
                            int D, void* stream);
 int msd_layernorm_pos_f32(float* d_x, const float* d_g, const float* d_b, float eps, const float* d_pos, int period,
                           int M, int D, void* stream);
+/* LayerNorm folded into the GEMMs around it (tcgen05 path; what msd_model_forward runs when the msd_block_weights carry *_ln):
+ *   msd_ln_stats_parts        : partial sums per row a producing GEMM of shape [M,N] writes (depends on its tile width)
+ *   msd_layernorm_pos_stats_f32: msd_layernorm_pos_f32 + d_x_bf16 [M,D] = bf16(x) + d_stats [M,parts,2] (slot 0 = {sum x, sum x^2})
+ *   msd_linear_resid_stats_f32: x fp32 [M,N] += A.W^T + bias (in place) + d_x_bf16 = bf16(x) + d_stats [M,parts,2] partial sums
+ *   msd_linear_lnfold_bf16    : out bf16 [M,N] = act(rstd_m * (xb.Wln^T - mean_m * s) + bias_ln), {mean, rstd} of row m from d_stats
+ *                               (var = E[x^2] - mean^2 over K columns, + eps) */
+int msd_ln_stats_parts(int N, int M);
+int msd_layernorm_pos_stats_f32(float* d_x, const float* d_g, const float* d_b, float eps, const float* d_pos, int period,
+                                void* d_x_bf16, float* d_stats, int parts, int M, int D, void* stream);
+int msd_linear_resid_stats_f32(const void* d_a, const void* d_w, const float* d_bias, float* d_x, void* d_x_bf16, float* d_stats,
+                               int parts, int M, int N, int K, void* stream);
+int msd_linear_lnfold_bf16(const void* d_x_bf16, const void* d_w_ln, const float* d_bias_ln, const float* d_ln_s,
+                           const float* d_stats, int parts, float eps, void* d_out, int M, int N, int K, int act, void* stream);
 /* qkv bf16 [B*T, 3*heads*64] -> out bf16 [B*T, heads*64]; softmax(q k^T / 8) v per (image, head); T <= 256. */
 int msd_attention_bf16(const void* d_qkv, void* d_out, int B, int T, int heads, void* stream);
 /* the same contraction on tcgen05 / TMEM / TMA (product path; msd_attention_bf16 is the mma.sync baseline): T == 144 */
@@ -332,12 +352,15 @@ int msd_tile_blend_f32(const float* d_restored, const int* d_gy, const int* d_gx
  * `tensors` is a HOST array of n entries whose pointers are device fp32 buffers of `numel` elements.
  *   msd_grad_sqnorm_f32: *d_sqnorm (device fp64) = sum over all tensors of sum g^2
  *   msd_adamw_step_f32 : decoupled weight decay, bias-corrected moments (step is 1-based); when max_grad_norm > 0 the gradient
- *                        is multiplied by min(1, max_grad_norm / (sqrt(*d_sqnorm) + 1e-6)) on the fly (gradients are not modified)
+ *                        is multiplied by min(1, max_grad_norm / (sqrt(*d_sqnorm) + 1e-6)) on the fly (gradients are not modified);
+ *                        a non-finite *d_sqnorm (inf / nan gradients, e.g. an overflowed fp16-scaled step) skips the whole update,
+ *                        as GradScaler.step does in the reference's loop (trainer.py:194-207), instead of poisoning the weights
  * ------------------------------------------------------------------------------------------------- */
 typedef struct msd_adamw_tensor {
   float* param; const float* grad; float* exp_avg; float* exp_avg_sq;
   long long numel;
   float lr, weight_decay;
+  int step;                 /* 1-based step count of THIS tensor (torch.optim.AdamW keeps one per parameter); 0 = use the call's `step` */
 } msd_adamw_tensor;
 int msd_grad_sqnorm_f32(const msd_adamw_tensor* tensors, int n, double* d_sqnorm, void* stream);
 int msd_adamw_step_f32(const msd_adamw_tensor* tensors, int n, float beta1, float beta2, float eps, int step, float max_grad_norm,

@@ -26,7 +26,8 @@ class ModelDesc(C.Structure):
 
 class BlockWeights(C.Structure):
     _fields_ = [(n, c_void_p) for n in (
-        "ln1_g", "ln1_b", "ln2_g", "ln2_b", "w_qkv", "b_qkv", "w_proj", "b_proj", "w_fc1", "b_fc1", "w_fc2", "b_fc2")]
+        "ln1_g", "ln1_b", "ln2_g", "ln2_b", "w_qkv", "b_qkv", "w_proj", "b_proj", "w_fc1", "b_fc1", "w_fc2", "b_fc2",
+        "w_qkv_ln", "s_qkv", "b_qkv_ln", "w_fc1_ln", "s_fc1", "b_fc1_ln")]
 
 
 class StageWeights(C.Structure):
@@ -79,7 +80,7 @@ class ModelGrads(C.Structure):
 
 class AdamWTensor(C.Structure):
     _fields_ = [("param", c_void_p), ("grad", c_void_p), ("exp_avg", c_void_p), ("exp_avg_sq", c_void_p), ("numel", C.c_longlong),
-                ("lr", c_float), ("weight_decay", c_float)]
+                ("lr", c_float), ("weight_decay", c_float), ("step", c_int)]
 
 
 # name -> (restype, argtypes); must list every symbol include/msd.h declares (tests/test_abi.py checks this)
@@ -116,6 +117,13 @@ SIGNATURES = {
                                        c_int, c_void_p]),
     "msd_layernorm_f32_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_void_p]),
     "msd_layernorm_pos_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "msd_ln_stats_parts": (c_int, [c_int, c_int]),
+    "msd_layernorm_pos_stats_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int, c_void_p, c_void_p, c_int,
+                                            c_int, c_int, c_void_p]),
+    "msd_linear_resid_stats_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                           c_void_p]),
+    "msd_linear_lnfold_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p, c_int, c_int,
+                                       c_int, c_int, c_void_p]),
     "msd_attention_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "msd_attention_tc5_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "msd_patchify_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),

@@ -11,7 +11,7 @@ void msd_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-extern "C" int msd_version(void) { return 1; }
+extern "C" int msd_version(void) { return 2; }
 
 extern "C" const char* msd_last_error(void) { return g_err; }
 

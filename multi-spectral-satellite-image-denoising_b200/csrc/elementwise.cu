@@ -33,12 +33,14 @@ __global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__
 // LayerNorm over the last dim, one warp per row, two-pass (mean, then centred variance) in registers.
 //   kMode 0: out_bf16[m] = LN(x[m])                      (block norm1/norm2, encoder.norm)
 //   kMode 1: x[m] = LN(x[m]) + pos[m % period]  (fp32)   (patch_embed.norm then + pos_embed, encoder.py:51,309)
+//   kMode 2: kMode 1 + out_bf16[m] = bf16(x[m]) and the row's {sum x, sum x^2} in stats[m][0] (slots 1..parts-1 zeroed): the
+//            first block's norm1 is folded into its qkv GEMM, which reads exactly what a stats-producing GEMM would have left
 // ---------------------------------------------------------------------------------------------------
 template <int kChunks, int kMode>
 __global__ void __launch_bounds__(256) layernorm_kernel(float* __restrict__ x, const float* __restrict__ g,
                                                         const float* __restrict__ bta, float eps,
                                                         __nv_bfloat16* __restrict__ out, const float* __restrict__ pos,
-                                                        int period, int M) {
+                                                        int period, int M, float2* __restrict__ stats = nullptr, int parts = 0) {
   constexpr int D = kChunks * 128;
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -59,6 +61,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(float* __restrict__ x, c
     q += (a * a + b * b) + (c * c + d * d);
   }
   const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / D) + eps);
+  float so = 0.0f, qo = 0.0f;
 #pragma unroll
   for (int i = 0; i < kChunks; ++i) {
     const int col = i * 128 + lane * 4;
@@ -78,18 +81,31 @@ __global__ void __launch_bounds__(256) layernorm_kernel(float* __restrict__ x, c
       const float4 pp = __ldg(reinterpret_cast<const float4*>(pos + (size_t)(row % period) * D + col));
       o.x += pp.x; o.y += pp.y; o.z += pp.z; o.w += pp.w;
       *reinterpret_cast<float4*>(xr + col) = o;
+      if (kMode == 2) {
+        uint2 pk;
+        pk.x = pack_bf16x2(o.x, o.y);
+        pk.y = pack_bf16x2(o.z, o.w);
+        *reinterpret_cast<uint2*>(out + (size_t)row * D + col) = pk;
+        so += (o.x + o.y) + (o.z + o.w);
+        qo = fmaf(o.x, o.x, fmaf(o.y, o.y, fmaf(o.z, o.z, fmaf(o.w, o.w, qo))));
+      }
     }
+  }
+  if (kMode == 2) {
+    so = warp_sum(so);
+    qo = warp_sum(qo);
+    for (int i = lane; i < parts; i += 32) stats[(size_t)row * parts + i] = i == 0 ? make_float2(so, qo) : make_float2(0.0f, 0.0f);
   }
 }
 
 template <int kMode>
 int launch_layernorm(float* x, const float* g, const float* b, float eps, __nv_bfloat16* out, const float* pos,
-                     int period, int M, int D, cudaStream_t s) {
+                     int period, int M, int D, cudaStream_t s, float2* stats = nullptr, int parts = 0) {
   MSD_REQUIRE(D % 128 == 0 && D >= 128 && D <= 1024, "layernorm: D=%d must be a multiple of 128 in [128,1024]", D);
   const unsigned blocks = (unsigned)((M + 7) / 8);
   switch (D / 128) {
 #define MSD_LN_CASE(n) \
-    case n: layernorm_kernel<n, kMode><<<blocks, 256, 0, s>>>(x, g, b, eps, out, pos, period, M); break;
+    case n: layernorm_kernel<n, kMode><<<blocks, 256, 0, s>>>(x, g, b, eps, out, pos, period, M, stats, parts); break;
     MSD_LN_CASE(1) MSD_LN_CASE(2) MSD_LN_CASE(3) MSD_LN_CASE(4) MSD_LN_CASE(5) MSD_LN_CASE(6) MSD_LN_CASE(7) MSD_LN_CASE(8)
 #undef MSD_LN_CASE
   }
@@ -207,6 +223,13 @@ extern "C" int msd_layernorm_pos_f32(float* d_x, const float* d_g, const float* 
                                      int period, int M, int D, void* stream) {
   MSD_REQUIRE(d_x && d_g && d_b && d_pos && M > 0 && period > 0, "layernorm_pos: bad arguments");
   return launch_layernorm<1>(d_x, d_g, d_b, eps, nullptr, d_pos, period, M, D, (cudaStream_t)stream);
+}
+
+extern "C" int msd_layernorm_pos_stats_f32(float* d_x, const float* d_g, const float* d_b, float eps, const float* d_pos,
+                                          int period, void* d_x_bf16, float* d_stats, int parts, int M, int D, void* stream) {
+  MSD_REQUIRE(d_x && d_g && d_b && d_pos && d_x_bf16 && d_stats && M > 0 && period > 0 && parts > 0 && parts <= 64, "layernorm_pos_stats: bad arguments");
+  return launch_layernorm<2>(d_x, d_g, d_b, eps, reinterpret_cast<__nv_bfloat16*>(d_x_bf16), d_pos, period, M, D, (cudaStream_t)stream,
+                             reinterpret_cast<float2*>(d_stats), parts);
 }
 
 extern "C" int msd_head1x1_nchw_f32(const void* d_x, const float* d_w, const float* d_b, float* d_y, int B, int H, int W,

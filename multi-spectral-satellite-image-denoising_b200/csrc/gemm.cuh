@@ -52,6 +52,20 @@ struct Problem {
   const float* head_b;      // [head_cout]
   float* head_out;          // [B, head_cout, H, W]
   int head_cout;            // <= 16
+  // LayerNorm folded into the GEMMs around it (encoder.py:39,136,154-176; tcgen05 path, EPI_ROWMAJOR only).
+  //   producer (proj / fc2, fp32 residual epilogue): additionally writes the bf16 copy of the new residual row (the next GEMM's A
+  //     operand) and, per (row, column tile, column half), the partial sums {sum x, sum x^2} of the columns it owns:
+  //     stats_out[m * stats_parts + slot], slot = 2 * (n0 / BN) + half; stats_parts = 2 * N / BN (see tc5_stats_parts())
+  //   consumer (qkv / fc1): A = bf16(x) un-normalised, Wt = bf16(gamma (.) W); the epilogue applies
+  //     out = rstd * (acc - mean * ln_s[n]) + bias[n]  with  ln_s[n] = sum_k Wt[n,k],  bias[n] = b[n] + sum_k beta[k] W[n,k]
+  //     and {mean, rstd} of row m from the ln_parts partial sums in ln_stats (fp32; var = E[x^2] - mean^2, + ln_eps)
+  __nv_bfloat16* out_bf16;  // producer: [M, ldo] bf16 copy of out, or null
+  float2* stats_out;        // producer: [M, stats_parts] partial {sum, sum sq}, or null
+  int stats_parts;
+  const float2* ln_stats;   // consumer: [M, ln_parts], or null
+  int ln_parts;
+  const float* ln_s;        // consumer: [N] column sums of the gamma-folded weights
+  float ln_eps, ln_inv_k;   // consumer: eps, 1 / (LayerNorm width)
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) { return act ? gelu_erf(v) : v; }
@@ -149,7 +163,14 @@ __device__ __forceinline__ void epilogue_store(const Problem& p, int m, int n, f
 int launch_tc5(const Problem& p, cudaStream_t s);
 int launch_hmma(const Problem& p, cudaStream_t s);
 bool tc5_can_fuse_head(const Problem& p, int head_cout);   // may this 3x3 conv carry the 1x1 head in its epilogue?
+int tc5_stats_parts(int N, int M);                         // partial LayerNorm sums per row a stats-producing GEMM of this shape writes
 
-inline int launch(const Problem& p, int backend, cudaStream_t s) { return backend == 1 ? launch_hmma(p, s) : launch_tc5(p, s); }
+inline int launch(const Problem& p, int backend, cudaStream_t s) {
+  if (backend == 1) {
+    MSD_REQUIRE(p.ln_stats == nullptr && p.stats_out == nullptr, "gemm: the folded LayerNorm epilogues exist on the tcgen05 backend only");
+    return launch_hmma(p, s);
+  }
+  return launch_tc5(p, s);
+}
 
 }  // namespace gemm

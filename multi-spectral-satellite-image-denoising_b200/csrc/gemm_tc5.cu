@@ -63,10 +63,11 @@ int make_map_planes_f32(CUtensorMap* tm, const void* base, uint64_t W, uint64_t 
 }
 
 int num_sms() {
-  static int n = 0;
+  static int cache[64] = {};          // per device: one process may drive several GPUs
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int& n = cache[dev & 63];
   if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (n <= 0) n = 148;
   }
@@ -89,7 +90,7 @@ extern template int launch_bn<16>(const Problem&, cudaStream_t);
 
 }  // namespace tc5
 
-int pick_bn_tc5(int N, int M, bool wave_aware) {
+int pick_bn_tc5(int N, int M, bool wave_aware, int min_bn = 16) {
   // Tile width: a divisor of N (2*BN fp32 accumulator columns must fit the 512 TMEM columns).  Wider tiles amortise the A
   // operand better, but the persistent grid runs whole waves of 148 CTAs: for the small GEMMs of the training step
   // (M = 9,216 rows at micro-batch 64) a narrower tile that fills its last wave beats a wider one that leaves it half empty.
@@ -101,7 +102,7 @@ int pick_bn_tc5(int N, int M, bool wave_aware) {
   double best_score = -1.0;
   for (int i = 0; i < 8; ++i) {
     const int c = cand[i];
-    if (N % c != 0) continue;
+    if (N % c != 0 || c < min_bn) continue;
     if (!wave_aware) return c;                                 // largest divisor
     const long long tiles = tiles_m * (N / c);
     const long long waves = (tiles + sms - 1) / sms;
@@ -113,12 +114,27 @@ int pick_bn_tc5(int N, int M, bool wave_aware) {
 
 bool tc5_can_fuse_head(const Problem& p, int head_cout) { return tc5::can_fuse_head(p, head_cout); }
 
+// A GEMM in front of a folded LayerNorm leaves 2 * N / BN partial row sums per row (one per column tile and column half); its
+// tile is at least 96 wide (32-column slabs, two halves), so at most 16 partials for N = 768.  Mirrors launch_tc5's tile choice.
+constexpr int kStatsMinBN = 96;
+int tc5_stats_parts(int N, int M) {
+  const int bn = pick_bn_tc5(N, M, true, kStatsMinBN);
+  return bn > 0 ? 2 * (N / bn) : 0;
+}
+
 int launch_tc5(const Problem& p, cudaStream_t s) {
   MSD_REQUIRE(p.N % 16 == 0, "gemm_tc5: N=%d must be a multiple of 16", p.N);
   MSD_REQUIRE(p.ldA % 8 == 0 && msd_aligned16(p.A) && msd_aligned16(p.Wt), "gemm_tc5: operands must be 16-byte aligned / pitched");
   // multi-tap (3x3 conv) problems keep the largest tile: their summation order (tap-major vs dx-merged) depends on the tile
   // width through the kernel mode, and results must not depend on the batch size (sharding invariance is tested bit-exactly)
-  const int bn = pick_bn_tc5(p.N, p.M, p.num_kb == p.kb_per_tap);
+  const bool ln_consumer = p.ln_stats != nullptr, ln_producer = p.stats_out != nullptr;
+  if (ln_consumer)
+    MSD_REQUIRE(p.mode == EPI_ROWMAJOR && !p.out_f32 && p.resid == nullptr && p.ln_s != nullptr && p.bias != nullptr && p.ln_parts > 0 &&
+                p.ln_parts <= 64 && msd_aligned16(p.ln_s) && !ln_producer, "gemm_tc5: a folded LayerNorm needs a bf16 row-major output, ln_s, bias and its partial sums");
+  if (ln_producer)
+    MSD_REQUIRE(p.mode == EPI_ROWMAJOR && p.out_f32 && !p.act && p.resid != nullptr && p.out_bf16 != nullptr && msd_aligned16(p.out_bf16) &&
+                p.stats_parts == tc5_stats_parts(p.N, p.M) && p.stats_parts > 0, "gemm_tc5: LayerNorm partial sums need the fp32 residual epilogue, a bf16 copy and stats_parts = tc5_stats_parts(N, M)");
+  const int bn = pick_bn_tc5(p.N, p.M, p.num_kb == p.kb_per_tap, ln_producer ? kStatsMinBN : 16);
   // wide tiles of large problems run on CTA pairs (cta_group::2): half the W traffic per CTA, deeper ring
   static const bool no_pair = getenv("MSD_NO_PAIR") != nullptr;
   const bool pair_ok = !no_pair && p.M >= 2048 && p.dbg_shift == 0 && p.dbg_bo == 0 &&

@@ -292,6 +292,9 @@ enum Epi : int {
   E_CONVT_RAW,      // pixel-shuffle scatter of acc + bias                            (training: pre-BatchNorm output)
   E_CONV_HEAD,      // NCHW fp32 = head_w . GELU(acc + bias) + head_b                 (head conv3x3 + 1x1, one kernel)
   E_CONV_SKIPADD,   // haloed NHWC bf16 = GELU(acc + bias + skip), skip read in the epilogue (ResidualBlock's second conv, 9 taps)
+  E_RM_BF16_LN,         // out bf16 = rstd (acc - mean ln_s) + bias                  (qkv behind a folded LayerNorm, see Problem)
+  E_RM_BF16_GELU_LN,    // out bf16 = GELU(rstd (acc - mean ln_s) + bias)            (fc1 behind a folded LayerNorm)
+  E_RM_F32_RESID_STATS, // E_RM_F32_RESID + bf16 copy of the row + partial LayerNorm sums (proj / fc2 in front of a folded LayerNorm)
   E_GENERIC         // any other combination of the Problem's flags (slower, runtime-branched)
 };
 
@@ -299,6 +302,8 @@ __host__ inline int classify(const Problem& p) {
   const bool idx32 = (unsigned long long)p.M * (unsigned long long)p.ldo < (1ull << 31);
   if (!idx32) return E_GENERIC;
   if (p.mode == EPI_ROWMAJOR) {
+    if (p.ln_stats != nullptr) return (!p.out_f32 && p.resid == nullptr) ? (p.act ? E_RM_BF16_GELU_LN : E_RM_BF16_LN) : E_GENERIC;
+    if (p.stats_out != nullptr) return (p.out_f32 && !p.act && p.resid != nullptr && p.out_bf16 != nullptr) ? E_RM_F32_RESID_STATS : E_GENERIC;
     if (p.out_f32 && !p.act && p.resid == nullptr) return E_RM_F32;
     if (p.out_f32 && !p.act && p.resid != nullptr) return E_RM_F32_RESID;
     if (!p.out_f32 && p.resid == nullptr) return p.act ? E_RM_BF16_GELU : E_RM_BF16;
@@ -322,18 +327,68 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];\n" ::"r"(smem_u32(bar) & 0xFEFFFFFFu) : "memory");
 }
 
+// folded LayerNorm, consumer side: {rstd, -mean * rstd} of accumulator row m from the partial sums the producing GEMM left
+__device__ __forceinline__ void ln_row_coeffs(const Problem& p, int m, float& a, float& c) {
+  float S = 0.0f, Q = 0.0f;
+  if (m < p.M) {
+    // ln_parts is even (two column halves per tile) and <= 16: all loads are issued before the first add (one L2 latency)
+    const float4* sp = reinterpret_cast<const float4*>(p.ln_stats + (size_t)m * p.ln_parts);
+    const int n4 = p.ln_parts >> 1;
+    float4 t[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t[i] = i < n4 ? __ldg(sp + i) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { S += t[i].x + t[i].z; Q += t[i].y + t[i].w; }
+  }
+  const float mean = S * p.ln_inv_k;
+  const float var = fmaxf(fmaf(Q, p.ln_inv_k, -mean * mean), 0.0f);
+  a = rsqrtf(var + p.ln_eps);
+  c = -mean * a;
+}
+// L2 prefetch of the rows a warp's epilogue is going to read in phase B (fp32 residual rows / bf16 skip rows of its 32 x ncols
+// block): issued before the warp waits for its accumulator, so that the loads behind the MMAs find their lines in L2
+__device__ __forceinline__ void prefetch_rows_l2(const void* base, size_t row_bytes_pitch, int row0, int rows_valid, uint32_t col_byte0,
+                                                 uint32_t bytes_per_row, int lane) {
+  const uint32_t lines = (bytes_per_row + 127u) >> 7;                   // 128-byte lines per row
+  const uint32_t total = 32u * lines;
+  for (uint32_t i = lane; i < total; i += 32) {
+    const uint32_t rr = i / lines, l = i - rr * lines;
+    if ((int)rr < rows_valid) {
+      const char* a = reinterpret_cast<const char*>(base) + (size_t)(row0 + rr) * row_bytes_pitch + col_byte0 + l * 128u;
+      asm volatile("prefetch.global.L2 [%0];\n" ::"l"(a));
+    }
+  }
+}
+// a warp's private copy of `ncols` (<= 32 * KMAX) consecutive floats of a per-column vector (the ln_s slice of its slabs)
+template <int KMAX>
+__device__ __forceinline__ void stage_column_slice(const float* __restrict__ src, uint32_t dst_s, int ncols, int lane) {
+  float b[KMAX];
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) { const int i = k * 32 + lane; b[k] = i < ncols ? __ldg(src + i) : 0.0f; }
+  __syncwarp();
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    const int i = k * 32 + lane;
+    if (i < ncols) asm volatile("st.shared.f32 [%0], %1;\n" ::"r"(dst_s + 4u * i), "f"(b[k]) : "memory");
+  }
+  __syncwarp();
+}
+
 template <int BN, int EPI, bool PAIR = false>
 __device__ __forceinline__ void epilogue_tile(const Problem& p, uint32_t stg_s, uint32_t bias_s, uint32_t taddr,
                                               uint64_t* tmem_empty_bar, int mrow0, int n0, int lane, int slab_begin, int slab_end,
-                                              HeadCtx* hc = nullptr) {
+                                              HeadCtx* hc = nullptr, float ln_a = 0.0f, float ln_c = 0.0f) {
   using C = Cfg<BN>;
   constexpr bool kHead = EPI == E_CONV_HEAD;
+  constexpr bool kLn = EPI == E_RM_BF16_LN || EPI == E_RM_BF16_GELU_LN;          // consumer of a folded LayerNorm
+  constexpr bool kStats = EPI == E_RM_F32_RESID_STATS && C::SC == 32;             // producer in front of one (8 lanes per staged row)
   static_assert(!kHead || (C::NSLAB == 1 && C::SC == 48), "the fused head epilogue is built for one 48-column slab");
   constexpr bool kSkipAdd = EPI == E_CONV_SKIPADD;
   constexpr bool kConv = EPI == E_CONV || EPI == E_CONV_RAW || kSkipAdd;
   constexpr bool kConvT = EPI == E_CONVT || EPI == E_CONVT_RAW;
-  constexpr bool kF32 = EPI == E_RM_F32 || EPI == E_RM_F32_RESID;
-  constexpr bool kGelu = EPI == E_RM_BF16_GELU || EPI == E_CONV || EPI == E_CONVT || kHead;
+  constexpr bool kF32 = EPI == E_RM_F32 || EPI == E_RM_F32_RESID || EPI == E_RM_F32_RESID_STATS;
+  constexpr bool kResid = EPI == E_RM_F32_RESID || EPI == E_RM_F32_RESID_STATS;
+  constexpr bool kGelu = EPI == E_RM_BF16_GELU || EPI == E_RM_BF16_GELU_LN || EPI == E_CONV || EPI == E_CONVT || kHead;
   constexpr int UPR = kF32 ? C::SC / 4 : C::SC / 8;        // 16-byte units per staged row (a power of two)
   constexpr uint32_t PITCH = (kF32 ? C::SC * 4 : C::SC * 2) + 16;
   const uint32_t rowpix = kHead ? row_info_head(p, mrow0 + lane) : (EPI == E_GENERIC || kConvT || kConv) ? row_info(p, mrow0 + lane) : 0u;
@@ -345,6 +400,13 @@ __device__ __forceinline__ void epilogue_tile(const Problem& p, uint32_t stg_s, 
     __syncwarp();
     if (lane == 0) { if (PAIR) mbar_arrive_leader(tmem_empty_bar); else mbar_arrive(tmem_empty_bar); }
     return;
+  }
+  // partial LayerNorm sums of this warp's rows over the slabs it owns: lane (g = lane >> 3, lane & 7) holds, for j = 0..7, the
+  // four columns `lane & 7` of row 4 j + g of every slab
+  float ps[kStats ? 8 : 1], pq[kStats ? 8 : 1];
+  if constexpr (kStats) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { ps[j] = 0.0f; pq[j] = 0.0f; }
   }
 #pragma unroll 1
   for (int slab = slab_begin; slab < slab_end; ++slab) {
@@ -370,13 +432,27 @@ __device__ __forceinline__ void epilogue_tile(const Problem& p, uint32_t stg_s, 
     } else {
       // ---- phase A
       const uint32_t bsl = bias_s + (uint32_t)(slab - slab_begin) * (C::SC * 4);
+      if constexpr (kLn) {
+        // folded LayerNorm: out = rstd * (acc - mean * s[n]) + b'[n] = ln_a * acc + (ln_c * s[n] + b'[n]); this lane's row owns
+        // ln_a = rstd, ln_c = -mean * rstd; the s slice sits behind the (bf16-pitched) staging rows of this warp
+        const uint32_t lsl = stg_s + 32u * PITCH + (uint32_t)(slab - slab_begin) * (C::SC * 4);
 #pragma unroll
-      for (int c = 0; c < C::SC / 4; ++c) {
-        const uint4 b = lds128(bsl + 16 * c);               // warp-uniform address: broadcast
-        r[4 * c] = __float_as_uint(__uint_as_float(r[4 * c]) + __uint_as_float(b.x));
-        r[4 * c + 1] = __float_as_uint(__uint_as_float(r[4 * c + 1]) + __uint_as_float(b.y));
-        r[4 * c + 2] = __float_as_uint(__uint_as_float(r[4 * c + 2]) + __uint_as_float(b.z));
-        r[4 * c + 3] = __float_as_uint(__uint_as_float(r[4 * c + 3]) + __uint_as_float(b.w));
+        for (int c = 0; c < C::SC / 4; ++c) {
+          const uint4 b = lds128(bsl + 16 * c), sv = lds128(lsl + 16 * c);
+          r[4 * c] = __float_as_uint(fmaf(ln_a, __uint_as_float(r[4 * c]), fmaf(ln_c, __uint_as_float(sv.x), __uint_as_float(b.x))));
+          r[4 * c + 1] = __float_as_uint(fmaf(ln_a, __uint_as_float(r[4 * c + 1]), fmaf(ln_c, __uint_as_float(sv.y), __uint_as_float(b.y))));
+          r[4 * c + 2] = __float_as_uint(fmaf(ln_a, __uint_as_float(r[4 * c + 2]), fmaf(ln_c, __uint_as_float(sv.z), __uint_as_float(b.z))));
+          r[4 * c + 3] = __float_as_uint(fmaf(ln_a, __uint_as_float(r[4 * c + 3]), fmaf(ln_c, __uint_as_float(sv.w), __uint_as_float(b.w))));
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < C::SC / 4; ++c) {
+          const uint4 b = lds128(bsl + 16 * c);               // warp-uniform address: broadcast
+          r[4 * c] = __float_as_uint(__uint_as_float(r[4 * c]) + __uint_as_float(b.x));
+          r[4 * c + 1] = __float_as_uint(__uint_as_float(r[4 * c + 1]) + __uint_as_float(b.y));
+          r[4 * c + 2] = __float_as_uint(__uint_as_float(r[4 * c + 2]) + __uint_as_float(b.z));
+          r[4 * c + 3] = __float_as_uint(__uint_as_float(r[4 * c + 3]) + __uint_as_float(b.w));
+        }
       }
       if constexpr (kHead) {
         // fused 1x1 head: GELU, round to bf16 (registers); once the head MMAs of this buffer's PREVIOUS tile have finished with A2
@@ -478,7 +554,7 @@ __device__ __forceinline__ void epilogue_tile(const Problem& p, uint32_t stg_s, 
           v[j] = make_uint4(w[0], w[1], w[2], w[3]);
         }
       }
-      if constexpr (EPI == E_RM_F32_RESID) {
+      if constexpr (kResid) {
         float4 e[UPR];
 #pragma unroll
         for (int j = 0; j < UPR; ++j) e[j] = live[j] ? *reinterpret_cast<const float4*>(p.resid + off[j]) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -486,6 +562,18 @@ __device__ __forceinline__ void epilogue_tile(const Problem& p, uint32_t stg_s, 
         for (int j = 0; j < UPR; ++j) {
           v[j].x = __float_as_uint(__uint_as_float(v[j].x) + e[j].x); v[j].y = __float_as_uint(__uint_as_float(v[j].y) + e[j].y);
           v[j].z = __float_as_uint(__uint_as_float(v[j].z) + e[j].z); v[j].w = __float_as_uint(__uint_as_float(v[j].w) + e[j].w);
+        }
+      }
+      if constexpr (kStats) {
+        // the new residual row also leaves as bf16 (A operand of the GEMM behind the folded LayerNorm) and feeds the row sums
+#pragma unroll
+        for (int j = 0; j < UPR; ++j) {
+          const float a = __uint_as_float(v[j].x), b = __uint_as_float(v[j].y), c = __uint_as_float(v[j].z), d = __uint_as_float(v[j].w);
+          if (live[j]) {
+            ps[j] += (a + b) + (c + d);
+            pq[j] = fmaf(a, a, fmaf(b, b, fmaf(c, c, fmaf(d, d, pq[j]))));
+            *reinterpret_cast<uint2*>(p.out_bf16 + off[j]) = make_uint2(pack_bf16x2(a, b), pack_bf16x2(c, d));
+          }
         }
       }
 #pragma unroll
@@ -497,6 +585,26 @@ __device__ __forceinline__ void epilogue_tile(const Problem& p, uint32_t stg_s, 
       }
       __syncwarp();
     }
+  }
+  if constexpr (kStats) {
+    // reduce-scatter over the 8 lanes that share a row (xor 4, 2, 1): 14 shuffles for the 2 x 8 partial sums; afterwards lane l
+    // holds the totals of row 4 (l & 7) + (l >> 3) over this warp's columns -> slot 2 (n0 / BN) + column half of that row
+    const bool b2 = (lane & 4) != 0, b1 = (lane & 2) != 0, b0 = (lane & 1) != 0;
+    float t[4], tq[4], u[2], uq[2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      t[i] = (b2 ? ps[i + 4] : ps[i]) + __shfl_xor_sync(0xffffffffu, b2 ? ps[i] : ps[i + 4], 4);
+      tq[i] = (b2 ? pq[i + 4] : pq[i]) + __shfl_xor_sync(0xffffffffu, b2 ? pq[i] : pq[i + 4], 4);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      u[i] = (b1 ? t[i + 2] : t[i]) + __shfl_xor_sync(0xffffffffu, b1 ? t[i] : t[i + 2], 2);
+      uq[i] = (b1 ? tq[i + 2] : tq[i]) + __shfl_xor_sync(0xffffffffu, b1 ? tq[i] : tq[i + 2], 2);
+    }
+    const float w = (b0 ? u[1] : u[0]) + __shfl_xor_sync(0xffffffffu, b0 ? u[0] : u[1], 1);
+    const float wq = (b0 ? uq[1] : uq[0]) + __shfl_xor_sync(0xffffffffu, b0 ? uq[0] : uq[1], 1);
+    const int rr = (lane & 7) * 4 + (lane >> 3);
+    if (rr < rows_valid) p.stats_out[(size_t)(mrow0 + rr) * p.stats_parts + (2 * (n0 / BN) + (slab_begin ? 1 : 0))] = make_float2(w, wq);
   }
 }
 
@@ -823,7 +931,19 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           if (i < ncols) asm volatile("st.shared.f32 [%0], %1;\n" ::"r"(bias_s + 4u * i), "f"(b[k]) : "memory");
         }
         __syncwarp();
+        if constexpr (MODE == MODE_PLAIN) {
+          if (p.ln_s != nullptr)      // folded LayerNorm: the column sums of the weights, behind the bf16-pitched staging rows
+            stage_column_slice<(C::SLAB_SPLIT * C::SC + 31) / 32>(p.ln_s + n0 + slab_begin * C::SC, stg_s + 32u * (C::SC * 2 + 16), ncols, lane);
+        }
       }
+      float ln_a = 0.0f, ln_c = 0.0f;
+      if constexpr (MODE == MODE_PLAIN) {
+        if (epi == E_RM_BF16_LN || epi == E_RM_BF16_GELU_LN) ln_row_coeffs(p, m0 + q * 32 + lane, ln_a, ln_c);
+        if (epi == E_RM_F32_RESID || epi == E_RM_F32_RESID_STATS)
+          prefetch_rows_l2(p.resid, (size_t)p.ldo * 4, m0 + q * 32, p.M - (m0 + q * 32), (uint32_t)(n0 + slab_begin * C::SC) * 4u, (uint32_t)ncols * 4u, lane);
+      }
+      if (epi == E_CONV_SKIPADD)
+        prefetch_rows_l2(p.skip, (size_t)p.ldo * 2, m0 + q * 32, p.M - (m0 + q * 32), (uint32_t)(n0 + slab_begin * C::SC) * 2u, (uint32_t)ncols * 2u, lane);
       mbar_wait(&tmem_full[as], aphase);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
@@ -850,6 +970,9 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         MSD_EPI_CASE(E_CONV_RAW)
         MSD_EPI_CASE(E_CONVT_RAW)
         MSD_EPI_CASE(E_CONV_SKIPADD)
+        MSD_EPI_CASE(E_RM_F32_RESID_STATS)
+        case E_RM_BF16_LN: epilogue_tile<BN, E_RM_BF16_LN>(p, stg_s, bias_s, taddr, &tmem_empty[as], m0 + q * 32, n0, lane, slab_begin, slab_end, nullptr, ln_a, ln_c); break;
+        case E_RM_BF16_GELU_LN: epilogue_tile<BN, E_RM_BF16_GELU_LN>(p, stg_s, bias_s, taddr, &tmem_empty[as], m0 + q * 32, n0, lane, slab_begin, slab_end, nullptr, ln_a, ln_c); break;
         default: epilogue_tile<BN, E_GENERIC>(p, stg_s, bias_s, taddr, &tmem_empty[as], m0 + q * 32, n0, lane, slab_begin, slab_end); break;
       }
 #undef MSD_EPI_CASE

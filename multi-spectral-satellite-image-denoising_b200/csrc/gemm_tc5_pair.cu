@@ -269,7 +269,19 @@ gemm_tc5_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           if (i < ncols) asm volatile("st.shared.f32 [%0], %1;\n" ::"r"(bias_s + 4u * i), "f"(b[k]) : "memory");
         }
         __syncwarp();
+        if constexpr (!MERGED) {
+          if (p.ln_s != nullptr)      // folded LayerNorm: the column sums of the weights, behind the bf16-pitched staging rows
+            stage_column_slice<(C::SLAB_SPLIT * E::SC + 31) / 32>(p.ln_s + n0 + slab_begin * E::SC, stg_s + 32u * (E::SC * 2 + 16), ncols, lane);
+        }
       }
+      float ln_a = 0.0f, ln_c = 0.0f;
+      if constexpr (!MERGED) {
+        if (epi == E_RM_BF16_LN || epi == E_RM_BF16_GELU_LN) ln_row_coeffs(p, m0 + q * 32 + lane, ln_a, ln_c);
+        if (epi == E_RM_F32_RESID || epi == E_RM_F32_RESID_STATS)
+          prefetch_rows_l2(p.resid, (size_t)p.ldo * 4, m0 + q * 32, p.M - (m0 + q * 32), (uint32_t)(n0 + slab_begin * E::SC) * 4u, (uint32_t)ncols * 4u, lane);
+      }
+      if (epi == E_CONV_SKIPADD)
+        prefetch_rows_l2(p.skip, (size_t)p.ldo * 2, m0 + q * 32, p.M - (m0 + q * 32), (uint32_t)(n0 + slab_begin * E::SC) * 2u, (uint32_t)ncols * 2u, lane);
       mbar_wait(&tmem_full[as], aphase);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
@@ -284,6 +296,9 @@ gemm_tc5_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         MSD_EPI_CASE(E_CONVT)
         MSD_EPI_CASE(E_CONVT_RAW)
         MSD_EPI_CASE(E_CONV_SKIPADD)
+        MSD_EPI_CASE(E_RM_F32_RESID_STATS)
+        case E_RM_BF16_LN: epilogue_tile<BN, E_RM_BF16_LN, true>(p, stg_s, bias_s, taddr, &tmem_empty[as], m0 + q * 32, n0, lane, slab_begin, slab_end, nullptr, ln_a, ln_c); break;
+        case E_RM_BF16_GELU_LN: epilogue_tile<BN, E_RM_BF16_GELU_LN, true>(p, stg_s, bias_s, taddr, &tmem_empty[as], m0 + q * 32, n0, lane, slab_begin, slab_end, nullptr, ln_a, ln_c); break;
         default: epilogue_tile<BN, E_GENERIC, true>(p, stg_s, bias_s, taddr, &tmem_empty[as], m0 + q * 32, n0, lane, slab_begin, slab_end); break;
       }
 #undef MSD_EPI_CASE

@@ -42,6 +42,14 @@ int make_linear(Problem& p, const void* a, const void* w, const float* bias, voi
   return MSD_OK;
 }
 
+// LayerNorm folded into the GEMMs around it (gemm.cuh Problem): consumer = qkv / fc1, producer = proj / fc2
+void fold_ln_consumer(Problem& p, const float* stats, int parts, const float* ln_s, float eps, int K) {
+  p.ln_stats = reinterpret_cast<const float2*>(stats); p.ln_parts = parts; p.ln_s = ln_s; p.ln_eps = eps; p.ln_inv_k = 1.0f / (float)K;
+}
+void fold_ln_producer(Problem& p, void* x_bf16, float* stats, int parts) {
+  p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(x_bf16); p.stats_out = reinterpret_cast<float2*>(stats); p.stats_parts = parts;
+}
+
 // skip_in_epilogue: the skip tensor is added by the epilogue warps (E_CONV_SKIPADD) and only nine taps are contracted; the
 // weight matrix keeps its ten-tap packing (row pitch 10 * Kpad), the identity tap is simply not used
 int make_conv3x3(Problem& p, const void* x, const void* w, const float* bias, const void* skip, void* y, int B, int H,
@@ -139,6 +147,29 @@ extern "C" int msd_linear_bf16(const void* d_a, const void* d_w, const float* d_
   return gemm::launch(p, backend, (cudaStream_t)stream);
 }
 
+extern "C" int msd_ln_stats_parts(int N, int M) { return (N > 0 && M > 0 && N % 16 == 0) ? gemm::tc5_stats_parts(N, M) : 0; }
+
+extern "C" int msd_linear_resid_stats_f32(const void* d_a, const void* d_w, const float* d_bias, float* d_x, void* d_x_bf16,
+                                          float* d_stats, int parts, int M, int N, int K, void* stream) {
+  Problem p;
+  MSD_REQUIRE(d_x_bf16 && d_stats, "linear_resid_stats: null pointer");
+  int rc = make_linear(p, d_a, d_w, d_bias, d_x, d_x, M, N, K, 0, 1);
+  if (rc) return rc;
+  fold_ln_producer(p, d_x_bf16, d_stats, parts);
+  return gemm::launch(p, 0, (cudaStream_t)stream);
+}
+
+extern "C" int msd_linear_lnfold_bf16(const void* d_x_bf16, const void* d_w_ln, const float* d_bias_ln, const float* d_ln_s,
+                                      const float* d_stats, int parts, float eps, void* d_out, int M, int N, int K, int act,
+                                      void* stream) {
+  Problem p;
+  MSD_REQUIRE(d_stats && d_ln_s && d_bias_ln, "linear_lnfold: null pointer");
+  int rc = make_linear(p, d_x_bf16, d_w_ln, d_bias_ln, d_out, nullptr, M, N, K, act, 0);
+  if (rc) return rc;
+  fold_ln_consumer(p, d_stats, parts, d_ln_s, eps, K);
+  return gemm::launch(p, 0, (cudaStream_t)stream);
+}
+
 // ResidualBlock skip connection on the tcgen05 path: added by the epilogue warps for >= 96 channels (the conv is bound by its
 // operand loads there: 0.574 -> 0.445 ms at 96 channels, 0.371 -> 0.35 at 192 / 384), as a tenth identity tap through the tensor
 // cores for 48 channels (that conv is bound by its epilogue warps: 0.633 vs 0.669 ms).  MSD_SKIP_TAP=1 / MSD_SKIP_EPI=1 force one
@@ -197,6 +228,7 @@ struct msd_model {
   bool profile = false;
   std::vector<cudaEvent_t> ev;      // 2 per launch
   bool head_fused = false;          // last forward ran the 1x1 head inside the head conv's epilogue
+  bool ln_fused = false;            // the blocks' LayerNorms are folded into the GEMMs around them (tcgen05 backend + *_ln weights)
   std::vector<int> prof_kind;       // 0 gemm/conv (tensor path), 1 attention, 2 layernorm, 3 other
   std::vector<double> prof_flops;   // algorithmic FLOPs of the launch (2*M*N*K on unpadded shapes)
   int prof_count = 0;
@@ -204,8 +236,10 @@ struct msd_model {
 
 namespace {
 
+constexpr int kLnMaxParts = 16;   // 2 * 768 / 96: the narrowest tile a stats-producing GEMM may pick
+
 struct WsLayout {
-  size_t a_pe, x, xn, qkv, att, h, stage[4][3], total;
+  size_t a_pe, x, xn, qkv, att, h, lnp, stage[4][3], total;
 };
 
 size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
@@ -222,6 +256,7 @@ WsLayout ws_layout(const msd_model* m, int B) {
   L.qkv = take(M * 3 * E * 2);
   L.att = take(M * E * 2);
   L.h = take(M * (size_t)d.mlp_hidden * 2);
+  L.lnp = take(M * (size_t)kLnMaxParts * 2 * sizeof(float));     // partial LayerNorm sums of the residual rows
   int hw = m->grid;
   for (int s = 0; s < 4; ++s) {
     hw *= 2;
@@ -257,6 +292,13 @@ extern "C" int msd_model_set_weights(msd_model* m, const msd_model_weights* w) {
   m->blocks.assign(w->blocks, w->blocks + m->d.depth);
   m->w.blocks = m->blocks.data();
   m->has_weights = true;
+  bool all_ln = m->d.gemm_backend == 0 && getenv("MSD_NO_LN_FUSION") == nullptr;
+  for (const msd_block_weights& b : m->blocks) {
+    const int n_set = (b.w_qkv_ln != nullptr) + (b.s_qkv != nullptr) + (b.b_qkv_ln != nullptr) + (b.w_fc1_ln != nullptr) + (b.s_fc1 != nullptr) + (b.b_fc1_ln != nullptr);
+    MSD_REQUIRE(n_set == 0 || n_set == 6, "model_set_weights: the folded-LayerNorm fields of a block must be all set or all NULL");
+    all_ln = all_ln && n_set == 6;
+  }
+  m->ln_fused = all_ln;
   return MSD_OK;
 }
 
@@ -269,7 +311,8 @@ extern "C" int msd_model_launch_count(const msd_model* m) {
   if (!m) return 0;
   // patchify + pe gemm + ln_pos + depth*(ln, qkv, attn, proj, ln, fc1, fc2) + final ln
   // + 4*(zero_halo + convT + 4 conv) + head conv (the 1x1 head rides in its epilogue on the tcgen05 path, else + head 1x1)
-  return 3 + 7 * m->d.depth + 1 + 4 * 6 + (m->head_fused ? 1 : 2);
+  // (with the LayerNorms folded into the GEMMs: 5 launches per block)
+  return 3 + (m->ln_fused ? 5 : 7) * m->d.depth + 1 + 4 * 6 + (m->head_fused ? 1 : 2);
 }
 
 extern "C" void msd_model_destroy(msd_model* m) {
@@ -358,21 +401,43 @@ extern "C" int msd_model_forward(msd_model* m, const float* d_x, const void* d_p
   }
   MSD_TRY(make_linear(p, a_pe, w.w_pe, w.b_pe, x, nullptr, M, E, Kpe, 0, 1));
   MSD_RUN(0, linear_flops(M, E, Kpe), gemm::launch(p, be, s));
-  MSD_RUN(2, 0.0, msd_layernorm_pos_f32(x, w.pe_ln_g, w.pe_ln_b, d.ln_eps_outer, w.pos_embed, m->tokens, M, E, stream));
+  // With folded LayerNorms (m->ln_fused) `xn` holds bf16(x), the un-normalised residual row, and `lnp` its partial {sum, sum sq}:
+  // written by LN+pos for block 0 and by every proj / fc2 epilogue after that; qkv / fc1 normalise in their epilogues.
+  const bool lnf = m->ln_fused;
+  const int parts = lnf ? gemm::tc5_stats_parts(E, M) : 0;
+  float* lnp = reinterpret_cast<float*>(ws + L.lnp);
+  if (lnf) {
+    MSD_REQUIRE(parts > 0 && parts <= kLnMaxParts, "model_forward: unexpected LayerNorm partial count %d", parts);
+    MSD_RUN(2, 0.0, msd_layernorm_pos_stats_f32(x, w.pe_ln_g, w.pe_ln_b, d.ln_eps_outer, w.pos_embed, m->tokens, xn, lnp, parts, M, E, stream));
+  } else {
+    MSD_RUN(2, 0.0, msd_layernorm_pos_f32(x, w.pe_ln_g, w.pe_ln_b, d.ln_eps_outer, w.pos_embed, m->tokens, M, E, stream));
+  }
 
   // 12 pre-norm blocks (encoder.py:312-319): x += proj(attn(LN1 x)); x += fc2(GELU(fc1(LN2 x)))
   for (int l = 0; l < d.depth; ++l) {
     const msd_block_weights& bw = m->blocks[l];
-    MSD_RUN(2, 0.0, msd_layernorm_f32_bf16(x, bw.ln1_g, bw.ln1_b, d.ln_eps_block, xn, M, E, stream));
-    MSD_TRY(make_linear(p, xn, bw.w_qkv, bw.b_qkv, qkv, nullptr, M, 3 * E, E, 0, 0));
+    if (lnf) {
+      MSD_TRY(make_linear(p, xn, bw.w_qkv_ln, bw.b_qkv_ln, qkv, nullptr, M, 3 * E, E, 0, 0));
+      fold_ln_consumer(p, lnp, parts, bw.s_qkv, d.ln_eps_block, E);
+    } else {
+      MSD_RUN(2, 0.0, msd_layernorm_f32_bf16(x, bw.ln1_g, bw.ln1_b, d.ln_eps_block, xn, M, E, stream));
+      MSD_TRY(make_linear(p, xn, bw.w_qkv, bw.b_qkv, qkv, nullptr, M, 3 * E, E, 0, 0));
+    }
     MSD_RUN(0, linear_flops(M, 3 * E, E), gemm::launch(p, be, s));
     MSD_RUN(1, 4.0 * B * d.num_heads * (double)m->tokens * m->tokens * 64, (be == 0 ? msd_attention_tc5_bf16 : msd_attention_bf16)(qkv, att, B, m->tokens, d.num_heads, stream));
     MSD_TRY(make_linear(p, att, bw.w_proj, bw.b_proj, x, x, M, E, E, 0, 1));
+    if (lnf) fold_ln_producer(p, xn, lnp, parts);
     MSD_RUN(0, linear_flops(M, E, E), gemm::launch(p, be, s));
-    MSD_RUN(2, 0.0, msd_layernorm_f32_bf16(x, bw.ln2_g, bw.ln2_b, d.ln_eps_block, xn, M, E, stream));
-    MSD_TRY(make_linear(p, xn, bw.w_fc1, bw.b_fc1, h, nullptr, M, d.mlp_hidden, E, 1, 0));
+    if (lnf) {
+      MSD_TRY(make_linear(p, xn, bw.w_fc1_ln, bw.b_fc1_ln, h, nullptr, M, d.mlp_hidden, E, 1, 0));
+      fold_ln_consumer(p, lnp, parts, bw.s_fc1, d.ln_eps_block, E);
+    } else {
+      MSD_RUN(2, 0.0, msd_layernorm_f32_bf16(x, bw.ln2_g, bw.ln2_b, d.ln_eps_block, xn, M, E, stream));
+      MSD_TRY(make_linear(p, xn, bw.w_fc1, bw.b_fc1, h, nullptr, M, d.mlp_hidden, E, 1, 0));
+    }
     MSD_RUN(0, linear_flops(M, d.mlp_hidden, E), gemm::launch(p, be, s));
     MSD_TRY(make_linear(p, h, bw.w_fc2, bw.b_fc2, x, x, M, E, d.mlp_hidden, 0, 1));
+    if (lnf && l + 1 < d.depth) fold_ln_producer(p, xn, lnp, parts);     // the final LayerNorm reads the fp32 rows itself
     MSD_RUN(0, linear_flops(M, E, d.mlp_hidden), gemm::launch(p, be, s));
   }
   // final LayerNorm (encoder.py:322); tokens [B,144,768] are the NHWC [B,12,12,768] map (satmae_restoration.py:128-133)

@@ -19,6 +19,7 @@ struct TensorTable {
   float* v[kMaxT];
   long long n[kMaxT];
   float lr[kMaxT], wd[kMaxT];
+  float bc1[kMaxT], isbc2[kMaxT];       // per-tensor bias corrections: 1 - beta1^step, 1 / sqrt(1 - beta2^step)
   int count;
 };
 
@@ -59,17 +60,19 @@ __device__ __forceinline__ void adamw_one(float& p, float g, float& m, float& v,
   p -= step_size * (m / denom);
 }
 
-__global__ void __launch_bounds__(kBlock) adamw_kernel(const TensorTable t, float b1, float b2, float eps, float bc1, float inv_sqrt_bc2,
-                                                       float max_norm, const double* __restrict__ sqnorm) {
+__global__ void __launch_bounds__(kBlock) adamw_kernel(const TensorTable t, float b1, float b2, float eps, float max_norm,
+                                                       const double* __restrict__ sqnorm) {
   float clip = 1.0f;
   if (max_norm > 0.0f && sqnorm != nullptr) {
-    const float c = max_norm / ((float)sqrt(*sqnorm) + 1e-6f);      // torch.nn.utils.clip_grad_norm_
+    const double sq = *sqnorm;
+    if (!isfinite(sq)) return;                                       // inf / nan gradients: skip the step (see msd.h)
+    const float c = max_norm / ((float)sqrt(sq) + 1e-6f);            // torch.nn.utils.clip_grad_norm_
     clip = c < 1.0f ? c : 1.0f;
   }
   const long long tid = (long long)blockIdx.x * kBlock + threadIdx.x, stride = (long long)gridDim.x * kBlock;
   for (int k = 0; k < t.count; ++k) {
     float* p = t.p[k]; const float* g = t.g[k]; float* m = t.m[k]; float* v = t.v[k];
-    const float lr = t.lr[k], decay = 1.0f - lr * t.wd[k], step_size = lr / bc1;
+    const float lr = t.lr[k], decay = 1.0f - lr * t.wd[k], step_size = lr / t.bc1[k], inv_sqrt_bc2 = t.isbc2[k];
     const long long n = t.n[k], n4 = n >> 2;
     const bool vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
                        reinterpret_cast<uintptr_t>(v)) & 15u) == 0;
@@ -89,9 +92,12 @@ __global__ void __launch_bounds__(kBlock) adamw_kernel(const TensorTable t, floa
   }
 }
 
-int fill(TensorTable& t, const msd_adamw_tensor* src, int n) {
+int fill(TensorTable& t, const msd_adamw_tensor* src, int n, float beta1 = 0.0f, float beta2 = 0.0f, int step = 1) {
   t.count = n;
   for (int k = 0; k < n; ++k) {
+    const int st = src[k].step > 0 ? src[k].step : step;
+    t.bc1[k] = 1.0f - powf(beta1, (float)st);
+    t.isbc2[k] = 1.0f / sqrtf(1.0f - powf(beta2, (float)st));
     MSD_REQUIRE(src[k].param && src[k].grad && src[k].exp_avg && src[k].exp_avg_sq && src[k].numel > 0, "adamw: null tensor %d", k);
     t.p[k] = src[k].param; t.g[k] = src[k].grad; t.m[k] = src[k].exp_avg; t.v[k] = src[k].exp_avg_sq;
     t.n[k] = src[k].numel; t.lr[k] = src[k].lr; t.wd[k] = src[k].weight_decay;
@@ -119,13 +125,11 @@ extern "C" int msd_adamw_step_f32(const msd_adamw_tensor* tensors, int n, float 
                                   const double* d_sqnorm, void* stream) {
   MSD_REQUIRE(tensors && n > 0 && step >= 1, "adamw_step: bad arguments");
   MSD_REQUIRE(max_grad_norm <= 0.0f || d_sqnorm != nullptr, "adamw_step: clipping needs the squared gradient norm");
-  const float bc1 = 1.0f - powf(beta1, (float)step);
-  const float inv_sqrt_bc2 = 1.0f / sqrtf(1.0f - powf(beta2, (float)step));
   for (int k0 = 0; k0 < n; k0 += kMaxT) {
     TensorTable t;
-    int rc = fill(t, tensors + k0, n - k0 < kMaxT ? n - k0 : kMaxT);
+    int rc = fill(t, tensors + k0, n - k0 < kMaxT ? n - k0 : kMaxT, beta1, beta2, step);
     if (rc) return rc;
-    adamw_kernel<<<148 * 8, kBlock, 0, (cudaStream_t)stream>>>(t, beta1, beta2, eps, bc1, inv_sqrt_bc2, max_grad_norm, d_sqnorm);
+    adamw_kernel<<<148 * 8, kBlock, 0, (cudaStream_t)stream>>>(t, beta1, beta2, eps, max_grad_norm, d_sqnorm);
     MSD_LAUNCH_CHECK();
   }
   return MSD_OK;

@@ -56,7 +56,13 @@ class AddSensorNoise(nn.Module):
         of the corrupted image (lets the restoration model skip its patchify pass).
         """
         if not x.is_cuda:
-            raise _lib.MsdError("AddSensorNoise: CUDA tensor required (libmsd_b200 has no CPU path); got " + str(x.device))
+            # The reference calls the transform per sample on a CPU tensor inside Dataset.__getitem__ (src/data/dataset.py:188-190).
+            # To keep that call site working unchanged the sample is staged through the current CUDA device: H2D copy, the same
+            # kernel, D2H copy.  This is NOT a CPU implementation -- without a CUDA device (or in a forked DataLoader worker, where
+            # CUDA cannot be initialised) it raises, as every other entry point does.
+            if not torch.cuda.is_available():
+                raise _lib.MsdError("AddSensorNoise: a CUDA device is required (libmsd_b200 has no CPU path); got " + str(x.device))
+            return self.forward(x.cuda(), patch_out).to(x.device)
         if x.dtype != torch.float32:
             raise _lib.MsdError(f"AddSensorNoise: float32 required, got {x.dtype}")
         is_batched = x.ndim == 4

@@ -43,6 +43,18 @@ def _bn_fold(bn: nn.BatchNorm2d):
     return scale, shift
 
 
+def pack_ln_folded_linear(weight: torch.Tensor, bias: torch.Tensor, ln_weight: torch.Tensor, ln_bias: torch.Tensor):
+    """LayerNorm folded into the Linear behind it (encoder.py:154-176: qkv(norm1(x)), fc1(norm2(x))):
+        Linear(LN(x))[n] = rstd * (sum_k x_k g_k W_nk - mean * sum_k g_k W_nk) + (b_n + sum_k beta_k W_nk)
+    -> (bf16 [N,K] gamma-scaled weight, fp32 [N] column sums OF THE ROUNDED weight (a constant row then cancels exactly),
+        fp32 [N] bias with the beta term).  The GEMM epilogue applies rstd / mean per row (csrc/gemm.cuh, Problem)."""
+    w = weight.detach().float()
+    wg = _bf16(w * ln_weight.detach().float()[None, :])
+    s = wg.float().sum(dim=1).contiguous()
+    b = (bias.detach().float() + w @ ln_bias.detach().float()).contiguous()
+    return wg, s, b
+
+
 def pack_conv3x3(conv: nn.Conv2d, bn: nn.BatchNorm2d, with_skip: bool = False):
     """[Cout,Cin,3,3] (+BN) -> bf16 [Cout, 9*Kpad] tap-major (ky,kx,ci), fp32 bias [Cout].
 
@@ -198,6 +210,14 @@ class SatMAERestoration(nn.Module):
             bw.w_proj, bw.b_proj = b16(t["proj_w"]), f32(t["proj_b"])
             bw.w_fc1, bw.b_fc1 = b16(t["fc1"].weight), f32(t["fc1"].bias)
             bw.w_fc2, bw.b_fc2 = b16(t["fc2"].weight), f32(t["fc2"].bias)
+            if not encoder_only and self.gemm_backend == 0:
+                # eval forward on the tcgen05 path: norm1 / norm2 ride in the qkv / fc1 GEMMs (no per-block LayerNorm kernel)
+                for wname, lnname, fields in (("qkv", "ln1", ("w_qkv_ln", "s_qkv", "b_qkv_ln")), ("fc1", "ln2", ("w_fc1_ln", "s_fc1", "b_fc1_ln"))):
+                    wt, bs = (t["qkv_w"], t["qkv_b"]) if wname == "qkv" else (t["fc1"].weight, t["fc1"].bias)
+                    packed = pack_ln_folded_linear(wt, bs, t[lnname].weight, t[lnname].bias)
+                    keep.extend(packed)
+                    for field, tensor in zip(fields, packed):
+                        setattr(bw, field, _lib.ptr(tensor))
         keep.append(blocks)
         w.blocks = C.cast(blocks, C.POINTER(_lib.BlockWeights))
         w.norm_g, w.norm_b = f32(enc.norm.weight), f32(enc.norm.bias)
@@ -245,6 +265,13 @@ class SatMAERestoration(nn.Module):
     def _apply(self, fn, recurse=True):
         """Moving / casting the module re-homes every parameter: drop the packed copies made from the old storage."""
         out = super()._apply(fn, recurse)
+        # the C handle owns a side stream and events created on the device it first ran on: a moved model gets a fresh handle
+        if self.__dict__.get("_handle") is not None:
+            try:
+                _lib.load().msd_model_destroy(self._handle)
+            except Exception:  # pragma: no cover
+                pass
+            self._handle = None
         self.__dict__.pop("_frozen_cache", None)
         self._packed, self._packed_key = None, None
         for k in ("_train_packed", "_train_static_key", "_train_versions", "_train_graph"):

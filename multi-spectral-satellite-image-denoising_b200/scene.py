@@ -3,9 +3,10 @@ tiles on a regular grid with overlap, every tile goes through the restoration mo
 back with separable linear-ramp weights.  The reference restores single tiles only: the tiling / blend defined
 here (and restated in oracle/scene.py) is the semantics.
 
-Multi-GPU: the tile grid is split into contiguous row bands, one per rank.  A rank also restores the one tile row above its
-band (halo recompute), so every scene row it owns gathers only tiles it holds and NO collective is needed on the data path;
-each rank returns its own band of scene rows.
+Multi-GPU: the tile grid is split into contiguous row bands, one per rank.  A rank also restores every tile row above its
+band that still covers one of its scene rows (halo recompute: normally one row, two when the edge-anchored last row sits
+closer than `overlap` to its neighbour), so every scene row it owns gathers only tiles it holds and NO collective is needed
+on the data path; each rank returns its own band of scene rows.
 """
 from __future__ import annotations
 
@@ -35,8 +36,9 @@ class BandPlan:
     pixel_rows: Tuple[int, int]    # [row0, row1) scene rows it writes
 
 
-def band_plan(gy: List[int], scene_h: int, rank: int, world: int) -> BandPlan:
-    """Contiguous split of the grid rows; pixel rows are cut at the origin of each band's first tile row."""
+def band_plan(gy: List[int], scene_h: int, rank: int, world: int, tile: int = 192) -> BandPlan:
+    """Contiguous split of the grid rows; pixel rows are cut at the origin of each band's first tile row.  The halo comes from the
+    geometry: every grid row above the band whose tiles reach into the band's first scene row (gy[r] + tile > row0)."""
     ny = len(gy)
     if not (0 <= rank < world):
         raise ValueError(f"rank {rank} outside world {world}")
@@ -48,7 +50,10 @@ def band_plan(gy: List[int], scene_h: int, rank: int, world: int) -> BandPlan:
     row0 = 0 if first == 0 else gy[first]
     nxt = last
     row1 = scene_h if nxt >= ny else gy[nxt]
-    return BandPlan((max(first - 1, 0), last), (first, last), (row0, row1))
+    halo = first
+    while halo > 0 and gy[halo - 1] + tile > row0:
+        halo -= 1
+    return BandPlan((halo, last), (first, last), (row0, row1))
 
 
 @torch.no_grad()
@@ -65,7 +70,7 @@ def restore_scene(model, scene: torch.Tensor, overlap: int = 32, batch: int = 25
     _lib.require_device(scene.device)
     gy, gx = grid_origins(H, tile, overlap), grid_origins(W, tile, overlap)
     ny, nx = len(gy), len(gx)
-    plan = band_plan(gy, H, rank, world)
+    plan = band_plan(gy, H, rank, world, tile)
     r0, r1 = plan.tile_rows
     row0, row1 = plan.pixel_rows
     if row1 <= row0:

@@ -127,6 +127,7 @@ class MetricsTracker:
             raise _lib.MsdError("MetricsTracker.all_reduce: nothing accumulated on this rank")
         dist.all_reduce(self._acc, op=dist.ReduceOp.SUM, group=group)
         self._dirty = True
+        self._pending = None      # a prefetch() issued before the collective holds the LOCAL sums: it must not be read afterwards
 
     def prefetch(self):
         """Start the device -> host copy of the running sums on the current stream (pinned buffer + event).  A later compute()

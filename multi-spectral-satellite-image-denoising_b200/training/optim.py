@@ -28,7 +28,8 @@ class FusedAdamW(torch.optim.Optimizer):
             with torch.enable_grad():
                 loss = closure()
         lib = _lib.load()
-        entries, keep, step_no, hyper, dev = [], [], None, None, None
+        # pass 1: validate everything BEFORE any state is touched (a raise must not leave half-advanced step counters)
+        todo, hyper, dev = [], None, None
         for group in self.param_groups:
             b1, b2 = group["betas"]
             for p in group["params"]:
@@ -36,22 +37,29 @@ class FusedAdamW(torch.optim.Optimizer):
                     continue
                 if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous()):
                     raise _lib.MsdError("FusedAdamW: contiguous fp32 CUDA parameters required (libmsd_b200 has no CPU path)")
-                st = self.state[p]
-                if len(st) == 0:
-                    st["step"] = torch.zeros((), dtype=torch.float32)
-                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
-                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
-                st["step"] += 1
-                k = int(st["step"])
-                if (step_no, hyper) != (None, None) and (step_no, hyper) != (k, (b1, b2, group["eps"])):
-                    raise _lib.MsdError("FusedAdamW: all parameters must share betas / eps and the step count")
-                step_no, hyper, dev = k, (b1, b2, group["eps"]), p.device
-                g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
-                keep.append(g)
-                e = _lib.AdamWTensor()
-                e.param, e.grad, e.exp_avg, e.exp_avg_sq = p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr()
-                e.numel, e.lr, e.weight_decay = p.numel(), float(group["lr"]), float(group["weight_decay"])
-                entries.append(e)
+                if p.grad.dtype != torch.float32 or p.grad.device != p.device:
+                    raise _lib.MsdError("FusedAdamW: fp32 gradients on the parameter's device required")
+                h = (b1, b2, group["eps"])
+                if hyper is not None and (h != hyper or p.device != dev):
+                    raise _lib.MsdError("FusedAdamW: all parameters must share betas / eps and one device")
+                hyper, dev = h, p.device
+                todo.append((p, group))
+        # pass 2: per-parameter state and step (torch.optim.AdamW keeps one step per parameter: a parameter that had no gradient
+        # for a while -- blocks unfrozen mid-run, a resumed checkpoint -- simply carries a smaller count)
+        entries, keep = [], []
+        for p, group in todo:
+            st = self.state[p]
+            if len(st) == 0:
+                st["step"] = torch.zeros((), dtype=torch.float32)
+                st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+            st["step"] += 1
+            g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
+            keep.append(g)
+            e = _lib.AdamWTensor()
+            e.param, e.grad, e.exp_avg, e.exp_avg_sq = p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr()
+            e.numel, e.lr, e.weight_decay, e.step = p.numel(), float(group["lr"]), float(group["weight_decay"]), int(st["step"])
+            entries.append(e)
         if not entries:
             return loss
         _lib.require_device(dev)
@@ -64,5 +72,8 @@ class FusedAdamW(torch.optim.Optimizer):
                 sq = torch.empty(1, dtype=torch.float64, device=dev)
                 _lib.check(lib.msd_grad_sqnorm_f32(table, len(entries), _lib.ptr(sq), s))
                 self.last_grad_sqnorm = sq
-            _lib.check(lib.msd_adamw_step_f32(table, len(entries), hyper[0], hyper[1], hyper[2], step_no, clip, _lib.ptr(sq), s))
+            _lib.check(lib.msd_adamw_step_f32(table, len(entries), hyper[0], hyper[1], hyper[2], 1, clip, _lib.ptr(sq), s))
+        # The kernel wrote the parameters through raw pointers: tell autograd (and every cache keyed on `_version`, e.g. the packed
+        # bf16 / transposed copies of SatMAERestoration) that they changed.
+        torch.autograd.graph.increment_version([p for p, _ in todo])
         return loss

@@ -37,7 +37,7 @@ def test_exports_are_plain_c():
 
 def test_version_and_host_only_entry_points():
     lib = _lib.load()
-    assert lib.msd_version() == 1
+    assert lib.msd_version() == 2
     # ((numel-1)/(256*grid*4)+1)*4  (ATen DistributionTemplates.h:60)
     assert lib.msd_philox_offset_increment(13, 1) == 4
     assert lib.msd_philox_offset_increment(256 * 13 * 192 * 192, 1184) == 408

@@ -16,7 +16,7 @@ import gpu_helpers as gh
 import recipes
 from msd_b200 import _lib
 from msd_b200.models import SatMAERestoration
-from msd_b200.models.satmae_restoration import pack_conv3x3, pack_convt2x2
+from msd_b200.models.satmae_restoration import pack_conv3x3, pack_convt2x2, pack_ln_folded_linear
 from oracle import model as omodel
 
 pytestmark = pytest.mark.gpu
@@ -162,6 +162,67 @@ def test_layernorm_and_pos():
     torch.testing.assert_close(x2, ref, rtol=1e-5, atol=1e-5)
 
 
+@pytest.mark.parametrize("M", [300, 1152, 2304, 2500, 4736])      # single-CTA tiles of several widths; >= 2048 rows: CTA pairs, ragged tail
+def test_layernorm_folded_into_the_gemms_around_it(M):
+    """encoder.py:154-176 without a LayerNorm kernel: the GEMM in front (proj / fc2 shape) leaves x fp32, bf16(x) and partial row
+    sums, the GEMM behind (qkv / fc1 shape) normalises in its epilogue.  Rows get a large common offset so that a wrong mean or a
+    missing `- mean * s` term cannot hide."""
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(M)
+    D, K1 = 768, 320
+    parts = lib.msd_ln_stats_parts(D, M)
+    assert 0 < parts <= 16
+    x0 = (torch.randn(M, D, generator=g) * 2 + torch.randn(M, 1, generator=g) * 3).cuda()
+    a = _bf(torch.randn(M, K1, generator=g)).cuda()
+    w = _bf(torch.randn(D, K1, generator=g) * K1 ** -0.5).cuda()
+    b = torch.randn(D, generator=g).cuda()
+    x = x0.clone()
+    xb = torch.full((M, D), float("nan"), dtype=torch.bfloat16, device="cuda")
+    stats = torch.full((M, parts, 2), float("nan"), device="cuda")
+    _lib.check(lib.msd_linear_resid_stats_f32(_lib.ptr(a), _lib.ptr(w), _lib.ptr(b), _lib.ptr(x), _lib.ptr(xb), _lib.ptr(stats), parts,
+                                              M, D, K1, _lib.stream_ptr()))
+    ref_x = x0 + a.float() @ w.float().t() + b
+    _close(x, ref_x, 2e-3)
+    assert torch.equal(xb, _bf(x))                                     # the bf16 copy is the rounding of the fp32 row it wrote
+    tot = stats.double().sum(1)
+    assert torch.allclose(tot[:, 0], x.double().sum(1), rtol=0, atol=1e-3 * D ** 0.5)
+    assert torch.allclose(tot[:, 1], x.double().pow(2).sum(1), rtol=2e-5, atol=1e-3)
+    # consumer: both epilogue variants (plain, GELU), both eps values, two output widths (N = 2304 / 3072 in the model)
+    gam, bet = (torch.randn(D, generator=g) * 0.3 + 1).cuda(), (torch.randn(D, generator=g) * 0.2).cuda()
+    for N, act, eps in ((2304, 0, 1e-5), (3072, 1, 1e-6), (256, 0, 1e-5)):
+        w2 = (torch.randn(N, D, generator=g) * D ** -0.5).cuda()
+        b2 = torch.randn(N, generator=g).cuda()
+        wg, s, bl = pack_ln_folded_linear(w2, b2, gam, bet)
+        out = torch.full((M, N), float("nan"), dtype=torch.bfloat16, device="cuda")
+        _lib.check(lib.msd_linear_lnfold_bf16(_lib.ptr(xb), _lib.ptr(wg), _lib.ptr(bl), _lib.ptr(s), _lib.ptr(stats), parts, eps,
+                                              _lib.ptr(out), M, N, D, act, _lib.stream_ptr()))
+        ref = F.linear(F.layer_norm(x, (D,), gam, bet, eps), w2, b2)
+        _close(out, F.gelu(ref) if act else ref)
+        # and against the un-fused kernels on the same operands (LayerNorm kernel -> bf16 -> GEMM): same error class
+        xn = torch.empty(M, D, dtype=torch.bfloat16, device="cuda")
+        _lib.check(lib.msd_layernorm_f32_bf16(_lib.ptr(x), _lib.ptr(gam), _lib.ptr(bet), eps, _lib.ptr(xn), M, D, _lib.stream_ptr()))
+        two = gh.linear(xn, _bf(w2), b2, act=act)
+        assert (out.float() - two.float()).abs().max().item() <= 3e-2 * ref.abs().max().item()
+
+
+def test_layernorm_pos_with_stats():
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(9)
+    M, D, parts = 300, 768, 6
+    x = (torch.randn(M, D, generator=g) * 3 + 0.5).cuda()
+    gam, bet, pos = torch.randn(D, generator=g).cuda(), torch.randn(D, generator=g).cuda(), torch.randn(144, D, generator=g).cuda()
+    x1, x2 = x.clone(), x.clone()
+    _lib.check(lib.msd_layernorm_pos_f32(_lib.ptr(x1), _lib.ptr(gam), _lib.ptr(bet), 1e-5, _lib.ptr(pos), 144, M, D, _lib.stream_ptr()))
+    xb = torch.empty(M, D, dtype=torch.bfloat16, device="cuda")
+    stats = torch.full((M, parts, 2), float("nan"), device="cuda")
+    _lib.check(lib.msd_layernorm_pos_stats_f32(_lib.ptr(x2), _lib.ptr(gam), _lib.ptr(bet), 1e-5, _lib.ptr(pos), 144, _lib.ptr(xb),
+                                               _lib.ptr(stats), parts, M, D, _lib.stream_ptr()))
+    assert torch.equal(x1, x2) and torch.equal(xb, _bf(x2))
+    assert torch.all(stats[:, 1:] == 0)
+    assert torch.allclose(stats[:, 0, 0].double(), x2.double().sum(1), atol=1e-2)
+    assert torch.allclose(stats[:, 0, 1].double(), x2.double().pow(2).sum(1), rtol=1e-5)
+
+
 @pytest.mark.parametrize("B", [1, 5, 40])
 @pytest.mark.parametrize("entry", ["msd_attention_tc5_bf16", "msd_attention_bf16"])
 def test_attention_vs_sdpa(entry, B):
@@ -270,8 +331,73 @@ def test_model_batch_independence_and_ragged_tiles(seeded_model):
     assert c["total"] == 96_371_197
     prof = m.profile_memory(batch_size=2)
     assert prof["batch_size"] == 2 and prof["peak_vram_gb"] > 0
-    assert m.launches_per_forward() == 113      # the 1x1 head rides in the head conv
+    assert m.launches_per_forward() == 89       # the 1x1 head rides in the head conv, the blocks' LayerNorms in their GEMMs
     m.cpu()
+
+
+def _oracle_on_gpu(sd, x, chunk=16):
+    """the fp32 oracle evaluated by torch on the device (TF32 off: true fp32 cuBLAS / cuDNN), in chunks"""
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        sd = {k: v.cuda() for k, v in sd.items()}
+        return torch.cat([omodel.restoration_forward(sd, x[i:i + chunk]) for i in range(0, x.shape[0], chunk)])
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+
+
+@pytest.mark.parametrize("B,perturbed", [(32, False), (32, True), (256, False)])
+def test_model_forward_at_benchmark_batch_vs_fp32_oracle(seeded_model, B, perturbed):
+    """The benchmark's own batch: >= 2,048 token rows put every encoder GEMM on the cta_group::2 pair kernels, stage 3 on the
+    resident-weight pair conv and the ResidualBlock skips on E_CONV_SKIPADD -- all under one whole-model check against the fp32
+    oracle evaluated by torch on the device (TF32 off).  Seeded reference weights: the BASELINE bounds (2e-2 max-abs, 1e-3 RMS).
+    Perturbed BatchNorm statistics / decoder biases (folding counts, outputs ~10x larger): the same accuracy relative to the output."""
+    sd = {k: v.clone() for k, v in seeded_model.state_dict().items()}
+    if perturbed:
+        recipes.perturb_decoder_stats(sd)
+    m = SatMAERestoration(recipes.base_config(), block_layout="fallback").eval()
+    m.load_state_dict(sd)
+    m.cuda()
+    x = recipes.model_input(B, seed=500 + B).cuda()
+    with torch.no_grad():
+        y = m(x)
+    ref = _oracle_on_gpu(sd, x)
+    err = (y - ref).abs()
+    rms, std = err.pow(2).mean().sqrt().item(), ref.std().item()
+    if not perturbed:
+        assert err.max().item() <= 2e-2 and rms <= 1e-3, f"max-abs {err.max().item():.3e}, rms {rms:.3e}"
+    assert rms <= 0.02 * std, f"relative rms {rms / std:.3%}"
+    # every image on its own, too (a tile-tail or halo bug would hit single images, not the batch RMS)
+    per_img = err.flatten(1).pow(2).mean(1).sqrt()
+    assert per_img.max().item() <= 0.03 * std, f"worst image rms {per_img.max().item():.3e} vs output std {std:.3e}"
+    assert m.launches_per_forward() == 89
+
+
+def test_model_forward_with_and_without_folded_layernorm(seeded_model, monkeypatch):
+    """A/B: the same weights through the stand-alone LayerNorm kernels (MSD_NO_LN_FUSION) -- both must sit inside the bounds
+    against the oracle and within bf16 noise of each other."""
+    sd = {k: v.clone() for k, v in seeded_model.state_dict().items()}
+    g = torch.Generator().manual_seed(3)
+    for k, v in sd.items():      # non-trivial LayerNorm affine terms (identity at init would hide a folding mistake)
+        if ".norm" in k and k.endswith("weight") and v.ndim == 1:
+            v.copy_(1 + 0.2 * torch.randn(v.shape, generator=g))
+        elif ".norm" in k and k.endswith("bias"):
+            v.copy_(0.1 * torch.randn(v.shape, generator=g))
+    x = recipes.model_input(3, seed=91)
+    ref = omodel.restoration_forward(sd, x)
+    outs = []
+    for no_fuse in (False, True):
+        if no_fuse:
+            monkeypatch.setenv("MSD_NO_LN_FUSION", "1")
+        m = SatMAERestoration(recipes.base_config(), block_layout="fallback").eval()
+        m.load_state_dict(sd)
+        m.cuda()
+        with torch.no_grad():
+            outs.append(m(x.cuda()).cpu())
+        assert m.launches_per_forward() == (113 if no_fuse else 89)
+        _check_pixels(outs[-1], ref)
+    assert (outs[0] - outs[1]).abs().max().item() <= 5e-3
 
 
 def test_forward_is_unchanged_after_moving_the_model_off_and_back_onto_the_device():

@@ -44,7 +44,8 @@ class _Affine(torch.nn.Module):
         return 0.5 * x + 1.0
 
 
-@pytest.mark.parametrize("H,W,overlap,world", [(384, 384, 0, 1), (500, 700, 32, 1), (500, 700, 32, 3), (1000, 433, 96, 2), (192, 192, 0, 1)])
+@pytest.mark.parametrize("H,W,overlap,world", [(384, 384, 0, 1), (500, 700, 32, 1), (500, 700, 32, 3), (1000, 433, 96, 2), (192, 192, 0, 1),
+                                                  (500, 433, 96, 5)])   # last: one rank per tile row, edge row 20 px below its neighbour
 def test_scene_tiling_and_blend_vs_oracle(H, W, overlap, world):
     gen = torch.Generator().manual_seed(H + W)
     scene = torch.randn(5, H, W, generator=gen)

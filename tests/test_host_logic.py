@@ -183,3 +183,25 @@ def test_frozen_parameter_cache_follows_the_parameter_not_the_address():
     assert m._cached_cast(a.reshape(-1), "flat", cast) is cv
     m.double()                                                                     # any _apply drops the packed copies
     assert "_frozen_cache" not in m.__dict__ and m._packed_key is None
+
+
+def test_layernorm_fold_algebra():
+    """pack_ln_folded_linear: Linear(LayerNorm(x)) == rstd * (x . (gamma (.) W)^T - mean * s) + b' -- the identity the GEMM epilogue
+    evaluates (csrc/gemm.cuh, Problem; reference encoder.py:154-176).  fp64 so that only the algebra is tested; the packed weight is
+    bf16-rounded, so the comparison uses the rounded weight on both sides."""
+    import torch.nn.functional as F
+    from msd_b200.models.satmae_restoration import pack_ln_folded_linear
+    g = torch.Generator().manual_seed(0)
+    D, N, M = 768, 96, 17
+    x = torch.randn(M, D, generator=g, dtype=torch.float64) * 2 + 3
+    w, b = torch.randn(N, D, generator=g) * D ** -0.5, torch.randn(N, generator=g)
+    gam, bet = 1 + 0.3 * torch.randn(D, generator=g), 0.2 * torch.randn(D, generator=g)
+    wg, s, bl = pack_ln_folded_linear(w, b, gam, bet)
+    assert wg.dtype == torch.bfloat16 and s.dtype == torch.float32 and bl.dtype == torch.float32
+    for eps in (1e-5, 1e-6):
+        mean, var = x.mean(1, keepdim=True), x.var(1, unbiased=False, keepdim=True)
+        rstd = (var + eps).rsqrt()
+        fused = rstd * (x @ wg.double().t() - mean * s.double()) + bl.double()
+        w_eff = wg.double() / gam.double()             # the weight the fold actually represents after bf16 rounding
+        ref = F.linear(F.layer_norm(x, (D,), gam.double(), None, eps), w_eff) + (b.double() + w.double() @ bet.double())
+        assert (fused - ref).abs().max().item() < 1e-5     # fp32 column sums are the only non-fp64 term

@@ -82,11 +82,37 @@ def convt(name, Cin, Cout, Hin, padded):
     timeit(fn, 2.0 * B * Hin * Hin * 4 * Cout * Cin, name)
 
 
+def lin_ln(name, N, K, act=0, producer=False):
+    """the folded-LayerNorm variants: producer = fp32 residual epilogue + bf16 copy + partial row sums; consumer = rstd/mean epilogue"""
+    if args.only and args.only != name:
+        return
+    parts = lib.msd_ln_stats_parts(768, M)
+    a = torch.randn(M, K, device=dev).to(bf)
+    w = (torch.randn(N, K, device=dev) * K ** -0.5).to(bf)
+    bias, lns = torch.randn(N, device=dev), torch.randn(N, device=dev)
+    stats = torch.rand(M, parts, 2, device=dev)
+    s = _lib.stream_ptr()
+    if producer:
+        x, xb = torch.zeros(M, N, device=dev), torch.empty(M, N, device=dev, dtype=bf)
+        def fn():
+            _lib.check(lib.msd_linear_resid_stats_f32(_lib.ptr(a), _lib.ptr(w), _lib.ptr(bias), _lib.ptr(x), _lib.ptr(xb), _lib.ptr(stats), parts, M, N, K, s))
+    else:
+        out = torch.empty(M, N, device=dev, dtype=bf)
+        def fn():
+            _lib.check(lib.msd_linear_lnfold_bf16(_lib.ptr(a), _lib.ptr(w), _lib.ptr(bias), _lib.ptr(lns), _lib.ptr(stats), parts, 1e-5, _lib.ptr(out), M, N, K, act, s))
+    timeit(fn, 2.0 * M * N * K, name)
+
+
 lin("pe", 768, 3328, out_f32=True)
 lin("qkv", 2304, 768)
 lin("proj", 768, 768, resid=True)
 lin("fc1", 3072, 768, act=1)
 lin("fc2", 768, 3072, resid=True)
+if args.backend == 0:
+    lin_ln("qkv_ln", 2304, 768)
+    lin_ln("proj_stats", 768, 768, producer=True)
+    lin_ln("fc1_ln", 3072, 768, act=1)
+    lin_ln("fc2_stats", 768, 3072, producer=True)
 convt("convt1", 768, 384, 12, False)
 conv("conv1", 384, 24, False)
 conv("conv1_skip", 384, 24, True)
