@@ -212,9 +212,10 @@ def train_step_bench(dev, world, steps=5, warmup=2, micro=64):
     from msd_b200.data import AddSensorNoise
     from msd_b200.models import SatMAERestoration
     from msd_b200.training import CombinedLoss, FusedAdamW
-    from msd_b200.training.distributed import allreduce_gradients
     torch.manual_seed(42)
     model = SatMAERestoration(recipes.base_config(), block_layout="fallback").to(dev).train()
+    if world > 1:
+        model.enable_data_parallel()                     # gradient all-reduce per group, on a side stream, under the backward
     noise = AddSensorNoise(*recipes.NOISE_CONFIGS["base"])
     crit = CombinedLoss(1.0, 0.1)
     opt = FusedAdamW(model.get_optimizer_param_groups(1e-4, 0.05), betas=(0.9, 0.999), max_grad_norm=1.0)
@@ -224,8 +225,7 @@ def train_step_bench(dev, world, steps=5, warmup=2, micro=64):
     def step():
         out = model(noise(clean))
         loss = crit(out, clean)
-        loss.backward()
-        allreduce_gradients(model.parameters())
+        loss.backward()                                  # world > 1: leaves rank-averaged gradients (overlapped NCCL all-reduces)
         opt.step()                                       # global-norm clip (1.0) + AdamW, one fused pass (csrc/optim.cu)
         opt.zero_grad(set_to_none=True)
         return loss
@@ -253,6 +253,87 @@ def train_step_bench(dev, world, steps=5, warmup=2, micro=64):
             "note": "corrupt + fwd + loss + bwd + clip/AdamW all in libmsd_b200 (bf16 tensor cores, fp32 accumulate / master weights)"}
 
 
+def loss_bench(dev, hbm, facts, micro=64, iters=10):
+    """MSE + 0.1 (1 - SSIM) forward + analytic backward (config C4's loss at micro-batch 64): reads pred and target, writes the
+    gradient = 5.75 MB per tile."""
+    from msd_b200.training import CombinedLoss
+    clean, pred = recipes.eurosat_tiles(32, seed=7)
+    clean = clean.repeat(micro // 32, 1, 1, 1).to(dev).contiguous()
+    pred = pred.repeat(micro // 32, 1, 1, 1).to(dev).contiguous()
+    crit = CombinedLoss(1.0, 0.1)
+
+    def one():
+        p = pred.detach().requires_grad_(True)
+        crit(p, clean).backward()
+
+    for _ in range(3):
+        one()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(iters):
+        one()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    nbytes = micro * 3 * TILE_ELEMS * 4
+    return {"kernel": "loss_fwd_kernel + loss_bwd_kernel: CombinedLoss forward + backward, micro-batch 64 (config C4)", "ms": ms,
+            "algorithmic_bytes": nbytes, "unit": "GB/s", "achieved": nbytes / ms / 1e6, "peak": hbm, "frac": nbytes / ms / 1e6 / hbm,
+            **facts.get("loss_kernels", {})}
+
+
+# ------------------------------------------------------------------------------------------------ full scene (C5)
+def scene_bench(model, dev, rank, world, size=10980, overlap=32, batch=256):
+    """BASELINE config C5: a synthetic 13 x 10980 x 10980 Sentinel-2 scene -> 192 x 192 tiles with overlap 32 (4,761 tiles), tile
+    rows sharded over the ranks in contiguous bands (halo rows recomputed, no data-path collective) -> restore -> overlap-blend
+    -> msd_export_u16 -> NCCL gather of the uint16 bands to rank 0 -> D2H into pinned host memory (the writer's buffer)."""
+    import torch.distributed as dist
+    from msd_b200.scene import grid_origins, restore_scene, scene_to_dn
+    g = torch.Generator(device=dev)
+    g.manual_seed(1)
+    scene = torch.empty(13, size, size, device=dev)
+    for c in range(13):
+        scene[c] = torch.rand(size, size, generator=g, device=dev) * 4 - 2
+    host = torch.empty(13, size, size, dtype=torch.uint16, pin_memory=True) if rank == 0 else None
+    small = scene[:, :400, :400].contiguous()
+    b, r = restore_scene(model, small, overlap=overlap, batch=4)                       # warm-up (kernels, allocator)
+    scene_to_dn(b, r, 400)
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e[0].record()
+    band, rows = restore_scene(model, scene, overlap=overlap, batch=batch, rank=rank, world=world)
+    e[1].record()
+    scene_to_dn(band, rows, size, rank, world, host_out=host)
+    e[2].record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e[0].elapsed_time(e[2]), e[0].elapsed_time(e[1])], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    n = len(grid_origins(size, 192, overlap)) ** 2
+    total_s, restore_s = ms[0].item() / 1e3, ms[1].item() / 1e3
+    ok = bool(torch.isfinite(band).all()) and (host is None or int(host[:, ::997, ::991].to(torch.int32).max()) <= 10000)
+    del scene, band
+    torch.cuda.empty_cache()
+    return {"scene": f"13x{size}x{size} fp32 (6.27 GB)", "tile": 192, "overlap": overlap, "tiles": n, "seconds": total_s,
+            "restore_blend_seconds": restore_s, "export_gather_d2h_seconds": total_s - restore_s, "tiles_per_s": n / total_s,
+            "scene_gb_per_s": 13 * size * size * 4 / 1e9 / total_s, "d2h_bytes": 13 * size * size * 2, "ranks": world,
+            "sharding": "contiguous tile-row bands, halo rows recomputed, no data-path collective; uint16 bands gathered to rank 0",
+            "ok": ok}
+
+
+def ncu_facts():
+    """Figures that only a profiler can give (DRAM bytes per launch, tensor-pipe / issue-slot activity): read from the newest
+    profiles/r*_ncu_metrics.json (written by tools/ncu_extract.py from the .ncu-rep captures), never typed into this file."""
+    files = sorted((ROOT / "profiles").glob("r*_ncu_metrics.json"))
+    if not files:
+        return {}
+    d = json.loads(files[-1].read_text())
+    d["source"] = f"profiles/{files[-1].name}"
+    return d
+
+
 # ------------------------------------------------------------------------------------------------ CUDA arm
 def main():
     ap = argparse.ArgumentParser()
@@ -264,6 +345,7 @@ def main():
     ap.add_argument("--backend", type=int, default=0, help="0 tcgen05 (product), 1 legacy mma.sync (A/B)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the C4 training-step measurement")
+    ap.add_argument("--no-scene", action="store_true", help="skip the C5 full-scene measurement")
     ap.add_argument("--profile-out", default=None, help="write the per-launch event profile (json) here")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -341,43 +423,70 @@ def main():
             if world > 1:
                 tracker.all_reduce()
         metrics_dev = tracker.compute()
+        # ---------------- roofline_hbm: the bandwidth-bound kernels of the same step, CUDA events on the launching stream
+        hev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
+        for it in range(K):
+            hev[it][0].record()
+            noisy_ = noise(clean_dev, patch_out=patches)
+            hev[it][1].record()
+            restored_ = model(noisy_, patches=patches)
+            hev[it][2].record()
+            tracker.update(restored_, clean_dev)
+            hev[it][3].record()
+        torch.cuda.synchronize()
+        corrupt_ms = sum(h[0].elapsed_time(h[1]) for h in hev) / K
+        metrics_ms = sum(h[2].elapsed_time(h[3]) for h in hev) / K
         # ---------------- e2e: host buffers in, metric sums out, every step.  The H2D copy of step i+1 runs on a
         # copy stream while step i computes (two device buffers); every step's copy is inside the timed region.
         copy_stream = torch.cuda.Stream(device=dev)
-        bufs = [torch.empty_like(clean_dev) for _ in range(2)]
+        from msd_b200.data import ingest_tiles
+        # mode "u16": the reference's real data flow (src/data/dataset.py:160-186) -- raw uint16 64x64 digital numbers in pinned
+        # host memory, 27 MB per step; the ingest kernel (scale, bilinear 64 -> 192, clamp, normalise) runs on the device in front
+        # of the corruption.  mode "f32": pre-processed fp32 192x192 tiles from the host, 491 MB per step.
+        gen = torch.Generator().manual_seed(100 + rank)
+        dn_host = torch.randint(0, 5200, (B, 13, 64, 64), generator=gen, dtype=torch.int32).to(torch.uint16).pin_memory()
         ready = [torch.cuda.Event() for _ in range(2)]
         freed = [torch.cuda.Event() for _ in range(2)]
 
-        def prefetch(i):
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(freed[i % 2])
-                bufs[i % 2].copy_(clean_host, non_blocking=True)
-                ready[i % 2].record(copy_stream)
+        def make_e2e(host_src):
+            bufs = [torch.empty(host_src.shape, dtype=host_src.dtype, device=dev) for _ in range(2)]
 
-        def e2e_run(steps):
-            for b in range(2):
-                freed[b].record()
-            prefetch(0)
-            out, prev = None, None
-            for i in range(steps):
-                if i + 1 < steps:
-                    prefetch(i + 1)
-                torch.cuda.current_stream().wait_event(ready[i % 2])
-                c = bufs[i % 2]
-                t = MetricsTracker()
-                noisy = noise(c, patch_out=patches)
-                restored = model(noisy, patches=patches)
-                t.update(restored, c)
-                t.prefetch()                                # D2H of the 5 fp64 sums of THIS step, behind its kernels
-                freed[i % 2].record()
-                if prev is not None:
-                    out = prev.compute()                    # read step i-1's result while step i runs (its launches are queued)
-                prev = t
-            out = prev.compute()
-            return out
+            def prefetch(i):
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(freed[i % 2])
+                    bufs[i % 2].copy_(host_src, non_blocking=True)
+                    ready[i % 2].record(copy_stream)
 
-        e2e_run(2)
-        ms_e2e = timed(lambda: e2e_run(K), 1)
+            def e2e_run(steps):
+                for b in range(2):
+                    freed[b].record()
+                prefetch(0)
+                out, prev = None, None
+                for i in range(steps):
+                    if i + 1 < steps:
+                        prefetch(i + 1)
+                    torch.cuda.current_stream().wait_event(ready[i % 2])
+                    c = bufs[i % 2]
+                    if c.dtype == torch.uint16:
+                        c = ingest_tiles(c, 192)                # raw digital numbers -> the model's normalisation, on the device
+                    t = MetricsTracker()
+                    noisy = noise(c, patch_out=patches)
+                    restored = model(noisy, patches=patches)
+                    t.update(restored, c)
+                    t.prefetch()                                # D2H of the 5 fp64 sums of THIS step, behind its kernels
+                    freed[i % 2].record()
+                    if prev is not None:
+                        out = prev.compute()                    # read step i-1's result while step i runs (its launches are queued)
+                    prev = t
+                out = prev.compute()
+                return out
+            return e2e_run
+
+        e2e_u16, e2e_f32 = make_e2e(dn_host), make_e2e(clean_host)
+        e2e_u16(2)
+        ms_e2e = timed(lambda: e2e_u16(K), 1)
+        e2e_f32(2)
+        ms_e2e_f32 = timed(lambda: e2e_f32(K), 1)
         # ---------------- roofline: per-launch CUDA events inside the library, same steps again
         lib = _lib.load()
         _lib.check(lib.msd_model_profile_enable(model._handle, 1))
@@ -400,7 +509,10 @@ def main():
     ms_step = ms_total / K
     value = world * B * K / (ms_total / 1e3)
     e2e_value = world * B * K / (ms_e2e / 1e3)
+    e2e_f32_value = world * B * K / (ms_e2e_f32 / 1e3)
+    facts = ncu_facts()
     pk = peaks()
+    hbm = pk["hbm_gbs"]
     gemm_ms, gemm_flops, gemm_n = agg.get(0, [0.0, 0.0, 0])
     family_tf = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
     # dominant kernel = the encoder GEMMs (patch embedding + 12 x {qkv, proj, fc1, fc2}): launch order is pe GEMM, LN+pos, then
@@ -414,6 +526,7 @@ def main():
     if args.backend != 0:
         achieved_tf, enc_ms, enc_flops, enc_n = family_tf, gemm_ms, gemm_flops, gemm_n
     launches_per_step = 2 + (model.launches_per_forward() - 1) + 2      # corrupt(2) + forward (patchify fused away) + metrics(fused pass + finalize)
+    n_forward_launches = model.launches_per_forward()
 
     line = {
         "metric": METRIC, "value": value, "unit": "img/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_step,
@@ -424,8 +537,12 @@ def main():
                    "noise": "gaussian 0.015, speckle 0.008, dead-band 0.08, thermal 0.005 (configs/base.yaml)",
                    "gemm_backend": "tcgen05" if args.backend == 0 else "mma.sync",
                    "l2": "per-step working set (491 MB clean + 6.2 GB activations) exceeds the 126 MB L2; no flush needed"},
-        "e2e": {"value": e2e_value, "unit": "img/s", "ms_per_step": ms_e2e / K, "h2d_bytes_per_step": B * TILE_ELEMS * 4,
-                "d2h_bytes_per_step": 40},
+        # headline e2e: the reference's real data flow -- raw uint16 64x64 digital numbers from pinned host memory, the dataset's
+        # preprocessing (src/data/dataset.py:160-186) as the ingest kernel in front of the corruption; e2e_f32: pre-processed fp32 tiles
+        "e2e": {"value": e2e_value, "unit": "img/s", "ms_per_step": ms_e2e / K, "h2d_bytes_per_step": B * 13 * 64 * 64 * 2,
+                "d2h_bytes_per_step": 40, "mode": "uint16 13x64x64 DN tiles (host, pinned) -> H2D -> ingest kernel -> corrupt -> restore -> metrics -> D2H of the 5 fp64 sums"},
+        "e2e_f32": {"value": e2e_f32_value, "unit": "img/s", "ms_per_step": ms_e2e_f32 / K, "h2d_bytes_per_step": B * TILE_ELEMS * 4,
+                    "d2h_bytes_per_step": 40, "mode": "fp32 13x192x192 tiles (host, pinned) -> H2D -> corrupt -> restore -> metrics -> D2H"},
         "gpu_launches": launches_per_step * K,
         "roofline": {"bound": "tensor", "kernel": "gemm_tc5_pair_kernel<256,0> (cta_group::2 tcgen05 GEMM): the encoder GEMMs pe/qkv/proj/fc1/fc2, 49 of its 54 launches per step" if args.backend == 0 else "gemm_hmma_kernel<BN> (whole GEMM/conv family)",
                      "achieved": achieved_tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": achieved_tf / pk["tf_sustained"],
@@ -434,11 +551,10 @@ def main():
                      # qkv GEMM, 36 of 70 launches are this shape class), ncu --set full, profiles/r1_v3_ncu_full_summaries.txt;
                      # its algorithmic bytes are 56.6 MB (A) + 3.5 MB (W) + 169.9 MB (out): the 126 MB L2 still holds part of the
                      # output when the capture ends, nothing is re-read
-                     "traffic": 181.7e6 if args.backend == 0 else None,
-                     "traffic_kernel": "gemm_tc5_pair_kernel<256,0> on the qkv shape (M=36864, N=2304, K=768), bytes per launch",
-                     "tensor_pipe_active_pct_ncu": {"qkv": 71.2, "fc2": 66.6, "conv 24x24x384": 75.5, "conv 96x96x96": 50.2,
-                                                    "conv 192x192x48": 32.6, "attention (tcgen05)": 22.5, "head conv + fused 1x1": 37.6,
-                                                   "source": "profiles/r1_v3_ncu_full_summaries.txt (GEMM kernels, unchanged since) + profiles/r1_v4_ncu_full_summaries.txt"},
+                     "traffic": facts.get("traffic_dominant_bytes") if args.backend == 0 else None,
+                     "traffic_kernel": facts.get("traffic_dominant_kernel"),
+                     "tensor_pipe_active_pct_ncu": facts.get("tensor_pipe_active_pct"),
+                     "ncu_source": facts.get("source"),
                      "launches_per_step": enc_n, "ms_per_step": enc_ms,
                      "algorithmic_gflop_per_step": enc_flops / 1e9,
                      "share_of_step": enc_ms / ms_step if ms_step > 0 else None,
@@ -448,13 +564,35 @@ def main():
                                 "algorithmic_gflop_per_step": gemm_flops / 1e9, "share_of_step": gemm_ms / ms_step if ms_step > 0 else None},
                      "other_ms_per_step": {"attention": agg.get(1, [0])[0], "layernorm": agg.get(2, [0])[0], "other_model": agg.get(3, [0])[0]},
                      "forward_tflops_whole_step": B * FWD_GFLOP_PER_IMG / ms_step / 1e3},
+        # the bandwidth-bound kernels of the same step: algorithmic bytes / CUDA-event time on the launching stream,
+        # against the measured copy bandwidth; issue_active_pct / dram_pct from the ncu captures (they are instruction-issue bound:
+        # the bit-exact torch Philox stream, the 11x11 blur and the SSIM rational cost more issue slots than HBM cycles)
+        "roofline_hbm": [
+            {"kernel": "corrupt_kernel (+ dead_mask_kernel): AddSensorNoise, also writes the bf16 patch-embed operand",
+             "ms": corrupt_ms, "algorithmic_bytes": B * (2 * TILE_ELEMS * 4 + TILE_ELEMS * 2), "unit": "GB/s",
+             "achieved": B * (2 * TILE_ELEMS * 4 + TILE_ELEMS * 2) / corrupt_ms / 1e6, "peak": hbm,
+             "frac": B * (2 * TILE_ELEMS * 4 + TILE_ELEMS * 2) / corrupt_ms / 1e6 / hbm, **facts.get("corrupt_kernel", {})},
+            {"kernel": "metrics_fused_kernel (+ finalize): PSNR / SSIM / SAM / RMSE, one pass over pred and target",
+             "ms": metrics_ms, "algorithmic_bytes": B * 2 * TILE_ELEMS * 4, "unit": "GB/s",
+             "achieved": B * 2 * TILE_ELEMS * 4 / metrics_ms / 1e6, "peak": hbm, "frac": B * 2 * TILE_ELEMS * 4 / metrics_ms / 1e6 / hbm,
+             **facts.get("metrics_fused_kernel", {})},
+            {"kernel": "layernorm_kernel: LN + pos_embed (+ bf16 copy, row sums) and the final LayerNorm; the 24 block LayerNorms ride in GEMM epilogues",
+             "ms": agg.get(2, [0.0])[0], "launches": agg.get(2, [0, 0, 0])[2],
+             "algorithmic_bytes": B * 144 * 768 * (4 + 4 + 2 + 4 + 2), "unit": "GB/s",
+             "achieved": (B * 144 * 768 * 16 / agg[2][0] / 1e6) if agg.get(2, [0.0])[0] > 0 else None, "peak": hbm,
+             "frac": (B * 144 * 768 * 16 / agg[2][0] / 1e6 / hbm) if agg.get(2, [0.0])[0] > 0 else None},
+        ],
         "clocks": clk.summary(),
         "quality": {k: float(v) for k, v in metrics_dev.items()},
     }
+    if not args.no_scene and args.backend == 0:
+        with torch.no_grad():
+            line["scene"] = scene_bench(model, dev, rank, world)
     if not args.no_train and args.backend == 0:
         del model
         torch.cuda.empty_cache()
         line["train_step"] = train_step_bench(dev, world)
+        line["roofline_hbm"].append(loss_bench(dev, hbm, facts))
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r = cpu_baseline_run(steps=8, warmup=2)
         line["cpu_baseline"] = {"value": r["value"], "unit": "img/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}

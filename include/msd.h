@@ -328,6 +328,14 @@ int msd_model_forward_train(msd_model* m, const float* d_x, int B, float* d_y, v
 int msd_model_backward(msd_model* m, const float* d_grad_y, int B, void* d_ws, size_t ws_bytes, const msd_model_grads* grads,
                        void* stream);
 
+/* Gradient groups for the data-parallel step ("gradients averaged over ranks, overlapped with backward").
+ * msd_model_backward records one event per group when that group's gradients are complete (main and weight-gradient stream):
+ *   group 0 = every decoder parameter, group 1 + j = encoder block depth-1-j (group 1 also encoder.norm), group depth+1 = patch
+ *   embedding, its LayerNorm and pos_embed.  msd_model_grad_group_wait makes `stream` wait for group k of the LAST backward, so the
+ *   caller can start that group's all-reduce on a communication stream while the rest of the backward is still running. */
+int msd_model_grad_groups(const msd_model* m);
+int msd_model_grad_group_wait(msd_model* m, int group, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------
  * Data formats either side of the path (csrc/ingest.cu).
  * msd_ingest_u16_f32: EuroSATMultiSpectral.__getitem__ preprocessing (src/data/dataset.py:160-186) for a batch of raw tiles:

@@ -151,6 +151,8 @@ SIGNATURES = {
     "msd_model_train_workspace_bytes": (c_size_t, [c_void_p, c_int]),
     "msd_model_forward_train": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "msd_model_backward": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_size_t, C.POINTER(ModelGrads), c_void_p]),
+    "msd_model_grad_groups": (c_int, [c_void_p]),
+    "msd_model_grad_group_wait": (c_int, [c_void_p, c_int, c_void_p]),
     "msd_ingest_u16_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "msd_export_u16": (c_int, [c_void_p, c_void_p, C.c_longlong, c_void_p]),
     "msd_tile_extract_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),

@@ -95,74 +95,97 @@ struct CorruptParams {
   const uint8_t* dead;      // [B*C] or null
   const float* stripe;      // [B*C*W] normals or null
   __nv_bfloat16* patch;     // optional bf16 patch operand
-  int64_t numel;
+  uint32_t numel;
   uint32_t T;               // torch threads of the full-size draws
   uint32_t rounds;
+  uint32_t hw, dplane, dpix; // H*W and T = dplane * hw + dpix: element e + T sits dplane planes and dpix pixels further
   FastDiv div_hw, div_c, div_w;
   int C, H, W;
   float sg, ss, st;
   uint64_t seed, off_g, off_s, off_t;
-  // patchify
-  int P, gridw;             // patch size, patches per row
+  int gridw;                // patches per row (patch size 16)
 };
 
+// kFast: every noise term on, dead-band mask present, no striping -- the configuration of every reference config
+// (configs/*.yaml); the flags are compile-time there, so the per-element code carries no predicates.  kPatch: also emit the
+// bf16 patch-embedding operand.  The generic instantiation <false, false> reads the flags at run time.
+// Instruction budget (the kernel is issue-bound, not HBM-bound): 3 Philox4x32-10 blocks (~130) + 6 Box-Muller pairs with
+// cuRAND's full-precision logf / sqrtf (~330, fixed by bit-exactness with torch) per 4 elements, + ~45 per element of index
+// arithmetic, fp32 ops and stores.
+template <bool kFast, bool kPatch>
 __global__ void __launch_bounds__(kThreads) corrupt_kernel(const CorruptParams p) {
+  __shared__ float tw[64];                                         // thermal weights (C <= 64), else read through __ldg
+  const bool has_g = kFast || p.sg > 0.0f, has_s = kFast || p.ss > 0.0f, has_t = kFast || p.st > 0.0f;
+  const bool has_dead = kFast || p.dead != nullptr, has_stripe = !kFast && p.stripe != nullptr;
+  const bool has_patch = kPatch || (!kFast && p.patch != nullptr);
+  const bool tw_smem = p.C <= 64;
+  if (has_t && tw_smem) {
+    if (threadIdx.x < p.C) tw[threadIdx.x] = __ldg(p.thermal_w + threadIdx.x);
+    __syncthreads();
+  }
   const uint32_t round = blockIdx.y;                               // torch-thread call number
   const uint32_t tid = blockIdx.x * kThreads + threadIdx.x;       // torch-thread index (T % 256 == 0)
-  const int64_t e0 = (int64_t)round * 4 * p.T + tid;
+  const uint32_t e0 = round * 4u * p.T + tid;                      // < 2^31 + 4T: fits 32 bits
 
+  // element ii = e0 + ii * T: (plane, pixel) of the first one by division, the others by adding T's (planes, pixels)
+  uint32_t plane[4], pix[4];
+  fd_divmod(e0, p.div_hw, plane[0], pix[0]);
+#pragma unroll
+  for (int ii = 1; ii < 4; ++ii) {
+    uint32_t q = pix[ii - 1] + p.dpix, pl = plane[ii - 1] + p.dplane;
+    if (q >= p.hw) { q -= p.hw; ++pl; }
+    pix[ii] = q; plane[ii] = pl;
+  }
   float x[4];
-  bool ok[4];
+  bool ok[4], dead[4];
 #pragma unroll
   for (int ii = 0; ii < 4; ++ii) {
-    int64_t e = e0 + (int64_t)ii * p.T;
+    const uint32_t e = e0 + (uint32_t)ii * p.T;
     ok[ii] = e < p.numel;
     x[ii] = ok[ii] ? __ldg(p.clean + e) : 0.0f;
+    dead[ii] = has_dead && ok[ii] && __ldg(p.dead + plane[ii]) != 0;
   }
   float n1[4] = {0, 0, 0, 0}, n2[4] = {0, 0, 0, 0}, n3[4] = {0, 0, 0, 0};
-  if (p.sg > 0.0f) {
+  if (has_g) {
     float4 r = torch_normal4(p.seed, p.off_g, tid, round);
     n1[0] = r.x; n1[1] = r.y; n1[2] = r.z; n1[3] = r.w;
   }
-  if (p.ss > 0.0f) {
+  if (has_s) {
     float4 r = torch_normal4(p.seed, p.off_s, tid, round);
     n2[0] = r.x; n2[1] = r.y; n2[2] = r.z; n2[3] = r.w;
   }
-  if (p.st > 0.0f) {
+  if (has_t) {
     float4 r = torch_normal4(p.seed, p.off_t, tid, round);
     n3[0] = r.x; n3[1] = r.y; n3[2] = r.z; n3[3] = r.w;
   }
 #pragma unroll
   for (int ii = 0; ii < 4; ++ii) {
     if (!ok[ii]) continue;
-    const uint32_t e = (uint32_t)(e0 + (int64_t)ii * p.T);
-    uint32_t plane, pix;            // plane = b*C + c
-    fd_divmod(e, p.div_hw, plane, pix);
-    uint32_t b, c;
-    fd_divmod(plane, p.div_c, b, c);
+    const uint32_t e = e0 + (uint32_t)ii * p.T;
+    uint32_t b, c;                  // plane = b*C + c
+    fd_divmod(plane[ii], p.div_c, b, c);
     float v = x[ii];
     // 1. additive Gaussian: corrupted + randn*sigma            (transforms.py:90-92)
-    if (p.sg > 0.0f) v = __fadd_rn(v, __fmul_rn(torch_normal_xf(n1[ii]), p.sg));
+    if (has_g) v = __fadd_rn(v, __fmul_rn(torch_normal_xf(n1[ii]), p.sg));
     // 2. speckle: corrupted * (1.0 + randn*sigma)               (transforms.py:95-97)
-    if (p.ss > 0.0f) v = __fmul_rn(v, __fadd_rn(__fmul_rn(torch_normal_xf(n2[ii]), p.ss), 1.0f));
+    if (has_s) v = __fmul_rn(v, __fadd_rn(__fmul_rn(torch_normal_xf(n2[ii]), p.ss), 1.0f));
     // 3. dead bands zeroed BEFORE thermal noise                 (transforms.py:100-106)
-    if (p.dead != nullptr && p.dead[plane]) v = 0.0f;
+    if (dead[ii]) v = 0.0f;
     // 4. thermal: corrupted + (randn*scale)*w_c                 (transforms.py:110-121)
-    if (p.st > 0.0f) v = __fadd_rn(v, __fmul_rn(__fmul_rn(torch_normal_xf(n3[ii]), p.st), __ldg(p.thermal_w + c)));
+    if (has_t) v = __fadd_rn(v, __fmul_rn(__fmul_rn(torch_normal_xf(n3[ii]), p.st), tw_smem ? tw[c] : __ldg(p.thermal_w + c)));
     uint32_t yy, xx;
-    fd_divmod(pix, p.div_w, yy, xx);
+    fd_divmod(pix[ii], p.div_w, yy, xx);
     // 5. striping: x + randn(B,C,1,W)*0.02                      (transforms.py:136-154)
-    if (p.stripe != nullptr) v = __fadd_rn(v, __fmul_rn(__ldg(p.stripe + (size_t)plane * p.W + xx), 0.02f));
+    if (has_stripe) v = __fadd_rn(v, __fmul_rn(__ldg(p.stripe + plane[ii] * (uint32_t)p.W + xx), 0.02f));
     // clamp(-3, 3), NaN-propagating like torch.clamp            (transforms.py:128)
     v = (v != v) ? v : fminf(fmaxf(v, -3.0f), 3.0f);
     p.noisy[e] = v;
-    if (p.patch != nullptr) {
-      // A[(b*gh + py)*gw + px][c*P*P + ky*P + kx]                (encoder.py:48-50)
-      // patch size is 16 (the only one the model supports): shifts instead of runtime integer divisions, 32-bit offsets
+    if (has_patch) {
+      // A[(b*gh + py)*gw + px][c*P*P + ky*P + kx]  (encoder.py:48-50), patch size 16: offset = b * (C*H*W) [= b*gw*gw * C*256]
+      // + (py*gw + px) * C*256 + c*256 + ky*16 + kx -- all of it < numel < 2^31, 32-bit arithmetic
       const uint32_t py = yy >> 4, ky = yy & 15u, px = xx >> 4, kx = xx & 15u;
-      const uint32_t row = (b * (uint32_t)p.gridw + py) * (uint32_t)p.gridw + px;
-      const uint32_t col = (c << 8) + (ky << 4) + kx;
-      p.patch[(size_t)row * ((size_t)p.C << 8) + col] = __float2bfloat16_rn(v);
+      const uint32_t off = ((b * (uint32_t)p.gridw + py) * (uint32_t)p.gridw + px) * ((uint32_t)p.C << 8) + (c << 8) + (ky << 4) + kx;
+      p.patch[off] = __float2bfloat16_rn(v);
     }
   }
 }
@@ -236,18 +259,24 @@ extern "C" int msd_corrupt_f32(const float* d_clean, float* d_noisy, const float
   cp.dead = p > 0.0f ? d_dead_mask : nullptr;
   cp.stripe = stripe ? d_stripe_ws : nullptr;
   cp.patch = reinterpret_cast<__nv_bfloat16*>(d_patch_bf16);
-  cp.numel = numel;
+  cp.numel = (uint32_t)numel;
   cp.T = 256u * torch_grid_full;
   cp.rounds = (uint32_t)((numel - 1) / (4ll * cp.T) + 1);
+  MSD_REQUIRE((uint64_t)cp.rounds * 4ull * cp.T < (1ull << 32), "corrupt: element index range exceeds 32 bits");
+  cp.hw = (uint32_t)(H * W); cp.dplane = cp.T / cp.hw; cp.dpix = cp.T % cp.hw;
   cp.div_hw = make_fastdiv((uint32_t)(H * W));
   cp.div_c = make_fastdiv((uint32_t)C);
   cp.div_w = make_fastdiv((uint32_t)W);
   cp.C = C; cp.H = H; cp.W = W;
   cp.sg = sg; cp.ss = ss; cp.st = st;
   cp.seed = seed; cp.off_g = off_g; cp.off_s = off_s; cp.off_t = off_t;
-  cp.P = 16; cp.gridw = W / 16;
+  cp.gridw = W / 16;
   MSD_REQUIRE(cp.rounds <= 65535, "corrupt: too many rounds");
-  corrupt_kernel<<<dim3(cp.T / kThreads, cp.rounds), kThreads, 0, s>>>(cp);
+  const dim3 grid(cp.T / kThreads, cp.rounds);
+  const bool fast = sg > 0.0f && ss > 0.0f && st > 0.0f && p > 0.0f && !stripe;
+  if (fast && cp.patch != nullptr) corrupt_kernel<true, true><<<grid, kThreads, 0, s>>>(cp);
+  else if (fast) corrupt_kernel<true, false><<<grid, kThreads, 0, s>>>(cp);
+  else corrupt_kernel<false, false><<<grid, kThreads, 0, s>>>(cp);
   MSD_LAUNCH_CHECK();
   return MSD_OK;
 }

@@ -34,7 +34,12 @@ constexpr uint64_t kSpinLimit = 4000000000ull;             // ~2 s of SM clocks:
 //         tile crosses L2->SM 3x instead of 9x; the stage also carries the three taps' W boxes.
 // MODE 2: MODE 1 + the whole packed weight matrix resident in shared memory (N == BN, one k-block per tap: the
 //         48-channel stage, 60 KB), so a stage is the A box only.
-constexpr int MODE_PLAIN = 0, MODE_MERGE3 = 1, MODE_MERGE3_RESIDENT = 2;
+// MODE 3: MODE 2 with FOUR TMEM accumulator buffers and four epilogue groups (16 warps), nine taps only (a skip connection is
+//         added by the epilogue, E_CONV_SKIPADD).  An experiment on the hypothesis that the 48-channel convs are bound by the
+//         latency of one epilogue warp-tile (~540 dependent instructions at IPC 0.2): they are not (0.562 vs 0.540 ms), so the
+//         mode is opt-in (MSD_RES4=1) and documents the negative result.
+constexpr int MODE_PLAIN = 0, MODE_MERGE3 = 1, MODE_MERGE3_RESIDENT = 2, MODE_MERGE3_RESIDENT4 = 3;
+__host__ __device__ constexpr bool mode_resident(int mode) { return mode == MODE_MERGE3_RESIDENT || mode == MODE_MERGE3_RESIDENT4; }
 constexpr int MERGE_ROWS = 136;   // 128 + 2 shifted rows, rounded up to a whole 8-row swizzle atom
 
 template <int BN, int MODE = MODE_PLAIN>
@@ -44,7 +49,8 @@ struct Cfg {
   static constexpr uint32_t A_STAGE_BYTES = (A_BOX_BYTES + 1023u) & ~1023u;
   static constexpr uint32_t B_STAGE_BYTES = MODE == MODE_PLAIN ? W_BOX_BYTES : MODE == MODE_MERGE3 ? 3 * W_BOX_BYTES : 0;
   static constexpr uint32_t STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr uint32_t RESIDENT_BYTES = MODE == MODE_MERGE3_RESIDENT ? 10 * W_BOX_BYTES : 0;
+  static constexpr uint32_t RESIDENT_BYTES = MODE == MODE_MERGE3_RESIDENT ? 10 * W_BOX_BYTES : MODE == MODE_MERGE3_RESIDENT4 ? 9 * W_BOX_BYTES : 0;
+  static constexpr int NBUF = MODE == MODE_MERGE3_RESIDENT4 ? 4 : 2;       // TMEM accumulator buffers = epilogue groups
   // epilogue staging: slabs of SC accumulator columns x 32 rows per epilogue warp (fp32 or bf16), row pitch padded by 16 B
   // (an odd number of 16-byte units: row-per-lane writes are conflict-free)
   // narrow tiles (one slab) run with a single column half = 8 epilogue warps: more warps would only take issue slots
@@ -55,12 +61,13 @@ struct Cfg {
   // plain mode may stage fp32 rows (fp32-output epilogues); the merged conv modes only ever stage bf16
   static constexpr uint32_t STG_PITCH = (MODE == MODE_PLAIN ? SC * 4 : SC * 2) + 16;
   static constexpr uint32_t STG_WARP_BYTES = 32 * STG_PITCH + SLAB_SPLIT * SC * 4;   // staged slab + this warp's bias slice
-  static constexpr int EPI_WARPS = NSLAB >= 2 ? kEpiWarps : kEpiWarps / 2;
+  static constexpr int EPI_WARPS = (NSLAB >= 2 || NBUF == 4) ? kEpiWarps : kEpiWarps / 2;
   static constexpr int THREADS = 128 + 32 * EPI_WARPS;
   static constexpr uint32_t STG_BYTES = EPI_WARPS * STG_WARP_BYTES;
   static constexpr int kStagesRaw = (int)((227u * 1024u - 1024u - 256u - STG_BYTES - RESIDENT_BYTES) / STAGE_BYTES);
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
-  static constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  static constexpr uint32_t TMEM_COLS = (NBUF * BN <= 32) ? 32 : (NBUF * BN <= 64) ? 64 : (NBUF * BN <= 128) ? 128 : (NBUF * BN <= 256) ? 256 : 512;
+  static_assert(NBUF * BN <= 512, "accumulator buffers exceed the 512 TMEM columns");
   static constexpr uint32_t SMEM_BYTES = kStages * STAGE_BYTES + RESIDENT_BYTES + STG_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static_assert(BN % SC == 0 && SC % 16 == 0, "slab must tile BN in 16-column TMEM loads");
   static_assert(kStages >= 3, "pipeline too shallow");
@@ -658,8 +665,8 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint64_t* full = bars;                     // [2][kStages]: one set per MMA issuer (tile parity), see the issuer loop
   uint64_t* empty = bars + 2 * C::kStages;
   uint64_t* tmem_full = bars + 3 * C::kStages;
-  uint64_t* tmem_empty = tmem_full + 2;
-  uint64_t* res_full = tmem_empty + 2;
+  uint64_t* tmem_empty = tmem_full + C::NBUF;
+  uint64_t* res_full = tmem_empty + C::NBUF;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -669,7 +676,7 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < C::kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&full[C::kStages + i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], C::EPI_WARPS / 2); }
+    for (int i = 0; i < C::NBUF; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], C::EPI_WARPS / C::NBUF); }
     mbar_init(res_full, 1);
     if constexpr (MODE == MODE_MERGE3_RESIDENT && BN == 48) {
       static_assert(C::kStages >= 8 && 2 * BN + 32 <= (int)C::TMEM_COLS && HEAD_SLOT_BYTES <= C::W_BOX_BYTES, "fused head: needs ring stages 6/7, 32 spare TMEM columns and the tenth-tap slot");
@@ -699,7 +706,7 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   // Ring length.  The resident-weight mode uses exactly TWO tiles' worth of stages (6 or 8 <= kStages): tile `it` then always
   // occupies stages (it & 1) * steps .. + steps, i.e. each MMA issuer (even / odd tiles) sees the SAME stages every tile and its
   // whole per-tile instruction stream has loop-invariant descriptors (issue_tile_resident below).
-  const int ring = (MODE == MODE_MERGE3_RESIDENT) ? min(C::kStages, 2 * (n_dy + has_skip) * kbpt) : C::kStages;
+  const int ring = mode_resident(MODE) ? min(C::kStages, 2 * (n_dy + has_skip) * kbpt) : C::kStages;
 
   // Producer and MMA warps run their loops with all 32 lanes converged and let one elected lane issue the
   // asynchronous instructions.  Both loops are the serial critical path of a CTA (one warp each, nothing to hide
@@ -708,7 +715,7 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (warp == 0) {
     // ===== TMA producer =====
     int stage = 0; uint32_t phase = 0;
-    if constexpr (MODE == MODE_MERGE3_RESIDENT) {
+    if constexpr (mode_resident(MODE)) {
       // the whole packed weight matrix (<= 10 taps x one k-block) stays in shared memory for the life of the CTA
       if (elect_one()) {
         mbar_arrive_expect_tx(res_full, (uint32_t)p.num_kb * C::W_BOX_BYTES);
@@ -775,14 +782,13 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const uint32_t a_lo0 = (smem_u32(smem_a) & 0x3FFFFu) >> 4, b_lo0 = (smem_u32(smem_b) & 0x3FFFFu) >> 4;
     const uint32_t r_lo0 = (smem_u32(smem_res) & 0x3FFFFu) >> 4;
     const int steps_per_tile = MODE == MODE_PLAIN ? p.num_kb : (n_dy + has_skip) * kbpt;
-    const uint32_t tmem_d = tmem_base + par * BN;
     int gstep = 0;
     uint32_t it = 0;
     // Each issuer has its own `full` barrier per stage (the producer signals the set of the tile's owner), and keeps one
     // parity bit per stage: a parity wait is only unambiguous for a waiter that has seen every earlier phase itself.
     uint64_t* full = bars + par * C::kStages;
     uint32_t pmask = 0;
-    if constexpr (MODE == MODE_MERGE3_RESIDENT) { mbar_wait(res_full, 0); tcgen05_fence_after(); }
+    if constexpr (mode_resident(MODE)) { mbar_wait(res_full, 0); tcgen05_fence_after(); }
     // fused 1x1 head (E_CONV_HEAD): D2 = A2 . (W2hi + W2lo)^T into 16 spare TMEM columns once the tile's epilogue lanes wrote A2
     bool head_pending = false;
     uint32_t head_parity = 0;
@@ -811,7 +817,10 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it, gstep += steps_per_tile) {
       if ((it & 1u) != par) continue;
       int stage = gstep % ring;
-      mbar_wait(&tmem_empty[par], ((it >> 1) & 1u) ^ 1u);
+      // accumulator buffer of tile `it`: it mod NBUF (this issuer's n-th tile alternates between its two buffers when there are four)
+      const uint32_t buf = it & (uint32_t)(C::NBUF - 1), uses = it / (uint32_t)C::NBUF;
+      const uint32_t tmem_d = tmem_base + buf * BN;
+      mbar_wait(&tmem_empty[buf], (uses & 1u) ^ 1u);
       tcgen05_fence_after();
       uint32_t acc = 0;                                   // first MMA of the tile overwrites the accumulator
       if constexpr (MODE == MODE_PLAIN) {
@@ -826,7 +835,7 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const uint32_t b_lo = b_lo0 + stage * (C::B_STAGE_BYTES >> 4);
             mma_kblock(tmem_d, a_lo, b_lo, (uint32_t)(p.dbg_bo & 7) << 17, idesc, nk, acc);
             tcgen05_commit(&empty[stage]);               // frees the smem stage once these MMAs retire
-            if (kb == p.num_kb - 1) tcgen05_commit(&tmem_full[par]);  // accumulator complete -> epilogue
+            if (kb == p.num_kb - 1) tcgen05_commit(&tmem_full[buf]);  // accumulator complete -> epilogue
           }
           __syncwarp();
           acc = 1;
@@ -834,15 +843,15 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           if (++stage == C::kStages) stage = 0;
         }
       } else {
-        if constexpr (MODE == MODE_MERGE3_RESIDENT) {
+        if constexpr (mode_resident(MODE)) {
           if (kbpt == 1 && nk_last == 3 && ring == 2 * (n_dy + has_skip)) {
             // 48-channel stage: straight-line issue, every descriptor = a per-issuer base + a compile-time offset
             const uint32_t a_base = a_lo0 + par * (uint32_t)(n_dy + has_skip) * (A_STAGE_BYTES >> 4);
             uint64_t* fullp = full + par * (n_dy + has_skip);
             uint64_t* emptyp = empty + par * (n_dy + has_skip);
             const uint32_t parity = (it >> 1) & 1u;
-            if (has_skip) issue_tile_resident<BN, 4, 3, A_STAGE_BYTES>(tmem_d, a_base, r_lo0, idesc, fullp, emptyp, &tmem_full[par], parity, p.skip_tap);
-            else issue_tile_resident<BN, 3, 3, A_STAGE_BYTES>(tmem_d, a_base, r_lo0, idesc, fullp, emptyp, &tmem_full[par], parity, 0);
+            if (has_skip) issue_tile_resident<BN, 4, 3, A_STAGE_BYTES>(tmem_d, a_base, r_lo0, idesc, fullp, emptyp, &tmem_full[buf], parity, p.skip_tap);
+            else issue_tile_resident<BN, 3, 3, A_STAGE_BYTES>(tmem_d, a_base, r_lo0, idesc, fullp, emptyp, &tmem_full[buf], parity, 0);
             if constexpr (BN == 48) {
               if (epi == E_CONV_HEAD) {
                 // fused 1x1 head of this issuer's PREVIOUS tile: its epilogue lanes wrote A2 while this tile's MMAs were being
@@ -867,19 +876,19 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             if (elect_one()) {
               const uint32_t a_lo = a_lo0 + stage * (A_STAGE_BYTES >> 4);
               if (is_skip) {                                                 // identity tap through the middle window
-                const uint32_t b_lo = (MODE == MODE_MERGE3_RESIDENT) ? r_lo0 + (p.skip_tap * kbpt + kc) * (C::W_BOX_BYTES >> 4)
+                const uint32_t b_lo = mode_resident(MODE) ? r_lo0 + (p.skip_tap * kbpt + kc) * (C::W_BOX_BYTES >> 4)
                                                                      : b_lo0 + stage * (C::B_STAGE_BYTES >> 4);
                 mma_kblock(tmem_d, a_lo + 8u, b_lo, 0u, idesc, nk, acc);
               } else {
-                const uint32_t b_lo = (MODE == MODE_MERGE3_RESIDENT) ? r_lo0 + (3 * dy * kbpt + kc) * (C::W_BOX_BYTES >> 4)
+                const uint32_t b_lo = mode_resident(MODE) ? r_lo0 + (3 * dy * kbpt + kc) * (C::W_BOX_BYTES >> 4)
                                                                      : b_lo0 + stage * (C::B_STAGE_BYTES >> 4);
-                const uint32_t b_step = (MODE == MODE_MERGE3_RESIDENT ? kbpt : 1) * (C::W_BOX_BYTES >> 4);
+                const uint32_t b_step = (mode_resident(MODE) ? kbpt : 1) * (C::W_BOX_BYTES >> 4);
                 mma_kblock(tmem_d, a_lo, b_lo, 0u, idesc, nk, acc);                       // dx = -1
                 mma_kblock(tmem_d, a_lo + 8u, b_lo + b_step, 0u, idesc, nk, 1u);           // dx =  0 (one row = 128 B down)
                 mma_kblock(tmem_d, a_lo + 16u, b_lo + 2u * b_step, 0u, idesc, nk, 1u);     // dx = +1
               }
               tcgen05_commit(&empty[stage]);
-              if (last) tcgen05_commit(&tmem_full[par]);
+              if (last) tcgen05_commit(&tmem_full[buf]);
             }
             __syncwarp();
             acc = 1;
@@ -893,7 +902,8 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // ===== epilogue: warp w may only read TMEM lanes 32*(w%4).. (hardware rule).  e = w-4: bit 2 selects the accumulator
     // buffer (even / odd tiles of this CTA), bit 3 the column half of the tile =====
     const int e = warp - 4;
-    const int q = warp & 3, grp = (e >> 2) & 1, half = e >> 3;
+    // two buffers: bit 2 of e = accumulator buffer, bit 3 = column half; four buffers: bits 2-3 = accumulator buffer, one column range
+    const int q = warp & 3, grp = (e >> 2) & (C::NBUF - 1), half = C::NBUF == 4 ? 0 : e >> 3;
     const uint32_t stg_s = smem_u32(smem_stg + e * C::STG_WARP_BYTES);
     const uint32_t bias_s = stg_s + 32 * C::STG_PITCH;
     const int slab_begin = half ? C::SLAB_SPLIT : 0, slab_end = half ? C::NSLAB : C::SLAB_SPLIT;
@@ -910,8 +920,8 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     HeadCtx hc;                       // fused 1x1 head: this warp's pending tile (E_CONV_HEAD only)
     hc.has_prev = false; hc.prev_rowpix = kRowSkip; hc.parity = 0; hc.d2_full = nullptr;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      if ((it & 1) != grp) continue;
-      const uint32_t as = it & 1, aphase = (it >> 1) & 1;
+      if ((it & (C::NBUF - 1)) != grp) continue;
+      const uint32_t as = it & (C::NBUF - 1), aphase = (it / C::NBUF) & 1;
       const int tm = tile / tiles_n;
       const int m0 = tm * BLOCK_M, n0 = (tile - tm * tiles_n) * BN;
       // this warp's bias slice -> smem (private to the warp), fetched before waiting for the accumulator and only when
@@ -957,6 +967,13 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           epilogue_tile<BN, E_CONV_HEAD>(p, stg_s, bias_s, taddr, &tmem_empty[as], m0 + q * 32, n0, lane, slab_begin, slab_end, &hc);
           continue;
         }
+      }
+      if constexpr (MODE == MODE_MERGE3_RESIDENT4) {
+        // 16 epilogue warps cap the kernel at 96 registers: only the three conv epilogues this mode is launched with are compiled in
+        if (epi == E_CONV) epilogue_tile<BN, E_CONV>(p, stg_s, bias_s, taddr, &tmem_empty[as], m0 + q * 32, n0, lane, slab_begin, slab_end);
+        else if (epi == E_CONV_SKIPADD) epilogue_tile<BN, E_CONV_SKIPADD>(p, stg_s, bias_s, taddr, &tmem_empty[as], m0 + q * 32, n0, lane, slab_begin, slab_end);
+        else epilogue_tile<BN, E_CONV_RAW>(p, stg_s, bias_s, taddr, &tmem_empty[as], m0 + q * 32, n0, lane, slab_begin, slab_end);
+        continue;
       }
       // one specialised instruction stream per fused epilogue (the switch is per tile, the loops inside are branch-free)
 #define MSD_EPI_CASE(E) case E: epilogue_tile<BN, E>(p, stg_s, bias_s, taddr, &tmem_empty[as], m0 + q * 32, n0, lane, slab_begin, slab_end); break;
@@ -1053,6 +1070,13 @@ int launch_bn(const Problem& p, cudaStream_t s) {
     static const bool no_merge = getenv("MSD_NO_MERGE3") != nullptr;     // A/B switch for the profiles
     if (!no_merge && is_conv3x3(p)) {
       if constexpr (BN == 48) {
+        // measured at B = 256: 0.562 ms vs 0.540 ms with two buffers / 8 epilogue warps (conv 192^2 x 48) and 0.643 vs 0.653 for the
+        // skip variant -- the epilogue is NOT what bounds this conv (L2 -> SM delivery of the three dy boxes + the shared-memory
+        // reads of N = 48 MMAs are); kept as an opt-in A/B mode (MSD_RES4=1), off by default
+        static const bool res4 = getenv("MSD_RES4") != nullptr;
+        const int e = classify(p);
+        if (res4 && p.N == BN && p.kb_per_tap == 1 && p.num_kb == 9 && (e == E_CONV || e == E_CONV_RAW || e == E_CONV_SKIPADD))
+          return launch_mode<BN, MODE_MERGE3_RESIDENT4>(p, s);
         if (p.N == BN && p.kb_per_tap == 1 && p.num_kb <= 10) return launch_mode<BN, MODE_MERGE3_RESIDENT>(p, s);
       }
       return launch_mode<BN, MODE_MERGE3>(p, s);

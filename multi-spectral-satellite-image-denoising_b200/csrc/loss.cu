@@ -18,12 +18,13 @@ using namespace ssim;
 
 struct FwdSmem {
   RawTile<2> raw;
-  HBlur<5> hb;
+  HBlur2<2> hb;               // packed pairs (p + t, p - t) and (p*p + t*t, p*t): one FFMA2 per tap (ssim_tile.cuh)
   double red[2][kThreads / 32];
 };
 struct BwdSmem {
   RawTile<3> raw;
-  HBlur<3> hb;
+  HBlur2<1> hb2;              // (dmu1 + de11, dmu1 - de11), packed
+  HBlur<1> hb;                // de12
 };
 
 template <bool kWriteDeriv>
@@ -40,12 +41,15 @@ loss_fwd_kernel(const float* __restrict__ pred, const float* __restrict__ target
   load_raw_plane(sm.raw.v[0], pred + poff, y0, x0, H, W);
   load_raw_plane(sm.raw.v[1], target + poff, y0, x0, H, W);
   __syncthreads();
-  hpass<2, 5>(sm.raw, sm.hb, [](int m, const float (&px)[2]) -> float {
-    return m == 0 ? px[0] : m == 1 ? px[1] : m == 2 ? px[0] * px[0] : m == 3 ? px[1] * px[1] : px[0] * px[1];
+  // Four maps, not the reference's five: S and its derivatives only use e11 + e22 (B2 below; dS/de11 = dS/de22), and the blur is
+  // linear.  Two maps per 64-bit register, one FFMA2 per tap; pair 0 is (p + t, p - t) so that both lanes are computed values
+  // (blur(p +- t) = mu1 +- mu2), see metrics.cu.
+  hpass2<2, 2>(sm.raw, sm.hb, [](int mp, const float (&px)[2]) -> f2 {
+    return mp == 0 ? pack2(px[0] + px[1], px[0] - px[1]) : pack2(fmaf(px[0], px[0], px[1] * px[1]), px[0] * px[1]);
   });
   __syncthreads();
-  float res[5][8];
-  vpass<5>(sm.hb, res);
+  f2 res2[2][8];
+  vpass2<2>(sm.hb, res2);
   const int x = threadIdx.x & 63, h = threadIdx.x >> 6;
   float s_ssim = 0.0f, s_sq = 0.0f;
   if (x0 + x < W) {
@@ -53,12 +57,15 @@ loss_fwd_kernel(const float* __restrict__ pred, const float* __restrict__ target
     for (int o = 0; o < 8; ++o) {
       const int yy = y0 + 8 * h + o;
       if (yy >= H) continue;
-      const float mu1 = res[0][o], mu2 = res[1][o], e11 = res[2][o], e22 = res[3][o], e12 = res[4][o];
+      float ms, md, esum, e12;
+      unpack2(res2[0][o], ms, md);
+      unpack2(res2[1][o], esum, e12);
+      const float mu1 = 0.5f * (ms + md), mu2 = 0.5f * (ms - md);
       const float mu1_sq = mu1 * mu1, mu2_sq = mu2 * mu2, mu1_mu2 = mu1 * mu2;
       const float A1 = 2.0f * mu1_mu2 + consts.C1;
       const float A2 = 2.0f * (e12 - mu1_mu2) + consts.C2;
       const float B1 = mu1_sq + mu2_sq + consts.C1;
-      const float B2 = (e11 - mu1_sq) + (e22 - mu2_sq) + consts.C2;
+      const float B2 = (esum - mu1_sq - mu2_sq) + consts.C2;
       const float S = (A1 * A2) / (B1 * B2);
       s_ssim += S;
       const float d = sm.raw.v[0][8 * h + o + R][x + R] - sm.raw.v[1][8 * h + o + R][x + R];
@@ -100,10 +107,14 @@ loss_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ target
 #pragma unroll
   for (int i = 0; i < 3; ++i) load_raw_plane(sm.raw.v[i], deriv + (size_t)i * numel + poff, y0, x0, H, W);
   __syncthreads();
-  hpass<3, 3>(sm.raw, sm.hb, [](int m, const float (&px)[3]) -> float { return m == 0 ? px[0] : m == 1 ? px[1] : px[2]; });
+  // blur(dmu1) and blur(de11) ride together as the packed pair (sum, difference); blur(de12) takes the scalar stencil
+  hpass2<3, 1>(sm.raw, sm.hb2, [](int, const float (&px)[3]) -> f2 { return pack2(px[0] + px[1], px[0] - px[1]); });
+  hpass<3, 1>(sm.raw, sm.hb, [](int, const float (&px)[3]) -> float { return px[2]; });
   __syncthreads();
-  float res[3][8];
-  vpass<3>(sm.hb, res);
+  f2 res2[1][8];
+  vpass2<1>(sm.hb2, res2);
+  float res12[1][8];
+  vpass<1>(sm.hb, res12);
   const int x = threadIdx.x & 63, h = threadIdx.x >> 6;
   if (x0 + x < W) {
 #pragma unroll
@@ -112,7 +123,10 @@ loss_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ target
       if (yy >= H) continue;
       const size_t e = poff + (size_t)yy * W + (x0 + x);
       const float p = __ldg(pred + e), t = __ldg(target + e);
-      const float gs = res[0][o] + 2.0f * p * res[1][o] + t * res[2][o];
+      float bs, bd;
+      unpack2(res2[0][o], bs, bd);
+      const float b_mu1 = 0.5f * (bs + bd), b_e11 = 0.5f * (bs - bd);
+      const float gs = b_mu1 + 2.0f * p * b_e11 + t * res12[0][o];
       grad[e] = k_ssim * gs + k_mse * (p - t);
     }
   }

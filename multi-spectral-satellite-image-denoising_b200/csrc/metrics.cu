@@ -76,7 +76,7 @@ ssim_mse_kernel(const float* __restrict__ pred, const float* __restrict__ target
 // ---- fused product path -----------------------------------------------------------------------------------------
 struct FusedSmem {
   RawTile<2> raw[2];          // ring of two bands: [buf].v[0] = pred halo tile, .v[1] = target halo tile  (TMA destinations)
-  HBlur<4> hb;
+  HBlur2<2> hb;               // horizontally blurred maps as packed pairs: (p, t) and (p*p + t*t, p*t)
   double red[4][kThreads / 32];
   uint64_t bar[2];
 };
@@ -137,12 +137,15 @@ metrics_fused_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_const
     const RawTile<2>& raw = sm.raw[buf];
     // maps: p, t, p*p + t*t, p*t.  The reference blurs p*p and t*t separately (metrics.py:105-117) but its ssim_map only uses
     // sigma1_sq + sigma2_sq (:118-121), and the blur is linear: one map of the sum saves a fifth of the stencil work.
-    hpass<2, 4, kXoff>(raw, sm.hb, [](int m, const float (&px)[2]) -> float {
-      return m == 0 ? px[0] : m == 1 ? px[1] : m == 2 ? fmaf(px[0], px[0], px[1] * px[1]) : px[0] * px[1];
+    // Two maps per 64-bit register, one FFMA2 per tap (ssim_tile.cuh): same per-lane arithmetic, half the FMA issue slots.
+    // Pair 0 is (p + t, p - t), not (p, t): both lanes are then freshly computed values the register allocator can place side
+    // by side (a pair of two LOADED values costs two MOVs per use); the blur is linear, so blur(p +- t) = mu1 +- mu2.
+    hpass2<2, 2, kXoff>(raw, sm.hb, [](int mp, const float (&px)[2]) -> f2 {
+      return mp == 0 ? pack2(px[0] + px[1], px[0] - px[1]) : pack2(fmaf(px[0], px[0], px[1] * px[1]), px[0] * px[1]);
     });
     __syncthreads();
-    float res[4][8];
-    vpass<4>(sm.hb, res);
+    f2 res2[2][8];
+    vpass2<2>(sm.hb, res2);
     float s_ssim = 0.0f, s_sq = 0.0f, s_abs = 0.0f;
 #pragma unroll
     for (int o = 0; o < 8; ++o) {
@@ -150,12 +153,15 @@ metrics_fused_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_const
       dot[o] = fmaf(a, bb, dot[o]);            // SAM: spectral dot product and norms, band by band (metrics.py:155-160)
       pp[o] = fmaf(a, a, pp[o]);
       tt[o] = fmaf(bb, bb, tt[o]);
-      if (col_ok && y0 + 8 * h + o < H) {
-        s_ssim += ssim_value_sum(res[0][o], res[1][o], res[2][o], res[3][o], consts);
-        const float d = a - bb;
-        s_sq = fmaf(d, d, s_sq);
-        s_abs += fabsf(d);
-      }
+      // branch-free: pixels outside the image (ragged last tile) are computed and masked out
+      const float keep = (col_ok && y0 + 8 * h + o < H) ? 1.0f : 0.0f;
+      float ms, md, esum, e12;
+      unpack2(res2[0][o], ms, md);             // mu1 + mu2, mu1 - mu2
+      unpack2(res2[1][o], esum, e12);
+      s_ssim = fmaf(keep, ssim_value_sumdiff(ms, md, esum, e12, consts), s_ssim);
+      const float d = (a - bb) * keep;
+      s_sq = fmaf(d, d, s_sq);
+      s_abs += fabsf(d);
     }
     d_ssim += (double)s_ssim; d_sq += (double)s_sq; d_abs += (double)s_abs;
     __syncthreads();                           // hb and ring slot `buf` are free again

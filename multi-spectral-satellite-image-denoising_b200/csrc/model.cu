@@ -170,10 +170,11 @@ extern "C" int msd_linear_lnfold_bf16(const void* d_x_bf16, const void* d_w_ln, 
   return gemm::launch(p, 0, (cudaStream_t)stream);
 }
 
-// ResidualBlock skip connection on the tcgen05 path: added by the epilogue warps for >= 96 channels (the conv is bound by its
-// operand loads there: 0.574 -> 0.445 ms at 96 channels, 0.371 -> 0.35 at 192 / 384), as a tenth identity tap through the tensor
-// cores for 48 channels (that conv is bound by its epilogue warps: 0.633 vs 0.669 ms).  MSD_SKIP_TAP=1 / MSD_SKIP_EPI=1 force one
-// way for A/B runs; the mma.sync baseline always takes the identity tap.
+// ResidualBlock skip connection on the tcgen05 path: added by the epilogue warps for >= 96 channels (E_CONV_SKIPADD: one A box
+// and a ninth of the MMAs less per tile than riding through the tensor cores as a tenth identity tap; 0.574 -> 0.445 ms at 96
+// channels, 0.371 -> 0.35 at 192 / 384), as the identity tap for 48 channels (0.633 vs 0.669 ms on 8 epilogue warps; with the
+// opt-in 16-warp mode MSD_RES4=1 the two are equal, 0.643 vs 0.653).  MSD_SKIP_TAP=1 / MSD_SKIP_EPI=1 force one way for A/B
+// runs; the mma.sync baseline always takes the identity tap.
 static bool skip_in_epilogue(int backend, int channels) {
   static const bool tap = getenv("MSD_SKIP_TAP") != nullptr, epi = getenv("MSD_SKIP_EPI") != nullptr;
   if (backend != 0 || tap) return false;
@@ -223,6 +224,9 @@ struct msd_model {
   // weight gradients run on a second stream, under the bandwidth-bound passes of the main stream (msd_model_backward)
   cudaStream_t side = nullptr;
   std::vector<cudaEvent_t> side_ev;
+  // one event per gradient group of the last backward (data-parallel training: the all-reduce of a group starts as soon as its
+  // event fires, while the rest of the backward runs): 0 = decoder, 1 + j = encoder block depth-1-j (+ encoder.norm), depth+1 = rest
+  std::vector<cudaEvent_t> grad_ev;
   int grid, tokens;
   // optional per-launch CUDA-event profile (bench.py's live roofline measurement)
   bool profile = false;
@@ -319,6 +323,7 @@ extern "C" void msd_model_destroy(msd_model* m) {
   if (!m) return;
   for (cudaEvent_t e : m->ev) cudaEventDestroy(e);
   for (cudaEvent_t e : m->side_ev) cudaEventDestroy(e);
+  for (cudaEvent_t e : m->grad_ev) cudaEventDestroy(e);
   if (m->side) cudaStreamDestroy(m->side);
   delete m;
 }
@@ -621,6 +626,13 @@ struct SideStream {
     e = nullptr;
     return MSD_OK;
   }
+  // every gradient enqueued so far -- on the main stream AND on the weight-gradient stream -- is complete when `e` fires
+  int mark_group(cudaEvent_t e) {
+    if (!enabled) { MSD_CHECK_CUDA(cudaEventRecord(e, main_s)); return MSD_OK; }
+    MSD_TRY(fork());                                 // the side stream catches up with the main stream's position ...
+    MSD_CHECK_CUDA(cudaEventRecord(e, side_s));      // ... so its next event covers both
+    return MSD_OK;
+  }
 };
 
 }  // namespace
@@ -763,6 +775,10 @@ extern "C" int msd_model_backward(msd_model* m, const float* d_grad_y, int B, vo
   SideStream ss;
   MSD_TRY(ss.init(m, s));
   void* side = (void*)ss.side_s;
+  if (m->grad_ev.empty()) {
+    m->grad_ev.resize((size_t)d.depth + 2);
+    for (auto& e : m->grad_ev) MSD_CHECK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
   // events of side-stream work still reading a buffer the main stream will overwrite later
   cudaEvent_t e_gA = nullptr, e_gB = nullptr, e_dys = nullptr, e_gbf = nullptr, e_dh = nullptr, e_dqkv = nullptr;
   auto ev_of = [&](unsigned char* buf) -> cudaEvent_t& { return buf == gA ? e_gA : e_gB; };
@@ -850,6 +866,7 @@ extern "C" int msd_model_backward(msd_model* m, const float* d_grad_y, int B, vo
     MSD_TRY(make_linear(p, ws + L.dys, sw.wT_up, nullptr, dst, nullptr, (int)rows_in, cin, 4 * c, 0, 0));
     MSD_TRY(gemm::launch(p, be, s));
   }
+  MSD_TRY(ss.mark_group(m->grad_ev[0]));            // gradient group 0: the whole decoder
   // ---- encoder.  g: fp32 gradient of the residual stream, gbf its bf16 copy (operand of the GEMMs)
   float* g = reinterpret_cast<float*>(ws + L.g);
   void *gbf = ws + L.gbf, *dh = ws + L.dh, *dxn = ws + L.dxn, *dqkv = ws + L.dqkv, *datt = ws + L.datt;
@@ -916,6 +933,7 @@ extern "C" int msd_model_backward(msd_model* m, const float* d_grad_y, int B, vo
     }
     MSD_TRY(ss.wait(e_gbf));                    // ... and the proj weight gradient
     MSD_TRY(msd_layernorm_bwd(dxn, 0, xin, bw.ln1_g, d.ln_eps_block, g, 1, gbf, tr ? bg.ln1_g : nullptr, tr ? bg.ln1_b : nullptr, M, E, stream));
+    MSD_TRY(ss.mark_group(m->grad_ev[(size_t)(d.depth - l)]));   // group 1 + (depth-1-l): block l (the first one also covers encoder.norm)
   }
   // ---- patch embedding: x0 = LN(pe) + pos_embed
   if (gr->pos_embed) MSD_TRY(msd_batch_sum_f32(g, gr->pos_embed, B, (long long)m->tokens * E, stream));
@@ -930,9 +948,19 @@ extern "C" int msd_model_backward(msd_model* m, const float* d_grad_y, int B, vo
   }
   MSD_TRY(bias_grad(gbf, M, E, gr->b_pe, E, sums, stream));
   // join: everything the side stream produced is ordered before whatever the caller enqueues next on `stream`
+  MSD_TRY(ss.mark_group(m->grad_ev[(size_t)d.depth + 1]));     // last group: patch embedding, pos_embed
   cudaEvent_t e_all = nullptr;
   MSD_TRY(ss.done(&e_all));
   MSD_TRY(ss.wait(e_all));
+  return MSD_OK;
+}
+
+extern "C" int msd_model_grad_groups(const msd_model* m) { return m ? m->d.depth + 2 : 0; }
+
+extern "C" int msd_model_grad_group_wait(msd_model* m, int group, void* stream) {
+  MSD_REQUIRE(m != nullptr && !m->grad_ev.empty(), "grad_group_wait: no backward has run on this model");
+  MSD_REQUIRE(group >= 0 && group < (int)m->grad_ev.size(), "grad_group_wait: group %d outside [0, %d)", group, (int)m->grad_ev.size());
+  MSD_CHECK_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, m->grad_ev[(size_t)group], 0));
   return MSD_OK;
 }
 

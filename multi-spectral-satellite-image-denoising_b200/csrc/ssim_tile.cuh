@@ -118,6 +118,98 @@ __device__ __forceinline__ void vpass(const HBlur<NMAPS>& hb, float (&res)[NMAPS
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Packed variant: TWO maps ride in the two fp32 lanes of a 64-bit register and every tap is one FFMA2 (fma.rn.f32x2, two IEEE
+// fp32 FMAs per issue slot on sm_100).  The stencil kernels are bound by instruction issue, not by the FMA pipe or HBM (ncu:
+// 72-80 % issue-active), so halving the FMA instruction count is worth more than anything else here.  Per lane the arithmetic
+// and its order are exactly those of hpass / vpass above: results are bit-identical.
+//   hb2[NPAIRS][42][64] float2 (same bytes as HBlur<2 * NPAIRS>); a row's 16-byte chunks are rotated by (group >> 1) inside each
+//   8-pixel group so that the horizontal pass's 128-bit stores (8 threads of a row, 64 B apart) spread over all banks; the
+//   vertical pass reads 8-byte pairs with lanes along x, a permutation inside each 64-byte group -- conflict-free both ways.
+// ------------------------------------------------------------------------------------------------------------------
+struct f2 {
+  unsigned long long v;
+};
+__device__ __forceinline__ f2 pack2(float lo, float hi) {
+  f2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f2 a, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v));
+}
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
+  f2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+  return d;
+}
+
+template <int NPAIRS>
+struct HBlur2 {
+  float2 v[NPAIRS][IH][TW];
+};
+
+__device__ __forceinline__ void fir8x2(const f2 (&in)[18], f2 (&out)[8]) {
+#pragma unroll
+  for (int o = 0; o < 8; ++o) {
+    f2 a = pack2(0.0f, 0.0f);
+#pragma unroll
+    for (int k = 0; k < 11; ++k) a = fma2(pack2(tap(k), tap(k)), in[o + k], a);
+    out[o] = a;
+  }
+}
+
+// Horizontal pass, packed.  PairFn(mp, raw values at one pixel) -> f2 holding maps (2 mp, 2 mp + 1) at that pixel.
+template <int NRAW, int NPAIRS, int XOFF = 0, typename PairFn>
+__device__ __forceinline__ void hpass2(const RawTile<NRAW>& raw, HBlur2<NPAIRS>& hb, PairFn pairfn) {
+  constexpr int NV = (18 + XOFF + 3) / 4;
+  static_assert(8 * (TW / 8 - 1) + 4 * NV <= PW, "padded raw row too short");
+  for (int item = threadIdx.x; item < IH * (TW / 8); item += kThreads) {
+    const int r = item >> 3, g = item & 7;
+    float in[NRAW][4 * NV];
+#pragma unroll
+    for (int i = 0; i < NRAW; ++i) {
+      const float4* src = reinterpret_cast<const float4*>(&raw.v[i][r][8 * g]);
+#pragma unroll
+      for (int q = 0; q < NV; ++q) {
+        float4 t = src[q];
+        in[i][4 * q + 0] = t.x; in[i][4 * q + 1] = t.y; in[i][4 * q + 2] = t.z; in[i][4 * q + 3] = t.w;
+      }
+    }
+#pragma unroll
+    for (int mp = 0; mp < NPAIRS; ++mp) {
+      f2 cur[18], out[8];
+#pragma unroll
+      for (int j = 0; j < 18; ++j) {
+        float px[NRAW];
+#pragma unroll
+        for (int i = 0; i < NRAW; ++i) px[i] = in[i][XOFF + j];
+        cur[j] = pairfn(mp, px);
+      }
+      fir8x2(cur, out);
+      // pixels 8g .. 8g+7 of the row = four 16-byte chunks (two float2 each); chunk q is stored at position (q + (g >> 1)) & 3
+      ulonglong2* dst = reinterpret_cast<ulonglong2*>(&hb.v[mp][r][8 * g]);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) dst[(q + (g >> 1)) & 3] = make_ulonglong2(out[2 * q].v, out[2 * q + 1].v);
+    }
+  }
+}
+
+// Vertical pass, packed: this thread's column x = tid & 63, rows 8h .. 8h+7; res[mp][o] = maps (2 mp, 2 mp + 1)
+template <int NPAIRS>
+__device__ __forceinline__ void vpass2(const HBlur2<NPAIRS>& hb, f2 (&res)[NPAIRS][8]) {
+  const int x = threadIdx.x & 63, h = threadIdx.x >> 6;
+  const int g = x >> 3, j = x & 7;
+  const int xs = 8 * g + 2 * (((j >> 1) + (g >> 1)) & 3) + (j & 1);       // where hpass2 put pixel x of a row
+#pragma unroll
+  for (int mp = 0; mp < NPAIRS; ++mp) {
+    f2 in[18];
+#pragma unroll
+    for (int i = 0; i < 18; ++i) in[i].v = *reinterpret_cast<const unsigned long long*>(&hb.v[mp][8 * h + i][xs]);
+    fir8x2(in, res[mp]);
+  }
+}
+
 // ssim_map value and (optionally) its partial derivatives wrt the blurred statistics
 struct SsimConsts {
   float C1, C2;
@@ -137,6 +229,15 @@ __device__ __forceinline__ float ssim_value_sum(float mu1, float mu2, float esum
   const float num = (2.0f * mu1_mu2 + c.C1) * (2.0f * s12 + c.C2);
   const float den = (mu1_sq + mu2_sq + c.C1) * ((esum - mu1_sq - mu2_sq) + c.C2);
   return num / den;
+}
+
+// the same map from blur(p + t) = mu1 + mu2 and blur(p - t) = mu1 - mu2:  mu1^2 + mu2^2 = (s^2 + d^2) / 2,  mu1 mu2 = (s^2 - d^2) / 4
+__device__ __forceinline__ float ssim_value_sumdiff(float ms, float md, float esum, float e12, const SsimConsts& c) {
+  const float s2 = ms * ms, d2 = md * md;
+  const float musq = 0.5f * (s2 + d2), mu12 = 0.25f * (s2 - d2);
+  const float num = (2.0f * mu12 + c.C1) * (2.0f * (e12 - mu12) + c.C2);
+  const float den = (musq + c.C1) * ((esum - musq) + c.C2);
+  return __fdividef(num, den);      // den >= C1 * C2 > 0 up to rounding; 2 ulp, no slow-path branch (the map is averaged to 1e-4)
 }
 
 }  // namespace ssim

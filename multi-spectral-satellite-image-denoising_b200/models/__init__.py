@@ -2,7 +2,8 @@
 from .blocks import ConvBlock, ResidualBlock, UpsampleBlock
 from .decoder import LightweightDecoder
 from .encoder import SatMAEEncoder, convert_block_keys
+from .export_graph import export_mode
 from .satmae_restoration import SatMAERestoration
 
 __all__ = ["SatMAERestoration", "SatMAEEncoder", "LightweightDecoder", "ConvBlock", "ResidualBlock", "UpsampleBlock",
-           "convert_block_keys"]
+           "convert_block_keys", "export_mode"]

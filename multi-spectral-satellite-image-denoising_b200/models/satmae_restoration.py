@@ -21,6 +21,7 @@ import torch.nn as nn
 from .. import _lib
 from .decoder import LightweightDecoder
 from .encoder import SatMAEEncoder
+from .export_graph import export_forward, export_graph_requested
 
 logger = logging.getLogger(__name__)
 
@@ -264,7 +265,11 @@ class SatMAERestoration(nn.Module):
 
     def _apply(self, fn, recurse=True):
         """Moving / casting the module re-homes every parameter: drop the packed copies made from the old storage."""
+        sig = lambda: [(t.data_ptr(), t.device, t.dtype) for t in list(self.parameters()) + list(self.buffers())]
+        before = sig()
         out = super()._apply(fn, recurse)
+        if sig() == before:                     # e.g. .to(device) on a model that already lives there (evaluate_model does that)
+            return out
         # the C handle owns a side stream and events created on the device it first ran on: a moved model gets a fresh handle
         if self.__dict__.get("_handle") is not None:
             try:
@@ -317,7 +322,12 @@ class SatMAERestoration(nn.Module):
         assert C_ == self.config["data"]["num_bands"], \
             f"Expected {self.config['data']['num_bands']} bands, got {C_}"
         if not x.is_cuda:
-            raise _lib.MsdError("SatMAERestoration.forward: CUDA tensor required (libmsd_b200 has no CPU path)")
+            if export_graph_requested():
+                # a tracer is recording (torch.onnx.export / torch.jit.trace, reference scripts/export.py:45-66) or the caller
+                # opened export_mode(): the graph DEFINITION in stock torch ops (models/export_graph.py), never a product path
+                return export_forward(self, x)
+            raise _lib.MsdError("SatMAERestoration.forward: CUDA tensor required (libmsd_b200 has no CPU path; the torch-op export "
+                                "graph is only evaluated under a tracer or msd_b200.models.export_mode())")
         if next(self.parameters()).device != x.device:
             raise _lib.MsdError("SatMAERestoration: model and input are on different devices")
         if B == 0:                              # empty batch: nothing to launch
@@ -455,30 +465,42 @@ class SatMAERestoration(nn.Module):
         self._packed_key = None
         return y, ws
 
+    def enable_data_parallel(self, group=None, enabled: bool = True):
+        """Data-parallel training (BASELINE config C4): average every gradient over the ranks of `group` INSIDE backward.  The
+        library's backward writes all gradients into one flat fp32 arena ordered by when they become ready (decoder, encoder
+        blocks last to first, patch embedding) and records an event per group; each group's all-reduce is enqueued on a
+        communication stream behind its event, so NCCL runs under the rest of the backward, on the arena itself (no concatenation,
+        no copy back).  `loss.backward()` then leaves averaged gradients in `.grad`; do not all-reduce them again."""
+        self._dp = (group,) if enabled else None
+        return self
+
     def _backward_train(self, grad_y: torch.Tensor, ws: torch.Tensor, B: int):
         """Runs msd_model_backward and returns {parameter name: fp32 gradient in the parameter's own layout}."""
+        from ..training.distributed import reduce_gradient_groups
         lib = _lib.load()
         enc, dec = self.encoder, self.decoder
         dev = grad_y.device
         E, depth = enc.embed_dim, enc.depth
-        bufs = {}
+        # every gradient buffer is a slice of ONE arena, laid out in the order the backward completes them (gradient groups of
+        # msd_model_backward: 0 = decoder, 1 + j = encoder block depth-1-j (+ encoder.norm), depth + 1 = patch embedding)
+        req = []           # (group, name, shape, setter)
 
-        def buf(name, *shape):
-            t = torch.empty(*shape, dtype=torch.float32, device=dev)
-            bufs[name] = t
-            return _lib.ptr(t)
+        def buf(group, name, setter, *shape):
+            req.append((group, name, tuple(shape), setter))
 
         def want(param):
             return param.requires_grad
 
         g = _lib.ModelGrads()
+        last = depth + 1
         pe = enc.patch_embed
         kpe = pe.proj.weight[0].numel()
-        if want(pe.proj.weight): g.w_pe = buf("encoder.patch_embed.proj.weight", E, kpe)
-        if want(pe.proj.bias): g.b_pe = buf("encoder.patch_embed.proj.bias", E)
+        if want(pe.proj.weight): buf(last, "encoder.patch_embed.proj.weight", lambda p_: setattr(g, "w_pe", p_), E, kpe)
+        if want(pe.proj.bias): buf(last, "encoder.patch_embed.proj.bias", lambda p_: setattr(g, "b_pe", p_), E)
         if want(pe.norm.weight):
-            g.pe_ln_g, g.pe_ln_b = buf("encoder.patch_embed.norm.weight", E), buf("encoder.patch_embed.norm.bias", E)
-        if want(enc.pos_embed): g.pos_embed = buf("encoder.pos_embed", enc.pos_embed.shape[1], E)
+            buf(last, "encoder.patch_embed.norm.weight", lambda p_: setattr(g, "pe_ln_g", p_), E)
+            buf(last, "encoder.patch_embed.norm.bias", lambda p_: setattr(g, "pe_ln_b", p_), E)
+        if want(enc.pos_embed): buf(last, "encoder.pos_embed", lambda p_: setattr(g, "pos_embed", p_), enc.pos_embed.shape[1], E)
         bg = (_lib.BlockGrads * depth)()
         names = {v: k for k, v in ((n, id(p)) for n, p in self.named_parameters())}
         for i, blk in enumerate(enc.blocks):
@@ -487,45 +509,76 @@ class SatMAERestoration(nn.Module):
             t = blk.tensors()
             hid = t["fc1"].weight.shape[0]
             for field, param, shape in (
-                    ("ln1_g", t["ln1"].weight, (E,)), ("ln1_b", t["ln1"].bias, (E,)), ("ln2_g", t["ln2"].weight, (E,)),
-                    ("ln2_b", t["ln2"].bias, (E,)), ("w_qkv", t["qkv_w"], (3 * E, E)), ("b_qkv", t["qkv_b"], (3 * E,)),
-                    ("w_proj", t["proj_w"], (E, E)), ("b_proj", t["proj_b"], (E,)), ("w_fc1", t["fc1"].weight, (hid, E)),
-                    ("b_fc1", t["fc1"].bias, (hid,)), ("w_fc2", t["fc2"].weight, (E, hid)), ("b_fc2", t["fc2"].bias, (E,))):
-                setattr(bg[i], field, buf(names[id(param)], *shape))
+                    ("w_fc2", t["fc2"].weight, (E, hid)), ("b_fc2", t["fc2"].bias, (E,)), ("w_fc1", t["fc1"].weight, (hid, E)),
+                    ("b_fc1", t["fc1"].bias, (hid,)), ("ln2_g", t["ln2"].weight, (E,)), ("ln2_b", t["ln2"].bias, (E,)),
+                    ("w_proj", t["proj_w"], (E, E)), ("b_proj", t["proj_b"], (E,)), ("w_qkv", t["qkv_w"], (3 * E, E)),
+                    ("b_qkv", t["qkv_b"], (3 * E,)), ("ln1_g", t["ln1"].weight, (E,)), ("ln1_b", t["ln1"].bias, (E,))):
+                buf(depth - i, names[id(param)], lambda p_, i=i, field=field: setattr(bg[i], field, p_), *shape)
         g.blocks = C.cast(bg, C.POINTER(_lib.BlockGrads))
-        g.norm_g, g.norm_b = buf("encoder.norm.weight", E), buf("encoder.norm.bias", E)
+        buf(1, "encoder.norm.weight", lambda p_: setattr(g, "norm_g", p_), E)
+        buf(1, "encoder.norm.bias", lambda p_: setattr(g, "norm_b", p_), E)
         mods = list(dec.upsample_blocks)
         per_stage = 1 + dec.num_residual_blocks
-        post = []          # (parameter name, buffer name, unpack function)
-        cin = E
-        for s in range(4):
-            c = dec.channels[s]
-            kpad = (c + 63) // 64 * 64
-            up = mods[s * per_stage]
-            sg = g.stages[s]
-            pfx = f"decoder.upsample_blocks.{s * per_stage}.upsample."
-            sg.w_up = buf(pfx + "0.weight", 4 * c, cin)
-            post.append((pfx + "0.weight", lambda t, c=c, cin=cin: t.view(2, 2, c, cin).permute(3, 2, 0, 1).contiguous()))
-            sg.bn_up_g, sg.bn_up_b = buf(pfx + "1.weight", c), buf(pfx + "1.bias", c)
-            bufs[pfx + "0.bias"] = torch.zeros(c, dtype=torch.float32, device=dev)      # a bias in front of BatchNorm has zero gradient
-            k = 0
-            for j in range(dec.num_residual_blocks):
-                rp = f"decoder.upsample_blocks.{s * per_stage + 1 + j}.block."
-                for ci, bi in ((0, 1), (3, 4)):
-                    sg.w_conv[k] = buf(rp + f"{ci}.weight", 9, kpad, c).value
-                    post.append((rp + f"{ci}.weight", lambda t, c=c: t[:, :c, :].permute(2, 1, 0).reshape(c, c, 3, 3).contiguous()))
-                    sg.bn_g[k], sg.bn_b[k] = buf(rp + f"{bi}.weight", c).value, buf(rp + f"{bi}.bias", c).value
-                    k += 1
-            cin = c
+        post = []          # (parameter name, unpack function): packed gradient layout -> the parameter's layout
+        zero_names = []    # a bias in front of BatchNorm has zero gradient
         c = dec.channels[-1]
         kpad = (c + 63) // 64 * 64
-        g.w_head3 = buf("decoder.head.0.weight", 9, kpad, c)
+        buf(0, "decoder.head.3.weight", lambda p_: setattr(g, "w_head1", p_), dec.out_channels, c)
+        buf(0, "decoder.head.3.bias", lambda p_: setattr(g, "b_head1", p_), dec.out_channels)
+        buf(0, "decoder.head.1.weight", lambda p_: setattr(g, "bn_head_g", p_), c)
+        buf(0, "decoder.head.1.bias", lambda p_: setattr(g, "bn_head_b", p_), c)
+        buf(0, "decoder.head.0.weight", lambda p_: setattr(g, "w_head3", p_), 9, kpad, c)
         post.append(("decoder.head.0.weight", lambda t, c=c: t[:, :c, :].permute(2, 1, 0).reshape(c, c, 3, 3).contiguous()))
-        bufs["decoder.head.0.bias"] = torch.zeros(c, dtype=torch.float32, device=dev)
-        g.bn_head_g, g.bn_head_b = buf("decoder.head.1.weight", c), buf("decoder.head.1.bias", c)
-        g.w_head1, g.b_head1 = buf("decoder.head.3.weight", dec.out_channels, c), buf("decoder.head.3.bias", dec.out_channels)
+        zero_names.append(("decoder.head.0.bias", c))
+        for s in reversed(range(4)):
+            c = dec.channels[s]
+            cin = E if s == 0 else dec.channels[s - 1]
+            kpad = (c + 63) // 64 * 64
+            sg = g.stages[s]
+            k = 2 * dec.num_residual_blocks
+            for j in reversed(range(dec.num_residual_blocks)):
+                rp = f"decoder.upsample_blocks.{s * per_stage + 1 + j}.block."
+                for ci, bi in ((3, 4), (0, 1)):
+                    k -= 1
+                    buf(0, rp + f"{bi}.weight", lambda p_, sg=sg, k=k: sg.bn_g.__setitem__(k, p_.value), c)
+                    buf(0, rp + f"{bi}.bias", lambda p_, sg=sg, k=k: sg.bn_b.__setitem__(k, p_.value), c)
+                    buf(0, rp + f"{ci}.weight", lambda p_, sg=sg, k=k: sg.w_conv.__setitem__(k, p_.value), 9, kpad, c)
+                    post.append((rp + f"{ci}.weight", lambda t, c=c: t[:, :c, :].permute(2, 1, 0).reshape(c, c, 3, 3).contiguous()))
+            pfx = f"decoder.upsample_blocks.{s * per_stage}.upsample."
+            buf(0, pfx + "1.weight", lambda p_, sg=sg: setattr(sg, "bn_up_g", p_), c)
+            buf(0, pfx + "1.bias", lambda p_, sg=sg: setattr(sg, "bn_up_b", p_), c)
+            buf(0, pfx + "0.weight", lambda p_, sg=sg: setattr(sg, "w_up", p_), 4 * c, cin)
+            post.append((pfx + "0.weight", lambda t, c=c, cin=cin: t.view(2, 2, c, cin).permute(3, 2, 0, 1).contiguous()))
+            zero_names.append((pfx + "0.bias", c))
+        # arena: groups in completion order, every slice 16-byte aligned
+        req.sort(key=lambda r: r[0])
+        off, spans, bounds, pads = 0, [], {}, []
+        for group, name, shape, _ in req:
+            n = 1
+            for d_ in shape:
+                n *= d_
+            spans.append((off, n))
+            lo, hi = bounds.get(group, (off, off))
+            bounds[group] = (min(lo, off), off + n)
+            if n % 4:
+                pads.append((off + n, off + (n + 3) // 4 * 4))
+            off += (n + 3) // 4 * 4
+        arena = torch.empty(off, dtype=torch.float32, device=dev)
+        for lo, hi in pads:        # alignment words between slices belong to no gradient; keep them defined for the collectives
+            arena[lo:hi].zero_()
+        bufs = {}
+        for (group, name, shape, setter), (o, n) in zip(req, spans):
+            t = arena[o:o + n].view(shape)
+            bufs[name] = t
+            setter(C.c_void_p(t.data_ptr()))
         with torch.cuda.device(dev):
             _lib.check(lib.msd_model_backward(self._handle, _lib.ptr(grad_y), B, _lib.ptr(ws), ws.numel(), C.byref(g), _lib.stream_ptr()))
+            dp = getattr(self, "_dp", None)
+            if dp is not None:
+                reduce_gradient_groups(arena, [bounds[k] for k in sorted(bounds)], sorted(bounds), dp[0],
+                                       lambda k, stream_ptr: _lib.check(lib.msd_model_grad_group_wait(self._handle, k, stream_ptr)))
+        for name, n in zero_names:
+            bufs[name] = torch.zeros(n, dtype=torch.float32, device=dev)
         for name, fn in post:
             bufs[name] = fn(bufs[name])
         out = {}

@@ -12,6 +12,7 @@ src.training.eval.evaluate_model.  Optional third-party modules the reference im
 from __future__ import annotations
 
 import importlib
+import importlib.machinery
 import runpy
 import sys
 import types
@@ -41,6 +42,9 @@ def _stub_missing():
         except ImportError:
             mod = _Stub(name)
             mod.__path__ = []
+            # importlib.util.find_spec() on a module already in sys.modules returns its __spec__ and raises if that is None
+            # (torch._dynamo.trace_rules probes "onnx" that way the first time an optimizer is built)
+            mod.__spec__ = importlib.machinery.ModuleSpec(name, loader=None, is_package=True)
             sys.modules[name] = mod
             if "." in name:
                 setattr(sys.modules[name.rsplit(".", 1)[0]], name.rsplit(".", 1)[1], mod)
@@ -80,12 +84,26 @@ def rebind(ref_root: Path) -> list[str]:
 
 def main(argv=None):
     argv = list(sys.argv[1:] if argv is None else argv)
+    if len(argv) >= 2 and argv[0] == "--log-level":
+        # The reference's dataset module logs a warning at import time, which configures the root logger at WARNING before the
+        # script's own basicConfig(level=INFO) runs (a no-op by then): its INFO lines -- the evaluation results among them -- are
+        # then invisible.  This launcher option configures logging first; the script itself is untouched.
+        import logging
+        logging.basicConfig(level=getattr(logging, argv[1].upper()), force=True)
+        argv = argv[2:]
     if not argv:
-        raise SystemExit("usage: python -m msd_b200.run <reference>/scripts/<script>.py [script args]")
+        raise SystemExit("usage: python -m msd_b200.run [--log-level LEVEL] <reference>/scripts/<script>.py [script args]")
     script = Path(argv[0]).resolve()
     patched = rebind(script.parent.parent)
     print(f"[msd_b200.run] rebound {len(patched)} names to libmsd_b200", file=sys.stderr)
     sys.argv = [str(script)] + argv[1:]
+    if script.name == "export.py":
+        # scripts/export.py builds the model on the CPU, traces it and evaluates it there as the ONNX ground truth
+        # (src/deployment/export_onnx.py:40-69, 216-219): the only script that needs the torch-op export graph
+        from msd_b200.models import export_mode
+        with export_mode():
+            runpy.run_path(str(script), run_name="__main__")
+        return
     runpy.run_path(str(script), run_name="__main__")
 
 

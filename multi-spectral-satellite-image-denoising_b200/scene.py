@@ -105,3 +105,39 @@ def restore_scene(model, scene: torch.Tensor, overlap: int = 32, batch: int = 25
         if full is not None:
             out.copy_(full[:, row0:row1])
     return out, (row0, row1)
+
+
+def scene_to_dn(band: torch.Tensor, rows: Tuple[int, int], scene_h: int, rank: int = 0, world: int = 1, host_out: torch.Tensor | None = None):
+    """Writer side of C5: a rank's restored band (fp32, model normalisation) -> Sentinel-2 digital numbers (uint16,
+    `msd_export_u16`), gathered to rank 0 over NCCL (one padded gather; the bands are the only data that moves) and copied into
+    `host_out` (pinned uint16 [C, scene_h, W]) when given.  Returns the full uint16 scene on rank 0 (device tensor), None elsewhere."""
+    from .data import export_tiles
+    C_, _, W = band.shape
+    dev = band.device
+    row0, row1 = rows
+    pad = (-band.numel()) % 4
+    flat = band.reshape(-1)
+    if pad:
+        flat = torch.cat([flat, flat.new_zeros(pad)])
+    dn = export_tiles(flat)[:band.numel()].view(C_, row1 - row0, W) if band.numel() else torch.empty(C_, 0, W, dtype=torch.uint16, device=dev)
+    if world == 1:
+        full = dn
+    else:
+        import torch.distributed as dist
+        spans = [None] * world
+        dist.all_gather_object(spans, (row0, row1))
+        hmax = max(b - a for a, b in spans)
+        mine = torch.zeros(C_, hmax, W, dtype=torch.int16, device=dev)
+        mine[:, :row1 - row0] = dn.view(torch.int16)
+        parts = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
+        dist.gather(mine, parts, dst=0)
+        if rank != 0:
+            return None
+        full = torch.empty(C_, scene_h, W, dtype=torch.int16, device=dev)
+        for (a, b), part in zip(spans, parts):
+            if b > a:
+                full[:, a:b] = part[:, :b - a]
+        full = full.view(torch.uint16)
+    if host_out is not None:
+        host_out.copy_(full, non_blocking=True)
+    return full

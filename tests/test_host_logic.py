@@ -205,3 +205,37 @@ def test_layernorm_fold_algebra():
         w_eff = wg.double() / gam.double()             # the weight the fold actually represents after bf16 rounding
         ref = F.linear(F.layer_norm(x, (D,), gam.double(), None, eps), w_eff) + (b.double() + w.double() @ bet.double())
         assert (fused - ref).abs().max().item() < 1e-5     # fp32 column sums are the only non-fp64 term
+
+
+def test_export_graph_is_the_reference_forward_and_only_runs_for_tracers(golden_model):
+    """scripts/export.py traces model.forward on the CPU.  Under a tracer (or export_mode()) the drop-in
+    evaluates its torch-op graph definition -- equal to the oracle / the reference's golden output to fp32 rounding, for both
+    block layouts -- and everywhere else a CPU tensor still raises (no CPU execution path)."""
+    import pytest
+    import recipes
+    from msd_b200 import MsdError
+    from msd_b200.models import SatMAERestoration, export_mode
+    from oracle import model as omodel
+    torch.manual_seed(42)
+    m = SatMAERestoration(recipes.base_config(), block_layout="fallback").eval()
+    x = recipes.model_input(2)[:1]
+    with pytest.raises(MsdError):
+        m(x)
+    with torch.no_grad(), export_mode():
+        y = m(x)
+    with pytest.raises(MsdError):                       # the switch does not leak out of the block
+        m(x)
+    ref = omodel.restoration_forward({k: v.clone() for k, v in m.state_dict().items()}, x)
+    assert (y - ref).abs().max().item() <= 2e-6
+    assert (y[:, :, ::4, ::4] - torch.from_numpy(golden_model["y_sub"])[:1]).abs().max().item() <= 2e-5      # the reference itself
+    with torch.no_grad():
+        traced = torch.jit.trace(m, x, check_trace=False)           # what torch.onnx.export does first (export_onnx.py:40-69)
+        assert torch.equal(traced(x), y)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    recipes.perturb_decoder_stats(sd)
+    t = SatMAERestoration(recipes.base_config(), block_layout="timm").eval()
+    t.load_state_dict(sd)
+    with torch.no_grad(), export_mode():
+        yt = t(x)
+    reft = omodel.restoration_forward(t.state_dict(), x, ln_eps_block=1e-6)
+    assert (yt - reft).abs().max().item() <= 2e-5 * max(1.0, reft.abs().max().item())

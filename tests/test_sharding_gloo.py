@@ -96,3 +96,31 @@ def test_gradient_allreduce_world2():
         for i in (0, 2, 3):
             assert grads[i].shape == [(7, 5), (1000,), (3, 3, 3, 3), (2,)][i]
             assert torch.allclose(grads[i], torch.full_like(grads[i], 1.5 * (i + 1)))
+
+
+def _group_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from msd_b200.training.distributed import reduce_gradient_groups
+    # an arena of three gradient groups with an alignment gap and an absent (empty) group in between
+    arena = torch.arange(40, dtype=torch.float32) * (rank + 1)
+    bounds, ids = [(0, 13), (16, 16), (16, 40)], [0, 3, 7]
+    n = reduce_gradient_groups(arena, bounds, ids, None, None)
+    out[rank] = (n, arena.clone())
+    dist.destroy_process_group()
+
+
+def test_gradient_group_reduction_world2():
+    """the in-place per-group averaging SatMAERestoration.enable_data_parallel() runs on its gradient arena (on CUDA: on a
+    communication stream behind each group's event; here the same code on CPU tensors over gloo)"""
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_group_worker, args=(world, 29523, out), nprocs=world, join=True)
+    base = torch.arange(40, dtype=torch.float32)
+    for rank in range(world):
+        n, arena = out[rank]
+        assert n == 2                                           # the empty group issues no collective
+        assert torch.allclose(arena[:13], base[:13] * 1.5) and torch.allclose(arena[16:], base[16:] * 1.5)
+        assert torch.equal(arena[13:16], base[13:16] * (rank + 1))          # the alignment gap is nobody's gradient: untouched

@@ -1,6 +1,6 @@
-# round 2 iteration run: GPU tests (stop at first failure), smoke, kernel micro-benchmarks, short bench with the per-launch event profile
+# round 2 iteration run: GPU tests (stop at first failure), smoke, micro-benchmarks, short bench with the per-launch event profile
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -q -p no:cacheprovider -m gpu -x > gpurun_out/t_gpu.log 2>&1; echo "gpu tests rc=$?"; tail -n 25 gpurun_out/t_gpu.log
+timeout 1200 python -m pytest tests -q -p no:cacheprovider -m gpu -x > gpurun_out/t_gpu.log 2>&1; echo "gpu tests rc=$?"; tail -n 25 gpurun_out/t_gpu.log
 timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -n 2 gpurun_out/smoke.log
-timeout 300 python tools/gemm_bench.py > gpurun_out/gemm_bench.txt 2>&1; cat gpurun_out/gemm_bench.txt
-timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --profile-out gpurun_out/profile.json > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; cut -c1-300 gpurun_out/bench.json; tail -n 3 gpurun_out/bench.err
+python tools/elem_bench.py 2>&1 | tee gpurun_out/elem_bench.txt
+timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --profile-out gpurun_out/profile.json > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; cut -c1-300 gpurun_out/bench.json; tail -n 5 gpurun_out/bench.err
