@@ -9,42 +9,72 @@
 //   the padding is zero, so the blur is self-adjoint).
 // Pass 1 (fwd): blur 5 maps, reduce sum((p-t)^2) and sum(S), write the 3 derivative maps.
 // Pass 2 (bwd): blur the 3 derivative maps and combine with p, t into grad_pred.
-#include "common.cuh"
+#include "gemm_tc5.cuh"
 #include "ssim_tile.cuh"
 
 namespace {
 
 using namespace ssim;
 
+// Halo tiles arrive by TMA when the rows are 16-byte aligned (W % 4 == 0): one 3-D box {80, 42, 1} per map over [planes, H, W],
+// out-of-image coordinates read as zero = the window's zero padding.  A box must start on a 16-byte boundary of the row, so it
+// starts at x0 - 8 and the stencil reads it kXoff = 3 columns further in (see metrics.cu).  Otherwise: per-thread guarded loads.
+constexpr uint32_t kTileBytes = IH * PW * 4;
+constexpr int kXoff = 3;
+
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* tm, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n"
+      ::"r"(gemm::tc5::smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(gemm::tc5::smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
 struct FwdSmem {
   RawTile<2> raw;
   HBlur2<2> hb;               // packed pairs (p + t, p - t) and (p*p + t*t, p*t): one FFMA2 per tap (ssim_tile.cuh)
   double red[2][kThreads / 32];
+  uint64_t bar;
 };
 struct BwdSmem {
   RawTile<3> raw;
   HBlur2<1> hb2;              // (dmu1 + de11, dmu1 - de11), packed
   HBlur<1> hb;                // de12
+  float pt[2][TH][TW];        // the tile's own pred / target pixels (TMA path): no dependent global loads at the tail of the CTA
+  uint64_t bar;
 };
 
-template <bool kWriteDeriv>
+template <bool kWriteDeriv, bool kTma>
 __global__ void __launch_bounds__(kThreads, 2)
-loss_fwd_kernel(const float* __restrict__ pred, const float* __restrict__ target, int H, int W, int tiles_x, int tiles_y,
+loss_fwd_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmT, const float* __restrict__ pred,
+                const float* __restrict__ target, int H, int W, int tiles_x, int tiles_y,
                 SsimConsts consts, size_t numel, float* __restrict__ deriv /*[3][numel]*/, double* __restrict__ acc /*[2]*/) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   FwdSmem& sm = *reinterpret_cast<FwdSmem*>(smem_raw);
+  constexpr int XO = kTma ? kXoff : 0;
   const int tile = blockIdx.x % (tiles_x * tiles_y);
   const int plane = blockIdx.x / (tiles_x * tiles_y);
   const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
   const int y0 = ty * TH, x0 = tx * TW;
   const size_t poff = (size_t)plane * H * W;
-  load_raw_plane(sm.raw.v[0], pred + poff, y0, x0, H, W);
-  load_raw_plane(sm.raw.v[1], target + poff, y0, x0, H, W);
-  __syncthreads();
+  if constexpr (kTma) {
+    if (threadIdx.x == 0) {
+      gemm::tc5::mbar_init(&sm.bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+      gemm::tc5::mbar_arrive_expect_tx(&sm.bar, 2 * kTileBytes);
+      tma_load_3d(&tmP, &sm.bar, &sm.raw.v[0][0][0], x0 - R - kXoff, y0 - R, plane);
+      tma_load_3d(&tmT, &sm.bar, &sm.raw.v[1][0][0], x0 - R - kXoff, y0 - R, plane);
+    }
+    __syncthreads();                       // the barrier's initialisation is visible to every waiter
+    gemm::tc5::mbar_wait(&sm.bar, 0);
+  } else {
+    load_raw_plane(sm.raw.v[0], pred + poff, y0, x0, H, W);
+    load_raw_plane(sm.raw.v[1], target + poff, y0, x0, H, W);
+    __syncthreads();
+  }
   // Four maps, not the reference's five: S and its derivatives only use e11 + e22 (B2 below; dS/de11 = dS/de22), and the blur is
   // linear.  Two maps per 64-bit register, one FFMA2 per tap; pair 0 is (p + t, p - t) so that both lanes are computed values
   // (blur(p +- t) = mu1 +- mu2), see metrics.cu.
-  hpass2<2, 2>(sm.raw, sm.hb, [](int mp, const float (&px)[2]) -> f2 {
+  hpass2<2, 2, XO>(sm.raw, sm.hb, [](int mp, const float (&px)[2]) -> f2 {
     return mp == 0 ? pack2(px[0] + px[1], px[0] - px[1]) : pack2(fmaf(px[0], px[0], px[1] * px[1]), px[0] * px[1]);
   });
   __syncthreads();
@@ -68,7 +98,7 @@ loss_fwd_kernel(const float* __restrict__ pred, const float* __restrict__ target
       const float B2 = (esum - mu1_sq - mu2_sq) + consts.C2;
       const float S = (A1 * A2) / (B1 * B2);
       s_ssim += S;
-      const float d = sm.raw.v[0][8 * h + o + R][x + R] - sm.raw.v[1][8 * h + o + R][x + R];
+      const float d = sm.raw.v[0][8 * h + o + R][x + R + XO] - sm.raw.v[1][8 * h + o + R][x + R + XO];
       s_sq = fmaf(d, d, s_sq);
       if (kWriteDeriv) {
         const float inv = 1.0f / (B1 * B2);
@@ -93,23 +123,41 @@ loss_fwd_kernel(const float* __restrict__ pred, const float* __restrict__ target
   }
 }
 
+template <bool kTma>
 __global__ void __launch_bounds__(kThreads, 2)
-loss_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ target, const float* __restrict__ deriv, int H,
+loss_bwd_kernel(const __grid_constant__ CUtensorMap tmD /* deriv as [3 * planes, H, W] */, const __grid_constant__ CUtensorMap tmPc,
+                const __grid_constant__ CUtensorMap tmTc /* pred / target, box {64, 32, 1} */, int planes, const float* __restrict__ pred,
+                const float* __restrict__ target, const float* __restrict__ deriv, int H,
                 int W, int tiles_x, int tiles_y, size_t numel, float k_ssim /* -w_ssim*scale/N */,
                 float k_mse /* 2*w_mse*scale/N */, float* __restrict__ grad) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   BwdSmem& sm = *reinterpret_cast<BwdSmem*>(smem_raw);
+  constexpr int XO = kTma ? kXoff : 0;
   const int tile = blockIdx.x % (tiles_x * tiles_y);
   const int plane = blockIdx.x / (tiles_x * tiles_y);
   const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
   const int y0 = ty * TH, x0 = tx * TW;
   const size_t poff = (size_t)plane * H * W;
+  if constexpr (kTma) {
+    if (threadIdx.x == 0) {
+      gemm::tc5::mbar_init(&sm.bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+      gemm::tc5::mbar_arrive_expect_tx(&sm.bar, 3 * kTileBytes + 2 * TH * TW * 4);
 #pragma unroll
-  for (int i = 0; i < 3; ++i) load_raw_plane(sm.raw.v[i], deriv + (size_t)i * numel + poff, y0, x0, H, W);
-  __syncthreads();
+      for (int i = 0; i < 3; ++i) tma_load_3d(&tmD, &sm.bar, &sm.raw.v[i][0][0], x0 - R - kXoff, y0 - R, i * planes + plane);
+      tma_load_3d(&tmPc, &sm.bar, &sm.pt[0][0][0], x0, y0, plane);
+      tma_load_3d(&tmTc, &sm.bar, &sm.pt[1][0][0], x0, y0, plane);
+    }
+    __syncthreads();
+    gemm::tc5::mbar_wait(&sm.bar, 0);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) load_raw_plane(sm.raw.v[i], deriv + (size_t)i * numel + poff, y0, x0, H, W);
+    __syncthreads();
+  }
   // blur(dmu1) and blur(de11) ride together as the packed pair (sum, difference); blur(de12) takes the scalar stencil
-  hpass2<3, 1>(sm.raw, sm.hb2, [](int, const float (&px)[3]) -> f2 { return pack2(px[0] + px[1], px[0] - px[1]); });
-  hpass<3, 1>(sm.raw, sm.hb, [](int, const float (&px)[3]) -> float { return px[2]; });
+  hpass2<3, 1, XO>(sm.raw, sm.hb2, [](int, const float (&px)[3]) -> f2 { return pack2(px[0] + px[1], px[0] - px[1]); });
+  hpass<3, 1, XO>(sm.raw, sm.hb, [](int, const float (&px)[3]) -> float { return px[2]; });
   __syncthreads();
   f2 res2[1][8];
   vpass2<1>(sm.hb2, res2);
@@ -122,7 +170,7 @@ loss_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ target
       const int yy = y0 + 8 * h + o;
       if (yy >= H) continue;
       const size_t e = poff + (size_t)yy * W + (x0 + x);
-      const float p = __ldg(pred + e), t = __ldg(target + e);
+      const float p = kTma ? sm.pt[0][8 * h + o][x] : __ldg(pred + e), t = kTma ? sm.pt[1][8 * h + o][x] : __ldg(target + e);
       float bs, bd;
       unpack2(res2[0][o], bs, bd);
       const float b_mu1 = 0.5f * (bs + bd), b_e11 = 0.5f * (bs - bd);
@@ -169,23 +217,39 @@ extern "C" int msd_loss_fwd_bwd_f32(const float* d_pred, const float* d_target, 
   consts.C2 = (float)((0.03 * (double)data_range) * (0.03 * (double)data_range));
   static PerDeviceOnce attr_set;
   if (attr_set.first()) {
-    MSD_CHECK_CUDA(cudaFuncSetAttribute(loss_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FwdSmem)));
-    MSD_CHECK_CUDA(cudaFuncSetAttribute(loss_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FwdSmem)));
-    MSD_CHECK_CUDA(cudaFuncSetAttribute(loss_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdSmem)));
+    MSD_CHECK_CUDA(cudaFuncSetAttribute(loss_fwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FwdSmem)));
+    MSD_CHECK_CUDA(cudaFuncSetAttribute(loss_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FwdSmem)));
+    MSD_CHECK_CUDA(cudaFuncSetAttribute(loss_fwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FwdSmem)));
+    MSD_CHECK_CUDA(cudaFuncSetAttribute(loss_fwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FwdSmem)));
+    MSD_CHECK_CUDA(cudaFuncSetAttribute(loss_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdSmem)));
+    MSD_CHECK_CUDA(cudaFuncSetAttribute(loss_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdSmem)));
   }
   const int tiles_x = (W + TW - 1) / TW, tiles_y = (H + TH - 1) / TH;
   const unsigned blocks = (unsigned)B * C * tiles_x * tiles_y;
-  if (d_grad_pred)
-    loss_fwd_kernel<true><<<blocks, kThreads, sizeof(FwdSmem), s>>>(d_pred, d_target, H, W, tiles_x, tiles_y, consts, numel, deriv, acc);
-  else
-    loss_fwd_kernel<false><<<blocks, kThreads, sizeof(FwdSmem), s>>>(d_pred, d_target, H, W, tiles_x, tiles_y, consts, numel, nullptr, acc);
+  const int planes = B * C;
+  CUtensorMap tmP, tmT, tmD, tmPc, tmTc;
+  // TMA needs 16-byte aligned rows; anything else (or a driver that refuses a map) takes the per-thread loads
+  bool tma = W % 4 == 0 && msd_aligned16(d_pred) && msd_aligned16(d_target) &&
+             gemm::tc5::make_map_planes_f32(&tmP, d_pred, (uint64_t)W, (uint64_t)H, (uint64_t)planes, PW, IH) == MSD_OK &&
+             gemm::tc5::make_map_planes_f32(&tmT, d_target, (uint64_t)W, (uint64_t)H, (uint64_t)planes, PW, IH) == MSD_OK;
+  if (tma && d_grad_pred)
+    tma = gemm::tc5::make_map_planes_f32(&tmD, deriv, (uint64_t)W, (uint64_t)H, 3ull * planes, PW, IH) == MSD_OK &&
+          gemm::tc5::make_map_planes_f32(&tmPc, d_pred, (uint64_t)W, (uint64_t)H, (uint64_t)planes, TW, TH) == MSD_OK &&
+          gemm::tc5::make_map_planes_f32(&tmTc, d_target, (uint64_t)W, (uint64_t)H, (uint64_t)planes, TW, TH) == MSD_OK;
+  if (!tma) { memset(&tmP, 0, sizeof(tmP)); tmT = tmP; tmD = tmP; }
+  if (!tma || !d_grad_pred) { tmD = tmP; tmPc = tmP; tmTc = tmP; }
+#define MSD_LOSS_FWD(WD, TM) loss_fwd_kernel<WD, TM><<<blocks, kThreads, sizeof(FwdSmem), s>>>(tmP, tmT, d_pred, d_target, H, W, tiles_x, tiles_y, consts, numel, d_grad_pred ? deriv : nullptr, acc)
+  if (d_grad_pred) { if (tma) MSD_LOSS_FWD(true, true); else MSD_LOSS_FWD(true, false); }
+  else { if (tma) MSD_LOSS_FWD(false, true); else MSD_LOSS_FWD(false, false); }
+#undef MSD_LOSS_FWD
   MSD_LAUNCH_CHECK();
   loss_finalize_kernel<<<1, 1, 0, s>>>(acc, (double)numel, w_mse, w_ssim, d_out);
   MSD_LAUNCH_CHECK();
   if (d_grad_pred) {
     const float k_ssim = (float)(-(double)w_ssim * (double)grad_scale / (double)numel);
     const float k_mse = (float)(2.0 * (double)w_mse * (double)grad_scale / (double)numel);
-    loss_bwd_kernel<<<blocks, kThreads, sizeof(BwdSmem), s>>>(d_pred, d_target, deriv, H, W, tiles_x, tiles_y, numel, k_ssim, k_mse, d_grad_pred);
+    if (tma) loss_bwd_kernel<true><<<blocks, kThreads, sizeof(BwdSmem), s>>>(tmD, tmPc, tmTc, planes, d_pred, d_target, deriv, H, W, tiles_x, tiles_y, numel, k_ssim, k_mse, d_grad_pred);
+    else loss_bwd_kernel<false><<<blocks, kThreads, sizeof(BwdSmem), s>>>(tmD, tmPc, tmTc, planes, d_pred, d_target, deriv, H, W, tiles_x, tiles_y, numel, k_ssim, k_mse, d_grad_pred);
     MSD_LAUNCH_CHECK();
   }
   return MSD_OK;

@@ -127,13 +127,14 @@ def scene_to_dn(band: torch.Tensor, rows: Tuple[int, int], scene_h: int, rank: i
         spans = [None] * world
         dist.all_gather_object(spans, (row0, row1))
         hmax = max(b - a for a, b in spans)
-        mine = torch.zeros(C_, hmax, W, dtype=torch.int16, device=dev)
-        mine[:, :row1 - row0] = dn.view(torch.int16)
+        # NCCL has no 16-bit integer type: the bands travel as bytes
+        mine = torch.zeros(C_, hmax, W * 2, dtype=torch.uint8, device=dev)
+        mine[:, :row1 - row0] = dn.view(torch.uint8).view(C_, row1 - row0, W * 2)
         parts = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
         dist.gather(mine, parts, dst=0)
         if rank != 0:
             return None
-        full = torch.empty(C_, scene_h, W, dtype=torch.int16, device=dev)
+        full = torch.empty(C_, scene_h, W * 2, dtype=torch.uint8, device=dev)
         for (a, b), part in zip(spans, parts):
             if b > a:
                 full[:, a:b] = part[:, :b - a]
