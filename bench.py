@@ -296,8 +296,8 @@ def scene_bench(model, dev, rank, world, size=10980, overlap=32, batch=256):
         scene[c] = torch.rand(size, size, generator=g, device=dev) * 4 - 2
     host = torch.empty(13, size, size, dtype=torch.uint16, pin_memory=True) if rank == 0 else None
     small = scene[:, :400, :400].contiguous()
-    b, r = restore_scene(model, small, overlap=overlap, batch=4)                       # warm-up (kernels, allocator)
-    scene_to_dn(b, r, 400)
+    b, r = restore_scene(model, small, overlap=overlap, batch=4, rank=rank, world=world)   # warm-up: kernels, allocator and the
+    scene_to_dn(b, r, 400, rank, world)                                                    # communicator's gather channels
     e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     torch.cuda.synchronize()
     if world > 1:
@@ -457,6 +457,8 @@ def main():
                     bufs[i % 2].copy_(host_src, non_blocking=True)
                     ready[i % 2].record(copy_stream)
 
+            trackers = [MetricsTracker(), MetricsTracker()]     # two, alternating: their pinned result buffers are allocated once
+
             def e2e_run(steps):
                 for b in range(2):
                     freed[b].record()
@@ -469,7 +471,8 @@ def main():
                     c = bufs[i % 2]
                     if c.dtype == torch.uint16:
                         c = ingest_tiles(c, 192)                # raw digital numbers -> the model's normalisation, on the device
-                    t = MetricsTracker()
+                    t = trackers[i % 2]
+                    t.reset()                                   # step i - 2's result was read during step i - 1
                     noisy = noise(c, patch_out=patches)
                     restored = model(noisy, patches=patches)
                     t.update(restored, c)
