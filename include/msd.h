@@ -371,6 +371,22 @@ typedef struct msd_adamw_tensor {
   int step;                 /* 1-based step count of THIS tensor (torch.optim.AdamW keeps one per parameter); 0 = use the call's `step` */
 } msd_adamw_tensor;
 int msd_grad_sqnorm_f32(const msd_adamw_tensor* tensors, int n, double* d_sqnorm, void* stream);
+/* Weight repack after an optimizer step: the fp32 master weights -> the bf16 / transposed / tap-flipped operands of
+ * msd_train_weights, one launch per 24 ops instead of a cast / permute / flip / pad launch per tensor.  `ops` is a HOST array.
+ *   CAST            dst bf16 [d0*d1]            = src
+ *   TRANSPOSE       dst bf16 [d1, d0]           = src[d0, d1]^T                       (W^T of a Linear, data gradient)
+ *   CONV3           dst bf16 [d0, 9*kpad]       = src[Cout=d0, Cin=d1, 3, 3] tap-major (ky, kx, ci), ci >= Cin zero
+ *   CONV3_DGRAD     dst bf16 [d1, T*kpad]       : Wd[ci, tap, co] = W[co, ci, 8 - tap]; flag != 0: T = 10, tap 9 = identity
+ *   CONVT           dst bf16 [4*d1, kpad]       = src[Cin=d0, Cout=d1, 2, 2] as rows (di, dj, o), ci >= Cin zero
+ *   CONVT_T         dst bf16 [d0, 4*d1]         = the transpose of the un-padded CONVT matrix
+ *   REPEAT_F32      dst fp32 [flag*d0]          = src[d0] repeated flag times                (ConvTranspose bias per sub-pixel) */
+enum { MSD_REPACK_CAST = 0, MSD_REPACK_TRANSPOSE = 1, MSD_REPACK_CONV3 = 2, MSD_REPACK_CONV3_DGRAD = 3, MSD_REPACK_CONVT = 4,
+       MSD_REPACK_CONVT_T = 5, MSD_REPACK_REPEAT_F32 = 6 };
+typedef struct msd_repack_op {
+  const float* src; void* dst;
+  int kind, d0, d1, kpad, flag;
+} msd_repack_op;
+int msd_repack_weights(const msd_repack_op* ops, int n, void* stream);
 int msd_adamw_step_f32(const msd_adamw_tensor* tensors, int n, float beta1, float beta2, float eps, int step, float max_grad_norm,
                        const double* d_sqnorm, void* stream);
 

@@ -83,6 +83,12 @@ class AdamWTensor(C.Structure):
                 ("lr", c_float), ("weight_decay", c_float), ("step", c_int)]
 
 
+class RepackOp(C.Structure):
+    _fields_ = [("src", c_void_p), ("dst", c_void_p), ("kind", c_int), ("d0", c_int), ("d1", c_int), ("kpad", c_int), ("flag", c_int)]
+
+
+REPACK_CAST, REPACK_TRANSPOSE, REPACK_CONV3, REPACK_CONV3_DGRAD, REPACK_CONVT, REPACK_CONVT_T, REPACK_REPEAT_F32 = range(7)
+
 # name -> (restype, argtypes); must list every symbol include/msd.h declares (tests/test_abi.py checks this)
 SIGNATURES = {
     "msd_version": (c_int, []),
@@ -160,6 +166,7 @@ SIGNATURES = {
                                    c_int, c_int, c_int, c_void_p]),
     "msd_grad_sqnorm_f32": (c_int, [C.POINTER(AdamWTensor), c_int, c_void_p, c_void_p]),
     "msd_adamw_step_f32": (c_int, [C.POINTER(AdamWTensor), c_int, c_float, c_float, c_float, c_int, c_float, c_void_p, c_void_p]),
+    "msd_repack_weights": (c_int, [C.POINTER(RepackOp), c_int, c_void_p]),
     "msd_wgrad_conv3x3_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                        c_void_p]),
 }

@@ -114,15 +114,11 @@ struct CorruptParams {
 // arithmetic, fp32 ops and stores.
 template <bool kFast, bool kPatch>
 __global__ void __launch_bounds__(kThreads) corrupt_kernel(const CorruptParams p) {
-  __shared__ float tw[64];                                         // thermal weights (C <= 64), else read through __ldg
   const bool has_g = kFast || p.sg > 0.0f, has_s = kFast || p.ss > 0.0f, has_t = kFast || p.st > 0.0f;
   const bool has_dead = kFast || p.dead != nullptr, has_stripe = !kFast && p.stripe != nullptr;
   const bool has_patch = kPatch || (!kFast && p.patch != nullptr);
-  const bool tw_smem = p.C <= 64;
-  if (has_t && tw_smem) {
-    if (threadIdx.x < p.C) tw[threadIdx.x] = __ldg(p.thermal_w + threadIdx.x);
-    __syncthreads();
-  }
+  // (the C thermal weights are read through the read-only path per element: staging them in shared memory put a block-wide
+  //  barrier in front of a 4-element-per-thread kernel -- 17 % of its stall samples)
   const uint32_t round = blockIdx.y;                               // torch-thread call number
   const uint32_t tid = blockIdx.x * kThreads + threadIdx.x;       // torch-thread index (T % 256 == 0)
   const uint32_t e0 = round * 4u * p.T + tid;                      // < 2^31 + 4T: fits 32 bits
@@ -172,7 +168,7 @@ __global__ void __launch_bounds__(kThreads) corrupt_kernel(const CorruptParams p
     // 3. dead bands zeroed BEFORE thermal noise                 (transforms.py:100-106)
     if (dead[ii]) v = 0.0f;
     // 4. thermal: corrupted + (randn*scale)*w_c                 (transforms.py:110-121)
-    if (has_t) v = __fadd_rn(v, __fmul_rn(__fmul_rn(torch_normal_xf(n3[ii]), p.st), tw_smem ? tw[c] : __ldg(p.thermal_w + c)));
+    if (has_t) v = __fadd_rn(v, __fmul_rn(__fmul_rn(torch_normal_xf(n3[ii]), p.st), __ldg(p.thermal_w + c)));
     uint32_t yy, xx;
     fd_divmod(pix[ii], p.div_w, yy, xx);
     // 5. striping: x + randn(B,C,1,W)*0.02                      (transforms.py:136-154)

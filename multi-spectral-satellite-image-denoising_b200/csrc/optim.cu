@@ -105,7 +105,97 @@ int fill(TensorTable& t, const msd_adamw_tensor* src, int n, float beta1 = 0.0f,
   return MSD_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Weight repack of the training step: after every optimizer step the fp32 master weights have to reappear as the bf16 /
+// transposed / tap-flipped operands the forward and the data-gradient GEMMs read.  One table-driven gather kernel (one thread
+// per DESTINATION element: coalesced bf16 stores, source reads served by L2 -- every weight matrix fits it) replaces the ~100
+// small cast / permute / flip / pad launches a step spent on this.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kMaxOps = 24;
+struct RepackTable {
+  const float* src[kMaxOps];
+  void* dst[kMaxOps];
+  long long n[kMaxOps];          // destination elements
+  int kind[kMaxOps], d0[kMaxOps], d1[kMaxOps], kpad[kMaxOps], flag[kMaxOps];
+  int count;
+};
+
+__device__ __forceinline__ float repack_value(const float* __restrict__ src, int kind, int d0, int d1, int kpad, int flag, long long i) {
+  switch (kind) {
+    case MSD_REPACK_CAST: return src[i];
+    case MSD_REPACK_TRANSPOSE: {            // src [d0 = N, d1 = K] -> dst [K, N]
+      const int k = (int)(i / d0), n = (int)(i - (long long)k * d0);
+      return src[(size_t)n * d1 + k];
+    }
+    case MSD_REPACK_CONV3: {                // src [d0 = Cout, d1 = Cin, 3, 3] -> dst [Cout, 9 * kpad] tap-major (ky, kx, ci)
+      const int row = 9 * kpad, co = (int)(i / row), r = (int)(i - (long long)co * row), tap = r / kpad, ci = r - tap * kpad;
+      return ci < d1 ? src[((size_t)co * d1 + ci) * 9 + tap] : 0.0f;
+    }
+    case MSD_REPACK_CONV3_DGRAD: {          // dst [Cin, T * kpad(Cout)]: Wd[ci, tap, co] = W[co, ci, 8 - tap]; tap 9 (flag) = identity
+      const int taps = flag ? 10 : 9, row = taps * kpad, ci = (int)(i / row), r = (int)(i - (long long)ci * row), tap = r / kpad, co = r - tap * kpad;
+      if (tap == 9) return co == ci ? 1.0f : 0.0f;
+      return co < d0 ? src[((size_t)co * d1 + ci) * 9 + (8 - tap)] : 0.0f;
+    }
+    case MSD_REPACK_CONVT: {                // src [d0 = Cin, d1 = Cout, 2, 2] -> dst [4 * Cout, kpad(Cin)] rows (di, dj, o)
+      const int rowi = (int)(i / kpad), ci = (int)(i - (long long)rowi * kpad), q = rowi / d1, o = rowi - q * d1;
+      return ci < d0 ? src[((size_t)ci * d1 + o) * 4 + q] : 0.0f;
+    }
+    case MSD_REPACK_CONVT_T: {              // dst [Cin, 4 * Cout] = the transpose of the un-padded matrix above
+      const int cols = 4 * d1, ci = (int)(i / cols), c = (int)(i - (long long)ci * cols), q = c / d1, o = c - q * d1;
+      return src[((size_t)ci * d1 + o) * 4 + q];
+    }
+    default: return src[i % d0];            // MSD_REPACK_REPEAT_F32: dst fp32 [flag * d0] = src repeated
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) repack_kernel(const RepackTable t) {
+  const long long tid = (long long)blockIdx.x * kBlock + threadIdx.x, stride = (long long)gridDim.x * kBlock;
+  for (int k = 0; k < t.count; ++k) {
+    const float* src = t.src[k];
+    const int kind = t.kind[k], d0 = t.d0[k], d1 = t.d1[k], kpad = t.kpad[k], flag = t.flag[k];
+    if (kind == MSD_REPACK_REPEAT_F32) {
+      float* dst = reinterpret_cast<float*>(t.dst[k]);
+      for (long long i = tid; i < t.n[k]; i += stride) dst[i] = repack_value(src, kind, d0, d1, kpad, flag, i);
+    } else {
+      // two destination elements per thread: 4-byte stores (every packed row has an even length)
+      __nv_bfloat162* dst = reinterpret_cast<__nv_bfloat162*>(t.dst[k]);
+      for (long long j = tid; 2 * j < t.n[k]; j += stride)
+        dst[j] = __floats2bfloat162_rn(repack_value(src, kind, d0, d1, kpad, flag, 2 * j), repack_value(src, kind, d0, d1, kpad, flag, 2 * j + 1));
+    }
+  }
+}
+
 }  // namespace
+
+extern "C" int msd_repack_weights(const msd_repack_op* ops, int n, void* stream) {
+  MSD_REQUIRE(ops != nullptr && n > 0, "repack_weights: bad arguments");
+  for (int k0 = 0; k0 < n; k0 += kMaxOps) {
+    RepackTable t;
+    t.count = n - k0 < kMaxOps ? n - k0 : kMaxOps;
+    for (int k = 0; k < t.count; ++k) {
+      const msd_repack_op& o = ops[k0 + k];
+      MSD_REQUIRE(o.src && o.dst && o.kind >= MSD_REPACK_CAST && o.kind <= MSD_REPACK_REPEAT_F32 && o.d0 > 0, "repack_weights: bad op %d", k0 + k);
+      long long cnt = 0;
+      switch (o.kind) {
+        case MSD_REPACK_CAST: cnt = (long long)o.d0 * (o.d1 > 0 ? o.d1 : 1); break;
+        case MSD_REPACK_TRANSPOSE: cnt = (long long)o.d0 * o.d1; break;
+        case MSD_REPACK_CONV3: cnt = (long long)o.d0 * 9 * o.kpad; break;
+        case MSD_REPACK_CONV3_DGRAD: cnt = (long long)o.d1 * (o.flag ? 10 : 9) * o.kpad; break;
+        case MSD_REPACK_CONVT: cnt = 4ll * o.d1 * o.kpad; break;
+        case MSD_REPACK_CONVT_T: cnt = 4ll * o.d1 * o.d0; break;
+        default: cnt = (long long)o.d0 * (o.flag > 0 ? o.flag : 1); break;
+      }
+      MSD_REQUIRE(o.kind == MSD_REPACK_REPEAT_F32 || cnt % 2 == 0, "repack_weights: op %d has an odd element count", k0 + k);
+      MSD_REQUIRE(o.kind < MSD_REPACK_CONV3 || o.kind > MSD_REPACK_CONVT || o.kpad > 0, "repack_weights: op %d needs kpad", k0 + k);
+      t.src[k] = o.src; t.dst[k] = o.dst; t.n[k] = cnt; t.kind[k] = o.kind; t.d0[k] = o.d0; t.d1[k] = o.d1; t.kpad[k] = o.kpad;
+      t.flag[k] = o.kind == MSD_REPACK_CAST ? 0 : o.flag;
+      if (o.kind == MSD_REPACK_CAST) { t.d0[k] = 1; }
+    }
+    repack_kernel<<<148 * 8, kBlock, 0, (cudaStream_t)stream>>>(t);
+    MSD_LAUNCH_CHECK();
+  }
+  return MSD_OK;
+}
 
 extern "C" int msd_grad_sqnorm_f32(const msd_adamw_tensor* tensors, int n, double* d_sqnorm, void* stream) {
   MSD_REQUIRE(tensors && d_sqnorm && n > 0, "grad_sqnorm: bad arguments");

@@ -11,7 +11,6 @@ from __future__ import annotations
 
 import ctypes as C
 import logging
-import os
 import weakref
 from typing import Dict
 
@@ -279,7 +278,7 @@ class SatMAERestoration(nn.Module):
             self._handle = None
         self.__dict__.pop("_frozen_cache", None)
         self._packed, self._packed_key = None, None
-        for k in ("_train_packed", "_train_static_key", "_train_versions", "_train_graph"):
+        for k in ("_train_packed", "_train_static_key", "_train_versions"):
             if k in self.__dict__:
                 self.__dict__[k] = None
         self._workspaces.clear()
@@ -364,50 +363,90 @@ class SatMAERestoration(nn.Module):
         return b
 
     @torch.no_grad()
-    def _pack_train(self):
-        """Un-folded bf16 weights + the transposed / tap-flipped copies the data-gradient GEMMs read (include/msd.h)."""
+    def _build_train_pack(self, device):
+        """The training step's operands: un-folded bf16 weights + the transposed / tap-flipped copies the data-gradient GEMMs read
+        (include/msd.h, msd_train_weights).  The destination buffers are allocated ONCE; what comes back is the C struct that
+        points at them and two op tables for msd_repack_weights (csrc/optim.cu): every op (first fill) and the ops of trainable
+        parameters only (re-run after each optimizer step -- one kernel launch instead of ~100 cast / permute / flip launches).
+        fp32 vectors (LayerNorm / BatchNorm / biases) are passed as aliases of the parameters themselves."""
         enc, dec = self.encoder, self.decoder
-        base, keep = self._pack(None, encoder_only=True)   # encoder part is shared with the eval packing
-        keep = list(keep)
+        keep, ops = [], []          # ops: (RepackOp, source parameter)
+
+        def alias(t):
+            a = t.detach()
+            if a.dtype != torch.float32 or not a.is_contiguous():
+                raise _lib.MsdError("training step: contiguous fp32 parameters required")
+            keep.append(a)
+            return _lib.ptr(a)
+
+        def packed(param, kind, shape, dtype=torch.bfloat16, d0=0, d1=0, kpad=0, flag=0):
+            dst = torch.empty(shape, dtype=dtype, device=device)
+            keep.append(dst)
+            op = _lib.RepackOp()
+            op.src, op.dst = param.data_ptr(), dst.data_ptr()
+            op.kind, op.d0, op.d1, op.kpad, op.flag = kind, d0, d1, kpad, flag
+            ops.append((op, param))
+            return _lib.ptr(dst)
+
+        def pad64(c):
+            return (c + 63) // 64 * 64
+
         tw = _lib.TrainWeights()
-        tw.enc = base
+        w = tw.enc
+        pe = enc.patch_embed
+        kpe = pe.proj.weight[0].numel()
+        w.w_pe = packed(pe.proj.weight, _lib.REPACK_CAST, (pe.proj.out_channels, kpe), d0=pe.proj.out_channels, d1=kpe)
+        w.b_pe, w.pe_ln_g, w.pe_ln_b = alias(pe.proj.bias), alias(pe.norm.weight), alias(pe.norm.bias)
+        w.pos_embed = alias(enc.pos_embed[0])
+        blocks = (_lib.BlockWeights * enc.depth)()
         tb = (_lib.TrainBlock * enc.depth)()
         for i, blk in enumerate(enc.blocks):
             t = blk.tensors()
-            for name, wt in (("wT_qkv", t["qkv_w"]), ("wT_proj", t["proj_w"]), ("wT_fc1", t["fc1"].weight), ("wT_fc2", t["fc2"].weight)):
-                wT = self._cached_cast(wt, "b16T", lambda a: _bf16(a.detach().t()))
-                keep.append(wT)
-                setattr(tb[i], name, _lib.ptr(wT))
+            bw = blocks[i]
+            bw.ln1_g, bw.ln1_b, bw.ln2_g, bw.ln2_b = alias(t["ln1"].weight), alias(t["ln1"].bias), alias(t["ln2"].weight), alias(t["ln2"].bias)
+            for name, wt, bias in (("qkv", t["qkv_w"], t["qkv_b"]), ("proj", t["proj_w"], t["proj_b"]),
+                                   ("fc1", t["fc1"].weight, t["fc1"].bias), ("fc2", t["fc2"].weight, t["fc2"].bias)):
+                n_, k_ = wt.shape
+                setattr(bw, "w_" + name, packed(wt, _lib.REPACK_CAST, (n_, k_), d0=n_, d1=k_))
+                setattr(bw, "b_" + name, alias(bias))
+                setattr(tb[i], "wT_" + name, packed(wt, _lib.REPACK_TRANSPOSE, (k_, n_), d0=n_, d1=k_))
             tb[i].trainable = int(any(p.requires_grad for p in blk.parameters()))
-        keep.append(tb)
+        keep.extend([blocks, tb])
+        w.blocks = C.cast(blocks, C.POINTER(_lib.BlockWeights))
         tw.blocks_t = C.cast(tb, C.POINTER(_lib.TrainBlock))
+        w.norm_g, w.norm_b = alias(enc.norm.weight), alias(enc.norm.bias)
         mods = list(dec.upsample_blocks)
         per_stage = 1 + dec.num_residual_blocks
         for s in range(4):
             up = mods[s * per_stage]
             ts = tw.stages[s]
-            w_up, b_up, wT_up = pack_convt2x2_raw(up.upsample[0].weight, up.upsample[0].bias)
-            keep.extend([w_up, b_up, wT_up])
-            ts.w_up, ts.b_up, ts.wT_up = _lib.ptr(w_up), _lib.ptr(b_up), _lib.ptr(wT_up)
+            ct, ctb = up.upsample[0].weight, up.upsample[0].bias
+            cin, cout = ct.shape[:2]
+            ts.w_up = packed(ct, _lib.REPACK_CONVT, (4 * cout, pad64(cin)), d0=cin, d1=cout, kpad=pad64(cin))
+            ts.wT_up = packed(ct, _lib.REPACK_CONVT_T, (cin, 4 * cout), d0=cin, d1=cout)
+            ts.b_up = packed(ctb, _lib.REPACK_REPEAT_F32, (4 * cout,), dtype=torch.float32, d0=cout, flag=4)
             ts.bn_up = self._bn_params(up.upsample[1], keep)
             k = 0
             for rb in mods[s * per_stage + 1:(s + 1) * per_stage]:
                 for conv, bn, first in ((rb.block[0], rb.block[1], True), (rb.block[3], rb.block[4], False)):
-                    wf, wd = pack_conv3x3_raw(conv.weight), pack_conv3x3_dgrad(conv.weight, with_identity=first)
-                    keep.extend([wf, wd])
-                    ts.w_conv[k], ts.wd_conv[k] = _lib.ptr(wf).value, _lib.ptr(wd).value
+                    co, ci = conv.weight.shape[:2]
+                    ts.w_conv[k] = packed(conv.weight, _lib.REPACK_CONV3, (co, 9 * pad64(ci)), d0=co, d1=ci, kpad=pad64(ci)).value
+                    ts.wd_conv[k] = packed(conv.weight, _lib.REPACK_CONV3_DGRAD, (ci, (10 if first else 9) * pad64(co)), d0=co, d1=ci,
+                                           kpad=pad64(co), flag=int(first)).value
                     ts.bn_conv[k] = self._bn_params(bn, keep)
                     k += 1
         h0, hbn, h3 = dec.head[0], dec.head[1], dec.head[3]
-        wf, wd = pack_conv3x3_raw(h0.weight), pack_conv3x3_dgrad(h0.weight)
-        hb = h0.bias.detach().float().contiguous()
-        w1, b1 = h3.weight.detach().float().reshape(dec.out_channels, -1).contiguous(), h3.bias.detach().float().contiguous()
-        keep.extend([wf, wd, hb, w1, b1])
-        tw.w_head3, tw.b_head3, tw.wd_head3 = _lib.ptr(wf), _lib.ptr(hb), _lib.ptr(wd)
+        co, ci = h0.weight.shape[:2]
+        tw.w_head3 = packed(h0.weight, _lib.REPACK_CONV3, (co, 9 * pad64(ci)), d0=co, d1=ci, kpad=pad64(ci))
+        tw.wd_head3 = packed(h0.weight, _lib.REPACK_CONV3_DGRAD, (ci, 9 * pad64(co)), d0=co, d1=ci, kpad=pad64(co))
+        tw.b_head3 = alias(h0.bias)
         tw.bn_head = self._bn_params(hbn, keep)
-        tw.w_head1, tw.b_head1 = _lib.ptr(w1), _lib.ptr(b1)
+        tw.w_head1, tw.b_head1 = alias(h3.weight.reshape(dec.out_channels, -1)), alias(h3.bias)
         tw.bn_eps, tw.bn_momentum = float(hbn.eps), float(hbn.momentum if hbn.momentum is not None else 0.1)
-        return tw, keep
+        all_ops = (_lib.RepackOp * len(ops))(*[o for o, _ in ops])
+        hot = [o for o, p in ops if p.requires_grad]
+        hot_ops = (_lib.RepackOp * max(len(hot), 1))(*hot)
+        return tw, keep, (all_ops, len(ops)), (hot_ops, len(hot))
 
     def _ensure_train_ready(self, device):
         lib = _lib.load()
@@ -417,37 +456,25 @@ class SatMAERestoration(nn.Module):
             d = self._desc()
             _lib.check(lib.msd_model_create(C.byref(d), C.byref(h)))
             self._handle = h
-        # The packed copies (bf16 casts, transposes, tap-flipped conv weights) must follow every optimizer step.  They are
-        # ~100 small device ops on fixed addresses, so they are captured ONCE into a CUDA graph and replayed per step: one
-        # launch instead of a host-bound stream of tiny kernels.  Copies of frozen parameters are cached outside the graph.
+        # The packed copies must follow every optimizer step.  Their buffers and the C struct are built once per parameter
+        # placement; afterwards one msd_repack_weights launch over the trainable parameters refreshes them whenever a parameter
+        # version moved (torch optimizers bump it, FusedAdamW does so explicitly).
         params, bufs = list(self.parameters()), list(self.buffers())
         static_key = (str(device), self.gemm_backend, tuple(p.data_ptr() for p in params), tuple(p.requires_grad for p in params),
                       tuple(b.data_ptr() for b in bufs))
-        versions = tuple(p._version for p in params)
-        if static_key != getattr(self, "_train_static_key", None):
-            self._train_graph = None
-            tw, keep = self._pack_train()                      # eager: warms up every op and fills the frozen-parameter cache
-            try:
-                if os.environ.get("MSD_NO_PACK_GRAPH"):
-                    raise RuntimeError("disabled by MSD_NO_PACK_GRAPH")
-                graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph):
-                    tw, keep = self._pack_train()
-                graph.replay()
-                self._train_graph = graph
-            except Exception as exc:  # pragma: no cover - capture is an optimisation of the plumbing only
-                logger.warning("weight-packing graph capture failed (%s); packing eagerly every step", exc)
-                tw, keep = self._pack_train()
-            _lib.check(lib.msd_model_set_train_weights(self._handle, C.byref(tw)))
-            self._train_packed, self._train_static_key, self._train_versions = (tw, keep), static_key, versions
-        elif versions != self._train_versions:
-            if self._train_graph is not None:
-                self._train_graph.replay()
-            else:
-                tw, keep = self._pack_train()
+        versions = (tuple(p._version for p in params if p.requires_grad), tuple(p._version for p in params if not p.requires_grad))
+        with torch.cuda.device(device):
+            if static_key != getattr(self, "_train_static_key", None):
+                tw, keep, all_ops, hot_ops = self._build_train_pack(device)
+                _lib.check(lib.msd_repack_weights(all_ops[0], all_ops[1], _lib.stream_ptr()))
                 _lib.check(lib.msd_model_set_train_weights(self._handle, C.byref(tw)))
-                self._train_packed = (tw, keep)
-            self._train_versions = versions
+                self._train_packed, self._train_static_key, self._train_versions = (tw, keep, all_ops, hot_ops), static_key, versions
+            elif versions != self._train_versions:
+                # frozen parameters only change through load_state_dict / manual edits: then everything is repacked
+                table = self._train_packed[3] if versions[1] == self._train_versions[1] else self._train_packed[2]
+                if table[1]:
+                    _lib.check(lib.msd_repack_weights(table[0], table[1], _lib.stream_ptr()))
+                self._train_versions = versions
         return lib
 
     def _forward_train(self, x: torch.Tensor):

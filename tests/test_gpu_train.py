@@ -481,3 +481,47 @@ def test_data_parallel_backward_averages_gradients(tmp_path):
     res = json.loads(out.read_text())
     assert res["world"] == 2 and res["tensors"] > 100
     assert res["worst_rel"] <= 2e-3, res
+
+
+def test_repack_kernel_matches_the_torch_packing_functions():
+    """msd_repack_weights (one launch after each optimizer step) against the torch restatements of every packed layout:
+    bf16 cast, Linear transpose, 3x3 conv tap-major (+ zero K padding), its tap-flipped data-gradient form (+ identity tap),
+    ConvTranspose rows (di, dj, o), its transpose, the per-sub-pixel bias -- bit for bit."""
+    import ctypes
+    from msd_b200.models.satmae_restoration import pack_conv3x3_dgrad, pack_conv3x3_raw, pack_convt2x2_raw
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(3)
+    dev = "cuda"
+    ops, want, got = [], [], []
+
+    def add(src, kind, ref, dtype=torch.bfloat16, **kw):
+        dst = torch.full(ref.shape, float("nan"), dtype=dtype, device=dev)
+        op = _lib.RepackOp()
+        op.src, op.dst, op.kind = src.data_ptr(), dst.data_ptr(), kind
+        for k, v in kw.items():
+            setattr(op, k, v)
+        ops.append(op); want.append(ref); got.append(dst)
+
+    lin = torch.randn(2304, 768, generator=g).to(dev)
+    add(lin, _lib.REPACK_CAST, lin.to(torch.bfloat16), d0=2304, d1=768)
+    add(lin, _lib.REPACK_TRANSPOSE, lin.t().contiguous().to(torch.bfloat16), d0=2304, d1=768)
+    keep = [lin]
+    for c in (48, 96, 384):
+        w = torch.randn(c, c, 3, 3, generator=g).to(dev)
+        kpad = (c + 63) // 64 * 64
+        keep.append(w)
+        add(w, _lib.REPACK_CONV3, pack_conv3x3_raw(w), d0=c, d1=c, kpad=kpad)
+        add(w, _lib.REPACK_CONV3_DGRAD, pack_conv3x3_dgrad(w, with_identity=True), d0=c, d1=c, kpad=kpad, flag=1)
+        add(w, _lib.REPACK_CONV3_DGRAD, pack_conv3x3_dgrad(w), d0=c, d1=c, kpad=kpad, flag=0)
+    for cin, cout in ((768, 384), (96, 48)):
+        ct, cb = torch.randn(cin, cout, 2, 2, generator=g).to(dev), torch.randn(cout, generator=g).to(dev)
+        keep.extend([ct, cb])
+        w_up, b_up, wT_up = pack_convt2x2_raw(ct, cb)
+        add(ct, _lib.REPACK_CONVT, w_up, d0=cin, d1=cout, kpad=(cin + 63) // 64 * 64)
+        add(ct, _lib.REPACK_CONVT_T, wT_up, d0=cin, d1=cout)
+        add(cb, _lib.REPACK_REPEAT_F32, b_up, dtype=torch.float32, d0=cout, flag=4)
+    table = (_lib.RepackOp * len(ops))(*ops)
+    _lib.check(lib.msd_repack_weights(table, len(ops), _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    for i, (a, b) in enumerate(zip(got, want)):
+        assert a.shape == b.shape and torch.equal(a, b.to(a.device)), f"op {i} (kind {ops[i].kind})"

@@ -17,10 +17,11 @@ src = Path(sys.argv[1]) if len(sys.argv) > 1 else ROOT / "gpurun_out"
 
 WANT = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "smsp__inst_executed.sum",
         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "sm__cycles_elapsed.max", "launch__grid_size",
-        "launch__registers_per_thread", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+        "launch__registers_per_thread", "dram__bytes_read.sum.pct_of_peak_sustained_elapsed", "dram__bytes_write.sum.pct_of_peak_sustained_elapsed",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "lts__t_bytes.sum", "sm__inst_executed_pipe_fma.sum",
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed"]
-UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "nsecond": 1e-9, "usecond": 1e-6, "msecond": 1e-3, "second": 1.0}
+UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0,
+        "nsecond": 1e-9, "usecond": 1e-6, "msecond": 1e-3, "second": 1.0}
 
 
 def load(rep: Path):
@@ -66,7 +67,7 @@ for label, (stem, elems) in CAPTURES.items():
     traffic = d.get("dram__bytes_read.sum", 0.0) + d.get("dram__bytes_write.sum", 0.0)
     entry = {"ncu_duration_us": round(d.get("gpu__time_duration.sum", 0.0) * 1e6, 2), "dram_bytes_per_launch": traffic,
              "issue_active_pct": d.get("smsp__issue_active.avg.pct_of_peak_sustained_active"),
-             "dram_throughput_pct": d.get("dram__throughput.avg.pct_of_peak_sustained_elapsed")}
+             "dram_pct_of_peak": round(d.get("dram__bytes_read.sum.pct_of_peak_sustained_elapsed", 0.0) + d.get("dram__bytes_write.sum.pct_of_peak_sustained_elapsed", 0.0), 1)}
     if elems:
         entry["thread_instructions_per_element"] = round(d.get("smsp__inst_executed.sum", 0.0) * 32 / elems, 1)
     if tp is not None and "kernel" not in label and label not in ("corrupt_kernel", "metrics_fused_kernel"):
