@@ -90,3 +90,20 @@ def test_export_is_the_inverse_of_the_ingest_scaling():
     dn = torch.randint(0, 10001, (2, 13, 192, 192), generator=gen)
     back = export_tiles(ingest_tiles(dn.to(torch.int32).cuda(), 192)).cpu().to(torch.int32)   # same size: no resampling
     assert (back - dn).abs().max().item() <= 1
+
+
+def test_scene_writer_exports_digital_numbers_into_a_host_buffer():
+    """scene_to_dn (the C5 writer): restored band -> msd_export_u16 -> pinned host buffer; single rank = the whole scene, equal to
+    the export formula of SURVEY 8f N4 applied to the blended band."""
+    from msd_b200.scene import scene_to_dn
+    gen = torch.Generator().manual_seed(9)
+    scene = (torch.rand(13, 230, 260, generator=gen) * 5 - 2.5).cuda()
+    model = _Affine().cuda()
+    band, rows = restore_scene(model, scene, overlap=32, batch=5)
+    host = torch.zeros(13, 230, 260, dtype=torch.uint16).pin_memory()
+    full = scene_to_dn(band, rows, 230, host_out=host)
+    torch.cuda.synchronize()
+    want = torch.round((band.cpu() * 0.25 + 0.5).clamp(0, 1) * 10000).to(torch.int32)
+    got = host.to(torch.int32)
+    assert torch.equal(full.cpu().to(torch.int32), got)
+    assert (got - want).abs().max().item() <= 1 and (got != want).float().mean().item() < 1e-3

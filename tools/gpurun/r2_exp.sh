@@ -1,2 +1,5 @@
 mkdir -p gpurun_out
-for i in 1 2; do python tools/gemm_bench.py --only conv4; MSD_DBG_BO=256 python tools/gemm_bench.py --only conv4; done 2>&1 | tee gpurun_out/exp_dx0.txt
+timeout 600 python -m pytest tests/test_gpu_scene.py tests/test_gpu_sweep.py -q -p no:cacheprovider 2>&1 | tail -4
+python tools/e2e_probe.py 2>&1 | tee gpurun_out/e2e_probe.txt
+timeout 900 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-train --no-scene > gpurun_out/bench20.json 2> gpurun_out/bench20.err; echo "bench rc=$?"; python -c "
+import json;b=json.load(open('gpurun_out/bench20.json'));print('value',b['value'],b['ms_per_step'],'e2e',b['e2e']['value'],'f32',b['e2e_f32']['value'],b['clocks'])"
