@@ -75,6 +75,29 @@ def test_evaluation_sweep_is_world_size_invariant(model):
     assert res1 == res2 and np.array_equal(two._acc.cpu().numpy(), acc1)
 
 
+def test_full_27000_tile_sweep_is_world_size_invariant(model):
+    """BASELINE config C3 at its full size: 27,000 EuroSAT-shaped tiles (106 global batches of 256, the last ragged) on one rank
+    vs the eight shards of an 8-rank run executed one after the other -- the per-shard fp64 sums add up to the single-rank sums
+    (the NCCL all-reduce of the real run is then a sum of five numbers per rank), every metric finite and inside its range."""
+    noise = AddSensorNoise(*recipes.NOISE_CONFIGS["base"])
+    n_tiles, batch = 27000, 256
+    one = MetricsTracker()
+    res = evaluation_sweep(model, noise, n_tiles, batch, rank=0, world=1, tracker=one)
+    acc1 = one._acc.cpu().numpy().copy()
+    assert int(acc1[4]) == n_tiles and np.isfinite(acc1).all()
+    assert 0 < res["psnr"] < 60 and -1 <= res["ssim"] <= 1 and 0 <= res["sam"] <= 180 and res["rmse"] > 0
+    total = np.zeros(5)
+    counts = []
+    for r in range(8):
+        t = MetricsTracker()
+        evaluation_sweep(model, noise, n_tiles, batch, rank=r, world=8, tracker=t, all_reduce=False)
+        part = t._acc.cpu().numpy()
+        counts.append(int(part[4]))
+        total += part
+    assert sum(counts) == n_tiles and max(counts) - min(counts) <= 256 + 256      # contiguous shards of 13-14 batches
+    assert np.allclose(total, acc1, rtol=1e-12, atol=0), (total, acc1)
+
+
 def test_tracker_prefetch_then_all_reduce_reads_the_reduced_sums(model):
     """prefetch() -> all_reduce() -> compute() must not return the pre-collective local sums.  Single-process group."""
     import torch.distributed as dist
