@@ -173,6 +173,16 @@ void msd_model_destroy(msd_model* m);
  * act: 0 none, 1 GELU(erf).  resid_f32 != NULL -> out fp32 = resid + A.W^T + bias (may alias out). */
 int msd_linear_bf16(const void* d_a, const void* d_w, const float* d_bias, void* d_out, const float* d_resid,
                     int M, int N, int K, int act, int out_f32, int backend, void* stream);
+/* The MLP of a training step (encoder.py:160-166 under autograd), GELU folded into the GEMMs either side of it (tcgen05 backend):
+ *   msd_linear_gelu_pre_bf16   d_pre = bf16(A . W^T + bias) and d_out = GELU(d_pre): fc1 leaves the pre-activation the backward
+ *                              needs and the activation fc2 reads from one epilogue (bit-identical to msd_linear_bf16 with act = 0
+ *                              followed by msd_gelu_fwd_bf16)
+ *   msd_linear_dgelu_bf16      d_out = bf16(bf16(A . W^T + bias) * gelu'(d_pre)): the fc2 data gradient, already multiplied by the
+ *                              GELU derivative (bit-identical to msd_linear_bf16 followed by msd_gelu_bwd_bf16)               */
+int msd_linear_gelu_pre_bf16(const void* d_a, const void* d_w, const float* d_bias, void* d_out, void* d_pre, int M, int N, int K,
+                             void* stream);
+int msd_linear_dgelu_bf16(const void* d_a, const void* d_w, const float* d_bias, const void* d_pre, void* d_out, int M, int N, int K,
+                          void* stream);
 /* 3x3 conv, pad 1, + bias + GELU, NHWC bf16 with a 1-pixel zero halo: x,y,skip are [B,(H+2),(W+2),C*] bf16;
  * w [Cout, 9*Kpad]; with a skip tensor (Cin == Cout) w is [Cout, 10*Kpad], the tenth tap being the identity, and the
  * result is GELU(conv + bias + skip) -- the skip connection is accumulated by the tensor cores like any other tap. */
@@ -237,20 +247,39 @@ int msd_f64_to_f32(const double* d_in, float* d_out, int n, void* stream);
  * d_stats fp32 [4][C] = {gamma*rstd, beta - mean*gamma*rstd, mean, rstd}; running stats updated in place; d_sums fp64 [2][C] scratch */
 int msd_bn_stats_bf16(const void* d_c, int B, int H, int W, int C, const float* d_gamma, const float* d_beta, float eps,
                       float momentum, float* d_running_mean, float* d_running_var, float* d_stats, double* d_sums, void* stream);
+/* The same in two steps -- d_sums fp64 [2][C] = {sum c, sum c^2} over [rows, C], then statistics + running-stat update from the
+ * sums (count = B*H*W) -- so that the first step can ride in the epilogue of the conv that writes c: */
+int msd_bn_sums_bf16(const void* d_c, long long rows, int C, double* d_sums, void* stream);
+int msd_bn_finalize(const double* d_sums, double count, int C, const float* d_gamma, const float* d_beta, float eps, float momentum,
+                    float* d_running_mean, float* d_running_var, float* d_stats, void* stream);
+/* nn.Conv2d(k3, pad 1) of a training forward (blocks.py:66-72): d_y = raw bf16 conv output (+ bias, no activation, zero halo) AND
+ * d_sums fp64 [2][Cout] = {sum y, sum y^2} of the stored values.  The 48- and 96-channel convs of the tcgen05 backend accumulate the
+ * sums in their epilogues (no second pass over d_y); other shapes run msd_bn_sums_bf16 behind the conv.  *fused_out (may be NULL)
+ * tells which. */
+int msd_conv3x3_stats_nhwc_bf16(const void* d_x, const void* d_w, const float* d_bias, void* d_y, double* d_sums, int B, int H, int W,
+                                int Cin, int Cout, int backend, int* fused_out, void* stream);
 /* y = GELU(BN(c) [+ skip]) on interior pixels, zero halo */
 int msd_bn_act_fwd_bf16(const void* d_c, const void* d_skip, const float* d_stats, void* d_y, int B, int H, int W, int C, void* stream);
 /* backward of the above: d_dz = grad of the pre-activation (= grad of the skip input), d_dc = grad of c (may alias d_dz),
- * d_dgamma / d_dbeta fp32 [C] (overwritten; NULL to skip), d_coef fp32 [2][C] and d_sums fp64 [2][C] scratch */
+ * d_dgamma / d_dbeta fp32 [C] (overwritten; NULL to skip), d_coef fp32 [2][C] and d_sums fp64 [2][C] scratch.
+ * d_dy must have zero halo rows like every haloed tensor the library writes (dz is formed as dy * gelu'(.) on all rows). */
 int msd_bn_act_bwd_bf16(const void* d_dy, const void* d_c, const void* d_skip, const float* d_stats, void* d_dz, void* d_dc,
                         float* d_dgamma, float* d_dbeta, float* d_coef, double* d_sums, int B, int H, int W, int C, void* stream);
 /* d_out = GELU(d_hpre) (erf form), n bf16 elements (n % 8 == 0) */
 int msd_gelu_fwd_bf16(const void* d_hpre, void* d_out, long long n, void* stream);
 /* d_out = d_dh * gelu'(d_hpre), n bf16 elements (n % 8 == 0), in place allowed */
 int msd_gelu_bwd_bf16(const void* d_dh, const void* d_hpre, void* d_out, long long n, void* stream);
+/* the same over a [rows, N] matrix, and d_colsum fp32 [N] += column sums of the result (the bias gradient of the Linear in front of
+ * the GELU); N % 256 == 0 */
+int msd_gelu_bwd_colsum_bf16(const void* d_dh, const void* d_hpre, void* d_out, float* d_colsum, int rows, int N, void* stream);
 /* LayerNorm backward over [M, D=768]: d_dy bf16 (or fp32 when dy_is_f32), d_x fp32 LN input; d_g fp32 [M,D] = (accumulate ?
  * d_g : 0) + dx; optional bf16 copy of d_g; d_dgamma / d_dbeta fp32 [D] ACCUMULATED into (NULL for frozen layers) */
 int msd_layernorm_bwd(const void* d_dy, int dy_is_f32, const float* d_x, const float* d_gamma, float eps, float* d_g, int accumulate,
                       void* d_g_bf16, float* d_dgamma, float* d_dbeta, int M, int D, void* stream);
+/* the same, and d_colsum fp32 [D] += column sums of the bf16 copy (NULL: none): that copy is the dY operand of the Linear whose output
+ * this gradient belongs to (fc2 / proj / patch embedding), so the sums are that layer's bias gradient */
+int msd_layernorm_bwd_colsum(const void* d_dy, int dy_is_f32, const float* d_x, const float* d_gamma, float eps, float* d_g,
+                             int accumulate, void* d_g_bf16, float* d_dgamma, float* d_dbeta, float* d_colsum, int M, int D, void* stream);
 /* ConvTranspose2d k2 s2 backward gather: d_dy haloed [B,2Hin+2,2Win+2,C] -> d_dys [rows_in, 4*C] (q = di*2+dj major) */
 int msd_convt_unshuffle_bf16(const void* d_dy, void* d_dys, int B, int Hin, int Win, int in_padded, int C, void* stream);
 /* head 1x1 backward: d_dy fp32 NCHW -> d_dh bf16 haloed [B,H+2,W+2,Cin] and d_dyt bf16 [rows,16] (dy on the pixel list) */

@@ -130,6 +130,8 @@ SIGNATURES = {
                                            c_void_p]),
     "msd_linear_lnfold_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p, c_int, c_int,
                                        c_int, c_int, c_void_p]),
+    "msd_linear_gelu_pre_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "msd_linear_dgelu_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "msd_attention_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "msd_attention_tc5_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "msd_patchify_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
@@ -141,12 +143,20 @@ SIGNATURES = {
     "msd_f64_to_f32": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "msd_bn_stats_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_float, c_void_p,
                                   c_void_p, c_void_p, c_void_p, c_void_p]),
+    "msd_bn_sums_bf16": (c_int, [c_void_p, C.c_longlong, c_int, c_void_p, c_void_p]),
+    "msd_bn_finalize": (c_int, [c_void_p, C.c_double, c_int, c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p, c_void_p,
+                                c_void_p]),
+    "msd_conv3x3_stats_nhwc_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                            c_int, C.POINTER(c_int), c_void_p]),
     "msd_bn_act_fwd_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "msd_bn_act_bwd_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                     c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "msd_gelu_bwd_bf16": (c_int, [c_void_p, c_void_p, c_void_p, C.c_longlong, c_void_p]),
+    "msd_gelu_bwd_colsum_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "msd_layernorm_bwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_float, c_void_p, c_int, c_void_p, c_void_p,
                                   c_void_p, c_int, c_int, c_void_p]),
+    "msd_layernorm_bwd_colsum": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_float, c_void_p, c_int, c_void_p, c_void_p,
+                                         c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "msd_convt_unshuffle_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "msd_head1x1_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "msd_batch_sum_f32": (c_int, [c_void_p, c_void_p, c_int, C.c_longlong, c_void_p]),

@@ -129,3 +129,47 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(v);
 }
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  float2 t;
+  t = unpack_bf16x2(u.x); f[0] = t.x; f[1] = t.y;
+  t = unpack_bf16x2(u.y); f[2] = t.x; f[3] = t.y;
+  t = unpack_bf16x2(u.z); f[4] = t.x; f[5] = t.y;
+  t = unpack_bf16x2(u.w); f[6] = t.x; f[7] = t.y;
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+}
+// exact-erf GELU and its derivative (nn.GELU() default): gelu'(z) = Phi(z) + z phi(z)
+// erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below the bf16 rounding of every consumer; common.cuh gelu_erf):
+// Phi(z) and phi(z) share one exp(-z^2/2)
+__device__ __forceinline__ float gelu_fwd(float z) { return gelu_erf(z); }
+__device__ __forceinline__ float gelu_grad(float z) {
+  const float az = fabsf(z) * 0.70710678118654752f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, az, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float e = __expf(-az * az);                       // = exp(-z^2 / 2)
+  const float erf_abs = fmaf(-poly * t, e, 1.0f);
+  return fmaf(0.5f, copysignf(erf_abs, z), 0.5f) + z * 0.3989422804014327f * e;
+}
+// dy * gelu'(z) for two elements at a time in half2 (tanh form, MUFU.TANH.F16x2):
+//   u = z (c0 + c1 z^2), t = tanh(u), gelu'(z) = 0.5 (1 + t) + 0.5 z (1 - t^2) (c0 + 3 c1 z^2)
+// |tanh form - erf form| <= 1e-3 on the derivative and fp16 evaluation (1e-3 relative) are both below the bf16 rounding of
+// the product that follows; z is clamped to +-8 (the derivative is 0 / 1 beyond, and fp16 z^2 must not overflow).
+__device__ __forceinline__ float2 gelu_grad2(float z0, float z1) {
+  const __half2 z = __floats2half2_rn(fminf(fmaxf(z0, -8.f), 8.f), fminf(fmaxf(z1, -8.f), 8.f));
+  const __half2 c0 = __float2half2_rn(0.7978845608f), c1 = __float2half2_rn(0.0356774081f), c3 = __float2half2_rn(0.1070322243f);
+  const __half2 half = __float2half2_rn(0.5f), one = __float2half2_rn(1.0f);
+  const __half2 z2 = __hmul2(z, z);
+  const __half2 u = __hmul2(z, __hfma2(z2, c1, c0));
+  uint32_t ui = *reinterpret_cast<const uint32_t*>(&u), ti;
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(ti) : "r"(ui));
+  const __half2 t = *reinterpret_cast<const __half2*>(&ti);
+  const __half2 sech2 = __hfma2(__hneg2(t), t, one);                          // 1 - t^2
+  const __half2 inner = __hmul2(__hmul2(half, z), __hfma2(z2, c3, c0));       // 0.5 z (c0 + 3 c1 z^2)
+  const __half2 g = __hfma2(sech2, inner, __hfma2(half, t, half));
+  return __half22float2(g);
+}
+

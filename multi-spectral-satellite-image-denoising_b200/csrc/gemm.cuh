@@ -66,6 +66,17 @@ struct Problem {
   int ln_parts;
   const float* ln_s;        // consumer: [N] column sums of the gamma-folded weights
   float ln_eps, ln_inv_k;   // consumer: eps, 1 / (LayerNorm width)
+  // Training-mode BatchNorm statistics out of the conv that produces the tensor (EPI_CONV, raw bf16 output, tcgen05 kernels that
+  // support it, see tc5_supports_bn_sums()): bn_sums[n] += sum over stored rows of c[., n], bn_sums[N + n] += sum of c^2 -- the
+  // bf16 values the epilogue stores (halo rows are stored as zeros and add nothing).  fp32 per-CTA partials in shared memory,
+  // one fp64 atomic per channel and CTA at the end.  The caller zeroes bn_sums.
+  double* bn_sums;
+  // Training-step MLP (EPI_ROWMAJOR, bf16 output, tcgen05 backend):
+  //   act = 1 with out_bf16 set (and no LayerNorm fields): the pre-activation acc + bias, rounded to bf16, goes to out_bf16 and
+  //     GELU of that rounded value to out -- fc1 leaves both tensors the backward needs, no separate GELU pass;
+  //   gelu_pre set (act = 0): out = bf16(bf16(acc + bias) * gelu'(gelu_pre[m, n])) -- the fc2 data gradient arrives already
+  //     multiplied by the GELU derivative (same roundings as the GEMM followed by msd_gelu_bwd_bf16).
+  const __nv_bfloat16* gelu_pre;
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) { return act ? gelu_erf(v) : v; }
@@ -164,10 +175,12 @@ int launch_tc5(const Problem& p, cudaStream_t s);
 int launch_hmma(const Problem& p, cudaStream_t s);
 bool tc5_can_fuse_head(const Problem& p, int head_cout);   // may this 3x3 conv carry the 1x1 head in its epilogue?
 int tc5_stats_parts(int N, int M);                         // partial LayerNorm sums per row a stats-producing GEMM of this shape writes
+bool tc5_supports_bn_sums(const Problem& p);               // will launch_tc5 route this conv to a kernel that accumulates bn_sums?
 
 inline int launch(const Problem& p, int backend, cudaStream_t s) {
   if (backend == 1) {
-    MSD_REQUIRE(p.ln_stats == nullptr && p.stats_out == nullptr, "gemm: the folded LayerNorm epilogues exist on the tcgen05 backend only");
+    MSD_REQUIRE(p.ln_stats == nullptr && p.stats_out == nullptr && p.bn_sums == nullptr && p.gelu_pre == nullptr && (p.out_bf16 == nullptr || p.stats_out != nullptr),
+                "gemm: the folded LayerNorm / column-sum / training-MLP epilogues exist on the tcgen05 backend only");
     return launch_hmma(p, s);
   }
   return launch_tc5(p, s);

@@ -122,8 +122,21 @@ int tc5_stats_parts(int N, int M) {
   return bn > 0 ? 2 * (N / bn) : 0;
 }
 
+// Column sums in the conv epilogue (Problem::bn_sums) exist in the two kernels that run the large decoder stages: the 48-channel
+// resident-weight conv (single CTAs) and the 96-channel dx-merged pair kernel; both keep their per-warp slots where the skip tap's
+// weights would sit.  Mirrors the routing of launch_tc5 / launch_bn below.
+bool tc5_supports_bn_sums(const Problem& p) {
+  static const bool off = getenv("MSD_NO_MERGE3") != nullptr || getenv("MSD_RES4") != nullptr || getenv("MSD_NO_PAIR") != nullptr ||
+                          getenv("MSD_PAIR48") != nullptr || getenv("MSD_NO_EPI_SUMS") != nullptr;
+  if (off || tc5::classify(p) != tc5::E_CONV_RAW || p.skip_tap >= 0 || p.head_out != nullptr || !tc5::is_conv3x3(p) || p.dbg_bo != 0) return false;
+  if (p.N == 48) return p.kb_per_tap == 1 && p.num_kb == 9;
+  if (p.N == 96) return p.M >= 2048 && p.kb_per_tap == 2 && p.num_kb == 18;
+  return false;
+}
+
 int launch_tc5(const Problem& p, cudaStream_t s) {
   MSD_REQUIRE(p.N % 16 == 0, "gemm_tc5: N=%d must be a multiple of 16", p.N);
+  MSD_REQUIRE(p.bn_sums == nullptr || tc5_supports_bn_sums(p), "gemm_tc5: this problem has no column-sum epilogue (ask tc5_supports_bn_sums first)");
   MSD_REQUIRE(p.ldA % 8 == 0 && msd_aligned16(p.A) && msd_aligned16(p.Wt), "gemm_tc5: operands must be 16-byte aligned / pitched");
   // multi-tap (3x3 conv) problems keep the largest tile: their summation order (tap-major vs dx-merged) depends on the tile
   // width through the kernel mode, and results must not depend on the batch size (sharding invariance is tested bit-exactly)
@@ -134,6 +147,10 @@ int launch_tc5(const Problem& p, cudaStream_t s) {
   if (ln_producer)
     MSD_REQUIRE(p.mode == EPI_ROWMAJOR && p.out_f32 && !p.act && p.resid != nullptr && p.out_bf16 != nullptr && msd_aligned16(p.out_bf16) &&
                 p.stats_parts == tc5_stats_parts(p.N, p.M) && p.stats_parts > 0, "gemm_tc5: LayerNorm partial sums need the fp32 residual epilogue, a bf16 copy and stats_parts = tc5_stats_parts(N, M)");
+  if (p.gelu_pre != nullptr)
+    MSD_REQUIRE(tc5::classify(p) == tc5::E_RM_BF16_DGELU && msd_aligned16(p.gelu_pre) && p.ldo % 8 == 0, "gemm_tc5: gelu_pre needs a plain bf16 row-major output");
+  if (p.out_bf16 != nullptr && !ln_producer)
+    MSD_REQUIRE(tc5::classify(p) == tc5::E_RM_BF16_GELU_PRE && msd_aligned16(p.out_bf16) && p.ldo % 8 == 0, "gemm_tc5: a pre-activation copy needs a bf16 row-major GELU output");
   // (narrower tiles for the short-K residual GEMM, proj, were measured and are not faster: 0.066 ms at BN = 256, 0.064 at 192,
   //  0.073 at 128, 0.078 at 96, 0.092 at 64 for M = 36,864)
   const int bn = pick_bn_tc5(p.N, p.M, p.num_kb == p.kb_per_tap, ln_producer ? kStatsMinBN : 16);

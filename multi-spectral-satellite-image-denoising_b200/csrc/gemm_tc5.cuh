@@ -74,6 +74,7 @@ struct Cfg {
   static_assert(SMEM_BYTES <= 227u * 1024u, "shared memory budget");
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N for M=128 must be a multiple of 16 in [16,256]");
   static_assert(W_BOX_BYTES % 1024 == 0, "stage bases must stay 1024-byte aligned for SWIZZLE_128B");
+  static_assert(MODE != MODE_MERGE3_RESIDENT || BN != 48 || (uint32_t)EPI_WARPS * 2u * BN * 4u <= W_BOX_BYTES, "column-sum slots must fit the tenth-tap slot");
 };
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -302,6 +303,8 @@ enum Epi : int {
   E_RM_BF16_LN,         // out bf16 = rstd (acc - mean ln_s) + bias                  (qkv behind a folded LayerNorm, see Problem)
   E_RM_BF16_GELU_LN,    // out bf16 = GELU(rstd (acc - mean ln_s) + bias)            (fc1 behind a folded LayerNorm)
   E_RM_F32_RESID_STATS, // E_RM_F32_RESID + bf16 copy of the row + partial LayerNorm sums (proj / fc2 in front of a folded LayerNorm)
+  E_RM_BF16_GELU_PRE,   // out_bf16 = bf16(acc + bias), out = GELU(that)                (training fc1: pre-activation + activation)
+  E_RM_BF16_DGELU,      // out bf16 = bf16(acc + bias) * gelu'(gelu_pre)                (training fc2 data gradient)
   E_GENERIC         // any other combination of the Problem's flags (slower, runtime-branched)
 };
 
@@ -311,6 +314,8 @@ __host__ inline int classify(const Problem& p) {
   if (p.mode == EPI_ROWMAJOR) {
     if (p.ln_stats != nullptr) return (!p.out_f32 && p.resid == nullptr) ? (p.act ? E_RM_BF16_GELU_LN : E_RM_BF16_LN) : E_GENERIC;
     if (p.stats_out != nullptr) return (p.out_f32 && !p.act && p.resid != nullptr && p.out_bf16 != nullptr) ? E_RM_F32_RESID_STATS : E_GENERIC;
+    if (p.gelu_pre != nullptr) return (!p.out_f32 && !p.act && p.resid == nullptr && p.out_bf16 == nullptr) ? E_RM_BF16_DGELU : E_GENERIC;
+    if (p.out_bf16 != nullptr) return (!p.out_f32 && p.act && p.resid == nullptr) ? E_RM_BF16_GELU_PRE : E_GENERIC;
     if (p.out_f32 && !p.act && p.resid == nullptr) return E_RM_F32;
     if (p.out_f32 && !p.act && p.resid != nullptr) return E_RM_F32_RESID;
     if (!p.out_f32 && p.resid == nullptr) return p.act ? E_RM_BF16_GELU : E_RM_BF16;
@@ -381,10 +386,31 @@ __device__ __forceinline__ void stage_column_slice(const float* __restrict__ src
   __syncwarp();
 }
 
+// Column sums in a conv epilogue (Problem::bn_sums): every epilogue warp keeps a private fp32 slot [2][N] in shared memory (zeroed
+// before its first tile); after the last tile the slots are added up in warp order and each CTA issues one fp64 atomic per entry.
+// Named barrier 2 belongs to the `nwarps` epilogue warps.
+__device__ __forceinline__ void bn_sums_zero(uint32_t slot_s, int N, int lane) {
+  for (int i = lane; i < 2 * N; i += 32) asm volatile("st.shared.f32 [%0], %1;\n" ::"r"(slot_s + 4u * (uint32_t)i), "f"(0.0f) : "memory");
+  __syncwarp();
+}
+__device__ __forceinline__ void bn_sums_flush(uint32_t slots_s, double* __restrict__ sums, int N, int tid, int nwarps) {
+  __syncwarp();
+  asm volatile("bar.sync 2, %0;\n" ::"r"(nwarps * 32) : "memory");
+  for (int i = tid; i < 2 * N; i += nwarps * 32) {
+    float acc = 0.0f;
+    for (int w = 0; w < nwarps; ++w) {
+      float v;
+      asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(v) : "r"(slots_s + 4u * (uint32_t)(w * 2 * N + i)));
+      acc += v;
+    }
+    atomicAdd(sums + i, (double)acc);
+  }
+}
+
 template <int BN, int EPI, bool PAIR = false>
 __device__ __forceinline__ void epilogue_tile(const Problem& p, uint32_t stg_s, uint32_t bias_s, uint32_t taddr,
                                               uint64_t* tmem_empty_bar, int mrow0, int n0, int lane, int slab_begin, int slab_end,
-                                              HeadCtx* hc = nullptr, float ln_a = 0.0f, float ln_c = 0.0f) {
+                                              HeadCtx* hc = nullptr, float ln_a = 0.0f, float ln_c = 0.0f, uint32_t sums_s = 0u) {
   using C = Cfg<BN>;
   constexpr bool kHead = EPI == E_CONV_HEAD;
   constexpr bool kLn = EPI == E_RM_BF16_LN || EPI == E_RM_BF16_GELU_LN;          // consumer of a folded LayerNorm
@@ -396,6 +422,8 @@ __device__ __forceinline__ void epilogue_tile(const Problem& p, uint32_t stg_s, 
   constexpr bool kF32 = EPI == E_RM_F32 || EPI == E_RM_F32_RESID || EPI == E_RM_F32_RESID_STATS;
   constexpr bool kResid = EPI == E_RM_F32_RESID || EPI == E_RM_F32_RESID_STATS;
   constexpr bool kGelu = EPI == E_RM_BF16_GELU || EPI == E_RM_BF16_GELU_LN || EPI == E_CONV || EPI == E_CONVT || kHead;
+  constexpr bool kPre = EPI == E_RM_BF16_GELU_PRE;          // two stores per slab: the bf16 pre-activation, then its GELU
+  constexpr bool kDGelu = EPI == E_RM_BF16_DGELU;
   constexpr int UPR = kF32 ? C::SC / 4 : C::SC / 8;        // 16-byte units per staged row (a power of two)
   constexpr uint32_t PITCH = (kF32 ? C::SC * 4 : C::SC * 2) + 16;
   const uint32_t rowpix = kHead ? row_info_head(p, mrow0 + lane) : (EPI == E_GENERIC || kConvT || kConv) ? row_info(p, mrow0 + lane) : 0u;
@@ -514,6 +542,39 @@ __device__ __forceinline__ void epilogue_tile(const Problem& p, uint32_t stg_s, 
         }
       }
       __syncwarp();
+      if constexpr (EPI == E_CONV_RAW) {
+        // column sums of the tensor being stored (Problem::bn_sums): the staged bf16 slab is read back transposed -- lane (g, cp) walks
+        // rows g, g + G, ... of column pair cp -- and added to this warp's private fp32 slot [2][N] (no atomics: one fixed summation
+        // order per warp, so a training step is reproducible)
+        if (sums_s != 0u) {
+          constexpr int CP = C::SC / 2, G = 32 / CP;                 // column pairs per slab, row groups per warp (48 -> 24 x 1, 32 -> 16 x 2)
+          const int cp = lane % CP, g = lane / CP;
+          const int rows_here = rows_valid < 32 ? rows_valid : 32;
+          float s0 = 0.0f, s1 = 0.0f, q0 = 0.0f, q1 = 0.0f;
+          if (g < G) {
+            for (int rr = g; rr < rows_here; rr += G) {
+              uint32_t w;
+              asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(w) : "r"(stg_s + (uint32_t)rr * PITCH + 4u * (uint32_t)cp));
+              const float f0 = __uint_as_float(w << 16), f1 = __uint_as_float(w & 0xFFFF0000u);
+              s0 += f0; s1 += f1;
+              q0 = fmaf(f0, f0, q0); q1 = fmaf(f1, f1, q1);
+            }
+          }
+#pragma unroll
+          for (int sh = CP; sh < 32 && G > 1; sh <<= 1) {
+            s0 += __shfl_xor_sync(0xffffffffu, s0, sh); s1 += __shfl_xor_sync(0xffffffffu, s1, sh);
+            q0 += __shfl_xor_sync(0xffffffffu, q0, sh); q1 += __shfl_xor_sync(0xffffffffu, q1, sh);
+          }
+          if (lane < CP) {
+            const uint32_t a = sums_s + 4u * (uint32_t)(n0 + nslab + 2 * cp), aq = a + 4u * (uint32_t)p.N;
+            float2 t, tq;
+            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];\n" : "=f"(t.x), "=f"(t.y) : "r"(a));
+            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];\n" : "=f"(tq.x), "=f"(tq.y) : "r"(aq));
+            asm volatile("st.shared.v2.f32 [%0], {%1, %2};\n" ::"r"(a), "f"(t.x + s0), "f"(t.y + s1) : "memory");
+            asm volatile("st.shared.v2.f32 [%0], {%1, %2};\n" ::"r"(aq), "f"(tq.x + q0), "f"(tq.y + q1) : "memory");
+          }
+        }
+      }
       // ---- phase B
       constexpr int EPU = kF32 ? 4 : 8;                     // elements per 16-byte unit
       uint4 v[UPR];
@@ -571,6 +632,24 @@ __device__ __forceinline__ void epilogue_tile(const Problem& p, uint32_t stg_s, 
           v[j].z = __float_as_uint(__uint_as_float(v[j].z) + e[j].z); v[j].w = __float_as_uint(__uint_as_float(v[j].w) + e[j].w);
         }
       }
+      if constexpr (kDGelu) {
+        // fc2 data gradient times the GELU derivative at fc1's pre-activation (read here, coalesced; its lines were prefetched to L2)
+        uint4 z[UPR];
+#pragma unroll
+        for (int j = 0; j < UPR; ++j) z[j] = live[j] ? __ldg(reinterpret_cast<const uint4*>(p.gelu_pre + off[j])) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int j = 0; j < UPR; ++j) {
+          uint32_t w[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+          const uint32_t z4[4] = {z[j].x, z[j].y, z[j].z, z[j].w};
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const float2 g = unpack_bf16x2(w[t]), zz = unpack_bf16x2(z4[t]);
+            const float2 d = gelu_grad2(zz.x, zz.y);
+            w[t] = pack_bf16x2(g.x * d.x, g.y * d.y);
+          }
+          v[j] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+      }
       if constexpr (kStats) {
         // the new residual row also leaves as bf16 (A operand of the GEMM behind the folded LayerNorm) and feeds the row sums
 #pragma unroll
@@ -587,10 +666,31 @@ __device__ __forceinline__ void epilogue_tile(const Problem& p, uint32_t stg_s, 
       for (int j = 0; j < UPR; ++j) {
         if (live[j]) {
           if constexpr (kF32) *reinterpret_cast<uint4*>(reinterpret_cast<float*>(p.out) + off[j]) = v[j];
+          else if constexpr (kPre) *reinterpret_cast<uint4*>(p.out_bf16 + off[j]) = v[j];
           else *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off[j]) = v[j];
         }
       }
       __syncwarp();
+      if constexpr (kPre) {
+        // second pass over the same slab: GELU of the bf16-rounded pre-activation (what msd_gelu_fwd_bf16 computes from the stored tensor)
+#pragma unroll
+        for (int c = 0; c < UPR; ++c) {
+          const float2 a0 = unpack_bf16x2(pack_bf16x2(__uint_as_float(r[8 * c]), __uint_as_float(r[8 * c + 1])));
+          const float2 a1 = unpack_bf16x2(pack_bf16x2(__uint_as_float(r[8 * c + 2]), __uint_as_float(r[8 * c + 3])));
+          const float2 a2 = unpack_bf16x2(pack_bf16x2(__uint_as_float(r[8 * c + 4]), __uint_as_float(r[8 * c + 5])));
+          const float2 a3 = unpack_bf16x2(pack_bf16x2(__uint_as_float(r[8 * c + 6]), __uint_as_float(r[8 * c + 7])));
+          const uint2 o0 = gelu4_to_bf16(make_float4(a0.x, a0.y, a1.x, a1.y)), o1 = gelu4_to_bf16(make_float4(a2.x, a2.y, a3.x, a3.y));
+          sts128(stg_s + lane * PITCH + c * 16, make_uint4(o0.x, o0.y, o1.x, o1.y));
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < UPR; ++j) {
+          const int u = j * 32 + lane;
+          const uint4 h = lds128(stg_s + (u / UPR) * PITCH + (u % UPR) * 16);
+          if (live[j]) *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off[j]) = h;
+        }
+        __syncwarp();
+      }
     }
   }
   if constexpr (kStats) {
@@ -916,6 +1016,14 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         asm volatile("bar.sync 1, %0;\n" ::"n"(C::EPI_WARPS * 32) : "memory");
       }
     }
+    // column sums of the stored tensor (training BatchNorm statistics): one slot per epilogue warp in the free tenth-tap slot
+    uint32_t sums_s = 0u;
+    if constexpr (MODE == MODE_MERGE3_RESIDENT && BN == 48) {
+      if (p.bn_sums != nullptr && epi == E_CONV_RAW) {
+        sums_s = smem_u32(smem_res + 9 * C::W_BOX_BYTES) + (uint32_t)e * (uint32_t)(2 * BN * 4);
+        bn_sums_zero(sums_s, BN, lane);
+      }
+    }
     int it = 0, bias_n0 = -1;
     HeadCtx hc;                       // fused 1x1 head: this warp's pending tile (E_CONV_HEAD only)
     hc.has_prev = false; hc.prev_rowpix = kRowSkip; hc.parity = 0; hc.d2_full = nullptr;
@@ -954,6 +1062,10 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
       if (epi == E_CONV_SKIPADD)
         prefetch_rows_l2(p.skip, (size_t)p.ldo * 2, m0 + q * 32, p.M - (m0 + q * 32), (uint32_t)(n0 + slab_begin * C::SC) * 2u, (uint32_t)ncols * 2u, lane);
+      if constexpr (MODE == MODE_PLAIN) {
+        if (epi == E_RM_BF16_DGELU)
+          prefetch_rows_l2(p.gelu_pre, (size_t)p.ldo * 2, m0 + q * 32, p.M - (m0 + q * 32), (uint32_t)(n0 + slab_begin * C::SC) * 2u, (uint32_t)ncols * 2u, lane);
+      }
       mbar_wait(&tmem_full[as], aphase);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
@@ -984,10 +1096,12 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         MSD_EPI_CASE(E_RM_F32_RESID)
         MSD_EPI_CASE(E_CONV)
         MSD_EPI_CASE(E_CONVT)
-        MSD_EPI_CASE(E_CONV_RAW)
+        case E_CONV_RAW: epilogue_tile<BN, E_CONV_RAW>(p, stg_s, bias_s, taddr, &tmem_empty[as], m0 + q * 32, n0, lane, slab_begin, slab_end, nullptr, 0.0f, 0.0f, sums_s); break;
         MSD_EPI_CASE(E_CONVT_RAW)
         MSD_EPI_CASE(E_CONV_SKIPADD)
         MSD_EPI_CASE(E_RM_F32_RESID_STATS)
+        MSD_EPI_CASE(E_RM_BF16_GELU_PRE)
+        MSD_EPI_CASE(E_RM_BF16_DGELU)
         case E_RM_BF16_LN: epilogue_tile<BN, E_RM_BF16_LN>(p, stg_s, bias_s, taddr, &tmem_empty[as], m0 + q * 32, n0, lane, slab_begin, slab_end, nullptr, ln_a, ln_c); break;
         case E_RM_BF16_GELU_LN: epilogue_tile<BN, E_RM_BF16_GELU_LN>(p, stg_s, bias_s, taddr, &tmem_empty[as], m0 + q * 32, n0, lane, slab_begin, slab_end, nullptr, ln_a, ln_c); break;
         default: epilogue_tile<BN, E_GENERIC>(p, stg_s, bias_s, taddr, &tmem_empty[as], m0 + q * 32, n0, lane, slab_begin, slab_end); break;
@@ -995,6 +1109,8 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #undef MSD_EPI_CASE
     }
     if constexpr (MODE == MODE_MERGE3_RESIDENT && BN == 48) {
+      if (p.bn_sums != nullptr && epi == E_CONV_RAW)
+        bn_sums_flush(smem_u32(smem_res + 9 * C::W_BOX_BYTES), p.bn_sums, BN, (int)threadIdx.x - 128, C::EPI_WARPS);
       if (epi == E_CONV_HEAD && hc.has_prev) {           // the last tile of this warp's accumulator buffer
         mbar_wait(hc.d2_full, hc.parity);
         tcgen05_fence_after();

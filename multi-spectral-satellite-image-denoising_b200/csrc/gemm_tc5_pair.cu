@@ -246,6 +246,15 @@ gemm_tc5_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const uint32_t bias_s = stg_s + 32 * E::STG_PITCH;
     const int slab_begin = half ? C::SLAB_SPLIT : 0, slab_end = half ? E::NSLAB : C::SLAB_SPLIT;
     const int ncols = (slab_end - slab_begin) * E::SC;
+    // column sums of the stored tensor (training BatchNorm statistics): one slot per epilogue warp behind the nine taps' weights
+    uint32_t sums_s = 0u;
+    if constexpr (MERGED) {
+      static_assert((uint32_t)C::EPI_WARPS * 2u * BN * 4u <= 2u * C::W_BOX_BYTES, "column-sum slots must fit the skip tap's two k-blocks");
+      if (p.bn_sums != nullptr && epi == E_CONV_RAW) {
+        sums_s = smem_u32(smem_res + (C::MAX_RES_KB - 2) * C::W_BOX_BYTES) + (uint32_t)e * (uint32_t)(2 * BN * 4);
+        bn_sums_zero(sums_s, BN, lane);
+      }
+    }
     int it = 0, bias_n0 = -1;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
       if ((it & 1) != grp) continue;
@@ -282,6 +291,10 @@ gemm_tc5_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       }
       if (epi == E_CONV_SKIPADD)
         prefetch_rows_l2(p.skip, (size_t)p.ldo * 2, m0 + q * 32, p.M - (m0 + q * 32), (uint32_t)(n0 + slab_begin * E::SC) * 2u, (uint32_t)ncols * 2u, lane);
+      if constexpr (!MERGED) {
+        if (epi == E_RM_BF16_DGELU)
+          prefetch_rows_l2(p.gelu_pre, (size_t)p.ldo * 2, m0 + q * 32, p.M - (m0 + q * 32), (uint32_t)(n0 + slab_begin * E::SC) * 2u, (uint32_t)ncols * 2u, lane);
+      }
       mbar_wait(&tmem_full[as], aphase);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
@@ -292,16 +305,22 @@ gemm_tc5_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         MSD_EPI_CASE(E_RM_BF16_GELU)
         MSD_EPI_CASE(E_RM_F32_RESID)
         MSD_EPI_CASE(E_CONV)
-        MSD_EPI_CASE(E_CONV_RAW)
+        case E_CONV_RAW: epilogue_tile<BN, E_CONV_RAW, true>(p, stg_s, bias_s, taddr, &tmem_empty[as], m0 + q * 32, n0, lane, slab_begin, slab_end, nullptr, 0.0f, 0.0f, sums_s); break;
         MSD_EPI_CASE(E_CONVT)
         MSD_EPI_CASE(E_CONVT_RAW)
         MSD_EPI_CASE(E_CONV_SKIPADD)
         MSD_EPI_CASE(E_RM_F32_RESID_STATS)
+        MSD_EPI_CASE(E_RM_BF16_GELU_PRE)
+        MSD_EPI_CASE(E_RM_BF16_DGELU)
         case E_RM_BF16_LN: epilogue_tile<BN, E_RM_BF16_LN, true>(p, stg_s, bias_s, taddr, &tmem_empty[as], m0 + q * 32, n0, lane, slab_begin, slab_end, nullptr, ln_a, ln_c); break;
         case E_RM_BF16_GELU_LN: epilogue_tile<BN, E_RM_BF16_GELU_LN, true>(p, stg_s, bias_s, taddr, &tmem_empty[as], m0 + q * 32, n0, lane, slab_begin, slab_end, nullptr, ln_a, ln_c); break;
         default: epilogue_tile<BN, E_GENERIC, true>(p, stg_s, bias_s, taddr, &tmem_empty[as], m0 + q * 32, n0, lane, slab_begin, slab_end); break;
       }
 #undef MSD_EPI_CASE
+    }
+    if constexpr (MERGED) {
+      if (p.bn_sums != nullptr && epi == E_CONV_RAW)
+        bn_sums_flush(smem_u32(smem_res + (C::MAX_RES_KB - 2) * C::W_BOX_BYTES), p.bn_sums, BN, (int)threadIdx.x - 128, C::EPI_WARPS);
     }
   }
   tcgen05_fence_before();

@@ -147,6 +147,26 @@ extern "C" int msd_linear_bf16(const void* d_a, const void* d_w, const float* d_
   return gemm::launch(p, backend, (cudaStream_t)stream);
 }
 
+extern "C" int msd_linear_gelu_pre_bf16(const void* d_a, const void* d_w, const float* d_bias, void* d_out, void* d_pre, int M, int N, int K,
+                                        void* stream) {
+  MSD_REQUIRE(d_pre != nullptr, "linear_gelu_pre: null pointer");
+  Problem p;
+  int rc = make_linear(p, d_a, d_w, d_bias, d_out, nullptr, M, N, K, 1, 0);
+  if (rc) return rc;
+  p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(d_pre);
+  return gemm::launch(p, 0, (cudaStream_t)stream);
+}
+
+extern "C" int msd_linear_dgelu_bf16(const void* d_a, const void* d_w, const float* d_bias, const void* d_pre, void* d_out, int M, int N,
+                                     int K, void* stream) {
+  MSD_REQUIRE(d_pre != nullptr, "linear_dgelu: null pointer");
+  Problem p;
+  int rc = make_linear(p, d_a, d_w, d_bias, d_out, nullptr, M, N, K, 0, 0);
+  if (rc) return rc;
+  p.gelu_pre = reinterpret_cast<const __nv_bfloat16*>(d_pre);
+  return gemm::launch(p, 0, (cudaStream_t)stream);
+}
+
 extern "C" int msd_ln_stats_parts(int N, int M) { return (N > 0 && M > 0 && N % 16 == 0) ? gemm::tc5_stats_parts(N, M) : 0; }
 
 extern "C" int msd_linear_resid_stats_f32(const void* d_a, const void* d_w, const float* d_bias, float* d_x, void* d_x_bf16,
@@ -187,6 +207,28 @@ extern "C" int msd_conv3x3_nhwc_bf16(const void* d_x, const void* d_w, const flo
   int rc = make_conv3x3(p, d_x, d_w, d_bias, d_skip, d_y, B, H, W, Cin, Cout, 1, skip_in_epilogue(backend, Cout));
   if (rc) return rc;
   return gemm::launch(p, backend, (cudaStream_t)stream);
+}
+
+// raw 3x3 conv of a training forward + the column sums BatchNorm needs: in the conv's epilogue where the kernel has them
+static int conv3x3_raw_with_sums(Problem& p, int backend, long long rows, int Cout, void* d_y, double* d_sums, int* fused_out, cudaStream_t s) {
+  const bool fused = backend == 0 && gemm::tc5_supports_bn_sums(p);
+  if (fused_out) *fused_out = fused ? 1 : 0;
+  if (!fused) {
+    const int rc = gemm::launch(p, backend, s);
+    return rc ? rc : msd_bn_sums_bf16(d_y, rows, Cout, d_sums, (void*)s);
+  }
+  MSD_CHECK_CUDA(cudaMemsetAsync(d_sums, 0, sizeof(double) * 2 * Cout, s));
+  p.bn_sums = d_sums;
+  return gemm::launch(p, backend, s);
+}
+
+extern "C" int msd_conv3x3_stats_nhwc_bf16(const void* d_x, const void* d_w, const float* d_bias, void* d_y, double* d_sums, int B, int H,
+                                           int W, int Cin, int Cout, int backend, int* fused_out, void* stream) {
+  MSD_REQUIRE(d_sums != nullptr, "conv3x3_stats: null pointer");
+  Problem p;
+  int rc = make_conv3x3(p, d_x, d_w, d_bias, nullptr, d_y, B, H, W, Cin, Cout, 0);
+  if (rc) return rc;
+  return conv3x3_raw_with_sums(p, backend, (long long)B * (H + 2) * (W + 2), Cout, d_y, d_sums, fused_out, (cudaStream_t)stream);
 }
 
 extern "C" int msd_conv3x3_head_nchw_f32(const void* d_x, const void* d_w, const float* d_bias, const float* d_head_w,
@@ -669,6 +711,8 @@ extern "C" int msd_model_forward_train(msd_model* m, const float* d_x, int B, fl
   unsigned char* ws = reinterpret_cast<unsigned char*>(d_ws);
   const int M = B * m->tokens, E = d.embed_dim, Kpe = d.in_channels * d.patch_size * d.patch_size, Hd = d.mlp_hidden;
   const int be = d.gemm_backend;
+  static const bool no_mlp_fusion = getenv("MSD_NO_MLP_FUSION") != nullptr;      // A/B switch: separate GELU passes
+  const bool mlp_fused = be == 0 && !no_mlp_fusion;
   Problem p;
   float* stats = reinterpret_cast<float*>(ws + L.stats);
   double* sums = reinterpret_cast<double*>(ws + L.sums);
@@ -695,9 +739,16 @@ extern "C" int msd_model_forward_train(msd_model* m, const float* d_x, int B, fl
     MSD_TRY(make_linear(p, att, bw.w_proj, bw.b_proj, xmid, xin, M, E, E, 0, 1));
     MSD_TRY(gemm::launch(p, be, s));
     MSD_TRY(msd_layernorm_f32_bf16(xmid, bw.ln2_g, bw.ln2_b, d.ln_eps_block, xn2, M, E, stream));
-    MSD_TRY(make_linear(p, xn2, bw.w_fc1, bw.b_fc1, hpre, nullptr, M, Hd, E, 0, 0));
-    MSD_TRY(gemm::launch(p, be, s));
-    MSD_TRY(msd_gelu_fwd_bf16(hpre, h, (long long)M * Hd, stream));
+    if (mlp_fused) {
+      // fc1 leaves both the pre-activation (backward) and its GELU (fc2 operand) from one epilogue
+      MSD_TRY(make_linear(p, xn2, bw.w_fc1, bw.b_fc1, h, nullptr, M, Hd, E, 1, 0));
+      p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(hpre);
+      MSD_TRY(gemm::launch(p, be, s));
+    } else {
+      MSD_TRY(make_linear(p, xn2, bw.w_fc1, bw.b_fc1, hpre, nullptr, M, Hd, E, 0, 0));
+      MSD_TRY(gemm::launch(p, be, s));
+      MSD_TRY(msd_gelu_fwd_bf16(hpre, h, (long long)M * Hd, stream));
+    }
     MSD_TRY(make_linear(p, h, bw.w_fc2, bw.b_fc2, xout, xmid, M, E, Hd, 0, 1));
     MSD_TRY(gemm::launch(p, be, s));
   }
@@ -726,13 +777,15 @@ extern "C" int msd_model_forward_train(msd_model* m, const float* d_x, int B, fl
       const msd_bn_params &b1 = sw.bn_conv[2 * rb], &b2 = sw.bn_conv[2 * rb + 1];
       float* s1 = stats + (size_t)bn_index(st, 1 + 2 * rb) * kStatsStride;
       float* s2 = stats + (size_t)bn_index(st, 2 + 2 * rb) * kStatsStride;
+      const long long rows = (long long)B * (hw + 2) * (hw + 2);
+      const double count = (double)B * hw * hw;
       MSD_TRY(make_conv3x3(p, in, sw.w_conv[2 * rb], nullptr, nullptr, c1, B, hw, hw, c, c, 0));
-      MSD_TRY(gemm::launch(p, be, s));
-      MSD_TRY(msd_bn_stats_bf16(c1, B, hw, hw, c, b1.gamma, b1.beta, tw.bn_eps, tw.bn_momentum, b1.running_mean, b1.running_var, s1, sums, stream));
+      MSD_TRY(conv3x3_raw_with_sums(p, be, rows, c, c1, sums, nullptr, s));
+      MSD_TRY(msd_bn_finalize(sums, count, c, b1.gamma, b1.beta, tw.bn_eps, tw.bn_momentum, b1.running_mean, b1.running_var, s1, stream));
       MSD_TRY(msd_bn_act_fwd_bf16(c1, nullptr, s1, y1, B, hw, hw, c, stream));
       MSD_TRY(make_conv3x3(p, y1, sw.w_conv[2 * rb + 1], nullptr, nullptr, c2, B, hw, hw, c, c, 0));
-      MSD_TRY(gemm::launch(p, be, s));
-      MSD_TRY(msd_bn_stats_bf16(c2, B, hw, hw, c, b2.gamma, b2.beta, tw.bn_eps, tw.bn_momentum, b2.running_mean, b2.running_var, s2, sums, stream));
+      MSD_TRY(conv3x3_raw_with_sums(p, be, rows, c, c2, sums, nullptr, s));
+      MSD_TRY(msd_bn_finalize(sums, count, c, b2.gamma, b2.beta, tw.bn_eps, tw.bn_momentum, b2.running_mean, b2.running_var, s2, stream));
       MSD_TRY(msd_bn_act_fwd_bf16(c2, in, s2, out, B, hw, hw, c, stream));
     }
     cur = T[9]; cin = c; in_pad = 1;
@@ -741,9 +794,9 @@ extern "C" int msd_model_forward_train(msd_model* m, const float* d_x, int B, fl
     const int c = d.dec_channels[3];
     float* sh = stats + (size_t)20 * kStatsStride;
     MSD_TRY(make_conv3x3(p, cur, tw.w_head3, tw.b_head3, nullptr, ws + L.head_c, B, hw, hw, c, c, 0));
-    MSD_TRY(gemm::launch(p, be, s));
-    MSD_TRY(msd_bn_stats_bf16(ws + L.head_c, B, hw, hw, c, tw.bn_head.gamma, tw.bn_head.beta, tw.bn_eps, tw.bn_momentum,
-                              tw.bn_head.running_mean, tw.bn_head.running_var, sh, sums, stream));
+    MSD_TRY(conv3x3_raw_with_sums(p, be, (long long)B * (hw + 2) * (hw + 2), c, ws + L.head_c, sums, nullptr, s));
+    MSD_TRY(msd_bn_finalize(sums, (double)B * hw * hw, c, tw.bn_head.gamma, tw.bn_head.beta, tw.bn_eps, tw.bn_momentum,
+                            tw.bn_head.running_mean, tw.bn_head.running_var, sh, stream));
     MSD_TRY(msd_bn_act_fwd_bf16(ws + L.head_c, nullptr, sh, ws + L.head_h, B, hw, hw, c, stream));
     MSD_TRY(msd_head1x1_nchw_f32(ws + L.head_h, tw.w_head1, tw.b_head1, d_y, B, hw, hw, c, d.out_channels, stream));
   }
@@ -766,6 +819,8 @@ extern "C" int msd_model_backward(msd_model* m, const float* d_grad_y, int B, vo
   unsigned char* ws = reinterpret_cast<unsigned char*>(d_ws);
   const int M = B * m->tokens, E = d.embed_dim, Kpe = d.in_channels * d.patch_size * d.patch_size, Hd = d.mlp_hidden;
   const int be = d.gemm_backend;
+  static const bool dgelu_fusion = getenv("MSD_DGELU_FUSION") != nullptr;       // A/B switch, see the fc2 data gradient below
+  const bool dgelu_fused = be == 0 && dgelu_fusion;
   Problem p;
   float* stats = reinterpret_cast<float*>(ws + L.stats);
   double* sums = reinterpret_cast<double*>(ws + L.sums);
@@ -872,8 +927,12 @@ extern "C" int msd_model_backward(msd_model* m, const float* d_grad_y, int B, vo
   void *gbf = ws + L.gbf, *dh = ws + L.dh, *dxn = ws + L.dxn, *dqkv = ws + L.dqkv, *datt = ws + L.datt;
   MSD_TRY(zero_f32(gr->norm_g, E, s));
   MSD_TRY(zero_f32(gr->norm_b, E, s));
-  MSD_TRY(msd_layernorm_bwd(dxn, 0, reinterpret_cast<const float*>(ws + L.xs + d.depth * L.s_xs), w.norm_g, d.ln_eps_outer, g, 0, gbf,
-                            gr->norm_g, gr->norm_b, M, E, stream));
+  // The bf16 copy of the residual-stream gradient each LayerNorm backward leaves is the dY operand of the Linear in front of it
+  // (fc2 / proj / the patch embedding), so its column sums -- that layer's bias gradient -- are accumulated by the same kernel.
+  auto fc2_bias_of = [&](int l) -> float* { return (l >= 0 && m->tblocks_t[l].trainable) ? gr->blocks[l].b_fc2 : nullptr; };
+  if (float* b = fc2_bias_of(d.depth - 1)) MSD_TRY(zero_f32(b, E, s));
+  MSD_TRY(msd_layernorm_bwd_colsum(dxn, 0, reinterpret_cast<const float*>(ws + L.xs + d.depth * L.s_xs), w.norm_g, d.ln_eps_outer, g, 0, gbf,
+                                   gr->norm_g, gr->norm_b, fc2_bias_of(d.depth - 1), M, E, stream));
   for (int l = d.depth - 1; l >= 0; --l) {
     const msd_block_weights& bw = m->tblocks[l];
     const msd_train_block& bt = m->tblocks_t[l];
@@ -886,15 +945,26 @@ extern "C" int msd_model_backward(msd_model* m, const float* d_grad_y, int B, vo
     // MLP branch: x_out = x_mid + fc2(GELU(fc1(LN2 x_mid)))
     MSD_TRY(ss.wait(e_dh));                     // the previous block's fc1 weight gradient still reads dh
     MSD_TRY(make_linear(p, gbf, bt.wT_fc2, nullptr, dh, nullptr, M, Hd, E, 0, 0));
+    // (the GELU derivative could ride in this GEMM's epilogue -- Problem::gelu_pre, MSD_DGELU_FUSION=1 -- but the ~25 instructions
+    //  per element pair make the 16 epilogue warps the critical path of a K = 768 GEMM: 68 us instead of 34 + 22 for the separate,
+    //  L2-resident pass below)
+    if (dgelu_fused) p.gelu_pre = reinterpret_cast<const __nv_bfloat16*>(hpre);
     MSD_TRY(gemm::launch(p, be, s));
     if (tr) {
       MSD_TRY(ss.fork());
       MSD_TRY(zero_f32(bg.w_fc2, (size_t)E * Hd, ss.side_s));
       MSD_TRY(msd_wgrad_linear_bf16(gbf, E, h, Hd, bg.w_fc2, Hd, M, E, Hd, side));
       MSD_TRY(ss.done(&e_gbf));
-      MSD_TRY(bias_grad(gbf, M, E, bg.b_fc2, E, sums, stream));
     }
-    MSD_TRY(msd_gelu_bwd_bf16(dh, hpre, dh, (long long)M * Hd, stream));
+    // dh *= gelu'(h_pre); the pass also leaves the column sums of its result = fc1's bias gradient
+    float* b_fc1 = tr ? bg.b_fc1 : nullptr;
+    if (b_fc1 != nullptr && !dgelu_fused && Hd % 256 == 0) {
+      MSD_TRY(zero_f32(b_fc1, Hd, s));
+      MSD_TRY(msd_gelu_bwd_colsum_bf16(dh, hpre, dh, b_fc1, M, Hd, stream));
+      b_fc1 = nullptr;
+    } else if (!dgelu_fused) {
+      MSD_TRY(msd_gelu_bwd_bf16(dh, hpre, dh, (long long)M * Hd, stream));
+    }
     MSD_TRY(make_linear(p, dh, bt.wT_fc1, nullptr, dxn, nullptr, M, E, Hd, 0, 0));
     MSD_TRY(gemm::launch(p, be, s));
     if (tr) {
@@ -902,12 +972,14 @@ extern "C" int msd_model_backward(msd_model* m, const float* d_grad_y, int B, vo
       MSD_TRY(zero_f32(bg.w_fc1, (size_t)E * Hd, ss.side_s));
       MSD_TRY(msd_wgrad_linear_bf16(dh, Hd, xn2, E, bg.w_fc1, E, M, Hd, E, side));
       MSD_TRY(ss.done(&e_dh));
-      MSD_TRY(bias_grad(dh, M, Hd, bg.b_fc1, Hd, sums, stream));
+      MSD_TRY(bias_grad(dh, M, Hd, b_fc1, Hd, sums, stream));
       MSD_TRY(zero_f32(bg.ln2_g, E, s));
       MSD_TRY(zero_f32(bg.ln2_b, E, s));
+      if (bg.b_proj) MSD_TRY(zero_f32(bg.b_proj, E, s));
     }
     MSD_TRY(ss.wait(e_gbf));                    // LayerNorm backward rewrites gbf, which the fc2 weight gradient reads
-    MSD_TRY(msd_layernorm_bwd(dxn, 0, xmid, bw.ln2_g, d.ln_eps_block, g, 1, gbf, tr ? bg.ln2_g : nullptr, tr ? bg.ln2_b : nullptr, M, E, stream));
+    MSD_TRY(msd_layernorm_bwd_colsum(dxn, 0, xmid, bw.ln2_g, d.ln_eps_block, g, 1, gbf, tr ? bg.ln2_g : nullptr, tr ? bg.ln2_b : nullptr,
+                                     tr ? bg.b_proj : nullptr, M, E, stream));
     // attention branch: x_mid = x_in + proj(attn(LN1 x_in))
     MSD_TRY(make_linear(p, gbf, bt.wT_proj, nullptr, datt, nullptr, M, E, E, 0, 0));
     MSD_TRY(gemm::launch(p, be, s));
@@ -916,7 +988,6 @@ extern "C" int msd_model_backward(msd_model* m, const float* d_grad_y, int B, vo
       MSD_TRY(zero_f32(bg.w_proj, (size_t)E * E, ss.side_s));
       MSD_TRY(msd_wgrad_linear_bf16(gbf, E, att, E, bg.w_proj, E, M, E, E, side));
       MSD_TRY(ss.done(&e_gbf));
-      MSD_TRY(bias_grad(gbf, M, E, bg.b_proj, E, sums, stream));
     }
     MSD_TRY(ss.wait(e_dqkv));                   // the previous block's qkv weight gradient still reads dqkv
     MSD_TRY(msd_attention_bwd_bf16(qkv, datt, dqkv, B, m->tokens, d.num_heads, stream));
@@ -932,21 +1003,23 @@ extern "C" int msd_model_backward(msd_model* m, const float* d_grad_y, int B, vo
       MSD_TRY(zero_f32(bg.ln1_b, E, s));
     }
     MSD_TRY(ss.wait(e_gbf));                    // ... and the proj weight gradient
-    MSD_TRY(msd_layernorm_bwd(dxn, 0, xin, bw.ln1_g, d.ln_eps_block, g, 1, gbf, tr ? bg.ln1_g : nullptr, tr ? bg.ln1_b : nullptr, M, E, stream));
+    if (float* b = fc2_bias_of(l - 1)) MSD_TRY(zero_f32(b, E, s));
+    MSD_TRY(msd_layernorm_bwd_colsum(dxn, 0, xin, bw.ln1_g, d.ln_eps_block, g, 1, gbf, tr ? bg.ln1_g : nullptr, tr ? bg.ln1_b : nullptr,
+                                     fc2_bias_of(l - 1), M, E, stream));
     MSD_TRY(ss.mark_group(m->grad_ev[(size_t)(d.depth - l)]));   // group 1 + (depth-1-l): block l (the first one also covers encoder.norm)
   }
   // ---- patch embedding: x0 = LN(pe) + pos_embed
   if (gr->pos_embed) MSD_TRY(msd_batch_sum_f32(g, gr->pos_embed, B, (long long)m->tokens * E, stream));
   MSD_TRY(zero_f32(gr->pe_ln_g, E, s));
   MSD_TRY(zero_f32(gr->pe_ln_b, E, s));
-  MSD_TRY(msd_layernorm_bwd(g, 1, reinterpret_cast<const float*>(ws + L.x0pre), w.pe_ln_g, d.ln_eps_outer, g, 0, gbf, gr->pe_ln_g, gr->pe_ln_b,
-                            M, E, stream));
+  if (gr->b_pe) MSD_TRY(zero_f32(gr->b_pe, E, s));
+  MSD_TRY(msd_layernorm_bwd_colsum(g, 1, reinterpret_cast<const float*>(ws + L.x0pre), w.pe_ln_g, d.ln_eps_outer, g, 0, gbf, gr->pe_ln_g,
+                                   gr->pe_ln_b, gr->b_pe, M, E, stream));
   if (gr->w_pe) {
     MSD_TRY(ss.fork());
     MSD_TRY(zero_f32(gr->w_pe, (size_t)E * Kpe, ss.side_s));
     MSD_TRY(msd_wgrad_linear_bf16(gbf, E, ws + L.a_pe, Kpe, gr->w_pe, Kpe, M, E, Kpe, side));
   }
-  MSD_TRY(bias_grad(gbf, M, E, gr->b_pe, E, sums, stream));
   // join: everything the side stream produced is ordered before whatever the caller enqueues next on `stream`
   MSD_TRY(ss.mark_group(m->grad_ev[(size_t)d.depth + 1]));     // last group: patch embedding, pos_embed
   cudaEvent_t e_all = nullptr;

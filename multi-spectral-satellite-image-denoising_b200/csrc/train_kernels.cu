@@ -6,55 +6,12 @@
 //
 // Layout conventions (see model.cu): decoder activations are NHWC bf16 [B, H+2, W+2, C] with a zero 1-pixel halo,
 // "rows" = padded pixels; encoder activations are [tokens, features].
+#include <cstdlib>
 #include "common.cuh"
 
 namespace {
 
 constexpr int kBlock = 256;
-
-__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
-  float2 t;
-  t = unpack_bf16x2(u.x); f[0] = t.x; f[1] = t.y;
-  t = unpack_bf16x2(u.y); f[2] = t.x; f[3] = t.y;
-  t = unpack_bf16x2(u.z); f[4] = t.x; f[5] = t.y;
-  t = unpack_bf16x2(u.w); f[6] = t.x; f[7] = t.y;
-}
-__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
-  return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
-}
-// exact-erf GELU and its derivative (nn.GELU() default): gelu'(z) = Phi(z) + z phi(z)
-// erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below the bf16 rounding of every consumer; common.cuh gelu_erf):
-// Phi(z) and phi(z) share one exp(-z^2/2)
-__device__ __forceinline__ float gelu_fwd(float z) { return gelu_erf(z); }
-__device__ __forceinline__ float gelu_grad(float z) {
-  const float az = fabsf(z) * 0.70710678118654752f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, az, 1.0f));
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  const float e = __expf(-az * az);                       // = exp(-z^2 / 2)
-  const float erf_abs = fmaf(-poly * t, e, 1.0f);
-  return fmaf(0.5f, copysignf(erf_abs, z), 0.5f) + z * 0.3989422804014327f * e;
-}
-// dy * gelu'(z) for two elements at a time in half2 (tanh form, MUFU.TANH.F16x2):
-//   u = z (c0 + c1 z^2), t = tanh(u), gelu'(z) = 0.5 (1 + t) + 0.5 z (1 - t^2) (c0 + 3 c1 z^2)
-// |tanh form - erf form| <= 1e-3 on the derivative and fp16 evaluation (1e-3 relative) are both below the bf16 rounding of
-// the product that follows; z is clamped to +-8 (the derivative is 0 / 1 beyond, and fp16 z^2 must not overflow).
-__device__ __forceinline__ float2 gelu_grad2(float z0, float z1) {
-  const __half2 z = __floats2half2_rn(fminf(fmaxf(z0, -8.f), 8.f), fminf(fmaxf(z1, -8.f), 8.f));
-  const __half2 c0 = __float2half2_rn(0.7978845608f), c1 = __float2half2_rn(0.0356774081f), c3 = __float2half2_rn(0.1070322243f);
-  const __half2 half = __float2half2_rn(0.5f), one = __float2half2_rn(1.0f);
-  const __half2 z2 = __hmul2(z, z);
-  const __half2 u = __hmul2(z, __hfma2(z2, c1, c0));
-  uint32_t ui = *reinterpret_cast<const uint32_t*>(&u), ti;
-  asm("tanh.approx.f16x2 %0, %1;" : "=r"(ti) : "r"(ui));
-  const __half2 t = *reinterpret_cast<const __half2*>(&ti);
-  const __half2 sech2 = __hfma2(__hneg2(t), t, one);                          // 1 - t^2
-  const __half2 inner = __hmul2(__hmul2(half, z), __hfma2(z2, c3, c0));       // 0.5 z (c0 + 3 c1 z^2)
-  const __half2 g = __hfma2(sech2, inner, __hfma2(half, t, half));
-  return __half22float2(g);
-}
 
 __device__ __forceinline__ bool interior_row(uint32_t p, const FastDiv& plane, const FastDiv& pitch, int H, int W) {
   uint32_t img, rem, yy, xx;
@@ -167,14 +124,35 @@ __global__ void __launch_bounds__(kBlock) bn_act_fwd_kernel(const __nv_bfloat16*
   }
 }
 
-// BatchNorm + GELU backward, pass 1: dz = dy * gelu'(scale c + shift [+ skip]) (0 on the halo), written as bf16, and the
-// per-channel sums  sum dz,  sum dz * c  are accumulated (sum dz * xhat = rstd (sum dz c - mean sum dz) is formed by the
-// finalize kernel: the loop then needs only scale / shift per channel, 32 registers less, three blocks per SM instead of two --
-// the pass was latency-bound at 36 % of the HBM rate with 16 warps per SM)
+// BatchNorm + GELU backward, pass 1: dz = dy * gelu'(scale c + shift [+ skip]), written as bf16, and the per-channel sums
+// sum dz, sum dz * c are accumulated (sum dz * xhat = rstd (sum dz c - mean sum dz) is formed by the finalize kernel, so the loop
+// needs only scale / shift per channel: three blocks per SM).
+// The pass was issue-bound (ncu: 30.6 thread-instructions per element, issue-active 67 %, 52 % of the HBM rate), so the loop is
+// written for instruction count: no interior test -- dy has zero halo rows (every producer in the library writes them), so dz and both
+// sums come out zero there by themselves; 32-bit element offsets shared by the four tensors; bf16 pairs unpacked with one shift and
+// one mask; the +-8 clamp of gelu' done on the packed half2 value.
+__device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
+// gelu'(z) for a packed pair, tanh form (see gelu_grad2 in common.cuh), |z| clamped to 8 in half2
+__device__ __forceinline__ float2 gelu_grad_pair(float z0, float z1) {
+  const __half2 lim = __float2half2_rn(8.0f);
+  const __half2 z = __hmax2(__hmin2(__floats2half2_rn(z0, z1), lim), __hneg2(lim));
+  const __half2 c0 = __float2half2_rn(0.7978845608f), c1 = __float2half2_rn(0.0356774081f), c3 = __float2half2_rn(0.1070322243f);
+  const __half2 half = __float2half2_rn(0.5f), one = __float2half2_rn(1.0f);
+  const __half2 z2 = __hmul2(z, z);
+  const __half2 u = __hmul2(z, __hfma2(z2, c1, c0));
+  uint32_t ui = *reinterpret_cast<const uint32_t*>(&u), ti;
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(ti) : "r"(ui));
+  const __half2 t = *reinterpret_cast<const __half2*>(&ti);
+  const __half2 sech2 = __hfma2(__hneg2(t), t, one);
+  const __half2 inner = __hmul2(__hmul2(half, z), __hfma2(z2, c3, c0));
+  return __half22float2(__hfma2(sech2, inner, __hfma2(half, t, half)));
+}
+template <bool kSkip>
 __global__ void __launch_bounds__(kBlock, 3) bn_act_bwd1_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ c,
                                                                 const __nv_bfloat16* __restrict__ skip, const float* __restrict__ stats,
-                                                                __nv_bfloat16* __restrict__ dz, double* __restrict__ sums, long long rows,
-                                                                int C, FastDiv plane, FastDiv pitch, int H, int W) {
+                                                                __nv_bfloat16* __restrict__ dz, double* __restrict__ sums, uint32_t total,
+                                                                int C) {
   extern __shared__ float sh[];
   const int vpr = C >> 3;
   const int rpi = kBlock / vpr;
@@ -185,43 +163,38 @@ __global__ void __launch_bounds__(kBlock, 3) bn_act_bwd1_kernel(const __nv_bfloa
   if (r0 < rpi) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) { sc[i] = stats[v * 8 + i]; sf[i] = stats[C + v * 8 + i]; }
-    // two rows per iteration, every load issued before the first use (the pass is latency-bound otherwise)
-    const long long stride = (long long)gridDim.x * rpi;
-    for (long long row = (long long)blockIdx.x * rpi + r0; row < rows; row += 2 * stride) {
+    // two rows per iteration, every load issued before the first use; `total` = rows * C elements (< 2^31)
+    const uint32_t stride = gridDim.x * (uint32_t)(rpi * C);
+    for (uint32_t off = (blockIdx.x * (uint32_t)rpi + (uint32_t)r0) * (uint32_t)C + (uint32_t)v * 8u; off < total; off += 2u * stride) {
       uint4 rg[2], rc[2], rs[2];
-      bool in[2];
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const long long r = row + u * stride;
-        in[u] = r < rows && interior_row((uint32_t)r, plane, pitch, H, W);
-        rg[u] = rc[u] = rs[u] = make_uint4(0u, 0u, 0u, 0u);
-        if (in[u]) {
-          rg[u] = __ldg(reinterpret_cast<const uint4*>(dy + r * C + v * 8));
-          rc[u] = __ldg(reinterpret_cast<const uint4*>(c + r * C + v * 8));
-          if (skip != nullptr) rs[u] = __ldg(reinterpret_cast<const uint4*>(skip + r * C + v * 8));
-        }
+      const bool two = off + stride < total;
+      rg[0] = __ldg(reinterpret_cast<const uint4*>(dy + off));
+      rc[0] = __ldg(reinterpret_cast<const uint4*>(c + off));
+      if (kSkip) rs[0] = __ldg(reinterpret_cast<const uint4*>(skip + off));
+      if (two) {
+        rg[1] = __ldg(reinterpret_cast<const uint4*>(dy + off + stride));
+        rc[1] = __ldg(reinterpret_cast<const uint4*>(c + off + stride));
+        if (kSkip) rs[1] = __ldg(reinterpret_cast<const uint4*>(skip + off + stride));
       }
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
-        const long long r = row + u * stride;
-        if (r >= rows) break;
-        uint4 o = make_uint4(0u, 0u, 0u, 0u);
-        if (in[u]) {
-          float g[8], f[8], s[8];
-          unpack8(rg[u], g); unpack8(rc[u], f); unpack8(rs[u], s);
+        if (u == 1 && !two) break;
+        const uint32_t g4[4] = {rg[u].x, rg[u].y, rg[u].z, rg[u].w}, c4[4] = {rc[u].x, rc[u].y, rc[u].z, rc[u].w};
+        const uint32_t k4[4] = {kSkip ? rs[u].x : 0u, kSkip ? rs[u].y : 0u, kSkip ? rs[u].z : 0u, kSkip ? rs[u].w : 0u};
+        uint32_t o[4];
 #pragma unroll
-          for (int k = 0; k < 8; k += 2) {
-            const float z0 = fmaf(f[k], sc[k], sf[k]) + s[k], z1 = fmaf(f[k + 1], sc[k + 1], sf[k + 1]) + s[k + 1];
-            const float2 gg = gelu_grad2(z0, z1);
-            const float d0 = g[k] * gg.x, d1 = g[k + 1] * gg.y;
-            g[k] = d0; g[k + 1] = d1;
-            s1[k] += d0; s1[k + 1] += d1;
-            s2[k] = fmaf(d0, f[k], s2[k]);
-            s2[k + 1] = fmaf(d1, f[k + 1], s2[k + 1]);
-          }
-          o = pack8(g);
+        for (int t = 0; t < 4; ++t) {
+          const float f0 = bf16_lo(c4[t]), f1 = bf16_hi(c4[t]);
+          float z0 = fmaf(f0, sc[2 * t], sf[2 * t]), z1 = fmaf(f1, sc[2 * t + 1], sf[2 * t + 1]);
+          if (kSkip) { z0 += bf16_lo(k4[t]); z1 += bf16_hi(k4[t]); }
+          const float2 gg = gelu_grad_pair(z0, z1);
+          const float d0 = bf16_lo(g4[t]) * gg.x, d1 = bf16_hi(g4[t]) * gg.y;
+          s1[2 * t] += d0; s1[2 * t + 1] += d1;
+          s2[2 * t] = fmaf(d0, f0, s2[2 * t]);
+          s2[2 * t + 1] = fmaf(d1, f1, s2[2 * t + 1]);
+          o[t] = pack_bf16x2(d0, d1);
         }
-        *reinterpret_cast<uint4*>(dz + r * C + v * 8) = o;
+        *reinterpret_cast<uint4*>(dz + off + (u ? stride : 0u)) = make_uint4(o[0], o[1], o[2], o[3]);
       }
     }
   }
@@ -307,6 +280,44 @@ __global__ void __launch_bounds__(kBlock) gelu_bwd_kernel(const __nv_bfloat16* _
   }
 }
 
+// The same over a [rows, N] matrix, and colsum[N] += column sums of the (bf16-rounded) result: the bias gradient of the Linear that
+// produced h_pre (fc1) comes out of the pass that forms its output gradient.  A block owns a stripe of 256 columns (32 vectors) and
+// every eighth row of its row group (one warp per row: 512 contiguous bytes); the eight warps are folded through shared memory
+// and each thread issues ONE atomic -- same-address atomics from different CTAs serialise in L2 (~20 ns each), so their number
+// per column (= gridDim.x), not their total, is what must stay small.
+__global__ void __launch_bounds__(kBlock) gelu_bwd_colsum_kernel(const __nv_bfloat16* __restrict__ dh, const __nv_bfloat16* __restrict__ hpre,
+                                                                 __nv_bfloat16* __restrict__ out, float* __restrict__ colsum, int rows, int vpr) {
+  __shared__ float red[kBlock / 32][256];
+  const int cv = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int v = blockIdx.y * 32 + cv;
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  for (int row = blockIdx.x * (kBlock / 32) + rl; row < rows; row += gridDim.x * (kBlock / 32)) {
+    const size_t i = (size_t)row * vpr + v;
+    float g[8], z[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(dh) + i), g);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(hpre) + i), z);
+#pragma unroll
+    for (int k = 0; k < 8; k += 2) {
+      const float2 gg = gelu_grad2(z[k], z[k + 1]);
+      g[k] *= gg.x; g[k + 1] *= gg.y;
+    }
+    const uint4 o = pack8(g);
+    reinterpret_cast<uint4*>(out)[i] = o;
+    unpack8(o, g);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] += g[k];
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) red[rl][cv * 8 + k] = acc[k];
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int w = 0; w < kBlock / 32; ++w) t += red[w][threadIdx.x];
+  atomicAdd(colsum + blockIdx.y * 256 + threadIdx.x, t);
+}
+
 // h = GELU(h_pre), bf16 elementwise (the training forward keeps both: h_pre for the backward, h as the fc2 operand)
 __global__ void __launch_bounds__(kBlock) gelu_fwd_kernel(const __nv_bfloat16* __restrict__ hpre, __nv_bfloat16* __restrict__ out, long long nvec) {
   for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < nvec; i += (long long)gridDim.x * kBlock) {
@@ -321,21 +332,24 @@ __global__ void __launch_bounds__(kBlock) gelu_fwd_kernel(const __nv_bfloat16* _
 // LayerNorm backward, one warp per row (D = 32 * 4 * NV):
 //   dxh = dy * gamma;  dx = rstd * (dxh - mean(dxh) - xhat * mean(dxh * xhat));  dgamma += dy * xhat;  dbeta += dy
 // dy is bf16 (GRAD_F32 = 0) or fp32.  g_out fp32 (+= when `accumulate`), optional bf16 copy of the result.
+// COLSUM: the column sums of that bf16 copy are accumulated into colsum[D] as well -- the copy is the dY operand of the Linear
+// whose output this gradient belongs to (fc2 / proj / patch embedding), so its column sums ARE that layer's bias gradient.
 // ---------------------------------------------------------------------------------------------------
-template <int NV, int GRAD_F32>
+template <int NV, int GRAD_F32, int COLSUM>
 __global__ void __launch_bounds__(kBlock) ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x,
                                                         const float* __restrict__ gamma, float eps, float* __restrict__ g_out,
                                                         int accumulate, __nv_bfloat16* __restrict__ g_bf16,
-                                                        float* __restrict__ dgamma, float* __restrict__ dbeta, int M) {
+                                                        float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                        float* __restrict__ colsum, int M) {
   constexpr int D = 128 * NV;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float gam[NV][4], dg[NV][4], db[NV][4];
+  float gam[NV][4], dg[NV][4], db[NV][4], cs[COLSUM ? NV : 1][4];
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
     const float4 t = *reinterpret_cast<const float4*>(gamma + (v * 32 + lane) * 4);
     gam[v][0] = t.x; gam[v][1] = t.y; gam[v][2] = t.z; gam[v][3] = t.w;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) dg[v][k] = db[v][k] = 0.f;
+    for (int k = 0; k < 4; ++k) { dg[v][k] = db[v][k] = 0.f; if (COLSUM) cs[v][k] = 0.f; }
   }
   for (int row = blockIdx.x * (kBlock / 32) + warp; row < M; row += gridDim.x * (kBlock / 32)) {
     float xv[NV][4], dyv[NV][4];
@@ -386,25 +400,29 @@ __global__ void __launch_bounds__(kBlock) ln_bwd_kernel(const void* __restrict__
         o[0] += t.x; o[1] += t.y; o[2] += t.z; o[3] += t.w;
       }
       *reinterpret_cast<float4*>(gp) = make_float4(o[0], o[1], o[2], o[3]);
-      if (g_bf16 != nullptr)
-        *reinterpret_cast<uint2*>(g_bf16 + (size_t)row * D + (v * 32 + lane) * 4) = make_uint2(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]));
+      const uint2 ob = make_uint2(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]));
+      if (g_bf16 != nullptr) *reinterpret_cast<uint2*>(g_bf16 + (size_t)row * D + (v * 32 + lane) * 4) = ob;
+      if (COLSUM) {
+        const float2 a = unpack_bf16x2(ob.x), b = unpack_bf16x2(ob.y);
+        cs[v][0] += a.x; cs[v][1] += a.y; cs[v][2] += b.x; cs[v][3] += b.y;
+      }
     }
   }
-  if (dgamma == nullptr) return;      // frozen LayerNorm: no parameter gradients
-  // fold the 8 warps of the block (one shared buffer, used for dgamma then dbeta), then one atomic per column per block
+  // fold the 8 warps of the block (one shared buffer, used for dgamma, dbeta, then the column sums), then one atomic per column
+  // per block; a frozen LayerNorm (dgamma == NULL) has no parameter gradients
   __shared__ float s_red[kBlock / 32][D];
 #pragma unroll 1
-  for (int pass = 0; pass < 2; ++pass) {
+  for (int pass = (dgamma == nullptr ? 2 : 0); pass < (COLSUM ? 3 : 2); ++pass) {
 #pragma unroll
     for (int v = 0; v < NV; ++v)
 #pragma unroll
-      for (int k = 0; k < 4; ++k) s_red[warp][(v * 32 + lane) * 4 + k] = pass == 0 ? dg[v][k] : db[v][k];
+      for (int k = 0; k < 4; ++k) s_red[warp][(v * 32 + lane) * 4 + k] = pass == 0 ? dg[v][k] : pass == 1 ? db[v][k] : cs[COLSUM ? v : 0][k];
     __syncthreads();
     for (int c = threadIdx.x; c < D; c += kBlock) {
       float a = 0.f;
 #pragma unroll
       for (int w = 0; w < kBlock / 32; ++w) a += s_red[w][c];
-      atomicAdd((pass == 0 ? dgamma : dbeta) + c, a);
+      atomicAdd((pass == 0 ? dgamma : pass == 1 ? dbeta : colsum) + c, a);
     }
     __syncthreads();
   }
@@ -519,24 +537,39 @@ extern "C" int msd_f64_to_f32(const double* d_in, float* d_out, int n, void* str
   return MSD_OK;
 }
 
-// training-mode BatchNorm statistics of a raw conv output c [B,H+2,W+2,C] (halo rows zero): d_stats fp32 [4][C] =
-// {gamma*rstd, beta - mean*gamma*rstd, mean, rstd}; running statistics updated in place (momentum, unbiased variance)
-extern "C" int msd_bn_stats_bf16(const void* d_c, int B, int H, int W, int C, const float* d_gamma, const float* d_beta, float eps,
-                                 float momentum, float* d_running_mean, float* d_running_var, float* d_stats, double* d_sums,
-                                 void* stream) {
-  MSD_REQUIRE(d_c && d_gamma && d_beta && d_stats && d_sums, "bn_stats: null pointer");
-  MSD_REQUIRE(C % 8 == 0 && C / 8 <= kBlock && C <= 1024, "bn_stats: unsupported channel count %d", C);
+// training-mode BatchNorm statistics of a raw conv output c [B,H+2,W+2,C] (halo rows zero), in two steps so that the first one can
+// ride in the epilogue of the conv that writes c (msd_conv3x3_stats_nhwc_bf16):
+//   msd_bn_sums_bf16     d_sums fp64 [2][C] = {sum c, sum c^2} over all rows
+//   msd_bn_finalize      d_stats fp32 [4][C] = {gamma*rstd, beta - mean*gamma*rstd, mean, rstd}; running statistics updated in
+//                        place (momentum, unbiased variance)
+extern "C" int msd_bn_sums_bf16(const void* d_c, long long rows, int C, double* d_sums, void* stream) {
+  MSD_REQUIRE(d_c && d_sums && rows > 0, "bn_sums: null pointer");
+  MSD_REQUIRE(C % 8 == 0 && C / 8 <= kBlock && C <= 1024, "bn_sums: unsupported channel count %d", C);
   cudaStream_t s = (cudaStream_t)stream;
-  const long long rows = (long long)B * (H + 2) * (W + 2);
   MSD_CHECK_CUDA(cudaMemsetAsync(d_sums, 0, sizeof(double) * 2 * C, s));
   const int rpi = kBlock / (C / 8);
   colsum_kernel<1><<<grid_for((rows + rpi - 1) / rpi * kBlock, 4), kBlock, 2 * kBlock * 8 * sizeof(float), s>>>(
       reinterpret_cast<const __nv_bfloat16*>(d_c), nullptr, nullptr, d_sums, rows, C, C);
   MSD_LAUNCH_CHECK();
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(d_sums, (double)B * H * W, d_gamma, d_beta, eps, momentum, d_running_mean,
-                                                      d_running_var, d_stats, C);
+  return MSD_OK;
+}
+
+extern "C" int msd_bn_finalize(const double* d_sums, double count, int C, const float* d_gamma, const float* d_beta, float eps, float momentum,
+                               float* d_running_mean, float* d_running_var, float* d_stats, void* stream) {
+  MSD_REQUIRE(d_sums && d_gamma && d_beta && d_stats && count > 0 && C > 0, "bn_finalize: bad arguments");
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_sums, count, d_gamma, d_beta, eps, momentum, d_running_mean,
+                                                                         d_running_var, d_stats, C);
   MSD_LAUNCH_CHECK();
   return MSD_OK;
+}
+
+extern "C" int msd_bn_stats_bf16(const void* d_c, int B, int H, int W, int C, const float* d_gamma, const float* d_beta, float eps,
+                                 float momentum, float* d_running_mean, float* d_running_var, float* d_stats, double* d_sums,
+                                 void* stream) {
+  MSD_REQUIRE(d_c && d_gamma && d_beta && d_stats && d_sums, "bn_stats: null pointer");
+  int rc = msd_bn_sums_bf16(d_c, (long long)B * (H + 2) * (W + 2), C, d_sums, stream);
+  if (rc) return rc;
+  return msd_bn_finalize(d_sums, (double)B * H * W, C, d_gamma, d_beta, eps, momentum, d_running_mean, d_running_var, d_stats, stream);
 }
 
 extern "C" int msd_bn_act_fwd_bf16(const void* d_c, const void* d_skip, const float* d_stats, void* d_y, int B, int H, int W, int C,
@@ -564,9 +597,16 @@ extern "C" int msd_bn_act_bwd_bf16(const void* d_dy, const void* d_c, const void
   const FastDiv plane = make_fastdiv((uint32_t)((H + 2) * (W + 2))), pitch = make_fastdiv((uint32_t)(W + 2));
   MSD_CHECK_CUDA(cudaMemsetAsync(d_sums, 0, sizeof(double) * 2 * C, s));
   const int rpi = kBlock / (C / 8);
-  bn_act_bwd1_kernel<<<grid_for((rows + rpi - 1) / rpi * kBlock, 16), kBlock, 2 * kBlock * 8 * sizeof(float), s>>>(
-      reinterpret_cast<const __nv_bfloat16*>(d_dy), reinterpret_cast<const __nv_bfloat16*>(d_c),
-      reinterpret_cast<const __nv_bfloat16*>(d_skip), d_stats, reinterpret_cast<__nv_bfloat16*>(d_dz), d_sums, rows, C, plane, pitch, H, W);
+  MSD_REQUIRE(rows * C < (1ll << 31), "bn_act_bwd: tensor too large for 32-bit element offsets");
+  const unsigned grid1 = grid_for((rows + rpi - 1) / rpi * kBlock, 12);
+  const size_t sh1 = 2 * kBlock * 8 * sizeof(float);
+  if (d_skip != nullptr)
+    bn_act_bwd1_kernel<true><<<grid1, kBlock, sh1, s>>>(reinterpret_cast<const __nv_bfloat16*>(d_dy), reinterpret_cast<const __nv_bfloat16*>(d_c),
+                                                        reinterpret_cast<const __nv_bfloat16*>(d_skip), d_stats,
+                                                        reinterpret_cast<__nv_bfloat16*>(d_dz), d_sums, (uint32_t)(rows * C), C);
+  else
+    bn_act_bwd1_kernel<false><<<grid1, kBlock, sh1, s>>>(reinterpret_cast<const __nv_bfloat16*>(d_dy), reinterpret_cast<const __nv_bfloat16*>(d_c),
+                                                         nullptr, d_stats, reinterpret_cast<__nv_bfloat16*>(d_dz), d_sums, (uint32_t)(rows * C), C);
   MSD_LAUNCH_CHECK();
   bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(d_sums, d_stats, (double)B * H * W, d_dgamma, d_dbeta, d_coef, C);
   MSD_LAUNCH_CHECK();
@@ -594,21 +634,42 @@ extern "C" int msd_gelu_bwd_bf16(const void* d_dh, const void* d_hpre, void* d_o
   return MSD_OK;
 }
 
+extern "C" int msd_gelu_bwd_colsum_bf16(const void* d_dh, const void* d_hpre, void* d_out, float* d_colsum, int rows, int N, void* stream) {
+  MSD_REQUIRE(d_dh && d_hpre && d_out && d_colsum && rows > 0, "gelu_bwd_colsum: null pointer");
+  MSD_REQUIRE(N % 256 == 0 && N > 0, "gelu_bwd_colsum: N=%d must be a multiple of 256", N);
+  const int stripes = N / 256;
+  int row_groups = (148 * 8 + stripes - 1) / stripes;                 // ~8 resident blocks per SM
+  const int max_groups = (rows + kBlock / 32 - 1) / (kBlock / 32);
+  if (row_groups > max_groups) row_groups = max_groups;
+  gelu_bwd_colsum_kernel<<<dim3((unsigned)row_groups, (unsigned)stripes), kBlock, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(d_dh), reinterpret_cast<const __nv_bfloat16*>(d_hpre), reinterpret_cast<__nv_bfloat16*>(d_out),
+      d_colsum, rows, N / 8);
+  MSD_LAUNCH_CHECK();
+  return MSD_OK;
+}
+
 // LayerNorm backward over rows of width D (768 in the reference model): see ln_bwd_kernel.  d_dgamma/d_dbeta are
 // ACCUMULATED into (zero them first); NULL skips the parameter gradients (frozen blocks).
-extern "C" int msd_layernorm_bwd(const void* d_dy, int dy_is_f32, const float* d_x, const float* d_gamma, float eps, float* d_g,
-                                 int accumulate, void* d_g_bf16, float* d_dgamma, float* d_dbeta, int M, int D, void* stream) {
+extern "C" int msd_layernorm_bwd_colsum(const void* d_dy, int dy_is_f32, const float* d_x, const float* d_gamma, float eps, float* d_g,
+                                        int accumulate, void* d_g_bf16, float* d_dgamma, float* d_dbeta, float* d_colsum, int M, int D,
+                                        void* stream) {
   MSD_REQUIRE(d_dy && d_x && d_gamma && d_g && M > 0, "layernorm_bwd: null pointer");
   MSD_REQUIRE(D == 768, "layernorm_bwd: only D=768 is built (got %d)", D);
   MSD_REQUIRE((d_dgamma == nullptr) == (d_dbeta == nullptr), "layernorm_bwd: dgamma and dbeta go together");
   cudaStream_t s = (cudaStream_t)stream;
   const unsigned blocks = (unsigned)(M / 8 + 1 < 148 * 2 ? M / 8 + 1 : 148 * 2);
-  if (dy_is_f32)
-    ln_bwd_kernel<6, 1><<<blocks, kBlock, 0, s>>>(d_dy, d_x, d_gamma, eps, d_g, accumulate, reinterpret_cast<__nv_bfloat16*>(d_g_bf16), d_dgamma, d_dbeta, M);
-  else
-    ln_bwd_kernel<6, 0><<<blocks, kBlock, 0, s>>>(d_dy, d_x, d_gamma, eps, d_g, accumulate, reinterpret_cast<__nv_bfloat16*>(d_g_bf16), d_dgamma, d_dbeta, M);
+  __nv_bfloat16* gb = reinterpret_cast<__nv_bfloat16*>(d_g_bf16);
+#define MSD_LN_BWD(F32, CS) ln_bwd_kernel<6, F32, CS><<<blocks, kBlock, 0, s>>>(d_dy, d_x, d_gamma, eps, d_g, accumulate, gb, d_dgamma, d_dbeta, d_colsum, M)
+  if (d_colsum != nullptr) { if (dy_is_f32) MSD_LN_BWD(1, 1); else MSD_LN_BWD(0, 1); }
+  else { if (dy_is_f32) MSD_LN_BWD(1, 0); else MSD_LN_BWD(0, 0); }
+#undef MSD_LN_BWD
   MSD_LAUNCH_CHECK();
   return MSD_OK;
+}
+
+extern "C" int msd_layernorm_bwd(const void* d_dy, int dy_is_f32, const float* d_x, const float* d_gamma, float eps, float* d_g,
+                                 int accumulate, void* d_g_bf16, float* d_dgamma, float* d_dbeta, int M, int D, void* stream) {
+  return msd_layernorm_bwd_colsum(d_dy, dy_is_f32, d_x, d_gamma, eps, d_g, accumulate, d_g_bf16, d_dgamma, d_dbeta, nullptr, M, D, stream);
 }
 
 extern "C" int msd_convt_unshuffle_bf16(const void* d_dy, void* d_dys, int B, int Hin, int Win, int in_padded, int C, void* stream) {

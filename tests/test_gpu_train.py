@@ -146,6 +146,84 @@ def test_batchnorm_train_fwd_bwd(B, H, W, C, with_skip):
     assert dc[:, 0].abs().max().item() == 0 and dz[:, :, -1].abs().max().item() == 0
 
 
+@pytest.mark.parametrize("B,H,W,C,bias,fused", [(2, 20, 12, 48, False, 1), (5, 40, 41, 48, True, 1), (3, 30, 31, 96, False, 1),
+                                                (1, 10, 14, 96, False, 0), (2, 8, 8, 192, False, 0), (64, 64, 64, 48, False, 1)])
+def test_conv3x3_with_batchnorm_sums_in_the_epilogue(B, H, W, C, bias, fused):
+    """Training forward of nn.Conv2d + nn.BatchNorm2d (blocks.py:66-72): the 48- / 96-channel convs leave sum c, sum c^2 of the tensor
+    they store from their own epilogues; the sums must be those of the stored bf16 values (what the separate pass computes), halo rows
+    and ragged last tiles included, and identical from run to run."""
+    from msd_b200.models.satmae_restoration import pack_conv3x3_raw
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(B * H + C)
+    w = torch.randn(C, C, 3, 3, generator=g) / (3 * C ** 0.5)
+    b = torch.randn(C, generator=g).cuda() if bias else None
+    x = _bf(torch.randn(B, C, H, W, generator=g)).float()
+    xh, wp = _halo(x).cuda(), pack_conv3x3_raw(w).cuda()
+    s = _lib.stream_ptr()
+    import ctypes
+
+    def run():
+        y = torch.full((B, H + 2, W + 2, C), 7.0, device="cuda", dtype=torch.bfloat16)
+        sums = torch.full((2, C), -1.0, dtype=torch.float64, device="cuda")
+        flag = ctypes.c_int(-1)
+        _lib.check(lib.msd_conv3x3_stats_nhwc_bf16(_lib.ptr(xh), _lib.ptr(wp), _lib.ptr(b), _lib.ptr(y), _lib.ptr(sums), B, H, W, C, C, 0,
+                                                   ctypes.byref(flag), s))
+        return y, sums, flag.value
+
+    y, sums, flag = run()
+    assert flag == fused
+    assert y[:, 0].abs().max().item() == 0 and y[:, :, 0].abs().max().item() == 0 and y[:, -1].abs().max().item() == 0 and y[:, :, -1].abs().max().item() == 0
+    ref = F.conv2d(x.cuda(), _bf(w).float().cuda(), b, padding=1)
+    _close(_interior(y).permute(0, 3, 1, 2), ref, 1e-2)
+    yd = y.double().reshape(-1, C)
+    want = torch.stack([yd.sum(0), (yd * yd).sum(0)])
+    scale = torch.stack([yd.abs().sum(0), (yd * yd).sum(0)]) + 1e-12
+    assert ((sums - want).abs() / scale).max().item() < 2e-6          # fp32 partial sums over <= a few thousand rows per warp
+    y2, sums2, _ = run()
+    assert torch.equal(y, y2) and (sums - sums2).abs().max().item() <= 1e-9 * scale.max().item()
+    # and the statistics BatchNorm derives from them
+    gamma, beta = torch.rand(C, device="cuda") + 0.5, torch.randn(C, device="cuda")
+    rm, rv = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+    stats = torch.empty(4, C, device="cuda")
+    _lib.check(lib.msd_bn_finalize(_lib.ptr(sums), float(B * H * W), C, _lib.ptr(gamma), _lib.ptr(beta), 1e-5, 0.1, _lib.ptr(rm), _lib.ptr(rv),
+                                   _lib.ptr(stats), s))
+    yi = _interior(y).float().reshape(-1, C)
+    mean, var = yi.mean(0), yi.var(0, unbiased=False)
+    assert torch.allclose(stats[2], mean, atol=1e-5, rtol=1e-4) and torch.allclose(stats[3], (var + 1e-5).rsqrt(), rtol=2e-4)
+    assert torch.allclose(rm, 0.1 * mean, atol=1e-5, rtol=1e-4)
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 256, 128), (4608, 3072, 768), (9216, 3072, 768), (1000, 768, 3072), (77, 96, 64), (2500, 192, 768)])
+def test_mlp_gelu_folded_into_the_gemms(M, N, K):
+    """fc1 with the pre-activation copy and the fc2 data gradient times gelu'(pre) (encoder.py:160-166 under autograd): both fused
+    epilogues reproduce the GEMM + elementwise-kernel pairs they replace bit for bit (single-CTA, pair and narrow tiles)."""
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(M + N)
+    a = _bf(torch.randn(M, K, generator=g)).cuda()
+    w = _bf(torch.randn(N, K, generator=g) / K ** 0.5).cuda()
+    b = torch.randn(N, generator=g).cuda()
+    s = _lib.stream_ptr()
+    pre0 = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    h0 = torch.empty_like(pre0)
+    _lib.check(lib.msd_linear_bf16(_lib.ptr(a), _lib.ptr(w), _lib.ptr(b), _lib.ptr(pre0), None, M, N, K, 0, 0, 0, s))
+    _lib.check(lib.msd_gelu_fwd_bf16(_lib.ptr(pre0), _lib.ptr(h0), M * N, s))
+    pre1, h1 = torch.full_like(pre0, 7.0), torch.full_like(pre0, 7.0)
+    _lib.check(lib.msd_linear_gelu_pre_bf16(_lib.ptr(a), _lib.ptr(w), _lib.ptr(b), _lib.ptr(h1), _lib.ptr(pre1), M, N, K, s))
+    assert torch.equal(pre0, pre1) and torch.equal(h0, h1)
+    _close(h1, F.gelu(a.float() @ w.float().t() + b), 1e-2)
+    # data gradient: dh = (dy . W2) * gelu'(pre); here `a` plays dy, `w` W2^T, and the pre-activation is an independent tensor
+    z = _bf(torch.randn(M, N, generator=g) * 1.5).cuda()
+    d0 = torch.empty_like(pre0)
+    _lib.check(lib.msd_linear_bf16(_lib.ptr(a), _lib.ptr(w), None, _lib.ptr(d0), None, M, N, K, 0, 0, 0, s))
+    _lib.check(lib.msd_gelu_bwd_bf16(_lib.ptr(d0), _lib.ptr(z), _lib.ptr(d0), M * N, s))
+    d1 = torch.full_like(pre0, 7.0)
+    _lib.check(lib.msd_linear_dgelu_bf16(_lib.ptr(a), _lib.ptr(w), None, _lib.ptr(z), _lib.ptr(d1), M, N, K, s))
+    assert torch.equal(d0, d1)
+    zr = z.float().requires_grad_(True)
+    F.gelu(zr).backward(a.float() @ w.float().t())
+    _close(d1, zr.grad, 1.5e-2)
+
+
 def test_gelu_bwd():
     lib = _lib.load()
     g = torch.Generator().manual_seed(5)
@@ -156,6 +234,16 @@ def test_gelu_bwd():
     dh_d, h_d = _bf(dh).cuda(), _bf(h.detach()).cuda()
     _lib.check(lib.msd_gelu_bwd_bf16(_lib.ptr(dh_d), _lib.ptr(h_d), _lib.ptr(out), 1000 * 3072, _lib.stream_ptr()))
     _close(out.cpu(), h.grad, 1e-2)
+    # the variant that also leaves the column sums of its result (fc1's bias gradient), in place, odd and even row counts
+    for rows, N in ((1000, 3072), (777, 3072), (33, 256)):
+        a, z = dh_d[:rows, :N].contiguous(), h_d[:rows, :N].contiguous()
+        want = torch.empty_like(a)
+        _lib.check(lib.msd_gelu_bwd_bf16(_lib.ptr(a), _lib.ptr(z), _lib.ptr(want), rows * N, _lib.stream_ptr()))
+        cs = torch.full((N,), 2.0, device="cuda")
+        _lib.check(lib.msd_gelu_bwd_colsum_bf16(_lib.ptr(a), _lib.ptr(z), _lib.ptr(a), _lib.ptr(cs), rows, N, _lib.stream_ptr()))
+        assert torch.equal(a, want)
+        ref = want.double().sum(0)
+        assert ((cs.double() - 2.0 - ref).abs().max() <= 1e-5 * want.double().abs().sum(0).max() + 1e-4).item()
 
 
 @pytest.mark.parametrize("M,f32_grad,accumulate,frozen", [(300, False, True, False), (1000, True, False, False), (77, False, False, True)])
@@ -185,6 +273,19 @@ def test_layernorm_bwd(M, f32_grad, accumulate, frozen):
     if not frozen:
         _close(dgam.cpu(), gamma.grad, 1e-4)
         _close(dbet.cpu(), beta.grad, 1e-4)
+    # the variant that also accumulates the column sums of the bf16 copy (the bias gradient of the Linear in front of the LayerNorm)
+    g2 = g0.clone().cuda()
+    gbf2 = torch.empty_like(gbf)
+    dgam2, dbet2 = torch.zeros(D, device="cuda"), torch.zeros(D, device="cuda")
+    cs = torch.full((D,), 3.0, device="cuda")
+    _lib.check(lib.msd_layernorm_bwd_colsum(_lib.ptr(dy_d), int(f32_grad), _lib.ptr(x_d), _lib.ptr(gamma_d), 1e-6, _lib.ptr(g2), int(accumulate),
+                                            _lib.ptr(gbf2), None if frozen else _lib.ptr(dgam2), None if frozen else _lib.ptr(dbet2),
+                                            _lib.ptr(cs), M, D, _lib.stream_ptr()))
+    assert torch.equal(g2, g_d) and torch.equal(gbf2, gbf)
+    ref_cs = gbf.double().sum(0)
+    assert ((cs.double() - 3.0 - ref_cs).abs().max() <= 1e-4 * gbf.double().abs().sum(0).max() + 1e-5).item()
+    if not frozen:
+        _close(dgam2.cpu(), gamma.grad, 1e-4)
 
 
 @pytest.mark.parametrize("B,Hin,padded,C", [(2, 6, True, 48), (3, 12, False, 384), (2, 5, True, 96)])

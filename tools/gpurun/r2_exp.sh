@@ -1,3 +1,3 @@
 mkdir -p gpurun_out
-python tools/graph_probe.py 2>&1 | tee gpurun_out/graph_probe.txt
-timeout 900 python -m pytest tests/test_gpu_model.py tests/test_gpu_sweep.py tests/test_gpu_scene.py -q -p no:cacheprovider -k "benchmark_batch or 27000 or writer" 2>&1 | tail -5
+for v in 16 6 3 2; do echo "== bwd1 per_sm $v"; MSD_BWD1_PER_SM=$v timeout 300 python tools/bn_bench.py --iters 10 2>&1 | grep -E "bn_act_bwd"; done | tee gpurun_out/exp_bwd1_grid.txt
+for v in 4 2 1; do echo "== colsum per_sm $v"; MSD_COLSUM_PER_SM=$v timeout 300 python tools/bn_bench.py --iters 10 2>&1 | grep -E "bn_sums"; done | tee -a gpurun_out/exp_bwd1_grid.txt
