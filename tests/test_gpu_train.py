@@ -466,6 +466,62 @@ def test_train_step_at_larger_batch_vs_oracle_on_device():
     assert max(errs) <= 0.2 and sorted(errs)[len(errs) // 2] <= 0.15, (max(errs), sorted(errs)[len(errs) // 2])
 
 
+def test_train_step_error_is_the_bf16_storage_error_tensor_by_tensor():
+    """The fp32-autograd comparisons above carry a flat mixed-precision envelope (up to 15-20 % relative RMS in the encoder).  This test
+    calibrates it: oracle/model_storage.py is the SAME fp32 torch graph with the library's bf16 storage points written in (every
+    activation / raw conv output / inter-layer gradient kept in bf16, bf16 operand copies of the weights), evaluated on the GPU with
+    TF32 off.  Its distance from plain fp32 autograd is what bf16 storage costs, per tensor, for this model and input -- two
+    independently rounded runs do not agree with EACH OTHER any better (rounding decisions decorrelate), so the meaningful statement
+    is: for every gradient tensor the library is no further from fp32 autograd than the storage emulation is, within 35 %
+    (measured: ratio 0.90 ... 1.29, median 1.04; profiles/r2_train_storage_check.txt).  A wrong kernel, a missing term or a
+    mis-scaled gradient shows up as a ratio far above 1 in the tensors behind it."""
+    import recipes
+    from msd_b200.models import SatMAERestoration
+    from oracle import model as omodel, model_storage
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    B = 8
+    torch.manual_seed(11)
+    model = SatMAERestoration(recipes.base_config(), block_layout="fallback")
+    sd = recipes.perturb_decoder_stats({k: v.clone() for k, v in model.state_dict().items()})
+    model.load_state_dict(sd)
+    sd = {k: v.cuda() for k, v in sd.items()}
+    clean, noisy = recipes.eurosat_tiles(B, seed=9)
+    clean, noisy = clean.cuda(), noisy.cuda()
+    model.cuda().train()
+    frozen = {n for n, p in model.named_parameters() if not p.requires_grad}
+
+    def oracle(fwd):
+        ref = {k: v.clone() for k, v in sd.items()}
+        for k, v in ref.items():
+            if v.is_floating_point() and "running_" not in k and k not in frozen:
+                v.requires_grad_(True)
+        y_ref = fwd(ref, noisy)
+        ((y_ref - clean) ** 2).mean().backward()
+        return y_ref.detach(), ref
+
+    y_st, ref_st = oracle(model_storage.restoration_forward_train)
+    y_32, ref_32 = oracle(omodel.restoration_forward_train)
+    y = model(noisy)
+    ((y - clean) ** 2).mean().backward()
+
+    def rel(a, b):
+        return ((a - b).pow(2).mean().sqrt() / (b.pow(2).mean().sqrt() + 1e-30)).item()
+
+    assert rel(y.detach(), y_32) <= 1.35 * rel(y_st, y_32) + 2e-3, (rel(y.detach(), y_32), rel(y_st, y_32))
+    rows = []
+    for n, p in model.named_parameters():
+        if n in frozen or n.endswith(("upsample.0.bias", "head.0.bias")):
+            continue
+        rows.append((rel(p.grad, ref_32[n].grad), rel(ref_st[n].grad, ref_32[n].grad), n))
+    bad = [r for r in rows if r[0] > 1.35 * r[1] + 2e-3]
+    assert not bad, bad[:8]
+    ratios = sorted(a / (b + 1e-9) for a, b, _ in rows)
+    assert ratios[len(ratios) // 2] <= 1.15, ratios[len(ratios) // 2]
+    # and the emulation itself shows the profile the flat envelope was derived from: ~1 % at the head, ~10 % and more in the encoder
+    assert max(b for _, b, _ in rows) >= 0.05
+
+
 def test_fused_adamw_with_clip_matches_torch():
     from msd_b200.training import FusedAdamW
     g = torch.Generator().manual_seed(0)
