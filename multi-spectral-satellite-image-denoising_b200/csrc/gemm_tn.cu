@@ -15,6 +15,7 @@
 //              of dc, and issues five M=128 MMAs per 16-row K step whose two 64-row halves are two consecutive taps (LBO = the
 //              byte distance between the two taps' windows) into five TMEM accumulators.
 // Partial sums are added to the fp32 output with red.global.add (the caller zeroes it first).
+#include <cstdlib>
 #include "gemm_tc5.cuh"
 
 namespace gemm {
@@ -62,7 +63,9 @@ __device__ __forceinline__ void red_add_v4_f32(float* addr, float a, float b, fl
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-template <int MODE, int NB>   // MODE 0 = linear (NB 64-column atoms of B per tile), 1 = conv3x3 (NB = 1)
+// MODE 0 = linear, 1 = conv3x3; NB = 64-column atoms of B loaded per tile; NCOLS = the MMA's N (<= 64 NB; the conv runs N = 96 over
+// two atoms -- every decoder width but 48 is a multiple of 96 -- or N = 48)
+template <int MODE, int NB, int NCOLS = 64 * NB>
 struct TnCfg {
   static constexpr uint32_t A_BYTES = MODE == 0 ? 2 * ATOM_BYTES : 3 * XBOX_BYTES;
   static constexpr uint32_t B_BYTES = NB * ATOM_BYTES;
@@ -71,15 +74,16 @@ struct TnCfg {
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr uint32_t SMEM_BYTES = kStages * STAGE_BYTES + 1024 + 256;
   static constexpr int NACC = MODE == 0 ? 1 : 5;
-  static constexpr int BN = 64 * NB;
+  static constexpr int BN = NCOLS;
+  static_assert(NCOLS % 16 == 0 && NCOLS <= 64 * NB && NCOLS > 64 * (NB - 1), "N must end inside the last loaded atom");
   static constexpr uint32_t TMEM_COLS = (NACC * BN <= 64) ? 64 : (NACC * BN <= 128) ? 128 : (NACC * BN <= 256) ? 256 : 512;
   static_assert(NACC * BN <= 512, "accumulators exceed TMEM");
 };
 
-template <int MODE, int NB>
+template <int MODE, int NB, int NCOLS = 64 * NB>
 __global__ void __launch_bounds__(kThreadsTn, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TnProblem p) {
-  using C = TnCfg<MODE, NB>;
+  using C = TnCfg<MODE, NB, NCOLS>;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::STAGE_BYTES);
@@ -161,7 +165,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const int t0 = 2 * g, t1 = 2 * g + 1;
               const uint32_t a0 = sa + (t0 / 3) * XBOX_BYTES + (t0 % 3) * 128 + k * 2048;
               const uint32_t a1 = g < 4 ? sa + (t1 / 3) * XBOX_BYTES + (t1 % 3) * 128 + k * 2048 : a0 + 128;
-              tcgen05_mma_bf16(tmem_base + g * 64, make_desc_mn(a0, a1 - a0), db, idesc, accum);
+              tcgen05_mma_bf16(tmem_base + g * C::BN, make_desc_mn(a0, a1 - a0), db, idesc, accum);
             }
           }
         }
@@ -217,9 +221,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
-template <int MODE, int NB>
+template <int MODE, int NB, int NCOLS = 64 * NB>
 int launch_tn(TnProblem& p, cudaStream_t s) {
-  using C = TnCfg<MODE, NB>;
+  using C = TnCfg<MODE, NB, NCOLS>;
   CUtensorMap tmA, tmB;
   int rc = make_map(&tmA, p.A, (uint64_t)p.a_cols, (uint64_t)p.rows, (uint64_t)p.ldA, MODE == 0 ? KB : XBOX_ROWS);
   if (rc) return rc;
@@ -227,7 +231,7 @@ int launch_tn(TnProblem& p, cudaStream_t s) {
   if (rc) return rc;
   static PerDeviceOnce attr_set;
   if (attr_set.first()) {
-    MSD_CHECK_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<MODE, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
+    MSD_CHECK_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<MODE, NB, NCOLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
   }
   p.num_kb = (int)((p.rows + KB - 1) / KB);
   const int tiles = p.tiles_m * p.tiles_n;
@@ -246,7 +250,7 @@ int launch_tn(TnProblem& p, cudaStream_t s) {
   }
   p.kb_per_split = (p.num_kb + splitk - 1) / splitk;
   p.splitk = (p.num_kb + p.kb_per_split - 1) / p.kb_per_split;
-  gemm_tn_kernel<MODE, NB><<<tiles * p.splitk, kThreadsTn, C::SMEM_BYTES, s>>>(tmA, tmB, p);
+  gemm_tn_kernel<MODE, NB, NCOLS><<<tiles * p.splitk, kThreadsTn, C::SMEM_BYTES, s>>>(tmA, tmB, p);
   MSD_LAUNCH_CHECK();
   return MSD_OK;
 }
@@ -286,6 +290,13 @@ extern "C" int msd_wgrad_conv3x3_bf16(const void* d_x, const void* d_dc, float* 
   p.pitch = W + 2;
   p.out = d_dw; p.ldo = ldo; p.out_cols = Cout; p.cinpad = cinpad;
   p.tiles_m = (Cin + 63) / 64;
+  // output-channel tile: the five M = 128 MMAs of a K step fetch 5 x 4 KB of x windows from shared memory whatever N is, so a wider N
+  // amortises them: N = 96 over two 64-column atoms of dc (5 x 96 accumulator columns fill TMEM) when Cout is a multiple of 96 -- the
+  // decoder's 96 / 192 / 384 -- measured at micro-batch 64: 205 -> 135 us at 96 channels, 133 -> 111 at 192, 139 -> 115 at 384; N = 48 for
+  // the 48-channel stage (203 -> 194 us); 64 otherwise
+  static const bool n64 = getenv("MSD_WGRAD_N64") != nullptr;          // A/B switch: the 64-wide tiles
+  if (!n64 && Cout % 96 == 0) { p.tiles_n = Cout / 96; return gemm::tn::launch_tn<1, 2, 96>(p, (cudaStream_t)stream); }
+  if (!n64 && Cout == 48) { p.tiles_n = 1; return gemm::tn::launch_tn<1, 1, 48>(p, (cudaStream_t)stream); }
   p.tiles_n = (Cout + 63) / 64;
   return gemm::tn::launch_tn<1, 1>(p, (cudaStream_t)stream);
 }

@@ -13,6 +13,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=64)
 ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("--only", type=int, default=0, help="decoder resolution to run alone (192, 96, 48, 24); 0 = everything")
+ap.add_argument("--wgrad", action="store_true", help="time the 3x3 conv weight gradients instead")
 args = ap.parse_args()
 lib = _lib.load()
 s = _lib.stream_ptr()
@@ -32,6 +33,19 @@ def timeit(fn, nbytes, name):
 
 
 B = args.batch
+if args.wgrad:
+    for (H, C) in ((192, 48), (96, 96), (48, 192), (24, 384)):
+        if args.only and H != args.only:
+            continue
+        x = torch.randn(B, H + 2, H + 2, C, device="cuda").to(torch.bfloat16)
+        dc = torch.randn(B, H + 2, H + 2, C, device="cuda").to(torch.bfloat16)
+        kpad = (C + 63) // 64 * 64
+        dw = torch.zeros(9, kpad, C, device="cuda")
+        T = x.numel() * 2
+        gflop = 2.0 * 9 * C * C * B * H * H / 1e9
+        timeit(lambda: _lib.check(lib.msd_wgrad_conv3x3_bf16(_lib.ptr(x), _lib.ptr(dc), _lib.ptr(dw), B, H, H, C, C, kpad, C, s)), 2 * T,
+               f"wgrad conv3x3 {H}x{H}x{C} ({gflop:.0f} GFLOP)")
+    sys.exit(0)
 for (H, C) in ((192, 48), (96, 96), (48, 192), (24, 384)):
     if args.only and H != args.only:
         continue

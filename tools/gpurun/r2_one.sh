@@ -1,4 +1,4 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_model.py -q -p no:cacheprovider -x -k "attention" 2>&1 | tail -5
-echo "== four threads per row"; timeout 300 python tools/attn_bench.py 2>&1 | tee gpurun_out/attn_bench.txt
-echo "== thread per row"; MSD_ATTN_THREAD_PER_ROW=1 timeout 300 python tools/attn_bench.py 2>&1 | tee -a gpurun_out/attn_bench.txt
+timeout 600 python -m pytest tests/test_gpu_train.py -q -p no:cacheprovider -x -k "wgrad" 2>&1 | tail -4
+echo "== N = 96 / 48 tiles"; timeout 300 python tools/bn_bench.py --wgrad 2>&1 | tee gpurun_out/wgrad_bench.txt
+echo "== N = 64 tiles"; MSD_WGRAD_N64=1 timeout 300 python tools/bn_bench.py --wgrad 2>&1 | tee -a gpurun_out/wgrad_bench.txt
