@@ -175,6 +175,7 @@ int launch_tc5(const Problem& p, cudaStream_t s);
 int launch_hmma(const Problem& p, cudaStream_t s);
 bool tc5_can_fuse_head(const Problem& p, int head_cout);   // may this 3x3 conv carry the 1x1 head in its epilogue?
 int tc5_stats_parts(int N, int M);                         // partial LayerNorm sums per row a stats-producing GEMM of this shape writes
+bool roll_geometry_ok(int H, int W, int C);                // does the rolling-row conv kernel (conv_roll.cu) take a C-channel H x W conv?
 bool tc5_supports_bn_sums(const Problem& p);               // will launch_tc5 route this conv to a kernel that accumulates bn_sums?
 
 inline int launch(const Problem& p, int backend, cudaStream_t s) {

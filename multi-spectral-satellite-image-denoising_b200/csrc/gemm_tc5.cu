@@ -90,6 +90,11 @@ extern template int launch_bn<16>(const Problem&, cudaStream_t);
 
 }  // namespace tc5
 
+namespace roll {   // conv_roll.cu: rolling-row formulation of the 48-channel 3x3 conv
+bool eligible(const Problem& p);
+int launch(const Problem& p, cudaStream_t s);
+}  // namespace roll
+
 int pick_bn_tc5(int N, int M, bool wave_aware, int min_bn = 16) {
   // Tile width: a divisor of N (2*BN fp32 accumulator columns must fit the 512 TMEM columns).  Wider tiles amortise the A
   // operand better, but the persistent grid runs whole waves of 148 CTAs: for the small GEMMs of the training step
@@ -138,6 +143,7 @@ int launch_tc5(const Problem& p, cudaStream_t s) {
   MSD_REQUIRE(p.N % 16 == 0, "gemm_tc5: N=%d must be a multiple of 16", p.N);
   MSD_REQUIRE(p.bn_sums == nullptr || tc5_supports_bn_sums(p), "gemm_tc5: this problem has no column-sum epilogue (ask tc5_supports_bn_sums first)");
   MSD_REQUIRE(p.ldA % 8 == 0 && msd_aligned16(p.A) && msd_aligned16(p.Wt), "gemm_tc5: operands must be 16-byte aligned / pitched");
+  if (roll::eligible(p)) return roll::launch(p, s);
   // multi-tap (3x3 conv) problems keep the largest tile: their summation order (tap-major vs dx-merged) depends on the tile
   // width through the kernel mode, and results must not depend on the batch size (sharding invariance is tested bit-exactly)
   const bool ln_consumer = p.ln_stats != nullptr, ln_producer = p.stats_out != nullptr;

@@ -142,6 +142,13 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
       : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
+// zero 16 consecutive fp32 accumulator columns of this thread's TMEM lane; completion via tmem_st_wait()
+__device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
+  const uint32_t z = 0u;
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};\n" ::"r"(taddr), "r"(z) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
 
 // explicit shared-space accesses for the epilogue staging buffers (generic LD/ST on a pointer derived from the dynamic
 // smem base go through the long-latency generic path and serialise against each other)
@@ -407,7 +414,8 @@ __device__ __forceinline__ void bn_sums_flush(uint32_t slots_s, double* __restri
   }
 }
 
-template <int BN, int EPI, bool PAIR = false>
+// ZERO: the accumulator columns are zeroed behind the read, before the buffer is handed back (conv_roll.cu: every MMA accumulates)
+template <int BN, int EPI, bool PAIR = false, bool ZERO = false>
 __device__ __forceinline__ void epilogue_tile(const Problem& p, uint32_t stg_s, uint32_t bias_s, uint32_t taddr,
                                               uint64_t* tmem_empty_bar, int mrow0, int n0, int lane, int slab_begin, int slab_end,
                                               HeadCtx* hc = nullptr, float ln_a = 0.0f, float ln_c = 0.0f, uint32_t sums_s = 0u) {
@@ -449,6 +457,11 @@ __device__ __forceinline__ void epilogue_tile(const Problem& p, uint32_t stg_s, 
 #pragma unroll
     for (int c = 0; c < C::SC / 16; ++c) tmem_ld16(taddr + slab * C::SC + c * 16, &r[c * 16]);
     tmem_ld_wait();
+    if constexpr (ZERO) {
+#pragma unroll
+      for (int c = 0; c < C::SC / 16; ++c) tmem_st16_zero(taddr + slab * C::SC + c * 16);
+      tmem_st_wait();
+    }
     if (slab == slab_end - 1) {
       tcgen05_fence_before();
       __syncwarp();

@@ -195,16 +195,16 @@ extern "C" int msd_linear_lnfold_bf16(const void* d_x_bf16, const void* d_w_ln, 
 // channels, 0.371 -> 0.35 at 192 / 384), as the identity tap for 48 channels (0.633 vs 0.669 ms on 8 epilogue warps; with the
 // opt-in 16-warp mode MSD_RES4=1 the two are equal, 0.643 vs 0.653).  MSD_SKIP_TAP=1 / MSD_SKIP_EPI=1 force one way for A/B
 // runs; the mma.sync baseline always takes the identity tap.
-static bool skip_in_epilogue(int backend, int channels) {
+static bool skip_in_epilogue(int backend, int channels, int H, int W) {
   static const bool tap = getenv("MSD_SKIP_TAP") != nullptr, epi = getenv("MSD_SKIP_EPI") != nullptr;
   if (backend != 0 || tap) return false;
-  return epi || channels >= 96;
+  return epi || channels >= 96 || gemm::roll_geometry_ok(H, W, channels);   // the rolling-row kernel adds the skip in its epilogue
 }
 
 extern "C" int msd_conv3x3_nhwc_bf16(const void* d_x, const void* d_w, const float* d_bias, const void* d_skip, void* d_y,
                                      int B, int H, int W, int Cin, int Cout, int backend, void* stream) {
   Problem p;
-  int rc = make_conv3x3(p, d_x, d_w, d_bias, d_skip, d_y, B, H, W, Cin, Cout, 1, skip_in_epilogue(backend, Cout));
+  int rc = make_conv3x3(p, d_x, d_w, d_bias, d_skip, d_y, B, H, W, Cin, Cout, 1, skip_in_epilogue(backend, Cout, H, W));
   if (rc) return rc;
   return gemm::launch(p, backend, (cudaStream_t)stream);
 }
@@ -505,12 +505,12 @@ extern "C" int msd_model_forward(msd_model* m, const float* d_x, const void* d_p
     // ResidualBlock 1: Z = GELU(X + BN(conv(GELU(BN(conv X)))))   (blocks.py:74-85)
     MSD_TRY(make_conv3x3(p, X, sw.w_conv[0], sw.b_conv[0], nullptr, Y, B, hw, hw, cout, cout));
     MSD_RUN(0, cf, gemm::launch(p, be, s));
-    MSD_TRY(make_conv3x3(p, Y, sw.w_conv[1], sw.b_conv[1], X, Z, B, hw, hw, cout, cout, 1, skip_in_epilogue(be, cout)));
+    MSD_TRY(make_conv3x3(p, Y, sw.w_conv[1], sw.b_conv[1], X, Z, B, hw, hw, cout, cout, 1, skip_in_epilogue(be, cout, hw, hw)));
     MSD_RUN(0, cf, gemm::launch(p, be, s));
     // ResidualBlock 2: X = GELU(Z + ...)
     MSD_TRY(make_conv3x3(p, Z, sw.w_conv[2], sw.b_conv[2], nullptr, Y, B, hw, hw, cout, cout));
     MSD_RUN(0, cf, gemm::launch(p, be, s));
-    MSD_TRY(make_conv3x3(p, Y, sw.w_conv[3], sw.b_conv[3], Z, X, B, hw, hw, cout, cout, 1, skip_in_epilogue(be, cout)));
+    MSD_TRY(make_conv3x3(p, Y, sw.w_conv[3], sw.b_conv[3], Z, X, B, hw, hw, cout, cout, 1, skip_in_epilogue(be, cout, hw, hw)));
     MSD_RUN(0, cf, gemm::launch(p, be, s));
     cur = X; cin = cout; in_pad = 1;
   }

@@ -93,6 +93,51 @@ def test_conv3x3_vs_torch(backend, cin, cout, H, W, B):
         _close(emulate.unhalo_nchw(y.cpu().float()), F.gelu(bn(conv(x))), 3e-2)     # and against the real conv
 
 
+@pytest.mark.parametrize("H,W,B", [(192, 192, 2), (6, 64, 1), (5, 128, 2), (8, 320, 1), (10, 192, 3), (2, 192, 1), (1, 256, 2), (64, 192, 9)])
+def test_conv48_rolling_rows_vs_tap_major_kernel_and_torch(H, W, B, monkeypatch):
+    """csrc/conv_roll.cu (the 48-channel 3x3 conv with the vertical taps stacked along N and output rows in a TMEM ring;
+    blocks.py:66-85) against the tap-major tcgen05 kernel it replaces: integer-valued operands make every partial sum exact,
+    so the two formulations must agree BIT FOR BIT (any slot / window / pair-strip indexing slip is an exact mismatch), with and
+    without the ResidualBlock skip; then random operands against torch's conv.  Shapes: full strips, pair strips, both, H = 1 / 2
+    (segments shorter than the ring), more steps than CTAs (ranges that cut strips in the middle)."""
+    g = torch.Generator().manual_seed(H * 1000 + W + B)
+    xi = torch.randint(-1, 2, (B, 48, H, W), generator=g).float()
+    si = torch.randint(-3, 4, (B, 48, H, W), generator=g).float()
+    wi = torch.randint(-1, 2, (48, 48, 3, 3), generator=g).float() * (torch.rand(48, 48, 3, 3, generator=g) < 0.3)
+    bi = torch.randint(-2, 3, (48,), generator=g).float()
+    kpad = 64
+    wp = torch.zeros(48, 3, 3, kpad); wp[..., :48] = wi.permute(0, 2, 3, 1)
+    w9 = _bf(wp.reshape(48, 9 * kpad)).cuda()
+    eye = torch.zeros(48, kpad); eye[:, :48] = torch.eye(48)
+    w10 = _bf(torch.cat([wp.reshape(48, 9 * kpad), eye], dim=1)).cuda()
+    xh, sh, bc = _bf(emulate.halo_nhwc(xi)).cuda(), _bf(emulate.halo_nhwc(si)).cuda(), bi.cuda()
+    outs = {}
+    for no_roll in ("0", "1"):
+        monkeypatch.setenv("MSD_NO_ROLL", no_roll)
+        outs[no_roll] = (gh.conv3x3(xh, w9, bc, None, B, H, W, 48, 48, 0).clone(), gh.conv3x3(xh, w10, bc, sh, B, H, W, 48, 48, 0).clone())
+    monkeypatch.setenv("MSD_NO_ROLL", "0")
+    for a, b in zip(outs["0"], outs["1"]):
+        assert torch.equal(a, b)
+        assert torch.all(a[:, 0] == 0) and torch.all(a[:, -1] == 0) and torch.all(a[:, :, 0] == 0) and torch.all(a[:, :, -1] == 0)
+    pre = F.conv2d(xi, wi, bi, padding=1)
+    _close(emulate.unhalo_nchw(outs["0"][0].cpu().float()), F.gelu(pre), 1e-2)
+    _close(emulate.unhalo_nchw(outs["0"][1].cpu().float()), F.gelu(pre + si), 1e-2)
+    # random operands, BatchNorm folded, against the real conv
+    torch.manual_seed(H + W)
+    conv = nn.Conv2d(48, 48, 3, padding=1, bias=False)
+    bn = nn.BatchNorm2d(48).eval()
+    bn.running_mean.normal_(0, 0.2); bn.running_var.uniform_(0.5, 1.5); bn.weight.data.normal_(1, 0.1); bn.bias.data.normal_(0, 0.1)
+    x = _bf(torch.randn(B, 48, H, W)).float()
+    skip = _bf(torch.randn(B, 48, H, W)).float()
+    with torch.no_grad():
+        w, b = pack_conv3x3(conv, bn)
+        ws, _ = pack_conv3x3(conv, bn, with_skip=True)
+        y = gh.conv3x3(_bf(emulate.halo_nhwc(x)).cuda(), w.cuda(), b.cuda(), None, B, H, W, 48, 48, 0)
+        ys = gh.conv3x3(_bf(emulate.halo_nhwc(x)).cuda(), ws.cuda(), b.cuda(), _bf(emulate.halo_nhwc(skip)).cuda(), B, H, W, 48, 48, 0)
+        _close(emulate.unhalo_nchw(y.cpu().float()), F.gelu(bn(conv(x))), 3e-2)
+        _close(emulate.unhalo_nchw(ys.cpu().float()), F.gelu(bn(conv(x)) + skip), 3e-2)
+
+
 @pytest.mark.parametrize("H,W,B,cout", [(20, 12, 2, 13), (40, 41, 3, 13), (9, 7, 1, 16), (33, 30, 2, 5)])
 def test_head_conv_with_fused_1x1_vs_separate_kernels(H, W, B, cout):
     """decoder head (decoder.py:76-81) in one kernel: conv3x3 + BN + GELU stays in the epilogue's registers (rounded to bf16 as
