@@ -108,7 +108,7 @@ conv_roll_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < UNITS; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < R; ++i) { mbar_init(&slot_full[i], 1); mbar_init(&slot_empty[i], 4); }
+    for (int i = 0; i < R; ++i) { mbar_init(&slot_full[i], 3); mbar_init(&slot_empty[i], 4); }     // three input rows feed an output row
     mbar_init(res_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
@@ -168,8 +168,14 @@ conv_roll_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
     }
-  } else if (warp == 1) {
-    // ===== MMA issuer =====
+  } else if (warp == 1 || warp == 3) {
+    // ===== MMA issuers: warp 1 takes the even input rows of this CTA, warp 3 the odd ones.  Every MMA accumulates, so the order
+    // in which the two instruction streams reach the tensor core does not matter; an output row is complete when the commits of
+    // its three input rows have arrived (slot_full counts 3).  One warp's per-row stream (two waits, 9-18 MMAs with their
+    // descriptor arithmetic, four commits) costs ~1,600 cycles of which ~500 are not spent waiting for the tensor core's queue;
+    // two streams hide that. =====
+    const uint32_t me = warp == 1 ? 0u : 1u;
+    uint32_t rowctr = 0;
     constexpr uint32_t HI = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO = 1024 B, version 1, SWIZZLE_128B
     constexpr uint32_t IDESC0 = make_idesc(BLOCK_M, 0);              // + (N >> 3) << 17
     constexpr uint32_t WB = W_BOX >> 4, UB = UNIT_BYTES >> 4;
@@ -187,6 +193,11 @@ conv_roll_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // valid groups j of this input row (output row o = s - 2 + j inside [0, n)); interior rows: 0 .. 2
         const int jlo = s >= 2 ? 0 : 2 - s, jhi = s < n ? 2 : n + 1 - s;
         const uint32_t u0 = ubase + (uint32_t)s;              // u0 - 2 + j = ring index of group j's output row
+        if (((rowctr++) & 1u) != me) {                        // the other issuer's row: step over its ring units
+          unit += pair ? 3 : 1;
+          if (unit >= UNITS) { unit -= UNITS; phase ^= 1; }
+          continue;
+        }
         if (jhi == 2) {                                       // a slot is touched for the first time: its previous use must be drained and zeroed
           mbar_wait(&slot_empty[u0 % R], (u0 / R) & 1u);
           tcgen05_fence_after();
@@ -197,7 +208,6 @@ conv_roll_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int n_a = (int)slot_lo + ng <= R ? ng : R - (int)slot_lo, n_b = ng - n_a;
         const uint32_t d_a = tmem_base + slot_lo * CH, id_a = IDESC0 | ((uint32_t)(n_a * CH >> 3) << 17), id_b = IDESC0 | ((uint32_t)(n_b * CH >> 3) << 17);
         const uint32_t b_a = r_lo0 + (uint32_t)jlo * WB, b_b = b_a + (uint32_t)n_a * WB;
-        uint64_t* const done = s >= 2 ? &slot_full[(u0 - 2u) % R] : nullptr;      // output row s - 2 is complete behind this row
         if (!pair) {
           mbar_wait(&full[unit], phase);
           tcgen05_fence_after();
@@ -212,7 +222,7 @@ conv_roll_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 if (n_b > 0) tcgen05_mma_bf16(tmem_base, da, ((uint64_t)HI << 32) | (b_b + (uint32_t)(dx * 3) * WB + 2u * k), id_b, 1u);
               }
             tcgen05_commit(&empty[unit]);
-            if (done != nullptr) tcgen05_commit(done);
+            for (int j = jlo; j <= jhi; ++j) tcgen05_commit(&slot_full[(u0 + (uint32_t)j + (uint32_t)(R - 2)) % R]);
           }
           __syncwarp();
           if (++unit == UNITS) { unit = 0; phase ^= 1; }
@@ -229,7 +239,8 @@ conv_roll_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 if (n_b > 0) tcgen05_mma_bf16(tmem_base, da, ((uint64_t)HI << 32) | (b_b + (uint32_t)(dx * 3) * WB + 2u * k), id_b, 1u);
               }
               tcgen05_commit(&empty[unit]);
-              if (dx == 2 && done != nullptr) tcgen05_commit(done);
+              if (dx == 2)
+                for (int j = jlo; j <= jhi; ++j) tcgen05_commit(&slot_full[(u0 + (uint32_t)j + (uint32_t)(R - 2)) % R]);
             }
             __syncwarp();
             if (++unit == UNITS) { unit = 0; phase ^= 1; }
