@@ -229,6 +229,7 @@ struct HeadCtx {
   uint64_t* a2_full;    // epilogue -> issuer: the A2 tile is written
   uint64_t* d2_full;    // issuer -> epilogue: D2 is complete
   uint32_t parity;      // phase parity of THIS tile on both barriers
+  uint32_t row0;        // row of this warp's first lane inside the 128-row A2 tile (32 x TMEM lane quadrant)
   // software pipeline of the epilogue lanes: D2 of this buffer's previous tile is read while this tile is handled
   bool has_prev;
   uint32_t prev_rowpix; // output offset of this lane's pixel in the previous tile (kRowSkip: none)
@@ -508,7 +509,7 @@ __device__ __forceinline__ void epilogue_tile(const Problem& p, uint32_t stg_s, 
         // operand (16-byte chunk c of row r at chunk position c ^ (r & 7) of the row's 128 bytes: the SWIZZLE_128B pattern,
         // conflict-free for row-per-lane stores), store the previous tile's pixel from D2, then hand A2 to the issuer.  The lanes
         // never wait for the D2 of the tile they just produced.
-        const uint32_t rr = (uint32_t)(mrow0 & 127) + (uint32_t)lane;          // row inside the 128-row tile
+        const uint32_t rr = hc->row0 + (uint32_t)lane;                         // row inside the 128-row tile
         const uint32_t row_s = hc->a2_s + (rr >> 3) * 1024u + (rr & 7u) * 128u;
         uint4 q[6];
 #pragma unroll
@@ -1088,7 +1089,7 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           hc.a2_s = smem_u32(smem_a + (6 + as) * A_STAGE_BYTES);
           hc.bias_s = smem_u32(smem_res + 9 * C::W_BOX_BYTES + HEAD_BIAS);
           hc.taddr_d2 = tmem_base + ((uint32_t)(q * 32) << 16) + 2 * BN + as * 16;
-          hc.a2_full = &hb[as]; hc.d2_full = &hb[2 + as]; hc.parity = aphase;
+          hc.a2_full = &hb[as]; hc.d2_full = &hb[2 + as]; hc.parity = aphase; hc.row0 = (uint32_t)(q * 32);
           epilogue_tile<BN, E_CONV_HEAD>(p, stg_s, bias_s, taddr, &tmem_empty[as], m0 + q * 32, n0, lane, slab_begin, slab_end, &hc);
           continue;
         }

@@ -138,7 +138,9 @@ def test_conv48_rolling_rows_vs_tap_major_kernel_and_torch(H, W, B, monkeypatch)
         _close(emulate.unhalo_nchw(ys.cpu().float()), F.gelu(bn(conv(x)) + skip), 3e-2)
 
 
-@pytest.mark.parametrize("H,W,B,cout", [(20, 12, 2, 13), (40, 41, 3, 13), (9, 7, 1, 16), (33, 30, 2, 5)])
+@pytest.mark.parametrize("H,W,B,cout", [(20, 12, 2, 13), (40, 41, 3, 13), (9, 7, 1, 16), (33, 30, 2, 5),
+                                        # geometries the rolling-row kernel takes (csrc/conv_roll.cu, E_CONV_HEAD): full + pair strips
+                                        (192, 192, 2, 13), (6, 64, 1, 13), (8, 320, 1, 16), (10, 128, 2, 5), (64, 192, 5, 13)])
 def test_head_conv_with_fused_1x1_vs_separate_kernels(H, W, B, cout):
     """decoder head (decoder.py:76-81) in one kernel: conv3x3 + BN + GELU stays in the epilogue's registers (rounded to bf16 as
     the two-kernel path stores it) and is contracted with the fp32 1x1 weights there.  Same activation as the two-kernel
