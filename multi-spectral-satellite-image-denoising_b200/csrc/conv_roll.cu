@@ -24,12 +24,13 @@
 //
 // Every MMA ACCUMULATES: a slot is zeroed by the epilogue warp that drained it (tcgen05.st behind the tcgen05.ld, before the slot
 // is handed back), so the issuer's per-row instruction stream has no first-touch special case -- nine MMAs with one D address
-// (eighteen when the ring wraps inside the row's three slots), two commits.  That stream must stay short: the issuer shares its
-// scheduler and instruction cache with four epilogue warps, and a first version with per-MMA descriptor arithmetic and a
+// (eighteen when the ring wraps inside the row's three slots) and a few commits.  That stream must stay short: the issuer shares
+// its scheduler and instruction cache with epilogue warps, and a first version with per-MMA descriptor arithmetic and a
 // three-way split of each row's first MMA spent ~2,000 cycles per row in the issuer alone (0.63 ms per layer, slower than tap-major).
 //
-// Roles: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-19 epilogue: four groups of four warps, group g
-// drains output rows u = g (mod 4) with the fused epilogues of gemm_tc5.cuh (bias + GELU [+ skip], bf16, coalesced).
+// Roles: warp 0 TMA producer, warp 1 (and 5) MMA issuer, warp 2 TMEM allocator, warp 3 issuer of the fused head's 1x1, then three
+// or four epilogue groups of four warps (RollCfg below); group g drains output rows u = g (mod GROUPS) with the fused epilogues
+// of gemm_tc5.cuh (bias + GELU [+ skip], bf16, coalesced).
 // Only interior pixels are computed; the kernel zeroes the halo of its output buffer itself (epilogue threads, before their first tile).
 #include "gemm_tc5.cuh"
 
@@ -44,25 +45,41 @@ constexpr int R = 8;                         // accumulator ring slots (output r
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t UNIT_BYTES = MERGE_ROWS * BLOCK_K * 2;       // one A ring unit: a 136-row box (full strip) or two 64-row boxes
 constexpr uint32_t FULL_TX = MERGE_ROWS * BLOCK_K * 2, PAIR_TX = 2 * 64 * BLOCK_K * 2;
-constexpr int UNITS = 6;
 constexpr uint32_t W_BOX = CH * BLOCK_K * 2;                    // 6144 B: one tap's weights, K-major SWIZZLE_128B
 constexpr uint32_t RES_BYTES = 9 * W_BOX;
-constexpr int GROUPS = 4, EPI_WARPS = 4 * GROUPS, THREADS = 128 + 32 * EPI_WARPS;
 constexpr uint32_t STG_WARP_BYTES = 32 * (CH * 2 + 16) + CH * 4;   // bf16 staging rows + the warp's bias copy
-constexpr uint32_t STG_BYTES = EPI_WARPS * STG_WARP_BYTES;
-constexpr uint32_t BAR_BYTES = 512;                               // 39 mbarriers + the TMEM base word
-constexpr uint32_t SMEM_BYTES = UNITS * UNIT_BYTES + RES_BYTES + STG_BYTES + 1024 + BAR_BYTES;
-static_assert(SMEM_BYTES <= 227u * 1024u, "shared memory budget");
+constexpr uint32_t BAR_BYTES = 512;                               // <= 41 mbarriers + the TMEM base word
+constexpr uint32_t A2_BYTES = BLOCK_M * BLOCK_K * 2;
+// Two layouts of the 640 threads, chosen per epilogue:
+//   three epilogue groups + TWO MMA issuers (warps 1 and 5) -- plain and fused-head epilogues.  One issuer's per-row stream (barrier
+//     waits, descriptor arithmetic, 9-18 MMAs, commits) costs ~1,600 cycles of which ~500 are not spent waiting for the tensor
+//     core's queue; the second issuer takes every other input row and hides them.  fp32 accumulation is not associative, so
+//     the two streams must reach the tensor core in ROW ORDER: an issuer queues its row's MMAs only when the other has handed
+//     over the turn behind its own row's last MMA.  That token only orders the MMAs if both warps sit on the SAME SM
+//     sub-partition (warp % 4 equal: they share one dispatch path to the tensor core) -- with warps 1 and 3 results differed
+//     in the last bit from run to run; with warps 1 and 5 they are bit-identical run to run and across batch compositions
+//     (tools/roll_bench.py checks both, tests compare bit for bit).  0.487 -> 0.449 ms per layer, fused head 0.496 -> 0.454.
+//   four epilogue groups + one issuer -- the skip-add epilogue, whose longer per-row epilogue needs the fourth group more than
+//     the second issuer (0.570 vs 0.597 ms).
 // Fused decoder head (E_CONV_HEAD, decoder.py:76-81; the scheme of gemm_tc5.cuh): the epilogue lanes write the GELU'd row as the
 // bf16 A2 operand of a second contraction D2[128 x 16] = A2[128 x 48] . W2^T (hi + lo bf16 split of the fp32 1x1 weights), issued
 // by a warp of its own (warp 3) into 16 spare TMEM columns per epilogue group, and store NCHW fp32 from D2 while they handle
 // their next row.  No staging rows are needed then: the area holds one A2 tile per group, W2 + biases, one bias copy.
-constexpr uint32_t A2_BYTES = BLOCK_M * BLOCK_K * 2;
-constexpr uint32_t HEAD_AREA = GROUPS * A2_BYTES + 4352 /* HEAD_SLOT_BYTES rounded */ + CH * 4;
-constexpr uint32_t SMEM_BYTES_HEAD = UNITS * UNIT_BYTES + RES_BYTES + HEAD_AREA + 1024 + BAR_BYTES;
-static_assert(SMEM_BYTES_HEAD <= 227u * 1024u && HEAD_SLOT_BYTES <= 4352 && R * CH + GROUPS * 16 <= (int)TMEM_COLS, "fused head budget");
+template <int EPI>
+struct RollCfg {
+  static constexpr bool kHead = EPI == E_CONV_HEAD;
+  static constexpr int GROUPS = EPI == E_CONV_SKIPADD ? 4 : 3;
+  static constexpr bool TWO = GROUPS == 3;                       // two MMA issuers (warps 1 and 5)
+  static constexpr int EPI_WARPS = 4 * GROUPS, EPI_BASE = TWO ? 8 : 4, THREADS = 32 * (EPI_BASE + EPI_WARPS);
+  static constexpr int UNITS = TWO ? 7 : 6;
+  static constexpr uint32_t STG_BYTES = kHead ? GROUPS * A2_BYTES + 4352 /* HEAD_SLOT_BYTES rounded */ + CH * 4 : EPI_WARPS * STG_WARP_BYTES;
+  static constexpr uint32_t SMEM_BYTES = UNITS * UNIT_BYTES + RES_BYTES + STG_BYTES + 1024 + BAR_BYTES;
+  static_assert(THREADS == 640, "640 threads keep 96 registers per thread for the epilogue warps");
+  static_assert(SMEM_BYTES <= 227u * 1024u, "shared memory budget");
+  static_assert(HEAD_SLOT_BYTES <= 4352 && R * CH + GROUPS * 16 <= (int)TMEM_COLS && 2 * UNITS + 2 * R + 1 + 2 * GROUPS + 2 <= 63, "fused head / barrier budget");
+};
 static_assert(UNIT_BYTES % 1024 == 0 && W_BOX % 1024 == 0, "operand tiles must stay 1024-byte aligned for SWIZZLE_128B");
-static_assert(R * CH <= (int)TMEM_COLS && R % GROUPS == 0, "accumulator ring");
+static_assert(R * CH <= (int)TMEM_COLS, "accumulator ring");
 
 struct Geo {
   int B, H, W;
@@ -92,16 +109,19 @@ __device__ __forceinline__ bool next_seg(const Geo& g, long long& t, long long t
 }
 
 template <int EPI>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(RollCfg<EPI>::THREADS, 1)
 conv_roll_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA64,
                  const __grid_constant__ CUtensorMap tmB, const Problem p, const Geo g) {
+  using K = RollCfg<EPI>;
+  constexpr int GROUPS = K::GROUPS, EPI_WARPS = K::EPI_WARPS, EPI_BASE = K::EPI_BASE, UNITS = K::UNITS;
+  constexpr bool TWO = K::TWO;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
   unsigned char* smem_a = smem;
   unsigned char* smem_res = smem + UNITS * UNIT_BYTES;
   unsigned char* smem_stg = smem_res + RES_BYTES;
-  constexpr bool kHead = EPI == E_CONV_HEAD;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_stg + (kHead ? HEAD_AREA : STG_BYTES));
+  constexpr bool kHead = K::kHead;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_stg + K::STG_BYTES);
   uint64_t* full = bars;                    // [UNITS]  producer -> issuer
   uint64_t* empty = full + UNITS;           // [UNITS]  issuer (tcgen05.commit) -> producer
   uint64_t* slot_full = empty + UNITS;      // [R]      issuer (tcgen05.commit) -> epilogue group
@@ -109,7 +129,8 @@ conv_roll_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* res_full = slot_empty + R;
   uint64_t* a2_full = res_full + 1;         // [GROUPS] epilogue group -> issuer: the A2 tile of the fused head is written
   uint64_t* d2_full = a2_full + GROUPS;     // [GROUPS] issuer (tcgen05.commit) -> epilogue group: D2 is complete
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(d2_full + GROUPS);
+  uint64_t* turn = d2_full + GROUPS;        // [2] issuer -> the other issuer: my row's MMAs are issued
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(turn + 2);
   unsigned char* smem_a2 = smem_stg;                                   // fused head: [GROUPS] A2 tiles, then W2 hi/lo + biases, then the conv bias
   unsigned char* smem_hslot = smem_stg + GROUPS * A2_BYTES;
 
@@ -121,7 +142,8 @@ conv_roll_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < UNITS; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < R; ++i) { mbar_init(&slot_full[i], 1); mbar_init(&slot_empty[i], 4); }
+    for (int i = 0; i < R; ++i) { mbar_init(&slot_full[i], 3); mbar_init(&slot_empty[i], 4); }     // three input rows feed an output row
+    mbar_init(&turn[0], 1); mbar_init(&turn[1], 1);
     mbar_init(res_full, 1);
     for (int i = 0; i < GROUPS; ++i) { mbar_init(&a2_full[i], 4); mbar_init(&d2_full[i], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -182,12 +204,8 @@ conv_roll_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
     }
-  } else if (warp == 1) {
-    // ===== MMA issuer.  ONE instruction stream on purpose: a second issuer warp on alternate input rows hides this warp's per-row
-    // overhead (two barrier waits, descriptor arithmetic: ~500 of ~1,600 cycles) and measured 0.444 instead of 0.488 ms per layer,
-    // but MMAs of different threads reach the tensor core in no defined order -- not even when the second thread issues only
-    // after the first has handed over a token behind its last MMA -- and fp32 accumulation is not associative: results then
-    // differ in the last bit from run to run, and the sharding-invariance tests of this repo compare bit for bit. =====
+  } else if (warp == 1 || (TWO && warp == 5)) {
+    // ===== MMA issuer(s): warp 1 alone, or warps 1 and 5 on alternate input rows with the turn token (RollCfg). =====
     constexpr uint32_t HI = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO = 1024 B, version 1, SWIZZLE_128B
     constexpr uint32_t IDESC0 = make_idesc(BLOCK_M, 0);              // + (N >> 3) << 17
     constexpr uint32_t WB = W_BOX >> 4, UB = UNIT_BYTES >> 4;
@@ -198,6 +216,8 @@ conv_roll_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint32_t ubase = 0;                      // output rows this CTA has started before the current segment
     long long t = t_begin;
     Seg sg;
+    const uint32_t me = warp == 1 ? 0u : 1u;
+    uint32_t rowctr = 0, turn_par = me ^ 1u;
     while (next_seg(g, t, t_end, sg)) {
       const bool pair = sg.strip == g.nfull;
       const int n = sg.n;
@@ -205,6 +225,11 @@ conv_roll_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // valid groups j of this input row (output row o = s - 2 + j inside [0, n)); interior rows: 0 .. 2
         const int jlo = s >= 2 ? 0 : 2 - s, jhi = s < n ? 2 : n + 1 - s;
         const uint32_t u0 = ubase + (uint32_t)s;              // u0 - 2 + j = ring index of group j's output row
+        if (TWO && ((rowctr++) & 1u) != me) {                 // the other issuer's row: step over its ring units
+          unit += pair ? 3 : 1;
+          if (unit >= UNITS) { unit -= UNITS; phase ^= 1; }
+          continue;
+        }
         if (jhi == 2) {                                       // a slot is touched for the first time: its previous use must be drained and zeroed
           mbar_wait(&slot_empty[u0 % R], (u0 / R) & 1u);
           tcgen05_fence_after();
@@ -217,6 +242,7 @@ conv_roll_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const uint32_t b_a = r_lo0 + (uint32_t)jlo * WB, b_b = b_a + (uint32_t)n_a * WB;
         if (!pair) {
           mbar_wait(&full[unit], phase);
+          if (TWO) { mbar_wait(&turn[me], turn_par); turn_par ^= 1u; }
           tcgen05_fence_after();
           if (elect_one()) {
             const uint32_t a_lo = a_lo0 + (uint32_t)unit * UB;
@@ -228,14 +254,16 @@ conv_roll_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 tcgen05_mma_bf16(d_a, da, ((uint64_t)HI << 32) | (b_a + (uint32_t)(dx * 3) * WB + 2u * k), id_a, 1u);
                 if (n_b > 0) tcgen05_mma_bf16(tmem_base, da, ((uint64_t)HI << 32) | (b_b + (uint32_t)(dx * 3) * WB + 2u * k), id_b, 1u);
               }
+            if (TWO) mbar_arrive(&turn[me ^ 1u]);
             tcgen05_commit(&empty[unit]);
-            if (s >= 2) tcgen05_commit(&slot_full[(u0 - 2u) % R]);                 // output row s - 2 is complete behind this row
+            for (int j = jlo; j <= jhi; ++j) tcgen05_commit(&slot_full[(u0 + (uint32_t)j + (uint32_t)(R - 2)) % R]);
           }
           __syncwarp();
           if (++unit == UNITS) { unit = 0; phase ^= 1; }
         } else {
           for (int dx = 0; dx < 3; ++dx) {
             mbar_wait(&full[unit], phase);
+            if (TWO && dx == 0) { mbar_wait(&turn[me], turn_par); turn_par ^= 1u; }
             tcgen05_fence_after();
             if (elect_one()) {
               const uint32_t a_lo = a_lo0 + (uint32_t)unit * UB;
@@ -245,8 +273,10 @@ conv_roll_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 tcgen05_mma_bf16(d_a, da, ((uint64_t)HI << 32) | (b_a + (uint32_t)(dx * 3) * WB + 2u * k), id_a, 1u);
                 if (n_b > 0) tcgen05_mma_bf16(tmem_base, da, ((uint64_t)HI << 32) | (b_b + (uint32_t)(dx * 3) * WB + 2u * k), id_b, 1u);
               }
+              if (TWO && dx == 2) mbar_arrive(&turn[me ^ 1u]);
               tcgen05_commit(&empty[unit]);
-              if (dx == 2 && s >= 2) tcgen05_commit(&slot_full[(u0 - 2u) % R]);
+              if (dx == 2)
+                for (int j = jlo; j <= jhi; ++j) tcgen05_commit(&slot_full[(u0 + (uint32_t)j + (uint32_t)(R - 2)) % R]);
             }
             __syncwarp();
             if (++unit == UNITS) { unit = 0; phase ^= 1; }
@@ -264,7 +294,7 @@ conv_roll_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tcgen05_fence_after();
       const uint32_t nrows = (uint32_t)(t_end - t_begin);
       for (uint32_t v = 0; v < nrows; ++v) {
-        const uint32_t grp = v & (GROUPS - 1);
+        const uint32_t grp = v % GROUPS;
         mbar_wait(&a2_full[grp], (v / GROUPS) & 1u);
         tcgen05_fence_after();
         if (elect_one()) {
@@ -283,9 +313,9 @@ conv_roll_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         __syncwarp();
       }
     }
-  } else if (warp >= 4) {
-    // ===== epilogue: warp w reads TMEM lanes 32 (w % 4) ..; group (w - 4) / 4 owns output rows u = group (mod 4) =====
-    const int e = warp - 4, q = warp & 3, grp = e >> 2;
+  } else if (warp >= EPI_BASE) {
+    // ===== epilogue: warp w reads TMEM lanes 32 (w % 4) ..; group (w - EPI_BASE) / 4 owns output rows u = group (mod GROUPS) =====
+    const int e = warp - EPI_BASE, q = warp & 3, grp = e >> 2;
     const uint32_t stg_s = kHead ? 0u : smem_u32(smem_stg + e * STG_WARP_BYTES);
     const uint32_t bias_s = kHead ? smem_u32(smem_hslot + 4352) : stg_s + 32 * (CH * 2 + 16);    // fused head: one copy for all warps
     if (!kHead || e == 0) {
@@ -309,7 +339,7 @@ conv_roll_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     HeadCtx hc;
     hc.has_prev = false; hc.prev_rowpix = kRowSkip; hc.parity = 0; hc.d2_full = nullptr;
     if constexpr (kHead) {
-      build_head_operand(p, smem_u32(smem_hslot), (int)threadIdx.x - 128, EPI_WARPS * 32);
+      build_head_operand(p, smem_u32(smem_hslot), (int)threadIdx.x - 32 * EPI_BASE, EPI_WARPS * 32);
       asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
       asm volatile("bar.sync 1, %0;\n" ::"n"(EPI_WARPS * 32 + 32) : "memory");     // + the issuer warp; also publishes the shared bias copy
       hc.a2_s = smem_u32(smem_a2 + grp * A2_BYTES);
@@ -322,7 +352,7 @@ conv_roll_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
       const int per_img = 2 * PW + 2 * g.H, vec = CH / 8;
       const long long total = (long long)g.B * per_img * vec;
-      for (long long i = (long long)blockIdx.x * (EPI_WARPS * 32) + (threadIdx.x - 128); i < total; i += (long long)gridDim.x * (EPI_WARPS * 32)) {
+      for (long long i = (long long)blockIdx.x * (EPI_WARPS * 32) + (threadIdx.x - 32 * EPI_BASE); i < total; i += (long long)gridDim.x * (EPI_WARPS * 32)) {
         const int v = (int)(i % vec);
         const long long tt = i / vec;
         const int k = (int)(tt % per_img), b = (int)(tt / per_img);
@@ -344,7 +374,7 @@ conv_roll_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       else m_base += (q < 2 ? 32 * q : (g.H >> 1) * PW + 32 * (q - 2));
       for (int o = 0; o < sg.n; ++o) {
         const uint32_t u = ubase + (uint32_t)o;
-        if ((int)(u & (GROUPS - 1)) != grp) continue;
+        if ((int)(u % GROUPS) != grp) continue;
         const uint32_t slot = u % R;
         const int mrow0 = m_base + o * PW;
         if constexpr (EPI == E_CONV_SKIPADD)
@@ -412,15 +442,15 @@ int launch(const Problem& p, cudaStream_t s) {
   const int epi = classify(p);
   static PerDeviceOnce attr_set;
   if (attr_set.first()) {
-    MSD_CHECK_CUDA(cudaFuncSetAttribute(conv_roll_kernel<E_CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    MSD_CHECK_CUDA(cudaFuncSetAttribute(conv_roll_kernel<E_CONV_SKIPADD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    MSD_CHECK_CUDA(cudaFuncSetAttribute(conv_roll_kernel<E_CONV_HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES_HEAD));
+    MSD_CHECK_CUDA(cudaFuncSetAttribute(conv_roll_kernel<E_CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RollCfg<E_CONV>::SMEM_BYTES));
+    MSD_CHECK_CUDA(cudaFuncSetAttribute(conv_roll_kernel<E_CONV_SKIPADD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RollCfg<E_CONV_SKIPADD>::SMEM_BYTES));
+    MSD_CHECK_CUDA(cudaFuncSetAttribute(conv_roll_kernel<E_CONV_HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RollCfg<E_CONV_HEAD>::SMEM_BYTES));
   }
   const long long sms = num_sms();
   const int grid = (int)(g.total < sms ? g.total : sms);
-  if (epi == E_CONV_HEAD) conv_roll_kernel<E_CONV_HEAD><<<grid, THREADS, SMEM_BYTES_HEAD, s>>>(tmA, tmA64, tmB, p, g);
-  else if (epi == E_CONV_SKIPADD) conv_roll_kernel<E_CONV_SKIPADD><<<grid, THREADS, SMEM_BYTES, s>>>(tmA, tmA64, tmB, p, g);
-  else conv_roll_kernel<E_CONV><<<grid, THREADS, SMEM_BYTES, s>>>(tmA, tmA64, tmB, p, g);
+  if (epi == E_CONV_HEAD) conv_roll_kernel<E_CONV_HEAD><<<grid, RollCfg<E_CONV_HEAD>::THREADS, RollCfg<E_CONV_HEAD>::SMEM_BYTES, s>>>(tmA, tmA64, tmB, p, g);
+  else if (epi == E_CONV_SKIPADD) conv_roll_kernel<E_CONV_SKIPADD><<<grid, RollCfg<E_CONV_SKIPADD>::THREADS, RollCfg<E_CONV_SKIPADD>::SMEM_BYTES, s>>>(tmA, tmA64, tmB, p, g);
+  else conv_roll_kernel<E_CONV><<<grid, RollCfg<E_CONV>::THREADS, RollCfg<E_CONV>::SMEM_BYTES, s>>>(tmA, tmA64, tmB, p, g);
   MSD_LAUNCH_CHECK();
   return MSD_OK;
 }

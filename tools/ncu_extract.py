@@ -19,7 +19,9 @@ WANT = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__
         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "sm__cycles_elapsed.max", "launch__grid_size",
         "launch__registers_per_thread", "dram__bytes_read.sum.pct_of_peak_sustained_elapsed", "dram__bytes_write.sum.pct_of_peak_sustained_elapsed",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "lts__t_bytes.sum", "sm__inst_executed_pipe_fma.sum",
-        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed"]
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__data_pipe_tc_wavefronts_mem_shared.sum", "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "lts__t_sectors_srcunit_tex_op_read.sum"]
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0,
         "nsecond": 1e-9, "usecond": 1e-6, "msecond": 1e-3, "second": 1.0}
 
@@ -45,6 +47,8 @@ TILE = 13 * 192 * 192
 CAPTURES = {
     "qkv (LayerNorm folded)": ("r2_prof_qkv_ln", None), "proj + LayerNorm sums": ("r2_prof_proj_stats", None),
     "conv 192x192x48": ("r2_prof_conv4", None), "attention (tcgen05)": ("r2_prof_attn", None),
+    "conv 192x192x48 (rolling rows)": ("r2_prof_conv4_roll", None), "conv 192x192x48 + skip (rolling rows)": ("r2_prof_conv4_skip_roll", None),
+    "head conv + fused 1x1 (rolling rows)": ("r2_prof_head_roll", None),
     "corrupt_kernel": ("r2_prof_corrupt", 256 * TILE), "metrics_fused_kernel": ("r2_prof_metrics", 256 * TILE),
     "loss_fwd_kernel": ("r2_prof_loss_fwd", 256 * TILE), "loss_bwd_kernel": ("r2_prof_loss_bwd", 256 * TILE),
 }
