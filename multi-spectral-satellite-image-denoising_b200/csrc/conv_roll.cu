@@ -72,7 +72,9 @@ struct RollCfg {
   static constexpr bool TWO = GROUPS == 3;                       // two MMA issuers (warps 1 and 5)
   static constexpr int EPI_WARPS = 4 * GROUPS, EPI_BASE = TWO ? 8 : 4, THREADS = 32 * (EPI_BASE + EPI_WARPS);
   static constexpr int UNITS = TWO ? 7 : 6;
-  static constexpr uint32_t STG_BYTES = kHead ? GROUPS * A2_BYTES + 4352 /* HEAD_SLOT_BYTES rounded */ + CH * 4 : EPI_WARPS * STG_WARP_BYTES;
+  // (training convs, E_CONV_RAW: + one [2][48] fp32 slot per epilogue warp for the BatchNorm column sums, Problem::bn_sums)
+  static constexpr uint32_t SUMS_BYTES = EPI == E_CONV_RAW ? EPI_WARPS * 2 * CH * 4 : 0;
+  static constexpr uint32_t STG_BYTES = kHead ? GROUPS * A2_BYTES + 4352 /* HEAD_SLOT_BYTES rounded */ + CH * 4 : EPI_WARPS * STG_WARP_BYTES + SUMS_BYTES;
   static constexpr uint32_t SMEM_BYTES = UNITS * UNIT_BYTES + RES_BYTES + STG_BYTES + 1024 + BAR_BYTES;
   static_assert(THREADS == 640, "640 threads keep 96 registers per thread for the epilogue warps");
   static_assert(SMEM_BYTES <= 227u * 1024u, "shared memory budget");
@@ -336,6 +338,13 @@ conv_roll_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive(&slot_empty[slot]);
     }
+    uint32_t sums_s = 0u;
+    if constexpr (EPI == E_CONV_RAW) {
+      if (p.bn_sums != nullptr) {
+        sums_s = smem_u32(smem_stg + EPI_WARPS * STG_WARP_BYTES) + (uint32_t)e * (uint32_t)(2 * CH * 4);
+        bn_sums_zero(sums_s, CH, lane);
+      }
+    }
     HeadCtx hc;
     hc.has_prev = false; hc.prev_rowpix = kRowSkip; hc.parity = 0; hc.d2_full = nullptr;
     if constexpr (kHead) {
@@ -385,11 +394,16 @@ conv_roll_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if constexpr (kHead) {
           hc.parity = (u / GROUPS) & 1u;
           epilogue_tile<CH, EPI, false, true>(p, stg_s, bias_s, taddr, &slot_empty[slot], mrow0, 0, lane, 0, 1, &hc);
+        } else if constexpr (EPI == E_CONV_RAW) {
+          epilogue_tile<CH, EPI, false, true>(p, stg_s, bias_s, taddr, &slot_empty[slot], mrow0, 0, lane, 0, 1, nullptr, 0.0f, 0.0f, sums_s);
         } else {
           epilogue_tile<CH, EPI, false, true>(p, stg_s, bias_s, taddr, &slot_empty[slot], mrow0, 0, lane, 0, 1);
         }
       }
       ubase += (uint32_t)sg.n;
+    }
+    if constexpr (EPI == E_CONV_RAW) {
+      if (p.bn_sums != nullptr) bn_sums_flush(smem_u32(smem_stg + EPI_WARPS * STG_WARP_BYTES), p.bn_sums, CH, (int)threadIdx.x - 32 * EPI_BASE, EPI_WARPS);
     }
     if constexpr (kHead) {
       if (hc.has_prev) {                                   // the last row of this warp's group
@@ -417,12 +431,13 @@ bool geometry_ok(int H, int W, int C) {
 
 bool eligible(const Problem& p) {
   if (p.mode != EPI_CONV || p.N != CH || p.kvalid != CH || p.ldA != CH || p.ldo != CH || p.kb_per_tap != 1 || p.num_kb != 9 || p.skip_tap >= 0 ||
-      p.bn_sums != nullptr || p.out_f32 || p.dbg_shift != 0 || p.dbg_bo != 0 || !is_conv3x3(p)) return false;
+      p.out_f32 || p.dbg_shift != 0 || p.dbg_bo != 0 || !is_conv3x3(p)) return false;
   if (!geometry_ok(p.H, p.W, p.N)) return false;
   const int e = classify(p);
   if (e == E_CONV_HEAD) return p.act && p.skip == nullptr && p.head_w != nullptr && p.head_cout >= 1 && p.head_cout <= 16 &&
                                (unsigned long long)(p.M / (int)p.plane.d + 1) * p.head_cout * p.H * p.W < (1ull << 31);
-  return e == E_CONV || e == E_CONV_SKIPADD;
+  if (p.bn_sums != nullptr && e != E_CONV_RAW) return false;
+  return e == E_CONV || e == E_CONV_SKIPADD || e == E_CONV_RAW;     // (raw: the training step's pre-BatchNorm convs and data gradients)
 }
 
 int launch(const Problem& p, cudaStream_t s) {
@@ -445,10 +460,12 @@ int launch(const Problem& p, cudaStream_t s) {
     MSD_CHECK_CUDA(cudaFuncSetAttribute(conv_roll_kernel<E_CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RollCfg<E_CONV>::SMEM_BYTES));
     MSD_CHECK_CUDA(cudaFuncSetAttribute(conv_roll_kernel<E_CONV_SKIPADD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RollCfg<E_CONV_SKIPADD>::SMEM_BYTES));
     MSD_CHECK_CUDA(cudaFuncSetAttribute(conv_roll_kernel<E_CONV_HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RollCfg<E_CONV_HEAD>::SMEM_BYTES));
+    MSD_CHECK_CUDA(cudaFuncSetAttribute(conv_roll_kernel<E_CONV_RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RollCfg<E_CONV_RAW>::SMEM_BYTES));
   }
   const long long sms = num_sms();
   const int grid = (int)(g.total < sms ? g.total : sms);
   if (epi == E_CONV_HEAD) conv_roll_kernel<E_CONV_HEAD><<<grid, RollCfg<E_CONV_HEAD>::THREADS, RollCfg<E_CONV_HEAD>::SMEM_BYTES, s>>>(tmA, tmA64, tmB, p, g);
+  else if (epi == E_CONV_RAW) conv_roll_kernel<E_CONV_RAW><<<grid, RollCfg<E_CONV_RAW>::THREADS, RollCfg<E_CONV_RAW>::SMEM_BYTES, s>>>(tmA, tmA64, tmB, p, g);
   else if (epi == E_CONV_SKIPADD) conv_roll_kernel<E_CONV_SKIPADD><<<grid, RollCfg<E_CONV_SKIPADD>::THREADS, RollCfg<E_CONV_SKIPADD>::SMEM_BYTES, s>>>(tmA, tmA64, tmB, p, g);
   else conv_roll_kernel<E_CONV><<<grid, RollCfg<E_CONV>::THREADS, RollCfg<E_CONV>::SMEM_BYTES, s>>>(tmA, tmA64, tmB, p, g);
   MSD_LAUNCH_CHECK();

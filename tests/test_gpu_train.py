@@ -147,7 +147,9 @@ def test_batchnorm_train_fwd_bwd(B, H, W, C, with_skip):
 
 
 @pytest.mark.parametrize("B,H,W,C,bias,fused", [(2, 20, 12, 48, False, 1), (5, 40, 41, 48, True, 1), (3, 30, 31, 96, False, 1),
-                                                (1, 10, 14, 96, False, 0), (2, 8, 8, 192, False, 0), (64, 64, 64, 48, False, 1)])
+                                                (1, 10, 14, 96, False, 0), (2, 8, 8, 192, False, 0), (64, 64, 64, 48, False, 1),
+                                                # geometries of the rolling-row kernel (csrc/conv_roll.cu, E_CONV_RAW): pair strips only, full + pair, full only
+                                                (3, 10, 192, 48, True, 1), (2, 5, 256, 48, False, 1), (9, 192, 192, 48, False, 1)])
 def test_conv3x3_with_batchnorm_sums_in_the_epilogue(B, H, W, C, bias, fused):
     """Training forward of nn.Conv2d + nn.BatchNorm2d (blocks.py:66-72): the 48- / 96-channel convs leave sum c, sum c^2 of the tensor
     they store from their own epilogues; the sums must be those of the stored bf16 values (what the separate pass computes), halo rows
