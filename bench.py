@@ -562,7 +562,7 @@ def main():
                      "algorithmic_gflop_per_step": enc_flops / 1e9,
                      "share_of_step": enc_ms / ms_step if ms_step > 0 else None,
                      # every tensor-core launch of the step (GEMMs, implicit 3x3 convs, ConvTranspose, the head conv with its fused 1x1)
-                     "family": {"kernels": "gemm_tc5_pair_kernel<BN,MERGED> / gemm_tc5_kernel<BN,MODE>", "achieved": family_tf,
+                     "family": {"kernels": "gemm_tc5_pair_kernel<BN,MERGED> / gemm_tc5_kernel<BN,MODE> / conv_roll_kernel<EPI> (stage-4 3x3 convs + fused head)", "achieved": family_tf,
                                 "frac": family_tf / pk["tf_sustained"], "launches_per_step": gemm_n, "ms_per_step": gemm_ms,
                                 "algorithmic_gflop_per_step": gemm_flops / 1e9, "share_of_step": gemm_ms / ms_step if ms_step > 0 else None},
                      "other_ms_per_step": {"attention": agg.get(1, [0])[0], "layernorm": agg.get(2, [0])[0], "other_model": agg.get(3, [0])[0]},
