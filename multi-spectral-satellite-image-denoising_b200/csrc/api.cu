@@ -1,6 +1,7 @@
 // Library-level entry points: version, thread-local error text, device check.
 #include "common.cuh"
 #include <string.h>
+#include <stdlib.h>
 
 static thread_local char g_err[512] = "";
 
@@ -9,6 +10,12 @@ void msd_set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+// programmatic dependent launch of the tensor-core kernel chain (common.cuh); read on every launch so that A/B runs can switch it
+bool msd_pdl_enabled() {
+  const char* e = getenv("MSD_NO_PDL");
+  return !(e != nullptr && e[0] == '1');
 }
 
 extern "C" int msd_version(void) { return 2; }

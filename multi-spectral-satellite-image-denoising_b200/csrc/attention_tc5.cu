@@ -78,6 +78,7 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* _
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
+  msd_pdl_enter();      // the prologue above ran under the previous kernel's tail; no global memory touched yet
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
   const int n_local = ((int)blockIdx.x < problems) ? (problems - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   const int E = heads * HD;
@@ -260,7 +261,7 @@ extern "C" int msd_attention_tc5_bf16(const void* d_qkv, void* d_out, int B, int
   }
   const int problems = B * heads;
   const int grid = problems < num_sms() ? problems : num_sms();
-  attention_tc5_kernel<<<(unsigned)grid, kThreadsA, SMEM_A, (cudaStream_t)stream>>>(tm, reinterpret_cast<__nv_bfloat16*>(d_out), heads, problems);
+  MSD_CHECK_CUDA(msd_launch_pdl(attention_tc5_kernel, dim3((unsigned)grid), dim3(kThreadsA), SMEM_A, (cudaStream_t)stream, tm, reinterpret_cast<__nv_bfloat16*>(d_out), heads, problems));
   MSD_LAUNCH_CHECK();
   return MSD_OK;
 }

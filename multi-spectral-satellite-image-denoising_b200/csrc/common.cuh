@@ -49,6 +49,30 @@ struct PerDeviceOnce {
 };
 
 // ---------------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL) for the chain of persistent tensor-core kernels of a forward / backward pass: a kernel
+// launched through msd_launch_pdl may become resident on an SM as soon as the previous kernel's CTA there has exited, run its
+// prologue (mbarrier init, TMEM allocation, tensor-map prefetch) under the previous kernel's tail, and only then wait for the
+// previous grid to complete with its memory visible (msd_pdl_enter(), called by every thread before the kernel's first access to
+// global memory -- reads AND writes, so no buffer the predecessor still uses is touched early).  msd_pdl_enter() first releases
+// this kernel's own dependents.  MSD_NO_PDL=1 launches everything fully serialised (A/B runs).
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void msd_pdl_enter() {
+  asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
+  asm volatile("griddepcontrol.wait;\n" ::: "memory");
+}
+bool msd_pdl_enabled();
+template <typename... KArgs, typename... Args>
+static inline cudaError_t msd_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = msd_pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// ---------------------------------------------------------------------------------------------------
 // exact unsigned division by a runtime constant (n < 2^31): q = (umulhi(n, m) + n) >> s
 // ---------------------------------------------------------------------------------------------------
 struct FastDiv {

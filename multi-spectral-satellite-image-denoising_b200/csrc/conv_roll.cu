@@ -157,6 +157,7 @@ conv_roll_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
+  msd_pdl_enter();      // the prologue above ran under the previous kernel's tail; no global memory touched yet
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
 
   // this CTA's range of steps
@@ -464,10 +465,10 @@ int launch(const Problem& p, cudaStream_t s) {
   }
   const long long sms = num_sms();
   const int grid = (int)(g.total < sms ? g.total : sms);
-  if (epi == E_CONV_HEAD) conv_roll_kernel<E_CONV_HEAD><<<grid, RollCfg<E_CONV_HEAD>::THREADS, RollCfg<E_CONV_HEAD>::SMEM_BYTES, s>>>(tmA, tmA64, tmB, p, g);
-  else if (epi == E_CONV_RAW) conv_roll_kernel<E_CONV_RAW><<<grid, RollCfg<E_CONV_RAW>::THREADS, RollCfg<E_CONV_RAW>::SMEM_BYTES, s>>>(tmA, tmA64, tmB, p, g);
-  else if (epi == E_CONV_SKIPADD) conv_roll_kernel<E_CONV_SKIPADD><<<grid, RollCfg<E_CONV_SKIPADD>::THREADS, RollCfg<E_CONV_SKIPADD>::SMEM_BYTES, s>>>(tmA, tmA64, tmB, p, g);
-  else conv_roll_kernel<E_CONV><<<grid, RollCfg<E_CONV>::THREADS, RollCfg<E_CONV>::SMEM_BYTES, s>>>(tmA, tmA64, tmB, p, g);
+  if (epi == E_CONV_HEAD) MSD_CHECK_CUDA(msd_launch_pdl(conv_roll_kernel<E_CONV_HEAD>, dim3(grid), dim3(RollCfg<E_CONV_HEAD>::THREADS), RollCfg<E_CONV_HEAD>::SMEM_BYTES, s, tmA, tmA64, tmB, p, g));
+  else if (epi == E_CONV_RAW) MSD_CHECK_CUDA(msd_launch_pdl(conv_roll_kernel<E_CONV_RAW>, dim3(grid), dim3(RollCfg<E_CONV_RAW>::THREADS), RollCfg<E_CONV_RAW>::SMEM_BYTES, s, tmA, tmA64, tmB, p, g));
+  else if (epi == E_CONV_SKIPADD) MSD_CHECK_CUDA(msd_launch_pdl(conv_roll_kernel<E_CONV_SKIPADD>, dim3(grid), dim3(RollCfg<E_CONV_SKIPADD>::THREADS), RollCfg<E_CONV_SKIPADD>::SMEM_BYTES, s, tmA, tmA64, tmB, p, g));
+  else MSD_CHECK_CUDA(msd_launch_pdl(conv_roll_kernel<E_CONV>, dim3(grid), dim3(RollCfg<E_CONV>::THREADS), RollCfg<E_CONV>::SMEM_BYTES, s, tmA, tmA64, tmB, p, g));
   MSD_LAUNCH_CHECK();
   return MSD_OK;
 }

@@ -809,6 +809,7 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
+  msd_pdl_enter();      // everything above ran under the previous kernel's tail; no global memory has been touched yet
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);   // same word for every lane; shuffle makes it provably uniform
   const int num_tiles = tiles_m * tiles_n;
 
@@ -1166,7 +1167,7 @@ int launch_mode(const Problem& p, cudaStream_t s) {
   const int tiles_m = (p.M + BLOCK_M - 1) / BLOCK_M, tiles_n = p.N / BN;
   const int tiles = tiles_m * tiles_n;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_tc5_kernel<BN, MODE><<<grid, C::THREADS, C::SMEM_BYTES, s>>>(tmA, tmB, tmS, p, tiles_m, tiles_n, classify(p));
+  MSD_CHECK_CUDA(msd_launch_pdl(gemm_tc5_kernel<BN, MODE>, dim3(grid), dim3(C::THREADS), C::SMEM_BYTES, s, tmA, tmB, tmS, p, tiles_m, tiles_n, classify(p)));
   MSD_LAUNCH_CHECK();
   return MSD_OK;
 }

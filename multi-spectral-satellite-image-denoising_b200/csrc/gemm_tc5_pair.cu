@@ -113,6 +113,7 @@ gemm_tc5_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   tcgen05_fence_before();
   cluster_sync_all();                              // barrier inits + TMEM of both CTAs visible before any cross-CTA traffic
   tcgen05_fence_after();
+  msd_pdl_enter();                                 // the prologue above ran under the previous kernel's tail; no global memory touched yet
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
   const int num_tiles = tiles_m2 * tiles_n;        // 256-row pair tiles
   const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
@@ -351,7 +352,7 @@ int launch_pair_mode(const Problem& p, cudaStream_t s) {
   const int tiles_m2 = (p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M), tiles_n = p.N / BN;
   const int tiles = tiles_m2 * tiles_n;
   const int clusters = tiles < num_sms() / 2 ? tiles : num_sms() / 2;
-  gemm_tc5_pair_kernel<BN, MERGED><<<2 * clusters, C::THREADS, C::SMEM_BYTES, s>>>(tmA, tmB, tmS, p, tiles_m2, tiles_n, classify(p));
+  MSD_CHECK_CUDA(msd_launch_pdl(gemm_tc5_pair_kernel<BN, MERGED>, dim3(2 * clusters), dim3(C::THREADS), C::SMEM_BYTES, s, tmA, tmB, tmS, p, tiles_m2, tiles_n, classify(p)));
   MSD_LAUNCH_CHECK();
   return MSD_OK;
 }
