@@ -37,6 +37,7 @@ __device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], 
 __global__ void __launch_bounds__(kThreads, 1) attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv,
                                                                     const __nv_bfloat16* __restrict__ dout,
                                                                     __nv_bfloat16* __restrict__ dqkv, int heads) {
+  msd_pdl_enter();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __nv_bfloat16(*Qs)[LDS] = reinterpret_cast<__nv_bfloat16(*)[LDS]>(smem_raw);
   __nv_bfloat16(*Ks)[LDS] = Qs + kT;
@@ -200,9 +201,9 @@ extern "C" int msd_attention_bwd_bf16(const void* d_qkv, const void* d_dout, voi
   if (attr_set.first()) {
     MSD_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
-  attention_bwd_kernel<<<(unsigned)(B * heads), kThreads, smem, (cudaStream_t)stream>>>(
+  MSD_CHECK_CUDA(msd_launch_pdl((attention_bwd_kernel), dim3((unsigned)(B * heads)), dim3(kThreads), smem, (cudaStream_t)stream, 
       reinterpret_cast<const __nv_bfloat16*>(d_qkv), reinterpret_cast<const __nv_bfloat16*>(d_dout),
-      reinterpret_cast<__nv_bfloat16*>(d_dqkv), heads);
+      reinterpret_cast<__nv_bfloat16*>(d_dqkv), heads));
   MSD_LAUNCH_CHECK();
   return MSD_OK;
 }

@@ -59,6 +59,7 @@ __device__ __forceinline__ float torch_uniform_xf(float r) {
 template <bool kNormal>
 __global__ void __launch_bounds__(kThreads) philox_fill_kernel(float* __restrict__ out, int64_t numel, uint64_t seed,
                                                                uint64_t offset, uint32_t T) {
+  msd_pdl_enter();
   // work item = (round = blockIdx.y, tid); component ii goes to element round*4T + ii*T + tid  (T % 256 == 0)
   const uint32_t round = blockIdx.y;
   const uint32_t tid = blockIdx.x * kThreads + threadIdx.x;
@@ -75,6 +76,7 @@ __global__ void __launch_bounds__(kThreads) philox_fill_kernel(float* __restrict
 // .x component of thread c's first draw at offset off0 + 4*b; mask = u < (float)p.
 __global__ void dead_mask_kernel(uint8_t* __restrict__ mask, int B, int C, float p, uint64_t seed, uint64_t off0,
                                  uint32_t T) {
+  msd_pdl_enter();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * C) return;
   int b = i / C, c = i - b * C;
@@ -114,6 +116,7 @@ struct CorruptParams {
 // arithmetic, fp32 ops and stores.
 template <bool kFast, bool kPatch>
 __global__ void __launch_bounds__(kThreads) corrupt_kernel(const CorruptParams p) {
+  msd_pdl_enter();
   const bool has_g = kFast || p.sg > 0.0f, has_s = kFast || p.ss > 0.0f, has_t = kFast || p.st > 0.0f;
   const bool has_dead = kFast || p.dead != nullptr, has_stripe = !kFast && p.stripe != nullptr;
   const bool has_patch = kPatch || (!kFast && p.patch != nullptr);
@@ -201,7 +204,7 @@ static int philox_fill(float* d_out, int64_t numel, uint64_t seed, uint64_t offs
   const uint32_t T = 256u * torch_grid;
   const int64_t rounds = (numel - 1) / (4ll * T) + 1;
   MSD_REQUIRE(rounds <= 65535, "philox_fill: too many rounds (%lld)", (long long)rounds);
-  philox_fill_kernel<kNormal><<<dim3(T / kThreads, (unsigned)rounds), kThreads, 0, (cudaStream_t)stream>>>(d_out, numel, seed, offset, T);
+  MSD_CHECK_CUDA(msd_launch_pdl((philox_fill_kernel<kNormal>), dim3(dim3(T / kThreads, (unsigned)rounds)), dim3(kThreads), 0, (cudaStream_t)stream, d_out, numel, seed, offset, T));
   MSD_LAUNCH_CHECK();
   return MSD_OK;
 }
@@ -243,7 +246,7 @@ extern "C" int msd_corrupt_f32(const float* d_clean, float* d_noisy, const float
 
   if (p > 0.0f) {
     int n = B * C;
-    dead_mask_kernel<<<(n + 127) / 128, 128, 0, s>>>(d_dead_mask, B, C, p, seed, off_m, 256u * torch_grid_mask);
+    MSD_CHECK_CUDA(msd_launch_pdl((dead_mask_kernel), dim3((n + 127) / 128), dim3(128), 0, s, d_dead_mask, B, C, p, seed, off_m, 256u * torch_grid_mask));
     MSD_LAUNCH_CHECK();
   }
   if (stripe) {
@@ -270,9 +273,9 @@ extern "C" int msd_corrupt_f32(const float* d_clean, float* d_noisy, const float
   MSD_REQUIRE(cp.rounds <= 65535, "corrupt: too many rounds");
   const dim3 grid(cp.T / kThreads, cp.rounds);
   const bool fast = sg > 0.0f && ss > 0.0f && st > 0.0f && p > 0.0f && !stripe;
-  if (fast && cp.patch != nullptr) corrupt_kernel<true, true><<<grid, kThreads, 0, s>>>(cp);
-  else if (fast) corrupt_kernel<true, false><<<grid, kThreads, 0, s>>>(cp);
-  else corrupt_kernel<false, false><<<grid, kThreads, 0, s>>>(cp);
+  if (fast && cp.patch != nullptr) MSD_CHECK_CUDA(msd_launch_pdl((corrupt_kernel<true, true>), dim3(grid), dim3(kThreads), 0, s, cp));
+  else if (fast) MSD_CHECK_CUDA(msd_launch_pdl((corrupt_kernel<true, false>), dim3(grid), dim3(kThreads), 0, s, cp));
+  else MSD_CHECK_CUDA(msd_launch_pdl((corrupt_kernel<false, false>), dim3(grid), dim3(kThreads), 0, s, cp));
   MSD_LAUNCH_CHECK();
   return MSD_OK;
 }

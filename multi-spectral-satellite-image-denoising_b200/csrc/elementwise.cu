@@ -11,6 +11,7 @@ namespace {
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ a, int B,
                                                        int C, int S, int P, int G) {
+  msd_pdl_enter();
   const int K = C * P * P;
   const int vec_per_row = K / 8;
   const size_t total = (size_t)B * G * G * vec_per_row;
@@ -41,6 +42,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(float* __restrict__ x, c
                                                         const float* __restrict__ bta, float eps,
                                                         __nv_bfloat16* __restrict__ out, const float* __restrict__ pos,
                                                         int period, int M, float2* __restrict__ stats = nullptr, int parts = 0) {
+  msd_pdl_enter();
   constexpr int D = kChunks * 128;
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -105,7 +107,7 @@ int launch_layernorm(float* x, const float* g, const float* b, float eps, __nv_b
   const unsigned blocks = (unsigned)((M + 7) / 8);
   switch (D / 128) {
 #define MSD_LN_CASE(n) \
-    case n: layernorm_kernel<n, kMode><<<blocks, 256, 0, s>>>(x, g, b, eps, out, pos, period, M, stats, parts); break;
+    case n: MSD_CHECK_CUDA(msd_launch_pdl((layernorm_kernel<n, kMode>), dim3(blocks), dim3(256), 0, s, x, g, b, eps, out, pos, period, M, stats, parts)); break;
     MSD_LN_CASE(1) MSD_LN_CASE(2) MSD_LN_CASE(3) MSD_LN_CASE(4) MSD_LN_CASE(5) MSD_LN_CASE(6) MSD_LN_CASE(7) MSD_LN_CASE(8)
 #undef MSD_LN_CASE
   }
@@ -121,6 +123,7 @@ template <int CIN, int COUT>   // compile-time upper bounds of Cin (multiple of 
 __global__ void __launch_bounds__(256) head1x1_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
                                                       const float* __restrict__ bias, float* __restrict__ y, int B, int H,
                                                       int W, int Cin, int Cout) {
+  msd_pdl_enter();
   // Two pixels per thread: every broadcast 128-bit weight load feeds 8 FMAs.  With one pixel per thread the kernel was bound
   // by the shared-memory return path (an LDS.128 occupies it for 4 cycles, the same as the 4 FMAs it fed), not by HBM or FMA.
   constexpr int PPT = 2;
@@ -207,7 +210,7 @@ extern "C" int msd_patchify_bf16(const float* d_x, void* d_a, int B, int C, int 
   const int G = S / P;
   const size_t total = (size_t)B * G * G * (C * P * P / 8);
   const unsigned blocks = (unsigned)((total + 255) / 256 < 148u * 16u ? (total + 255) / 256 : 148u * 16u);
-  patchify_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_x, reinterpret_cast<__nv_bfloat16*>(d_a), B, C, S, P, G);
+  MSD_CHECK_CUDA(msd_launch_pdl((patchify_kernel), dim3(blocks), dim3(256), 0, (cudaStream_t)stream, d_x, reinterpret_cast<__nv_bfloat16*>(d_a), B, C, S, P, G));
   MSD_LAUNCH_CHECK();
   return MSD_OK;
 }
@@ -240,9 +243,9 @@ extern "C" int msd_head1x1_nchw_f32(const void* d_x, const float* d_w, const flo
   MSD_REQUIRE(npix < (1ull << 30), "head1x1: too many pixels");
   const unsigned blocks = (unsigned)((npix + 511) / 512 < 148u * 8u ? (npix + 511) / 512 : 148u * 8u);
   if (Cin == 48 && Cout == 13)
-    head1x1_kernel<48, 13><<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(d_x), d_w, d_b, d_y, B, H, W, Cin, Cout);
+    MSD_CHECK_CUDA(msd_launch_pdl((head1x1_kernel<48, 13>), dim3(blocks), dim3(256), 0, (cudaStream_t)stream, reinterpret_cast<const __nv_bfloat16*>(d_x), d_w, d_b, d_y, B, H, W, Cin, Cout));
   else
-    head1x1_kernel<64, 16><<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(d_x), d_w, d_b, d_y, B, H, W, Cin, Cout);
+    MSD_CHECK_CUDA(msd_launch_pdl((head1x1_kernel<64, 16>), dim3(blocks), dim3(256), 0, (cudaStream_t)stream, reinterpret_cast<const __nv_bfloat16*>(d_x), d_w, d_b, d_y, B, H, W, Cin, Cout));
   MSD_LAUNCH_CHECK();
   return MSD_OK;
 }

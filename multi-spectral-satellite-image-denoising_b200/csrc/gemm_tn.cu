@@ -83,6 +83,7 @@ struct TnCfg {
 template <int MODE, int NB, int NCOLS = 64 * NB>
 __global__ void __launch_bounds__(kThreadsTn, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TnProblem p) {
+  msd_pdl_enter();
   using C = TnCfg<MODE, NB, NCOLS>;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
@@ -250,7 +251,7 @@ int launch_tn(TnProblem& p, cudaStream_t s) {
   }
   p.kb_per_split = (p.num_kb + splitk - 1) / splitk;
   p.splitk = (p.num_kb + p.kb_per_split - 1) / p.kb_per_split;
-  gemm_tn_kernel<MODE, NB, NCOLS><<<tiles * p.splitk, kThreadsTn, C::SMEM_BYTES, s>>>(tmA, tmB, p);
+  MSD_CHECK_CUDA(msd_launch_pdl((gemm_tn_kernel<MODE, NB, NCOLS>), dim3(tiles * p.splitk), dim3(kThreadsTn), C::SMEM_BYTES, s, tmA, tmB, p));
   MSD_LAUNCH_CHECK();
   return MSD_OK;
 }

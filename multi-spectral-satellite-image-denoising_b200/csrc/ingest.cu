@@ -15,6 +15,7 @@ namespace {
 constexpr int kBlock = 256;
 
 __global__ void __launch_bounds__(kBlock) image_max_u16_kernel(const uint16_t* __restrict__ dn, float* __restrict__ scale, long long per_image) {
+  msd_pdl_enter();
   __shared__ unsigned smax[kBlock / 32];
   const uint16_t* src = dn + (long long)blockIdx.x * per_image;
   unsigned m = 0;
@@ -43,6 +44,7 @@ __device__ __forceinline__ void src_index(int dst, float scale, int in_size, int
 __global__ void __launch_bounds__(kBlock) ingest_kernel(const uint16_t* __restrict__ dn, const float* __restrict__ scale,
                                                         float* __restrict__ out, int planes_per_image, int h, int w, int S,
                                                         float sh, float sw, long long total) {
+  msd_pdl_enter();
   for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < total; i += (long long)gridDim.x * kBlock) {
     const int x = (int)(i % S);
     const long long t = i / S;
@@ -72,6 +74,7 @@ __global__ void __launch_bounds__(kBlock) ingest_kernel(const uint16_t* __restri
 __global__ void __launch_bounds__(kBlock) ingest_plane_kernel(const uint16_t* __restrict__ dn, const float* __restrict__ scale,
                                                               float* __restrict__ out, int planes_per_image, int h, int w, int S,
                                                               float sh, float sw) {
+  msd_pdl_enter();
   extern __shared__ float tile[];                       // [h][w], already divided by the image's scale
   const int plane = blockIdx.x;
   const float div = __ldg(scale + plane / planes_per_image);
@@ -107,6 +110,7 @@ __global__ void __launch_bounds__(kBlock) ingest_plane_kernel(const uint16_t* __
 __global__ void __launch_bounds__(kBlock) tile_extract_kernel(const float* __restrict__ scene, const int* __restrict__ ty0,
                                                               const int* __restrict__ tx0, float* __restrict__ tiles, int C, int H,
                                                               int W, int S, long long total4) {
+  msd_pdl_enter();
   const int s4 = S / 4;
   for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < total4; i += (long long)gridDim.x * kBlock) {
     const int xv = (int)(i % s4);
@@ -135,6 +139,7 @@ __global__ void __launch_bounds__(kBlock) tile_blend_kernel(const float* __restr
                                                             const int* __restrict__ gx, const int* __restrict__ tile_index, int ny, int nx,
                                                             float* __restrict__ out, int C, int H, int W, int S, int ramp, int row0,
                                                             int row1, long long total) {
+  msd_pdl_enter();
   for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < total; i += (long long)gridDim.x * kBlock) {
     const int X = (int)(i % W);
     long long t = i / W;
@@ -172,6 +177,7 @@ __global__ void __launch_bounds__(kBlock) tile_blend_kernel(const float* __restr
 
 // inverse of the ingest normalisation: restored fp32 in [-2, 2] -> Sentinel-2 digital numbers (reflectance x 10000, uint16)
 __global__ void __launch_bounds__(kBlock) export_kernel(const float* __restrict__ x, uint16_t* __restrict__ dn, long long n4) {
+  msd_pdl_enter();
   for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < n4; i += (long long)gridDim.x * kBlock) {
     const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
     auto q = [](float t) -> uint32_t {
@@ -192,15 +198,15 @@ unsigned grid_for(long long items) {
 extern "C" int msd_ingest_u16_f32(const uint16_t* d_dn, float* d_out, float* d_scale_ws, int B, int C, int h, int w, int S, void* stream) {
   MSD_REQUIRE(d_dn && d_out && d_scale_ws && B > 0 && C > 0 && h > 0 && w > 0 && S > 0, "ingest: bad arguments");
   cudaStream_t s = (cudaStream_t)stream;
-  image_max_u16_kernel<<<(unsigned)B, kBlock, 0, s>>>(d_dn, d_scale_ws, (long long)C * h * w);
+  MSD_CHECK_CUDA(msd_launch_pdl((image_max_u16_kernel), dim3((unsigned)B), dim3(kBlock), 0, s, d_dn, d_scale_ws, (long long)C * h * w));
   MSD_LAUNCH_CHECK();
   const long long total = (long long)B * C * S * S;
   const size_t plane_smem = (size_t)h * w * sizeof(float);
   if (S % 4 == 0 && S / 4 <= kBlock && plane_smem <= 48 * 1024 && msd_aligned16(d_out) && (long long)B * C < (1ll << 31)) {
     const dim3 block((unsigned)(S / 4), (unsigned)(kBlock / (S / 4) > 0 ? kBlock / (S / 4) : 1));
-    ingest_plane_kernel<<<(unsigned)(B * C), block, plane_smem, s>>>(d_dn, d_scale_ws, d_out, C, h, w, S, (float)h / (float)S, (float)w / (float)S);
+    MSD_CHECK_CUDA(msd_launch_pdl((ingest_plane_kernel), dim3((unsigned)(B * C)), dim3(block), plane_smem, s, d_dn, d_scale_ws, d_out, C, h, w, S, (float)h / (float)S, (float)w / (float)S));
   } else {
-    ingest_kernel<<<grid_for(total), kBlock, 0, s>>>(d_dn, d_scale_ws, d_out, C, h, w, S, (float)h / (float)S, (float)w / (float)S, total);
+    MSD_CHECK_CUDA(msd_launch_pdl((ingest_kernel), dim3(grid_for(total)), dim3(kBlock), 0, s, d_dn, d_scale_ws, d_out, C, h, w, S, (float)h / (float)S, (float)w / (float)S, total));
   }
   MSD_LAUNCH_CHECK();
   return MSD_OK;
@@ -210,7 +216,7 @@ extern "C" int msd_tile_extract_f32(const float* d_scene, const int* d_ty0, cons
                                     int W, int S, void* stream) {
   MSD_REQUIRE(d_scene && d_ty0 && d_tx0 && d_tiles && n_tiles > 0 && S % 4 == 0 && H >= S && W >= S, "tile_extract: bad arguments");
   const long long total4 = (long long)n_tiles * C * S * (S / 4);
-  tile_extract_kernel<<<grid_for(total4), kBlock, 0, (cudaStream_t)stream>>>(d_scene, d_ty0, d_tx0, d_tiles, C, H, W, S, total4);
+  MSD_CHECK_CUDA(msd_launch_pdl((tile_extract_kernel), dim3(grid_for(total4)), dim3(kBlock), 0, (cudaStream_t)stream, d_scene, d_ty0, d_tx0, d_tiles, C, H, W, S, total4));
   MSD_LAUNCH_CHECK();
   return MSD_OK;
 }
@@ -220,8 +226,8 @@ extern "C" int msd_tile_blend_f32(const float* d_restored, const int* d_gy, cons
   MSD_REQUIRE(d_restored && d_gy && d_gx && d_tile_index && d_out, "tile_blend: null pointer");
   MSD_REQUIRE(ny > 0 && nx > 0 && ramp >= 1 && 0 <= row0 && row0 < row1 && row1 <= H, "tile_blend: bad grid / rows");
   const long long total = (long long)C * (row1 - row0) * W;
-  tile_blend_kernel<<<grid_for(total), kBlock, 0, (cudaStream_t)stream>>>(d_restored, d_gy, d_gx, d_tile_index, ny, nx, d_out, C, H, W, S,
-                                                                         ramp, row0, row1, total);
+  MSD_CHECK_CUDA(msd_launch_pdl((tile_blend_kernel), dim3(grid_for(total)), dim3(kBlock), 0, (cudaStream_t)stream, d_restored, d_gy, d_gx, d_tile_index, ny, nx, d_out, C, H, W, S,
+                                                                         ramp, row0, row1, total));
   MSD_LAUNCH_CHECK();
   return MSD_OK;
 }
@@ -229,7 +235,7 @@ extern "C" int msd_tile_blend_f32(const float* d_restored, const int* d_gy, cons
 extern "C" int msd_export_u16(const float* d_x, uint16_t* d_dn, long long numel, void* stream) {
   MSD_REQUIRE(d_x && d_dn && numel > 0 && numel % 4 == 0, "export: bad arguments");
   MSD_REQUIRE(msd_aligned16(d_x) && (reinterpret_cast<uintptr_t>(d_dn) & 7u) == 0, "export: pointers must be 16- / 8-byte aligned");
-  export_kernel<<<grid_for(numel / 4), kBlock, 0, (cudaStream_t)stream>>>(d_x, d_dn, numel / 4);
+  MSD_CHECK_CUDA(msd_launch_pdl((export_kernel), dim3(grid_for(numel / 4)), dim3(kBlock), 0, (cudaStream_t)stream, d_x, d_dn, numel / 4));
   MSD_LAUNCH_CHECK();
   return MSD_OK;
 }

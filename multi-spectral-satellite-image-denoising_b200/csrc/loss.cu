@@ -48,6 +48,7 @@ __global__ void __launch_bounds__(kThreads, 2)
 loss_fwd_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmT, const float* __restrict__ pred,
                 const float* __restrict__ target, int H, int W, int tiles_x, int tiles_y,
                 SsimConsts consts, size_t numel, float* __restrict__ deriv /*[3][numel]*/, double* __restrict__ acc /*[2]*/) {
+  msd_pdl_enter();
   extern __shared__ __align__(128) unsigned char smem_raw[];
   FwdSmem& sm = *reinterpret_cast<FwdSmem*>(smem_raw);
   constexpr int XO = kTma ? kXoff : 0;
@@ -130,6 +131,7 @@ loss_bwd_kernel(const __grid_constant__ CUtensorMap tmD /* deriv as [3 * planes,
                 const float* __restrict__ target, const float* __restrict__ deriv, int H,
                 int W, int tiles_x, int tiles_y, size_t numel, float k_ssim /* -w_ssim*scale/N */,
                 float k_mse /* 2*w_mse*scale/N */, float* __restrict__ grad) {
+  msd_pdl_enter();
   extern __shared__ __align__(128) unsigned char smem_raw[];
   BwdSmem& sm = *reinterpret_cast<BwdSmem*>(smem_raw);
   constexpr int XO = kTma ? kXoff : 0;
@@ -181,6 +183,7 @@ loss_bwd_kernel(const __grid_constant__ CUtensorMap tmD /* deriv as [3 * planes,
 }
 
 __global__ void loss_finalize_kernel(const double* __restrict__ acc, double n, float w_mse, float w_ssim, float* out) {
+  msd_pdl_enter();
   const float mse = (float)(acc[0] / n);
   const float ssim_loss = 1.0f - (float)(acc[1] / n);
   out[0] = w_mse * mse + w_ssim * ssim_loss;
@@ -238,18 +241,18 @@ extern "C" int msd_loss_fwd_bwd_f32(const float* d_pred, const float* d_target, 
           gemm::tc5::make_map_planes_f32(&tmTc, d_target, (uint64_t)W, (uint64_t)H, (uint64_t)planes, TW, TH) == MSD_OK;
   if (!tma) { memset(&tmP, 0, sizeof(tmP)); tmT = tmP; tmD = tmP; }
   if (!tma || !d_grad_pred) { tmD = tmP; tmPc = tmP; tmTc = tmP; }
-#define MSD_LOSS_FWD(WD, TM) loss_fwd_kernel<WD, TM><<<blocks, kThreads, sizeof(FwdSmem), s>>>(tmP, tmT, d_pred, d_target, H, W, tiles_x, tiles_y, consts, numel, d_grad_pred ? deriv : nullptr, acc)
+#define MSD_LOSS_FWD(WD, TM) MSD_CHECK_CUDA(msd_launch_pdl((loss_fwd_kernel<WD, TM>), dim3(blocks), dim3(kThreads), sizeof(FwdSmem), s, tmP, tmT, d_pred, d_target, H, W, tiles_x, tiles_y, consts, numel, d_grad_pred ? deriv : nullptr, acc))
   if (d_grad_pred) { if (tma) MSD_LOSS_FWD(true, true); else MSD_LOSS_FWD(true, false); }
   else { if (tma) MSD_LOSS_FWD(false, true); else MSD_LOSS_FWD(false, false); }
 #undef MSD_LOSS_FWD
   MSD_LAUNCH_CHECK();
-  loss_finalize_kernel<<<1, 1, 0, s>>>(acc, (double)numel, w_mse, w_ssim, d_out);
+  MSD_CHECK_CUDA(msd_launch_pdl((loss_finalize_kernel), dim3(1), dim3(1), 0, s, acc, (double)numel, w_mse, w_ssim, d_out));
   MSD_LAUNCH_CHECK();
   if (d_grad_pred) {
     const float k_ssim = (float)(-(double)w_ssim * (double)grad_scale / (double)numel);
     const float k_mse = (float)(2.0 * (double)w_mse * (double)grad_scale / (double)numel);
-    if (tma) loss_bwd_kernel<true><<<blocks, kThreads, sizeof(BwdSmem), s>>>(tmD, tmPc, tmTc, planes, d_pred, d_target, deriv, H, W, tiles_x, tiles_y, numel, k_ssim, k_mse, d_grad_pred);
-    else loss_bwd_kernel<false><<<blocks, kThreads, sizeof(BwdSmem), s>>>(tmD, tmPc, tmTc, planes, d_pred, d_target, deriv, H, W, tiles_x, tiles_y, numel, k_ssim, k_mse, d_grad_pred);
+    if (tma) MSD_CHECK_CUDA(msd_launch_pdl((loss_bwd_kernel<true>), dim3(blocks), dim3(kThreads), sizeof(BwdSmem), s, tmD, tmPc, tmTc, planes, d_pred, d_target, deriv, H, W, tiles_x, tiles_y, numel, k_ssim, k_mse, d_grad_pred));
+    else MSD_CHECK_CUDA(msd_launch_pdl((loss_bwd_kernel<false>), dim3(blocks), dim3(kThreads), sizeof(BwdSmem), s, tmD, tmPc, tmTc, planes, d_pred, d_target, deriv, H, W, tiles_x, tiles_y, numel, k_ssim, k_mse, d_grad_pred));
     MSD_LAUNCH_CHECK();
   }
   return MSD_OK;

@@ -27,6 +27,7 @@ struct SsimSmem {
 __global__ void __launch_bounds__(kThreads, 2)
 ssim_mse_kernel(const float* __restrict__ pred, const float* __restrict__ target, int C, int H, int W, int tiles_x,
                 int tiles_y, SsimConsts consts, double* __restrict__ acc /*[B][4]*/) {
+  msd_pdl_enter();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SsimSmem& sm = *reinterpret_cast<SsimSmem*>(smem_raw);
   const int tile = blockIdx.x % (tiles_x * tiles_y);
@@ -95,6 +96,7 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap* tm, uint64_t* bar
 __global__ void __launch_bounds__(kThreads, 2)
 metrics_fused_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmT, int C, int H, int W,
                      int tiles_x, int tiles_y, SsimConsts consts, float eps, double* __restrict__ acc /*[B][4]*/) {
+  msd_pdl_enter();
   using gemm::tc5::mbar_init; using gemm::tc5::mbar_wait; using gemm::tc5::mbar_arrive_expect_tx;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   FusedSmem& sm = *reinterpret_cast<FusedSmem*>(smem_raw);
@@ -193,6 +195,7 @@ metrics_fused_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_const
 __global__ void __launch_bounds__(256)
 sam_kernel(const float* __restrict__ pred, const float* __restrict__ target, int C, int HW, int chunks_per_image,
            float eps, double* __restrict__ acc) {
+  msd_pdl_enter();
   const int b = blockIdx.x / chunks_per_image;
   const int chunk = blockIdx.x - b * chunks_per_image;
   const float* p = pred + (size_t)b * C * HW;
@@ -225,6 +228,7 @@ sam_kernel(const float* __restrict__ pred, const float* __restrict__ target, int
 // per-image metrics + the tracker's running sums (metrics.py:39-46, 121, 170, 189-191, 252-258)
 __global__ void metrics_finalize_kernel(const double* __restrict__ acc, int B, int C, int HW, double data_range,
                                         double* __restrict__ per_image, double* __restrict__ sums) {
+  msd_pdl_enter();
   __shared__ double sh[4][32];
   double loc[4] = {0, 0, 0, 0};
   for (int b = threadIdx.x; b < B; b += blockDim.x) {
@@ -276,8 +280,8 @@ extern "C" int msd_metrics_f32(const float* d_pred, const float* d_target, int B
     if (fused_attr_set.first()) {
       MSD_CHECK_CUDA(cudaFuncSetAttribute(metrics_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem)));
     }
-    metrics_fused_kernel<<<(unsigned)B * tiles_x * tiles_y, kThreads, sizeof(FusedSmem), s>>>(tmP, tmT, C, H, W, tiles_x, tiles_y, consts,
-                                                                                             1e-8f, d_scratch);
+    MSD_CHECK_CUDA(msd_launch_pdl((metrics_fused_kernel), dim3((unsigned)B * tiles_x * tiles_y), dim3(kThreads), sizeof(FusedSmem), s, tmP, tmT, C, H, W, tiles_x, tiles_y, consts,
+                                                                                             1e-8f, d_scratch));
     MSD_LAUNCH_CHECK();
   } else {
     static PerDeviceOnce attr_set;
@@ -285,13 +289,13 @@ extern "C" int msd_metrics_f32(const float* d_pred, const float* d_target, int B
       MSD_CHECK_CUDA(cudaFuncSetAttribute(ssim_mse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SsimSmem)));
     }
     const unsigned blocks = (unsigned)B * C * tiles_x * tiles_y;
-    ssim_mse_kernel<<<blocks, kThreads, sizeof(SsimSmem), s>>>(d_pred, d_target, C, H, W, tiles_x, tiles_y, consts, d_scratch);
+    MSD_CHECK_CUDA(msd_launch_pdl((ssim_mse_kernel), dim3(blocks), dim3(kThreads), sizeof(SsimSmem), s, d_pred, d_target, C, H, W, tiles_x, tiles_y, consts, d_scratch));
     MSD_LAUNCH_CHECK();
     const int chunks = (HW + 1023) / 1024;
-    sam_kernel<<<(unsigned)B * chunks, 256, 0, s>>>(d_pred, d_target, C, HW, chunks, 1e-8f, d_scratch);
+    MSD_CHECK_CUDA(msd_launch_pdl((sam_kernel), dim3((unsigned)B * chunks), dim3(256), 0, s, d_pred, d_target, C, HW, chunks, 1e-8f, d_scratch));
     MSD_LAUNCH_CHECK();
   }
-  metrics_finalize_kernel<<<1, 256, 0, s>>>(d_scratch, B, C, HW, (double)data_range, d_per_image, d_sums);
+  MSD_CHECK_CUDA(msd_launch_pdl((metrics_finalize_kernel), dim3(1), dim3(256), 0, s, d_scratch, B, C, HW, (double)data_range, d_per_image, d_sums));
   MSD_LAUNCH_CHECK();
   return MSD_OK;
 }

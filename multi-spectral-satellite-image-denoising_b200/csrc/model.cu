@@ -110,6 +110,7 @@ int make_convt(Problem& p, const void* x, const void* w, const float* bias, void
 
 // zero the 1-pixel halo of a [B, H+2, W+2, C] bf16 buffer (the ConvTranspose scatter only writes the interior)
 __global__ void __launch_bounds__(256) zero_halo_kernel(__nv_bfloat16* __restrict__ buf, int B, int H, int W, int C) {
+  msd_pdl_enter();
   const int per_img = 2 * (W + 2) + 2 * H;  // halo pixels per image
   const int vec = C / 8;
   const size_t total = (size_t)B * per_img * vec;
@@ -129,7 +130,7 @@ __global__ void __launch_bounds__(256) zero_halo_kernel(__nv_bfloat16* __restric
 int zero_halo(void* buf, int B, int H, int W, int C, cudaStream_t s) {
   const size_t total = (size_t)B * (2 * (W + 2) + 2 * H) * (C / 8);
   const unsigned blocks = (unsigned)((total + 255) / 256 < 148u * 8u ? (total + 255) / 256 : 148u * 8u);
-  zero_halo_kernel<<<blocks, 256, 0, s>>>(reinterpret_cast<__nv_bfloat16*>(buf), B, H, W, C);
+  MSD_CHECK_CUDA(msd_launch_pdl((zero_halo_kernel), dim3(blocks), dim3(256), 0, s, reinterpret_cast<__nv_bfloat16*>(buf), B, H, W, C));
   MSD_LAUNCH_CHECK();
   return MSD_OK;
 }

@@ -24,6 +24,7 @@ struct TensorTable {
 };
 
 __global__ void __launch_bounds__(kBlock) sqnorm_kernel(const TensorTable t, double* __restrict__ out) {
+  msd_pdl_enter();
   float acc = 0.f;
   const long long tid = (long long)blockIdx.x * kBlock + threadIdx.x, stride = (long long)gridDim.x * kBlock;
   for (int k = 0; k < t.count; ++k) {
@@ -62,6 +63,7 @@ __device__ __forceinline__ void adamw_one(float& p, float g, float& m, float& v,
 
 __global__ void __launch_bounds__(kBlock) adamw_kernel(const TensorTable t, float b1, float b2, float eps, float max_norm,
                                                        const double* __restrict__ sqnorm) {
+  msd_pdl_enter();
   float clip = 1.0f;
   if (max_norm > 0.0f && sqnorm != nullptr) {
     const double sq = *sqnorm;
@@ -149,6 +151,7 @@ __device__ __forceinline__ float repack_value(const float* __restrict__ src, int
 }
 
 __global__ void __launch_bounds__(kBlock) repack_kernel(const RepackTable t) {
+  msd_pdl_enter();
   const long long tid = (long long)blockIdx.x * kBlock + threadIdx.x, stride = (long long)gridDim.x * kBlock;
   for (int k = 0; k < t.count; ++k) {
     const float* src = t.src[k];
@@ -191,7 +194,7 @@ extern "C" int msd_repack_weights(const msd_repack_op* ops, int n, void* stream)
       t.flag[k] = o.kind == MSD_REPACK_CAST ? 0 : o.flag;
       if (o.kind == MSD_REPACK_CAST) { t.d0[k] = 1; }
     }
-    repack_kernel<<<148 * 8, kBlock, 0, (cudaStream_t)stream>>>(t);
+    MSD_CHECK_CUDA(msd_launch_pdl((repack_kernel), dim3(148 * 8), dim3(kBlock), 0, (cudaStream_t)stream, t));
     MSD_LAUNCH_CHECK();
   }
   return MSD_OK;
@@ -205,7 +208,7 @@ extern "C" int msd_grad_sqnorm_f32(const msd_adamw_tensor* tensors, int n, doubl
     TensorTable t;
     int rc = fill(t, tensors + k0, n - k0 < kMaxT ? n - k0 : kMaxT);
     if (rc) return rc;
-    sqnorm_kernel<<<148 * 4, kBlock, 0, s>>>(t, d_sqnorm);
+    MSD_CHECK_CUDA(msd_launch_pdl((sqnorm_kernel), dim3(148 * 4), dim3(kBlock), 0, s, t, d_sqnorm));
     MSD_LAUNCH_CHECK();
   }
   return MSD_OK;
@@ -219,7 +222,7 @@ extern "C" int msd_adamw_step_f32(const msd_adamw_tensor* tensors, int n, float 
     TensorTable t;
     int rc = fill(t, tensors + k0, n - k0 < kMaxT ? n - k0 : kMaxT, beta1, beta2, step);
     if (rc) return rc;
-    adamw_kernel<<<148 * 8, kBlock, 0, (cudaStream_t)stream>>>(t, beta1, beta2, eps, max_grad_norm, d_sqnorm);
+    MSD_CHECK_CUDA(msd_launch_pdl((adamw_kernel), dim3(148 * 8), dim3(kBlock), 0, (cudaStream_t)stream, t, beta1, beta2, eps, max_grad_norm, d_sqnorm));
     MSD_LAUNCH_CHECK();
   }
   return MSD_OK;

@@ -29,6 +29,7 @@ template <int MODE>   // 0: sum a | 1: sum a, sum a^2 | 2: sum a, sum a*xhat(b)
 __global__ void __launch_bounds__(kBlock) colsum_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
                                                         const float* __restrict__ stats /* [4][C]: .., .., mean, rstd */,
                                                         double* __restrict__ sums /* [2][C] */, long long rows, int C, int ld) {
+  msd_pdl_enter();
   extern __shared__ float sh[];   // [2][kBlock][8]
   const int vpr = C >> 3;
   const int rpi = kBlock / vpr;
@@ -90,6 +91,7 @@ __global__ void __launch_bounds__(kBlock) colsum_kernel(const __nv_bfloat16* __r
 __global__ void bn_finalize_kernel(const double* __restrict__ sums, double count, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, float eps, float momentum, float* __restrict__ running_mean,
                                    float* __restrict__ running_var, float* __restrict__ stats, int C) {
+  msd_pdl_enter();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const double mean = sums[c] / count;
@@ -112,6 +114,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, double count
 __global__ void __launch_bounds__(kBlock) bn_act_fwd_kernel(const __nv_bfloat16* __restrict__ c, const __nv_bfloat16* __restrict__ skip,
                                                             const float* __restrict__ stats, __nv_bfloat16* __restrict__ y,
                                                             long long rows, int C, FastDiv plane, FastDiv pitch, int H, int W) {
+  msd_pdl_enter();
   const int vpr = C >> 3;
   const int rpi = kBlock / vpr;
   const int v = threadIdx.x % vpr, r0 = threadIdx.x / vpr;
@@ -167,6 +170,7 @@ __global__ void __launch_bounds__(kBlock, 3) bn_act_bwd1_kernel(const __nv_bfloa
                                                                 const __nv_bfloat16* __restrict__ skip, const float* __restrict__ stats,
                                                                 __nv_bfloat16* __restrict__ dz, double* __restrict__ sums, uint32_t total,
                                                                 int C) {
+  msd_pdl_enter();
   extern __shared__ float sh[];
   const int vpr = C >> 3;
   const int rpi = kBlock / vpr;
@@ -231,6 +235,7 @@ __global__ void __launch_bounds__(kBlock, 3) bn_act_bwd1_kernel(const __nv_bfloa
 // dgamma = sum dz*xhat, dbeta = sum dz, coefficients k1 = sum dz / N, k2 = sum dz*xhat / N
 __global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums, const float* __restrict__ stats, double count,
                                        float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ coef, int C) {
+  msd_pdl_enter();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const double sdz = sums[c];
@@ -246,6 +251,7 @@ __global__ void __launch_bounds__(kBlock) bn_act_bwd2_kernel(const __nv_bfloat16
                                                              const float* __restrict__ stats, const float* __restrict__ coef,
                                                              __nv_bfloat16* __restrict__ dc, long long rows, int C, FastDiv plane,
                                                              FastDiv pitch, int H, int W) {
+  msd_pdl_enter();
   const int vpr = C >> 3;
   const int rpi = kBlock / vpr;
   const int v = threadIdx.x % vpr, r0 = threadIdx.x / vpr;
@@ -274,6 +280,7 @@ __global__ void __launch_bounds__(kBlock) bn_act_bwd2_kernel(const __nv_bfloat16
 
 // fp64 [n] -> fp32 [n] (bias gradients out of the column-sum accumulators)
 __global__ void f64_to_f32_kernel(const double* __restrict__ in, float* __restrict__ out, int n) {
+  msd_pdl_enter();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = (float)in[i];
 }
@@ -281,6 +288,7 @@ __global__ void f64_to_f32_kernel(const double* __restrict__ in, float* __restri
 // dh_pre = dh * gelu'(h_pre), bf16 elementwise (in place allowed)
 __global__ void __launch_bounds__(kBlock) gelu_bwd_kernel(const __nv_bfloat16* __restrict__ dh, const __nv_bfloat16* __restrict__ hpre,
                                                           __nv_bfloat16* __restrict__ out, long long nvec) {
+  msd_pdl_enter();
   for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < nvec; i += (long long)gridDim.x * kBlock) {
     float g[8], z[8];
     unpack8(__ldg(reinterpret_cast<const uint4*>(dh) + i), g);
@@ -301,6 +309,7 @@ __global__ void __launch_bounds__(kBlock) gelu_bwd_kernel(const __nv_bfloat16* _
 // per column (= gridDim.x), not their total, is what must stay small.
 __global__ void __launch_bounds__(kBlock) gelu_bwd_colsum_kernel(const __nv_bfloat16* __restrict__ dh, const __nv_bfloat16* __restrict__ hpre,
                                                                  __nv_bfloat16* __restrict__ out, float* __restrict__ colsum, int rows, int vpr) {
+  msd_pdl_enter();
   __shared__ float red[kBlock / 32][256];
   const int cv = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int v = blockIdx.y * 32 + cv;
@@ -334,6 +343,7 @@ __global__ void __launch_bounds__(kBlock) gelu_bwd_colsum_kernel(const __nv_bflo
 
 // h = GELU(h_pre), bf16 elementwise (the training forward keeps both: h_pre for the backward, h as the fc2 operand)
 __global__ void __launch_bounds__(kBlock) gelu_fwd_kernel(const __nv_bfloat16* __restrict__ hpre, __nv_bfloat16* __restrict__ out, long long nvec) {
+  msd_pdl_enter();
   for (long long i = (long long)blockIdx.x * kBlock + threadIdx.x; i < nvec; i += (long long)gridDim.x * kBlock) {
     float z[8];
     unpack8(__ldg(reinterpret_cast<const uint4*>(hpre) + i), z);
@@ -369,6 +379,7 @@ __global__ void __launch_bounds__(kLnThreads, 1) ln_bwd_kernel(const void* __res
                                                                int accumulate, __nv_bfloat16* __restrict__ g_bf16,
                                                                float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                                float* __restrict__ colsum, int M) {
+  msd_pdl_enter();
   constexpr int NV = kLnNV, D = kLnD, PAIRS = kLnThreads / 64;
   __shared__ float s_red[kLnThreads / 32][kLnHalf];
   __shared__ float s_x[PAIRS][4][2];                 // per pair: {sum x, sum (x-mean)^2, m1, m2} x {half 0, half 1}
@@ -473,6 +484,7 @@ __global__ void __launch_bounds__(kLnThreads, 1) ln_bwd_kernel(const void* __res
 __global__ void __launch_bounds__(kBlock) unshuffle_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dys,
                                                            long long rows, int C, FastDiv in_plane, FastDiv in_pitch, int in_pad,
                                                            int Hin, int Win) {
+  msd_pdl_enter();
   const int vpr = C >> 3;
   const long long total = rows * 4 * vpr;
   const int out_pitch = 2 * Win + 2;
@@ -502,6 +514,7 @@ template <int CIN>
 __global__ void __launch_bounds__(kBlock) head1x1_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ w,
                                                              __nv_bfloat16* __restrict__ dh, __nv_bfloat16* __restrict__ dyt, int B,
                                                              int H, int W, int Cin, int Cout) {
+  msd_pdl_enter();
   __shared__ __align__(16) float sw[16 * CIN];
   for (int i = threadIdx.x; i < 16 * CIN; i += kBlock) sw[i] = (i / CIN < Cout && i % CIN < Cin) ? w[(i / CIN) * Cin + i % CIN] : 0.f;
   __syncthreads();
@@ -538,6 +551,7 @@ __global__ void __launch_bounds__(kBlock) head1x1_bwd_kernel(const float* __rest
 
 // out[i] = sum_b in[b * n + i]   (positional-embedding gradient: sum over the batch)
 __global__ void __launch_bounds__(kBlock) batch_sum_kernel(const float* __restrict__ in, float* __restrict__ out, int B, long long n) {
+  msd_pdl_enter();
   for (long long i = ((long long)blockIdx.x * kBlock + threadIdx.x) * 4; i < n; i += (long long)gridDim.x * kBlock * 4) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int b = 0; b < B; ++b) {
@@ -563,8 +577,8 @@ extern "C" int msd_colsum_bf16(const void* d_a, long long rows, int C, double* d
   for (int c0 = 0; c0 < C; c0 += 2048) {      // 256 threads x 8 channels per pass over the rows
     const int cc = C - c0 < 2048 ? C - c0 : 2048;
     const int rpi = kBlock / (cc / 8);
-    colsum_kernel<0><<<grid_for((rows + rpi - 1) / rpi * kBlock, 4), kBlock, 2 * kBlock * 8 * sizeof(float), (cudaStream_t)stream>>>(
-        reinterpret_cast<const __nv_bfloat16*>(d_a) + c0, nullptr, nullptr, d_sums + c0, rows, cc, C);
+    MSD_CHECK_CUDA(msd_launch_pdl((colsum_kernel<0>), dim3(grid_for((rows + rpi - 1) / rpi * kBlock, 4)), dim3(kBlock), 2 * kBlock * 8 * sizeof(float), (cudaStream_t)stream, 
+        reinterpret_cast<const __nv_bfloat16*>(d_a) + c0, nullptr, nullptr, d_sums + c0, rows, cc, C));
     MSD_LAUNCH_CHECK();
   }
   return MSD_OK;
@@ -572,7 +586,7 @@ extern "C" int msd_colsum_bf16(const void* d_a, long long rows, int C, double* d
 
 extern "C" int msd_f64_to_f32(const double* d_in, float* d_out, int n, void* stream) {
   MSD_REQUIRE(d_in && d_out && n > 0, "f64_to_f32: bad arguments");
-  f64_to_f32_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_in, d_out, n);
+  MSD_CHECK_CUDA(msd_launch_pdl((f64_to_f32_kernel), dim3((n + 255) / 256), dim3(256), 0, (cudaStream_t)stream, d_in, d_out, n));
   MSD_LAUNCH_CHECK();
   return MSD_OK;
 }
@@ -588,8 +602,8 @@ extern "C" int msd_bn_sums_bf16(const void* d_c, long long rows, int C, double* 
   cudaStream_t s = (cudaStream_t)stream;
   MSD_CHECK_CUDA(cudaMemsetAsync(d_sums, 0, sizeof(double) * 2 * C, s));
   const int rpi = kBlock / (C / 8);
-  colsum_kernel<1><<<grid_for((rows + rpi - 1) / rpi * kBlock, 4), kBlock, 2 * kBlock * 8 * sizeof(float), s>>>(
-      reinterpret_cast<const __nv_bfloat16*>(d_c), nullptr, nullptr, d_sums, rows, C, C);
+  MSD_CHECK_CUDA(msd_launch_pdl((colsum_kernel<1>), dim3(grid_for((rows + rpi - 1) / rpi * kBlock, 4)), dim3(kBlock), 2 * kBlock * 8 * sizeof(float), s, 
+      reinterpret_cast<const __nv_bfloat16*>(d_c), nullptr, nullptr, d_sums, rows, C, C));
   MSD_LAUNCH_CHECK();
   return MSD_OK;
 }
@@ -597,8 +611,8 @@ extern "C" int msd_bn_sums_bf16(const void* d_c, long long rows, int C, double* 
 extern "C" int msd_bn_finalize(const double* d_sums, double count, int C, const float* d_gamma, const float* d_beta, float eps, float momentum,
                                float* d_running_mean, float* d_running_var, float* d_stats, void* stream) {
   MSD_REQUIRE(d_sums && d_gamma && d_beta && d_stats && count > 0 && C > 0, "bn_finalize: bad arguments");
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_sums, count, d_gamma, d_beta, eps, momentum, d_running_mean,
-                                                                         d_running_var, d_stats, C);
+  MSD_CHECK_CUDA(msd_launch_pdl((bn_finalize_kernel), dim3((C + 127) / 128), dim3(128), 0, (cudaStream_t)stream, d_sums, count, d_gamma, d_beta, eps, momentum, d_running_mean,
+                                                                         d_running_var, d_stats, C));
   MSD_LAUNCH_CHECK();
   return MSD_OK;
 }
@@ -617,9 +631,9 @@ extern "C" int msd_bn_act_fwd_bf16(const void* d_c, const void* d_skip, const fl
   MSD_REQUIRE(d_c && d_stats && d_y && C % 8 == 0 && C / 8 <= kBlock, "bn_act_fwd: bad arguments");
   const long long rows = (long long)B * (H + 2) * (W + 2);
   MSD_REQUIRE(rows < (1ll << 31), "bn_act_fwd: too many pixels");
-  bn_act_fwd_kernel<<<grid_for((rows + kBlock / (C / 8) - 1) / (kBlock / (C / 8)) * kBlock, 16), kBlock, 0, (cudaStream_t)stream>>>(
+  MSD_CHECK_CUDA(msd_launch_pdl((bn_act_fwd_kernel), dim3(grid_for((rows + kBlock / (C / 8) - 1) / (kBlock / (C / 8)) * kBlock, 16)), dim3(kBlock), 0, (cudaStream_t)stream, 
       reinterpret_cast<const __nv_bfloat16*>(d_c), reinterpret_cast<const __nv_bfloat16*>(d_skip), d_stats,
-      reinterpret_cast<__nv_bfloat16*>(d_y), rows, C, make_fastdiv((uint32_t)((H + 2) * (W + 2))), make_fastdiv((uint32_t)(W + 2)), H, W);
+      reinterpret_cast<__nv_bfloat16*>(d_y), rows, C, make_fastdiv((uint32_t)((H + 2) * (W + 2))), make_fastdiv((uint32_t)(W + 2)), H, W));
   MSD_LAUNCH_CHECK();
   return MSD_OK;
 }
@@ -641,35 +655,35 @@ extern "C" int msd_bn_act_bwd_bf16(const void* d_dy, const void* d_c, const void
   const unsigned grid1 = grid_for((rows + rpi - 1) / rpi * kBlock, 12);
   const size_t sh1 = 2 * kBlock * 8 * sizeof(float);
   if (d_skip != nullptr)
-    bn_act_bwd1_kernel<true><<<grid1, kBlock, sh1, s>>>(reinterpret_cast<const __nv_bfloat16*>(d_dy), reinterpret_cast<const __nv_bfloat16*>(d_c),
+    MSD_CHECK_CUDA(msd_launch_pdl((bn_act_bwd1_kernel<true>), dim3(grid1), dim3(kBlock), sh1, s, reinterpret_cast<const __nv_bfloat16*>(d_dy), reinterpret_cast<const __nv_bfloat16*>(d_c),
                                                         reinterpret_cast<const __nv_bfloat16*>(d_skip), d_stats,
-                                                        reinterpret_cast<__nv_bfloat16*>(d_dz), d_sums, (uint32_t)(rows * C), C);
+                                                        reinterpret_cast<__nv_bfloat16*>(d_dz), d_sums, (uint32_t)(rows * C), C));
   else
-    bn_act_bwd1_kernel<false><<<grid1, kBlock, sh1, s>>>(reinterpret_cast<const __nv_bfloat16*>(d_dy), reinterpret_cast<const __nv_bfloat16*>(d_c),
-                                                         nullptr, d_stats, reinterpret_cast<__nv_bfloat16*>(d_dz), d_sums, (uint32_t)(rows * C), C);
+    MSD_CHECK_CUDA(msd_launch_pdl((bn_act_bwd1_kernel<false>), dim3(grid1), dim3(kBlock), sh1, s, reinterpret_cast<const __nv_bfloat16*>(d_dy), reinterpret_cast<const __nv_bfloat16*>(d_c),
+                                                         nullptr, d_stats, reinterpret_cast<__nv_bfloat16*>(d_dz), d_sums, (uint32_t)(rows * C), C));
   MSD_LAUNCH_CHECK();
-  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(d_sums, d_stats, (double)B * H * W, d_dgamma, d_dbeta, d_coef, C);
+  MSD_CHECK_CUDA(msd_launch_pdl((bn_bwd_finalize_kernel), dim3((C + 127) / 128), dim3(128), 0, s, d_sums, d_stats, (double)B * H * W, d_dgamma, d_dbeta, d_coef, C));
   MSD_LAUNCH_CHECK();
-  bn_act_bwd2_kernel<<<grid_for((rows + rpi - 1) / rpi * kBlock, 16), kBlock, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(d_dz),
+  MSD_CHECK_CUDA(msd_launch_pdl((bn_act_bwd2_kernel), dim3(grid_for((rows + rpi - 1) / rpi * kBlock, 16)), dim3(kBlock), 0, s, reinterpret_cast<const __nv_bfloat16*>(d_dz),
                                                                  reinterpret_cast<const __nv_bfloat16*>(d_c), d_stats, d_coef,
-                                                                 reinterpret_cast<__nv_bfloat16*>(d_dc), rows, C, plane, pitch, H, W);
+                                                                 reinterpret_cast<__nv_bfloat16*>(d_dc), rows, C, plane, pitch, H, W));
   MSD_LAUNCH_CHECK();
   return MSD_OK;
 }
 
 extern "C" int msd_gelu_fwd_bf16(const void* d_hpre, void* d_out, long long n, void* stream) {
   MSD_REQUIRE(d_hpre && d_out && n > 0 && n % 8 == 0, "gelu_fwd: bad arguments");
-  gelu_fwd_kernel<<<grid_for(n / 8), kBlock, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(d_hpre),
-                                                                        reinterpret_cast<__nv_bfloat16*>(d_out), n / 8);
+  MSD_CHECK_CUDA(msd_launch_pdl((gelu_fwd_kernel), dim3(grid_for(n / 8)), dim3(kBlock), 0, (cudaStream_t)stream, reinterpret_cast<const __nv_bfloat16*>(d_hpre),
+                                                                        reinterpret_cast<__nv_bfloat16*>(d_out), n / 8));
   MSD_LAUNCH_CHECK();
   return MSD_OK;
 }
 
 extern "C" int msd_gelu_bwd_bf16(const void* d_dh, const void* d_hpre, void* d_out, long long n, void* stream) {
   MSD_REQUIRE(d_dh && d_hpre && d_out && n > 0 && n % 8 == 0, "gelu_bwd: bad arguments");
-  gelu_bwd_kernel<<<grid_for(n / 8), kBlock, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(d_dh),
+  MSD_CHECK_CUDA(msd_launch_pdl((gelu_bwd_kernel), dim3(grid_for(n / 8)), dim3(kBlock), 0, (cudaStream_t)stream, reinterpret_cast<const __nv_bfloat16*>(d_dh),
                                                                         reinterpret_cast<const __nv_bfloat16*>(d_hpre),
-                                                                        reinterpret_cast<__nv_bfloat16*>(d_out), n / 8);
+                                                                        reinterpret_cast<__nv_bfloat16*>(d_out), n / 8));
   MSD_LAUNCH_CHECK();
   return MSD_OK;
 }
@@ -681,9 +695,9 @@ extern "C" int msd_gelu_bwd_colsum_bf16(const void* d_dh, const void* d_hpre, vo
   int row_groups = (148 * 8 + stripes - 1) / stripes;                 // ~8 resident blocks per SM
   const int max_groups = (rows + kBlock / 32 - 1) / (kBlock / 32);
   if (row_groups > max_groups) row_groups = max_groups;
-  gelu_bwd_colsum_kernel<<<dim3((unsigned)row_groups, (unsigned)stripes), kBlock, 0, (cudaStream_t)stream>>>(
+  MSD_CHECK_CUDA(msd_launch_pdl((gelu_bwd_colsum_kernel), dim3(dim3((unsigned)row_groups, (unsigned)stripes)), dim3(kBlock), 0, (cudaStream_t)stream, 
       reinterpret_cast<const __nv_bfloat16*>(d_dh), reinterpret_cast<const __nv_bfloat16*>(d_hpre), reinterpret_cast<__nv_bfloat16*>(d_out),
-      d_colsum, rows, N / 8);
+      d_colsum, rows, N / 8));
   MSD_LAUNCH_CHECK();
   return MSD_OK;
 }
@@ -699,7 +713,7 @@ extern "C" int msd_layernorm_bwd_colsum(const void* d_dy, int dy_is_f32, const f
   cudaStream_t s = (cudaStream_t)stream;
   const unsigned blocks = (unsigned)((M + 7) / 8 < 148 ? (M + 7) / 8 : 148);
   __nv_bfloat16* gb = reinterpret_cast<__nv_bfloat16*>(d_g_bf16);
-#define MSD_LN_BWD(F32, CS) ln_bwd_kernel<F32, CS><<<blocks, kLnThreads, 0, s>>>(d_dy, d_x, d_gamma, eps, d_g, accumulate, gb, d_dgamma, d_dbeta, d_colsum, M)
+#define MSD_LN_BWD(F32, CS) MSD_CHECK_CUDA(msd_launch_pdl((ln_bwd_kernel<F32, CS>), dim3(blocks), dim3(kLnThreads), 0, s, d_dy, d_x, d_gamma, eps, d_g, accumulate, gb, d_dgamma, d_dbeta, d_colsum, M))
   if (d_colsum != nullptr) { if (dy_is_f32) MSD_LN_BWD(1, 1); else MSD_LN_BWD(0, 1); }
   else { if (dy_is_f32) MSD_LN_BWD(1, 0); else MSD_LN_BWD(0, 0); }
 #undef MSD_LN_BWD
@@ -717,9 +731,9 @@ extern "C" int msd_convt_unshuffle_bf16(const void* d_dy, void* d_dys, int B, in
   const int ph = in_padded ? Hin + 2 : Hin, pw = in_padded ? Win + 2 : Win;
   const long long rows = (long long)B * ph * pw;
   MSD_REQUIRE(rows < (1ll << 31), "unshuffle: too many pixels");
-  unshuffle_kernel<<<grid_for(rows * 4 * (C / 8)), kBlock, 0, (cudaStream_t)stream>>>(
+  MSD_CHECK_CUDA(msd_launch_pdl((unshuffle_kernel), dim3(grid_for(rows * 4 * (C / 8))), dim3(kBlock), 0, (cudaStream_t)stream, 
       reinterpret_cast<const __nv_bfloat16*>(d_dy), reinterpret_cast<__nv_bfloat16*>(d_dys), rows, C,
-      make_fastdiv((uint32_t)(ph * pw)), make_fastdiv((uint32_t)pw), in_padded, Hin, Win);
+      make_fastdiv((uint32_t)(ph * pw)), make_fastdiv((uint32_t)pw), in_padded, Hin, Win));
   MSD_LAUNCH_CHECK();
   return MSD_OK;
 }
@@ -730,18 +744,18 @@ extern "C" int msd_head1x1_bwd(const float* d_dy, const float* d_w, void* d_dh, 
   MSD_REQUIRE(Cin % 8 == 0 && Cin <= 64 && Cout <= 16 && Cout > 0, "head1x1_bwd: Cin=%d (<=64, %%8) Cout=%d (<=16)", Cin, Cout);
   const long long rows = (long long)B * (H + 2) * (W + 2);
   if (Cin <= 48)
-    head1x1_bwd_kernel<48><<<grid_for(rows), kBlock, 0, (cudaStream_t)stream>>>(d_dy, d_w, reinterpret_cast<__nv_bfloat16*>(d_dh),
-                                                                               reinterpret_cast<__nv_bfloat16*>(d_dyt), B, H, W, Cin, Cout);
+    MSD_CHECK_CUDA(msd_launch_pdl((head1x1_bwd_kernel<48>), dim3(grid_for(rows)), dim3(kBlock), 0, (cudaStream_t)stream, d_dy, d_w, reinterpret_cast<__nv_bfloat16*>(d_dh),
+                                                                               reinterpret_cast<__nv_bfloat16*>(d_dyt), B, H, W, Cin, Cout));
   else
-    head1x1_bwd_kernel<64><<<grid_for(rows), kBlock, 0, (cudaStream_t)stream>>>(d_dy, d_w, reinterpret_cast<__nv_bfloat16*>(d_dh),
-                                                                               reinterpret_cast<__nv_bfloat16*>(d_dyt), B, H, W, Cin, Cout);
+    MSD_CHECK_CUDA(msd_launch_pdl((head1x1_bwd_kernel<64>), dim3(grid_for(rows)), dim3(kBlock), 0, (cudaStream_t)stream, d_dy, d_w, reinterpret_cast<__nv_bfloat16*>(d_dh),
+                                                                               reinterpret_cast<__nv_bfloat16*>(d_dyt), B, H, W, Cin, Cout));
   MSD_LAUNCH_CHECK();
   return MSD_OK;
 }
 
 extern "C" int msd_batch_sum_f32(const float* d_in, float* d_out, int B, long long n, void* stream) {
   MSD_REQUIRE(d_in && d_out && B > 0 && n > 0 && n % 4 == 0, "batch_sum: bad arguments");
-  batch_sum_kernel<<<grid_for(n / 4), kBlock, 0, (cudaStream_t)stream>>>(d_in, d_out, B, n);
+  MSD_CHECK_CUDA(msd_launch_pdl((batch_sum_kernel), dim3(grid_for(n / 4)), dim3(kBlock), 0, (cudaStream_t)stream, d_in, d_out, B, n));
   MSD_LAUNCH_CHECK();
   return MSD_OK;
 }
