@@ -45,6 +45,8 @@ struct Problem {
   FastDiv in_plane, in_pitch, cout_div;
   int in_pad, Hin, Win;
   int out_plane, out_pitch; // (2Hin+2)*(2Win+2), 2Win+2
+  int zero_out_halo;        // EPI_CONVT, tcgen05 kernels: the epilogue threads zero the 1-pixel halo of the output buffer before their
+                            // first tile (the pixel-shuffle scatter only writes the interior) -- no separate zero-halo launch
   // EPI_CONV with the decoder's 1x1 head fused behind it (decoder.py:76-81; tcgen05 resident-weight conv mode only):
   // the GELU'd tile never goes to HBM -- each epilogue lane contracts its accumulator row (rounded to bf16, as the two-kernel
   // path stores it) with the fp32 1x1 weights and stores NCHW fp32 straight into the model output.  `out` is unused then.

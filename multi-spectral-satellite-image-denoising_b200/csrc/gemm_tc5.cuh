@@ -415,6 +415,26 @@ __device__ __forceinline__ void bn_sums_flush(uint32_t slots_s, double* __restri
   }
 }
 
+// EPI_CONVT with Problem::zero_out_halo: zero the 1-pixel halo of the haloed NHWC output [B, 2Hin+2, 2Win+2, ldo] (16-byte units),
+// grid-strided over the epilogue threads of all CTAs; `tid` / `nthreads` number the epilogue threads of this CTA
+__device__ __forceinline__ void zero_convt_out_halo(const Problem& p, int tid, int nthreads) {
+  const int Ho = 2 * p.Hin, Wo = 2 * p.Win, PW = Wo + 2, PH = Ho + 2;
+  const int B = p.M / (int)p.in_plane.d;
+  const int per_img = 2 * PW + 2 * Ho, vec = p.ldo / 8;
+  const long long total = (long long)B * per_img * vec;
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
+  for (long long i = (long long)blockIdx.x * nthreads + tid; i < total; i += (long long)gridDim.x * nthreads) {
+    const int v = (int)(i % vec);
+    const long long tt = i / vec;
+    const int k = (int)(tt % per_img), b = (int)(tt / per_img);
+    int yy, xx;
+    if (k < PW) { yy = 0; xx = k; }
+    else if (k < 2 * PW) { yy = Ho + 1; xx = k - PW; }
+    else { const int r = k - 2 * PW; yy = 1 + (r >> 1); xx = (r & 1) ? Wo + 1 : 0; }
+    *reinterpret_cast<uint4*>(out + (((size_t)b * PH + yy) * PW + xx) * p.ldo + v * 8) = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
 // ZERO: the accumulator columns are zeroed behind the read, before the buffer is handed back (conv_roll.cu: every MMA accumulates)
 template <int BN, int EPI, bool PAIR = false, bool ZERO = false>
 __device__ __forceinline__ void epilogue_tile(const Problem& p, uint32_t stg_s, uint32_t bias_s, uint32_t taddr,
@@ -1017,6 +1037,7 @@ gemm_tc5_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // ===== epilogue: warp w may only read TMEM lanes 32*(w%4).. (hardware rule).  e = w-4: bit 2 selects the accumulator
     // buffer (even / odd tiles of this CTA), bit 3 the column half of the tile =====
     const int e = warp - 4;
+    if (p.mode == EPI_CONVT && p.zero_out_halo) zero_convt_out_halo(p, (int)threadIdx.x - 128, C::EPI_WARPS * 32);
     // two buffers: bit 2 of e = accumulator buffer, bit 3 = column half; four buffers: bits 2-3 = accumulator buffer, one column range
     const int q = warp & 3, grp = (e >> 2) & (C::NBUF - 1), half = C::NBUF == 4 ? 0 : e >> 3;
     const uint32_t stg_s = smem_u32(smem_stg + e * C::STG_WARP_BYTES);

@@ -242,6 +242,7 @@ gemm_tc5_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   } else if (warp >= 4) {
     // ===== epilogue (both CTAs, own 128 rows) =====
     const int e = warp - 4;
+    if (p.mode == EPI_CONVT && p.zero_out_halo) zero_convt_out_halo(p, (int)threadIdx.x - 128, C::EPI_WARPS * 32);
     const int q = warp & 3, grp = (e >> 2) & 1, half = e >> 3;
     const uint32_t stg_s = smem_u32(smem_stg + e * C::STG_WARP_BYTES);
     const uint32_t bias_s = stg_s + 32 * E::STG_PITCH;

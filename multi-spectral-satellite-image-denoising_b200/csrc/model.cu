@@ -84,8 +84,10 @@ int make_conv3x3(Problem& p, const void* x, const void* w, const float* bias, co
   return MSD_OK;
 }
 
+// zero_halo_in_kernel: the tcgen05 kernels zero the output halo themselves (Problem::zero_out_halo); the mma.sync baseline needs
+// zero_halo() in front
 int make_convt(Problem& p, const void* x, const void* w, const float* bias, void* y, int B, int Hin, int Win, int in_padded,
-               int Cin, int Cout, int act = 1) {
+               int Cin, int Cout, int act = 1, bool zero_halo_in_kernel = false) {
   MSD_REQUIRE(x && w && y, "convt: null pointer");
   MSD_REQUIRE(B > 0 && Hin > 0 && Win > 0 && Cin % 8 == 0 && Cout % 16 == 0, "convt: bad shape");
   const int ph = in_padded ? Hin + 2 : Hin, pw = in_padded ? Win + 2 : Win;
@@ -105,6 +107,7 @@ int make_convt(Problem& p, const void* x, const void* w, const float* bias, void
   p.in_pad = in_padded; p.Hin = Hin; p.Win = Win;
   p.out_plane = (2 * Hin + 2) * (2 * Win + 2);
   p.out_pitch = 2 * Win + 2;
+  p.zero_out_halo = zero_halo_in_kernel ? 1 : 0;
   return MSD_OK;
 }
 
@@ -246,10 +249,12 @@ extern "C" int msd_conv3x3_head_nchw_f32(const void* d_x, const void* d_w, const
 extern "C" int msd_convt2x2_nhwc_bf16(const void* d_x, const void* d_w, const float* d_bias, void* d_y, int B, int Hin,
                                       int Win, int in_padded, int Cin, int Cout, int backend, void* stream) {
   Problem p;
-  int rc = make_convt(p, d_x, d_w, d_bias, d_y, B, Hin, Win, in_padded, Cin, Cout);
+  int rc = make_convt(p, d_x, d_w, d_bias, d_y, B, Hin, Win, in_padded, Cin, Cout, 1, backend == 0);
   if (rc) return rc;
-  rc = zero_halo(d_y, B, 2 * Hin, 2 * Win, Cout, (cudaStream_t)stream);
-  if (rc) return rc;
+  if (backend != 0) {
+    rc = zero_halo(d_y, B, 2 * Hin, 2 * Win, Cout, (cudaStream_t)stream);
+    if (rc) return rc;
+  }
   return gemm::launch(p, backend, (cudaStream_t)stream);
 }
 
@@ -357,9 +362,9 @@ extern "C" size_t msd_model_workspace_bytes(const msd_model* m, int B) {
 extern "C" int msd_model_launch_count(const msd_model* m) {
   if (!m) return 0;
   // patchify + pe gemm + ln_pos + depth*(ln, qkv, attn, proj, ln, fc1, fc2) + final ln
-  // + 4*(zero_halo + convT + 4 conv) + head conv (the 1x1 head rides in its epilogue on the tcgen05 path, else + head 1x1)
+  // + 4*([zero_halo, mma.sync backend only] + convT + 4 conv) + head conv (the 1x1 head rides in its epilogue on the tcgen05 path, else + head 1x1)
   // (with the LayerNorms folded into the GEMMs: 5 launches per block)
-  return 3 + (m->ln_fused ? 5 : 7) * m->d.depth + 1 + 4 * 6 + (m->head_fused ? 1 : 2);
+  return 3 + (m->ln_fused ? 5 : 7) * m->d.depth + 1 + 4 * (m->d.gemm_backend == 0 ? 5 : 6) + (m->head_fused ? 1 : 2);
 }
 
 extern "C" void msd_model_destroy(msd_model* m) {
@@ -498,8 +503,8 @@ extern "C" int msd_model_forward(msd_model* m, const float* d_x, const void* d_p
     const msd_stage_weights& sw = w.stages[st];
     const int cout = d.dec_channels[st];
     void *X = ws + L.stage[st][0], *Y = ws + L.stage[st][1], *Z = ws + L.stage[st][2];
-    MSD_RUN(3, 0.0, zero_halo(X, B, 2 * hw, 2 * hw, cout, s));
-    MSD_TRY(make_convt(p, cur, sw.w_up, sw.b_up, X, B, hw, hw, in_pad, cin, cout));
+    if (be != 0) MSD_RUN(3, 0.0, zero_halo(X, B, 2 * hw, 2 * hw, cout, s));
+    MSD_TRY(make_convt(p, cur, sw.w_up, sw.b_up, X, B, hw, hw, in_pad, cin, cout, 1, be == 0));
     MSD_RUN(0, 2.0 * B * hw * hw * 4.0 * cout * cin, gemm::launch(p, be, s));
     hw *= 2;
     const double cf = 2.0 * B * hw * hw * (double)cout * 9.0 * cout;   // algorithmic: the identity skip tap is not counted
@@ -764,8 +769,8 @@ extern "C" int msd_model_forward_train(msd_model* m, const float* d_x, int B, fl
     const int c = d.dec_channels[st];
     unsigned char* T[10];
     for (int k = 0; k < 10; ++k) T[k] = ws + L.dec[st][k];
-    MSD_TRY(zero_halo(T[0], B, 2 * hw, 2 * hw, c, s));
-    MSD_TRY(make_convt(p, cur, sw.w_up, sw.b_up, T[0], B, hw, hw, in_pad, cin, c, 0));
+    if (be != 0) MSD_TRY(zero_halo(T[0], B, 2 * hw, 2 * hw, c, s));
+    MSD_TRY(make_convt(p, cur, sw.w_up, sw.b_up, T[0], B, hw, hw, in_pad, cin, c, 0, be == 0));
     MSD_TRY(gemm::launch(p, be, s));
     hw *= 2;
     float* st_up = stats + (size_t)bn_index(st, 0) * kStatsStride;
