@@ -362,6 +362,38 @@ def test_model_with_folded_batchnorm_stats_and_timm_layout(seeded_model, golden_
     assert (y3 - ref3).abs().pow(2).mean().sqrt().item() <= 0.02 * ref3.std().item()
 
 
+def test_rolling_conv_is_deterministic_and_pdl_changes_nothing(seeded_model, monkeypatch):
+    """Two properties the bit-exact sharding tests rest on.  (1) csrc/conv_roll.cu issues its MMAs from two warps into the same
+    TMEM accumulators; they sit on one SM sub-partition and hand a token over after each input row, which orders the fp32
+    accumulation: repeated launches (all 148 CTAs busy) must agree bit for bit.  (2) Programmatic dependent launch
+    (common.cuh msd_launch_pdl) only moves kernel prologues under the previous kernel's tail: the whole forward with MSD_NO_PDL=1
+    is bit-identical."""
+    torch.manual_seed(3)
+    B, H, W = 40, 192, 192
+    x = _bf(torch.randn(B, H + 2, W + 2, 48, device="cuda"))
+    sk = _bf(torch.randn(B, H + 2, W + 2, 48, device="cuda"))
+    w = _bf(torch.randn(48, 10 * 64, device="cuda") * 432 ** -0.5)
+    b = torch.randn(48, device="cuda")
+    for skip in (None, sk):
+        y0 = gh.conv3x3(x, w, b, skip, B, H, W, 48, 48, 0).clone()
+        for _ in range(6):
+            assert torch.equal(gh.conv3x3(x, w, b, skip, B, H, W, 48, 48, 0), y0)
+        y1 = gh.conv3x3(x[7:19].contiguous(), w, b, None if skip is None else skip[7:19].contiguous(), 12, H, W, 48, 48, 0)
+        assert torch.equal(y1, y0[7:19])
+    m = seeded_model
+    m.gemm_backend = 0
+    m._handle = None
+    m.cuda()
+    xin = recipes.model_input(9, seed=5).cuda()
+    with torch.no_grad():
+        y_pdl = m(xin).clone()
+        monkeypatch.setenv("MSD_NO_PDL", "1")
+        y_ser = m(xin).clone()
+        monkeypatch.setenv("MSD_NO_PDL", "0")
+    assert torch.equal(y_pdl, y_ser)
+    m.cpu()
+
+
 def test_model_batch_independence_and_ragged_tiles(seeded_model):
     """B=9 -> 1296 token rows (not a multiple of the 128-row tile) and ragged conv tiles; every image must come
     out exactly as it does in a batch of 2 (no cross-image leakage through halos / tile tails)."""
