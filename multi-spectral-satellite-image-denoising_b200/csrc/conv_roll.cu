@@ -382,9 +382,9 @@ conv_roll_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int m_base = (sg.img * PH + sg.o0 + 1) * PW + sg.strip * 128 + 1;
       if (!pair) m_base += 32 * q;
       else m_base += (q < 2 ? 32 * q : (g.H >> 1) * PW + 32 * (q - 2));
-      for (int o = 0; o < sg.n; ++o) {
+      // this group's rows of the segment: u = ubase + o with u = grp (mod GROUPS)
+      for (int o = (int)(((uint32_t)grp + (uint32_t)GROUPS - ubase % (uint32_t)GROUPS) % (uint32_t)GROUPS); o < sg.n; o += GROUPS) {
         const uint32_t u = ubase + (uint32_t)o;
-        if ((int)(u % GROUPS) != grp) continue;
         const uint32_t slot = u % R;
         const int mrow0 = m_base + o * PW;
         if constexpr (EPI == E_CONV_SKIPADD)
